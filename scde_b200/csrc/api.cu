@@ -1,0 +1,1109 @@
+// api.cu -- the C ABI of libscde_b200 (include/scde_b200.h): contexts, device buffers, the orchestration of
+// scde.posteriors / scde.expression.difference on the device, and nothing else.  No CPU fallback: every compute
+// entry point fails with SCDE_B200_ENODEVICE when there is no CUDA device.
+#include "../../include/scde_b200.h"
+#include "common.cuh"
+#include "hostmath.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace scde {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return SCDE_B200_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return SCDE_B200_ENODEVICE;
+    return SCDE_B200_ECUDA;
+}
+
+template <class T>
+struct DBuf {  // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+};
+
+struct StageTimer {
+    std::vector<cudaEvent_t> pool;
+    struct Span {
+        int stage;
+        int e0, e1;
+    };
+    std::vector<Span> spans;
+    size_t used = 0;
+    int launches[SCDE_B200_T_COUNT] = {0};
+    ~StageTimer() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+    void reset() {
+        spans.clear();
+        used = 0;
+        memset(launches, 0, sizeof(launches));
+    }
+    int get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            pool.push_back(e);
+        }
+        return (int)used++;
+    }
+    int begin(cudaStream_t st) {
+        int i = get();
+        if (i >= 0) cudaEventRecord(pool[i], st);
+        return i;
+    }
+    void end(int stage, int e0, cudaStream_t st, int n_launch) {
+        int i = get();
+        if (i >= 0 && e0 >= 0) {
+            cudaEventRecord(pool[i], st);
+            spans.push_back({stage, e0, i});
+        }
+        launches[stage] += n_launch;
+    }
+    void collect(scde_b200_stats *s) {
+        for (int i = 0; i < SCDE_B200_T_COUNT; ++i) {
+            s->ms[i] = 0;
+            s->launches[i] = launches[i];
+        }
+        for (auto &sp : spans) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pool[sp.e0], pool[sp.e1]) == cudaSuccess) s->ms[sp.stage] += ms;
+        }
+        int tot = 0;
+        for (int i = 0; i < SCDE_B200_T_TOTAL; ++i) tot += launches[i];
+        s->launches[SCDE_B200_T_TOTAL] = tot;
+    }
+};
+
+}  // namespace scde
+
+using namespace scde;
+
+struct scde_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n_sm = 148;
+    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled
+};
+
+namespace {
+
+inline int table_ld(int K) { return K <= KP_TILED ? KP_TILED : round_up(K, 8); }
+
+struct LpTable {
+    int n_cells = 0, n_genes = 0, K = 0, ld = 0, ld_ridx = 0;
+    int64_t n_rows = 0;
+    double sentinel = 0;
+    DBuf<int32_t> row_off, row_x, row_mode, ridx, n_unique, err;
+    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp;
+};
+
+#define CHECK_CTX(ctx)                                                  \
+    do {                                                                \
+        if (!(ctx)) {                                                   \
+            set_error("null context");                                  \
+            return SCDE_B200_EINVAL;                                    \
+        }                                                               \
+        SCDE_CUDA(cudaSetDevice((ctx)->device));                        \
+    } while (0)
+
+// rows of the table from the per-cell model rows; t.row_off / t.row_x / t.n_rows must be set
+int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_models, const double *mag_dev,
+               int local_theta, int sqlogit, StageTimer *tm) {
+    cudaStream_t st = ctx->stream;
+    const size_t cl = (size_t)t.n_cells * t.ld;
+    SCDE_CUDA(t.mu.ensure(cl));
+    SCDE_CUDA(t.lcfp.ensure(cl));
+    SCDE_CUDA(t.lcfpr.ensure(cl));
+    if (local_theta) SCDE_CUDA(t.theta.ensure(cl));
+    SCDE_CUDA(t.maxcfp.ensure(t.n_cells));
+    SCDE_CUDA(t.table.ensure((size_t)t.n_rows * t.ld));
+    SCDE_CUDA(t.row_mode.ensure((size_t)t.n_rows));
+    CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld};
+    int e0 = tm ? tm->begin(st) : -1;
+    SCDE_CUDA(launch_cell_prep(models_dev, ld_models, nullptr, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
+    SCDE_CUDA(launch_lp_rows(models_dev, ld_models, nullptr, t.n_cells, t.row_off.p, t.row_x.p, t.n_rows, prep, t.K,
+                             local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, st));
+    if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, 2);
+    return SCDE_B200_OK;
+}
+
+// unique-count indices from raw counts (device, column-major, leading dimension ldc, genes [g0, g0+G))
+int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev, int64_t ldc, int g0, int G, int C,
+                      StageTimer *tm) {
+    cudaStream_t st = ctx->stream;
+    t.n_cells = C;
+    t.n_genes = G;
+    t.ld_ridx = C;
+    SCDE_CUDA(t.n_unique.ensure(C));
+    SCDE_CUDA(t.row_off.ensure((size_t)C + 1));
+    SCDE_CUDA(t.err.ensure(1));
+    SCDE_CUDA(t.ridx.ensure((size_t)G * C));
+    int e0 = tm ? tm->begin(st) : -1;
+    SCDE_CUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
+    SCDE_CUDA(launch_dedup_count(counts_dev, ldc, g0, G, C, t.n_unique.p, t.err.p, st));
+    SCDE_CUDA(launch_exclusive_scan(t.n_unique.p, t.row_off.p, C, st));
+    int32_t total = 0, err = 0;
+    SCDE_CUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));  // the table is sized by the number of distinct (cell, count) pairs
+    if (err & 1) {
+        set_error("negative count in the count matrix");
+        return SCDE_B200_EINVAL;
+    }
+    if (err & 2) {
+        set_error("a cell has >= 32768 distinct count values among the processed genes (hash capacity)");
+        return SCDE_B200_ELIMIT;
+    }
+    t.n_rows = total;
+    SCDE_CUDA(t.row_x.ensure((size_t)total));
+    SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p, st));
+    if (tm) tm->end(SCDE_B200_T_DEDUP, e0, st, 3);
+    return SCDE_B200_OK;
+}
+
+struct JointScratch {
+    DBuf<double> W;
+    DBuf<int32_t> idx;
+};
+
+// jp_dev[G][ld_jp] = joint posterior of the listed cells under the draws boot_idx_dev (n_boot x D, device).
+int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev, int n_list,
+              const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
+              JointScratch &scr, StageTimer *tm, int64_t *contract_cells) {
+    cudaStream_t st = ctx->stream;
+    const int n_w_rows = round_up(n_list, 8);
+    const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
+    SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WP_TILED));
+    int e0 = tm ? tm->begin(st) : -1;
+    SCDE_CUDA(launch_build_w(boot_idx_dev, n_boot, D, n_list, scr.W.p, n_w_rows, st));
+    SCDE_CUDA(cudaMemsetAsync(jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
+    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
+    ContractArgs a;
+    a.table = t.table.p;
+    a.ld_table = t.ld;
+    a.ridx = t.ridx.p;
+    a.ld_ridx = t.ld_ridx;
+    a.cell_ids = cell_ids_dev;
+    a.n_list = n_list;
+    a.W = scr.W.p;
+    a.n_w_rows = n_w_rows;
+    a.n_boot = n_boot;
+    a.scale = scale;
+    a.n_genes = t.n_genes;
+    a.K = t.K;
+    a.jp = jp_dev;
+    a.ld_jp = ld_jp;
+    bool tiled = contract_tiled_supported(a);
+    if (ctx->contract_kernel == 1) tiled = false;
+    if (ctx->contract_kernel == 2 && !tiled) {
+        set_error("tiled contraction kernel forced but unsupported for K=%d", t.K);
+        return SCDE_B200_EINVAL;
+    }
+    e0 = tm ? tm->begin(st) : -1;
+    int nl = 0;
+    if (tiled)
+        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, st, &nl));
+    else
+        SCDE_CUDA(launch_contract_generic(a, st, &nl));
+    if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
+    if (contract_cells) *contract_cells += n_list;
+    return SCDE_B200_OK;
+}
+
+std::vector<int32_t> gen_boot(int seed, int n, int n_boot) {
+    std::vector<int32_t> v((size_t)n_boot * n);
+    scde_b200_boot_indices(seed, n, n_boot, v.data());
+    return v;
+}
+
+template <class T>
+int upload(DBuf<T> &d, const T *h, size_t n, cudaStream_t st) {
+    SCDE_CUDA(d.ensure(n));
+    if (n) SCDE_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return SCDE_B200_OK;
+}
+#define TRY(x)                          \
+    do {                                \
+        int _r = (x);                   \
+        if (_r != SCDE_B200_OK) return _r; \
+    } while (0)
+
+int validate_index(const int32_t *v, size_t n, int lo, int hi, const char *what) {
+    for (size_t i = 0; i < n; ++i)
+        if (v[i] < lo || v[i] >= hi) {
+            set_error("%s[%zu] = %d outside [%d, %d)", what, i, v[i], lo, hi);
+            return SCDE_B200_EINVAL;
+        }
+    return SCDE_B200_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int scde_b200_version(void) { return SCDE_B200_VERSION; }
+const char *scde_b200_last_error(void) { return g_err.c_str(); }
+
+int scde_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int scde_b200_create(int device, scde_b200_ctx **out) {
+    if (!out) return SCDE_B200_EINVAL;
+    *out = nullptr;
+    int n = scde_b200_device_count();
+    if (n <= 0) {
+        set_error("no CUDA device available (libscde_b200 has no CPU fallback)");
+        return SCDE_B200_ENODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (have %d)", device, n);
+        return SCDE_B200_EINVAL;
+    }
+    SCDE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SCDE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; libscde_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return SCDE_B200_ENODEVICE;
+    }
+    scde_b200_ctx *c = new scde_b200_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+    }
+    *out = c;
+    return SCDE_B200_OK;
+}
+
+void scde_b200_destroy(scde_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void *scde_b200_stream(scde_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int scde_b200_synchronize(scde_b200_ctx *ctx) {
+    CHECK_CTX(ctx);
+    SCDE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which) {
+    if (!ctx || which < 0 || which > 2) return SCDE_B200_EINVAL;
+    ctx->contract_kernel = which;
+    return SCDE_B200_OK;
+}
+
+int scde_b200_measure_fp64_peak(scde_b200_ctx *ctx, double *tflops) {
+    CHECK_CTX(ctx);
+    if (!tflops) return SCDE_B200_EINVAL;
+    DBuf<double> sink;
+    SCDE_CUDA(sink.ensure(1));
+    const int iters = 20000, blocks = ctx->n_sm * 8;
+    cudaEvent_t e0, e1;
+    SCDE_CUDA(cudaEventCreate(&e0));
+    SCDE_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        SCDE_CUDA(cudaEventRecord(e0, ctx->stream));
+        SCDE_CUDA(launch_fp64_peak(sink.p, iters, blocks, ctx->stream));
+        SCDE_CUDA(cudaEventRecord(e1, ctx->stream));
+        SCDE_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SCDE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 16 * (double)iters * 256 * blocks;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return SCDE_B200_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+int scde_b200_cell_table(scde_b200_ctx *ctx, const double *model_row12, const int32_t *unique_counts, int32_t n_counts,
+                         const double *magnitudes, int32_t n_grid, int32_t local_theta, int32_t square_logit_conc,
+                         int32_t n_cells_for_clamp, double *out, int32_t *modes) {
+    CHECK_CTX(ctx);
+    if (!model_row12 || !unique_counts || !magnitudes || !out || n_counts < 0 || n_grid < 1 || n_cells_for_clamp < 1) {
+        set_error("cell_table: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    LpTable t;
+    t.n_cells = 1;
+    t.K = n_grid;
+    t.ld = table_ld(n_grid);
+    t.n_rows = n_counts;
+    t.sentinel = -DBL_MAX / n_cells_for_clamp / 1.1;
+    DBuf<double> d_models, d_mag;
+    TRY(upload(d_models, model_row12, 12, st));
+    TRY(upload(d_mag, magnitudes, (size_t)n_grid, st));
+    int32_t off[2] = {0, n_counts};
+    TRY(upload(t.row_off, off, 2, st));
+    TRY(upload(t.row_x, unique_counts, (size_t)n_counts, st));
+    TRY(fill_table(ctx, t, d_models.p, 1, d_mag.p, local_theta, square_logit_conc, nullptr));
+    if (n_counts > 0) {
+        SCDE_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n_grid, t.table.p, sizeof(double) * t.ld, sizeof(double) * n_grid,
+                                    n_counts, cudaMemcpyDeviceToHost, st));
+        if (modes)
+            SCDE_CUDA(cudaMemcpyAsync(modes, t.row_mode.p, sizeof(int32_t) * n_counts, cudaMemcpyDeviceToHost, st));
+    }
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
+                           const int32_t *ucl_offsets, const int32_t *uci, int32_t n_genes, const double *magnitudes,
+                           int32_t n_grid, int32_t n_boot, const int32_t *boot_idx, int32_t D, int32_t return_individual,
+                           int32_t local_theta, int32_t square_logit_conc, int32_t ensemble, int32_t modes_flag,
+                           int32_t post_flag, double *jp, double *modes, double *post) {
+    cudaStream_t st = ctx->stream;
+    (void)return_individual;
+    if (!models || !ucl_flat || !ucl_offsets || !uci || !magnitudes || !jp || n_cells < 1 || n_genes < 0 || n_grid < 1 ||
+        n_boot < 0) {
+        set_error("log_boot_posterior: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    if (ucl_offsets[0] != 0) {
+        set_error("ucl_offsets[0] must be 0");
+        return SCDE_B200_EINVAL;
+    }
+    for (int c = 0; c < n_cells; ++c) {
+        if (ucl_offsets[c + 1] < ucl_offsets[c]) {
+            set_error("ucl_offsets not monotone at cell %d", c);
+            return SCDE_B200_EINVAL;
+        }
+        const int nu = ucl_offsets[c + 1] - ucl_offsets[c];
+        TRY(validate_index(uci + (size_t)c * n_genes, (size_t)n_genes, 0, nu, "uci"));
+    }
+    if (modes_flag && !modes) {
+        set_error("modes requested but the output pointer is NULL");
+        return SCDE_B200_EINVAL;
+    }
+    if (post_flag && !post) {
+        set_error("post requested but the output pointer is NULL");
+        return SCDE_B200_EINVAL;
+    }
+    if (n_genes == 0) return SCDE_B200_OK;
+    LpTable t;
+    t.n_cells = n_cells;
+    t.n_genes = n_genes;
+    t.K = n_grid;
+    t.ld = table_ld(n_grid);
+    t.ld_ridx = n_cells;
+    t.n_rows = ucl_offsets[n_cells];
+    const double minlogprob = -DBL_MAX / n_cells / 1.1;  // src/jpmatLogBoot.cpp:127,372
+    t.sentinel = -DBL_MAX / (double)(D > n_cells ? D : n_cells) / 1.1;
+    DBuf<double> d_models, d_mag, d_jp, d_out, d_rs;
+    DBuf<int32_t> d_uci, d_boot;
+    TRY(upload(d_models, models, (size_t)n_cells * 12, st));
+    TRY(upload(d_mag, magnitudes, (size_t)n_grid, st));
+    TRY(upload(t.row_off, ucl_offsets, (size_t)n_cells + 1, st));
+    TRY(upload(t.row_x, ucl_flat, (size_t)t.n_rows, st));
+    TRY(upload(d_uci, uci, (size_t)n_genes * n_cells, st));
+    SCDE_CUDA(t.ridx.ensure((size_t)n_genes * n_cells));
+    SCDE_CUDA(launch_uci_to_ridx(d_uci.p, n_genes, n_cells, t.row_off.p, t.ridx.p, t.ld_ridx, st));
+    TRY(fill_table(ctx, t, d_models.p, n_cells, d_mag.p, local_theta, square_logit_conc, nullptr));
+    const int ld_jp = t.ld;
+    SCDE_CUDA(d_jp.ensure((size_t)n_genes * ld_jp));
+    JointScratch scr;
+    if (ensemble) {
+        ContractArgs a{};
+        a.table = t.table.p;
+        a.ld_table = t.ld;
+        a.ridx = t.ridx.p;
+        a.ld_ridx = t.ld_ridx;
+        a.cell_ids = nullptr;
+        a.n_list = n_cells;
+        a.n_genes = n_genes;
+        a.K = n_grid;
+        a.jp = d_jp.p;
+        a.ld_jp = ld_jp;
+        SCDE_CUDA(d_rs.ensure((size_t)t.n_rows));
+        SCDE_CUDA(launch_ensemble(a, d_rs.p, t.n_rows, st));
+    } else {
+        std::vector<int32_t> gen;
+        int nb = n_boot, dd = D;
+        double scale = (double)n_boot;
+        if (n_boot == 0) {  // plain product over all cells, src/jpmatLogBoot.cpp:239-249
+            gen.resize(n_cells);
+            for (int c = 0; c < n_cells; ++c) gen[c] = c;
+            boot_idx = gen.data();
+            nb = 1;
+            dd = n_cells;
+            scale = 1.0;
+        }
+        TRY(validate_index(boot_idx, (size_t)nb * dd, 0, n_cells, "boot_idx"));
+        TRY(upload(d_boot, boot_idx, (size_t)nb * dd, st));
+        TRY(run_joint(ctx, t, nullptr, n_cells, d_boot.p, nb, dd, scale, d_jp.p, ld_jp, scr, nullptr, nullptr));
+    }
+    SCDE_CUDA(d_out.ensure((size_t)n_genes * n_grid));
+    SCDE_CUDA(launch_transpose_out(d_jp.p, ld_jp, n_genes, n_grid, d_out.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(jp, d_out.p, sizeof(double) * (size_t)n_genes * n_grid, cudaMemcpyDeviceToHost, st));
+    if (modes_flag) {
+        DBuf<double> d_modes;
+        SCDE_CUDA(d_modes.ensure((size_t)n_genes * n_cells));
+        SCDE_CUDA(launch_gather_modes(t.ridx.p, t.ld_ridx, n_genes, n_cells, t.row_mode.p, d_mag.p, d_modes.p, st));
+        SCDE_CUDA(cudaMemcpyAsync(modes, d_modes.p, sizeof(double) * (size_t)n_genes * n_cells, cudaMemcpyDeviceToHost, st));
+        SCDE_CUDA(cudaStreamSynchronize(st));
+    }
+    if (post_flag) {
+        DBuf<double> d_post;
+        const size_t np = (size_t)n_cells * n_genes * n_grid;
+        SCDE_CUDA(d_post.ensure(np));
+        SCDE_CUDA(launch_gather_post(t.ridx.p, t.ld_ridx, n_genes, n_cells, t.table.p, t.ld, n_grid, t.sentinel, minlogprob,
+                                     d_post.p, st));
+        SCDE_CUDA(cudaMemcpyAsync(post, d_post.p, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+        SCDE_CUDA(cudaStreamSynchronize(st));
+    }
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_log_boot_posterior(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
+                                 const int32_t *ucl_offsets, const int32_t *uci, int32_t n_genes,
+                                 const double *magnitudes, int32_t n_grid, int32_t n_boot, int32_t seed,
+                                 const int32_t *boot_idx, int32_t return_individual, int32_t local_theta,
+                                 int32_t square_logit_conc, int32_t ensemble, double *jp, double *modes, double *post) {
+    CHECK_CTX(ctx);
+    if (n_cells < 1 || n_boot < 0) {
+        set_error("log_boot_posterior: n_cells must be >= 1 and n_boot >= 0");
+        return SCDE_B200_EINVAL;
+    }
+    std::vector<int32_t> gen;
+    if (!boot_idx && n_boot > 0 && !ensemble) {
+        gen = gen_boot(seed, n_cells, n_boot);
+        boot_idx = gen.data();
+    }
+    const int mf = (return_individual == 1 || return_individual == 3);
+    const int pf = (return_individual == 2 || return_individual == 3);
+    return log_boot_common(ctx, models, n_cells, ucl_flat, ucl_offsets, uci, n_genes, magnitudes, n_grid, n_boot, boot_idx,
+                           n_cells, return_individual, local_theta, square_logit_conc, ensemble, mf, pf, jp, modes, post);
+}
+
+int scde_b200_log_boot_batch_posterior(scde_b200_ctx *ctx, const double *models, int32_t n_cells,
+                                       const int32_t *ucl_flat, const int32_t *ucl_offsets, const int32_t *uci,
+                                       int32_t n_genes, const double *magnitudes, int32_t n_grid, int32_t n_levels,
+                                       const int32_t *batchil_offsets, const int32_t *batchil_cells,
+                                       const int32_t *composition, int32_t n_boot, int32_t seed, const int32_t *boot_idx,
+                                       int32_t return_individual, int32_t local_theta, int32_t square_logit_conc,
+                                       double *jp, double *modes, double *post) {
+    CHECK_CTX(ctx);
+    if (n_cells < 1 || n_levels < 1 || !batchil_offsets || !batchil_cells || !composition || n_boot < 1) {
+        set_error("log_boot_batch_posterior: bad arguments (the reference has no n_boot == 0 branch here)");
+        return SCDE_B200_EINVAL;
+    }
+    int D = 0;
+    for (int k = 0; k < n_levels; ++k)
+        if (composition[k] > 0) D += composition[k];
+    if (D < 1) {
+        set_error("log_boot_batch_posterior: empty composition");
+        return SCDE_B200_EINVAL;
+    }
+    TRY(validate_index(batchil_cells, (size_t)batchil_offsets[n_levels], 0, n_cells, "batchil"));
+    std::vector<int32_t> gen;
+    if (!boot_idx) {
+        gen.resize((size_t)n_boot * D);
+        int r = scde_b200_batch_boot_indices(seed, n_levels, batchil_offsets, batchil_cells, composition, n_boot, gen.data());
+        if (r != SCDE_B200_OK) {
+            set_error("log_boot_batch_posterior: a sampled batch level has an empty pool");
+            return r;
+        }
+        boot_idx = gen.data();
+    }
+    const int mf = (return_individual == 1);  // src/jpmatLogBoot.cpp:441,455,501
+    const int pf = (return_individual == 2 || return_individual == 3);
+    return log_boot_common(ctx, models, n_cells, ucl_flat, ucl_offsets, uci, n_genes, magnitudes, n_grid, n_boot, boot_idx, D,
+                           return_individual, local_theta, square_logit_conc, 0, mf, pf, jp, modes, post);
+}
+
+// --------------------------------------------------------------------------------------------
+static int jpmat_common(scde_b200_ctx *ctx, const double *matl, int n_mat, int n_rows, int n_cols, int n_boot,
+                        const int32_t *boot_idx, int D, double *jp) {
+    cudaStream_t st = ctx->stream;
+    if (!matl || !jp || n_mat < 1 || n_rows < 0 || n_cols < 1 || n_boot < 0) {
+        set_error("jpmat_log_boot: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    if (n_rows == 0) return SCDE_B200_OK;
+    TRY(validate_index(boot_idx, (size_t)n_boot * D, 0, n_mat, "boot_idx"));
+    LpTable t;
+    t.n_cells = n_mat;
+    t.n_genes = n_rows;
+    t.K = n_cols;
+    t.ld = table_ld(n_cols);
+    t.ld_ridx = n_mat;
+    t.n_rows = (int64_t)n_mat * n_rows;
+    const size_t sz = (size_t)n_rows * n_cols;
+    DBuf<double> d_in, d_jp, d_out;
+    DBuf<int32_t> d_boot;
+    TRY(upload(d_in, matl, sz * n_mat, st));
+    SCDE_CUDA(t.table.ensure((size_t)t.n_rows * t.ld));
+    SCDE_CUDA(cudaMemsetAsync(t.table.p, 0, sizeof(double) * (size_t)t.n_rows * t.ld, st));
+    for (int m = 0; m < n_mat; ++m)
+        SCDE_CUDA(launch_transpose_in(d_in.p + sz * m, n_rows, n_cols, t.table.p + (size_t)m * n_rows * t.ld, t.ld, st));
+    std::vector<int32_t> ridx((size_t)n_rows * n_mat);
+    for (int g = 0; g < n_rows; ++g)
+        for (int m = 0; m < n_mat; ++m) ridx[(size_t)g * n_mat + m] = m * n_rows + g;
+    TRY(upload(t.ridx, ridx.data(), ridx.size(), st));
+    TRY(upload(d_boot, boot_idx, (size_t)n_boot * D, st));
+    SCDE_CUDA(d_jp.ensure((size_t)n_rows * t.ld));
+    JointScratch scr;
+    if (n_boot > 0) {
+        // not divided by n_boot: src/jpmatLogBoot.cpp:36-38
+        TRY(run_joint(ctx, t, nullptr, n_mat, d_boot.p, n_boot, D, 1.0, d_jp.p, t.ld, scr, nullptr, nullptr));
+    } else {
+        SCDE_CUDA(cudaMemsetAsync(d_jp.p, 0, sizeof(double) * (size_t)n_rows * t.ld, st));
+    }
+    SCDE_CUDA(d_out.ensure(sz));
+    SCDE_CUDA(launch_transpose_out(d_jp.p, t.ld, n_rows, n_cols, d_out.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(jp, d_out.p, sizeof(double) * sz, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_jpmat_log_boot(scde_b200_ctx *ctx, const double *matl, int32_t n_mat, int32_t n_rows, int32_t n_cols,
+                             int32_t n_boot, int32_t seed, const int32_t *boot_idx, double *jp) {
+    CHECK_CTX(ctx);
+    if (n_mat < 1 || n_boot < 0) {
+        set_error("jpmat_log_boot: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    std::vector<int32_t> gen;
+    if (!boot_idx) {
+        gen = gen_boot(seed, n_mat, n_boot);
+        boot_idx = gen.data();
+    }
+    return jpmat_common(ctx, matl, n_mat, n_rows, n_cols, n_boot, boot_idx, n_mat, jp);
+}
+
+int scde_b200_jpmat_log_batch_boot(scde_b200_ctx *ctx, const double *matl, int32_t n_levels,
+                                   const int32_t *pool_offsets, const int32_t *composition, int32_t n_rows,
+                                   int32_t n_cols, int32_t n_boot, int32_t seed, const int32_t *boot_idx, double *jp) {
+    CHECK_CTX(ctx);
+    if (n_levels < 1 || !pool_offsets || !composition || n_boot < 0) {
+        set_error("jpmat_log_batch_boot: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    const int n_mat = pool_offsets[n_levels];
+    int D = 0;
+    for (int k = 0; k < n_levels; ++k)
+        if (composition[k] > 0) D += composition[k];
+    std::vector<int32_t> gen, cells(n_mat);
+    if (!boot_idx) {
+        for (int i = 0; i < n_mat; ++i) cells[i] = i;
+        gen.resize((size_t)n_boot * D);
+        int r = scde_b200_batch_boot_indices(seed, n_levels, pool_offsets, cells.data(), composition, n_boot, gen.data());
+        if (r != SCDE_B200_OK) {
+            set_error("jpmat_log_batch_boot: a sampled pool is empty");
+            return r;
+        }
+        boot_idx = gen.data();
+    }
+    return jpmat_common(ctx, matl, n_mat, n_rows, n_cols, n_boot, boot_idx, D, jp);
+}
+
+// --------------------------------------------------------------------------------------------
+int scde_b200_mat_slide_mult(scde_b200_ctx *ctx, const double *m1, const double *m2, int32_t n_rows, int32_t n,
+                             double *out) {
+    CHECK_CTX(ctx);
+    if (!m1 || !m2 || !out || n_rows < 0 || n < 1) {
+        set_error("mat_slide_mult: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    if (n_rows == 0) return SCDE_B200_OK;
+    cudaStream_t st = ctx->stream;
+    const int nout = 2 * n - 1, ld = round_up(n, 8), ldo = round_up(nout, 8);
+    DBuf<double> d_in, d1, d2, d_raw, d_out;
+    const size_t sz = (size_t)n_rows * n;
+    SCDE_CUDA(d_in.ensure(sz));
+    SCDE_CUDA(d1.ensure((size_t)n_rows * ld));
+    SCDE_CUDA(d2.ensure((size_t)n_rows * ld));
+    SCDE_CUDA(cudaMemcpyAsync(d_in.p, m1, sizeof(double) * sz, cudaMemcpyHostToDevice, st));
+    SCDE_CUDA(launch_transpose_in(d_in.p, n_rows, n, d1.p, ld, st));
+    SCDE_CUDA(cudaMemcpyAsync(d_in.p, m2, sizeof(double) * sz, cudaMemcpyHostToDevice, st));
+    SCDE_CUDA(launch_transpose_in(d_in.p, n_rows, n, d2.p, ld, st));
+    SCDE_CUDA(d_raw.ensure((size_t)n_rows * ldo));
+    RatioArgs a{};
+    a.p1 = d1.p;
+    a.p2 = d2.p;
+    a.ld = ld;
+    a.n_genes = n_rows;
+    a.n = n;
+    a.ld_post = ldo;
+    a.raw = d_raw.p;
+    SCDE_CUDA(launch_ratio_summary(a, st));
+    SCDE_CUDA(d_out.ensure((size_t)n_rows * nout));
+    SCDE_CUDA(launch_transpose_out(d_raw.p, ldo, n_rows, nout, d_out.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * (size_t)n_rows * nout, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_ratio_posterior_summary(scde_b200_ctx *ctx, const double *pmat1, const double *pmat2, int32_t n_genes,
+                                      int32_t n, const double *prior_y, const int32_t *zero_index, int32_t n_zero,
+                                      int32_t *idx, double *z, double *posterior) {
+    CHECK_CTX(ctx);
+    if (!pmat1 || !pmat2 || n_genes < 0 || n < 1 || !zero_index || (n_zero != 1 && n_zero != n_genes)) {
+        set_error("ratio_posterior_summary: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    if (n_genes == 0) return SCDE_B200_OK;
+    TRY(validate_index(zero_index, (size_t)n_zero, 1, 2 * n, "zero_index"));
+    cudaStream_t st = ctx->stream;
+    const int nout = 2 * n - 1, ld = round_up(n, 8), ldo = round_up(nout, 8);
+    DBuf<double> d_in, d1, d2, d_prior, d_post, d_out, d_z;
+    DBuf<int32_t> d_zi, d_idx;
+    const size_t sz = (size_t)n_genes * n;
+    SCDE_CUDA(d_in.ensure(sz));
+    SCDE_CUDA(d1.ensure((size_t)n_genes * ld));
+    SCDE_CUDA(d2.ensure((size_t)n_genes * ld));
+    SCDE_CUDA(cudaMemcpyAsync(d_in.p, pmat1, sizeof(double) * sz, cudaMemcpyHostToDevice, st));
+    SCDE_CUDA(launch_transpose_in(d_in.p, n_genes, n, d1.p, ld, st));
+    SCDE_CUDA(cudaMemcpyAsync(d_in.p, pmat2, sizeof(double) * sz, cudaMemcpyHostToDevice, st));
+    SCDE_CUDA(launch_transpose_in(d_in.p, n_genes, n, d2.p, ld, st));
+    if (prior_y) TRY(upload(d_prior, prior_y, (size_t)n, st));
+    TRY(upload(d_zi, zero_index, (size_t)n_zero, st));
+    SCDE_CUDA(d_idx.ensure((size_t)3 * n_genes));
+    SCDE_CUDA(d_z.ensure((size_t)n_genes));
+    if (posterior) SCDE_CUDA(d_post.ensure((size_t)n_genes * ldo));
+    RatioArgs a{};
+    a.p1 = d1.p;
+    a.p2 = d2.p;
+    a.ld = ld;
+    a.n_genes = n_genes;
+    a.n = n;
+    a.prior = prior_y ? d_prior.p : nullptr;
+    a.zero_index = d_zi.p;
+    a.n_zero = n_zero;
+    a.idx = d_idx.p;
+    a.z = d_z.p;
+    a.post = posterior ? d_post.p : nullptr;
+    a.ld_post = ldo;
+    SCDE_CUDA(launch_ratio_summary(a, st));
+    if (idx) SCDE_CUDA(cudaMemcpyAsync(idx, d_idx.p, sizeof(int32_t) * 3 * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+    if (z) SCDE_CUDA(cudaMemcpyAsync(z, d_z.p, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+    if (posterior) {
+        SCDE_CUDA(d_out.ensure((size_t)n_genes * nout));
+        SCDE_CUDA(launch_transpose_out(d_post.p, ldo, n_genes, nout, d_out.p, st));
+        SCDE_CUDA(cudaMemcpyAsync(posterior, d_out.p, sizeof(double) * (size_t)n_genes * nout, cudaMemcpyDeviceToHost, st));
+    }
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, int32_t n_genes, int32_t n_cells,
+                                   const double *corr_b, const double *corr_a, double *out) {
+    CHECK_CTX(ctx);
+    if (!counts || !corr_b || !corr_a || !out || n_genes < 0 || n_cells < 0) {
+        set_error("expression_magnitude: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    const size_t n = (size_t)n_genes * n_cells;
+    if (n == 0) return SCDE_B200_OK;
+    cudaStream_t st = ctx->stream;
+    DBuf<int32_t> d_c;
+    DBuf<double> d_b, d_a, d_o;
+    TRY(upload(d_c, counts, n, st));
+    TRY(upload(d_b, corr_b, (size_t)n_cells, st));
+    TRY(upload(d_a, corr_a, (size_t)n_cells, st));
+    SCDE_CUDA(d_o.ensure(n));
+    SCDE_CUDA(launch_magnitude(d_c.p, (int64_t)n, n_genes, d_b.p, d_a.p, d_o.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(out, d_o.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// scde.expression.difference on the device (R/functions.R:304-408)
+struct scde_b200_diff_job {
+    int G = 0, C = 0, K = 0, n_boot = 0, n_levels = 0;
+    int local_theta = 0, sqlogit = 0, want_post = 0, has_batch = 0;
+    int n_group[2] = {0, 0};
+    int n_zero = 1;
+    DBuf<int32_t> counts;  // [C][G] (column-major shard)
+    DBuf<double> models, mag, prior_y;
+    DBuf<int32_t> cell_ids[2];  // group cell lists
+    DBuf<int32_t> boot[4];
+    int D[4] = {0, 0, 0, 0};
+    DBuf<int32_t> zi, zi_adj;
+    LpTable table;
+    JointScratch scr;
+    DBuf<double> jp[4];
+    DBuf<double> post, bpost, apost;  // [G][ld] gene-major ratio posteriors
+    DBuf<int32_t> idx, bidx, aidx;
+    DBuf<double> z, bz, az;
+    DBuf<double> tbuf;  // transposition scratch for downloads
+    StageTimer timer;
+    int64_t contract_cells = 0;
+    bool ran = false;
+};
+
+extern "C" {
+
+int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int32_t want_posteriors,
+                          scde_b200_diff_job **out) {
+    CHECK_CTX(ctx);
+    if (!a || !out) return SCDE_B200_EINVAL;
+    *out = nullptr;
+    if (!a->counts || !a->models || !a->prior_x || !a->prior_y || !a->group || a->n_genes < 1 || a->n_cells < 1 ||
+        a->n_grid < 2 || a->n_boot < 1) {
+        set_error("expression_difference: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    int g0 = a->gene_begin, g1 = a->gene_end;
+    if (g0 == 0 && g1 == 0) g1 = a->n_genes;
+    if (g0 < 0 || g1 > a->n_genes || g0 >= g1) {
+        set_error("gene range [%d, %d) invalid for %d genes", g0, g1, a->n_genes);
+        return SCDE_B200_EINVAL;
+    }
+    const int G = g1 - g0, C = a->n_cells, K = a->n_grid;
+    std::vector<int32_t> ids[2];
+    for (int c = 0; c < C; ++c)
+        if (a->group[c] == 0 || a->group[c] == 1) ids[a->group[c]].push_back(c);
+    if (ids[0].empty() || ids[1].empty()) {
+        set_error("both groups need at least one cell");
+        return SCDE_B200_EINVAL;
+    }
+    const bool has_batch = a->batch != nullptr && a->n_batch_levels > 1;
+    if (a->n_zero != 1 && a->n_zero != a->n_genes) {
+        set_error("n_zero must be 1 or n_genes");
+        return SCDE_B200_EINVAL;
+    }
+    if (!a->zero_index || (has_batch && !a->zero_index_adjusted)) {
+        set_error("zero_index (and zero_index_adjusted with batch) are required");
+        return SCDE_B200_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    scde_b200_diff_job *j = new scde_b200_diff_job();
+    auto fail = [&](int r) {
+        delete j;
+        return r;
+    };
+#define JTRY(x)                                \
+    do {                                       \
+        int _r = (x);                          \
+        if (_r != SCDE_B200_OK) return fail(_r); \
+    } while (0)
+#define JCUDA(x)                                                                    \
+    do {                                                                            \
+        cudaError_t _e = (x);                                                       \
+        if (_e != cudaSuccess) return fail(cuda_fail(_e, #x, __FILE__, __LINE__));   \
+    } while (0)
+    j->G = G;
+    j->C = C;
+    j->K = K;
+    j->n_boot = a->n_boot;
+    j->local_theta = a->local_theta;
+    j->sqlogit = a->square_logit_conc;
+    j->want_post = want_posteriors;
+    j->has_batch = has_batch;
+    j->n_levels = has_batch ? a->n_batch_levels : 0;
+    j->n_zero = a->n_zero;
+    // counts shard: rows [g0, g1) of every column
+    JCUDA(j->counts.ensure((size_t)G * C));
+    JCUDA(cudaMemcpy2DAsync(j->counts.p, sizeof(int32_t) * G, a->counts + g0, sizeof(int32_t) * (size_t)a->n_genes,
+                            sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
+    JTRY(upload(j->models, a->models, (size_t)C * 12, st));
+    JTRY(upload(j->prior_y, a->prior_y, (size_t)K, st));
+    std::vector<double> mag(K);
+    for (int k = 0; k < K; ++k) {  // R/functions.R:575-577
+        double m = std::pow(10.0, a->prior_x[k]) - 1;
+        if (m < 0) m = 0;
+        mag[k] = std::log(m);
+    }
+    JTRY(upload(j->mag, mag.data(), (size_t)K, st));
+    for (int i = 0; i < 2; ++i) {
+        j->n_group[i] = (int)ids[i].size();
+        JTRY(upload(j->cell_ids[i], ids[i].data(), ids[i].size(), st));
+    }
+    // draws
+    for (int i = 0; i < 2; ++i) {
+        const int n = j->n_group[i];
+        std::vector<int32_t> gen;
+        const int32_t *bi = a->boot_idx[i];
+        if (!bi) {
+            gen = gen_boot(a->seed, n, a->n_boot);
+            bi = gen.data();
+        }
+        JTRY(validate_index(bi, (size_t)a->n_boot * n, 0, n, "boot_idx"));
+        JTRY(upload(j->boot[i], bi, (size_t)a->n_boot * n, st));
+        j->D[i] = n;
+        JCUDA(cudaStreamSynchronize(st));  // `gen` goes out of scope
+    }
+    if (has_batch) {
+        const int L = a->n_batch_levels;
+        std::vector<int32_t> off(L + 1, 0), cells;
+        for (int c = 0; c < C; ++c) {
+            if (a->batch[c] < 0 || a->batch[c] >= L) {
+                set_error("batch[%d] = %d outside [0, %d)", c, a->batch[c], L);
+                return fail(SCDE_B200_EINVAL);
+            }
+            off[a->batch[c] + 1]++;
+        }
+        for (int l = 0; l < L; ++l) off[l + 1] += off[l];
+        cells.resize(C);
+        {
+            std::vector<int32_t> pos(off.begin(), off.end() - 1);
+            for (int c = 0; c < C; ++c) cells[pos[a->batch[c]]++] = c;  // tapply(0:(n-1), batch, I): ascending
+        }
+        for (int i = 0; i < 2; ++i) {
+            std::vector<int32_t> comp(L, 0);  // table(batch[ii])
+            for (int c : ids[i]) comp[a->batch[c]]++;
+            const int D = j->n_group[i];
+            std::vector<int32_t> gen;
+            const int32_t *bi = a->boot_idx[2 + i];
+            if (!bi) {
+                gen.resize((size_t)a->n_boot * D);
+                JTRY(scde_b200_batch_boot_indices(a->seed, L, off.data(), cells.data(), comp.data(), a->n_boot, gen.data()));
+                bi = gen.data();
+            }
+            JTRY(validate_index(bi, (size_t)a->n_boot * D, 0, C, "batch boot_idx"));
+            JTRY(upload(j->boot[2 + i], bi, (size_t)a->n_boot * D, st));
+            j->D[2 + i] = D;
+            JCUDA(cudaStreamSynchronize(st));
+        }
+    }
+    {
+        std::vector<int32_t> zi(a->n_zero == 1 ? 1 : G);
+        for (size_t i = 0; i < zi.size(); ++i) zi[i] = a->zero_index[a->n_zero == 1 ? 0 : g0 + i];
+        JTRY(validate_index(zi.data(), zi.size(), 1, 2 * K, "zero_index"));
+        JTRY(upload(j->zi, zi.data(), zi.size(), st));
+        if (has_batch) {
+            for (size_t i = 0; i < zi.size(); ++i) zi[i] = a->zero_index_adjusted[a->n_zero == 1 ? 0 : g0 + i];
+            JTRY(validate_index(zi.data(), zi.size(), 1, 4 * K - 2, "zero_index_adjusted"));
+            JTRY(upload(j->zi_adj, zi.data(), zi.size(), st));
+        }
+        JCUDA(cudaStreamSynchronize(st));
+    }
+    const int ld = table_ld(K), nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    for (int i = 0; i < (has_batch ? 4 : 2); ++i) JCUDA(j->jp[i].ensure((size_t)G * ld));
+    JCUDA(j->idx.ensure((size_t)3 * G));
+    JCUDA(j->z.ensure((size_t)G));
+    if (want_posteriors || has_batch) JCUDA(j->post.ensure((size_t)G * ldo));
+    if (has_batch) {
+        JCUDA(j->bpost.ensure((size_t)G * ldo));
+        JCUDA(j->bidx.ensure((size_t)3 * G));
+        JCUDA(j->bz.ensure((size_t)G));
+        JCUDA(j->aidx.ensure((size_t)3 * G));
+        JCUDA(j->az.ensure((size_t)G));
+        if (want_posteriors) JCUDA(j->apost.ensure((size_t)G * lda));
+    }
+    j->table.K = K;
+    j->table.ld = ld;
+    j->table.sentinel = -DBL_MAX / C / 1.1;
+    JCUDA(cudaStreamSynchronize(st));
+    *out = j;
+    return SCDE_B200_OK;
+#undef JTRY
+#undef JCUDA
+}
+
+int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
+    CHECK_CTX(ctx);
+    if (!j) return SCDE_B200_EINVAL;
+    cudaStream_t st = ctx->stream;
+    StageTimer &tm = j->timer;
+    tm.reset();
+    j->contract_cells = 0;
+    const int G = j->G, C = j->C, K = j->K;
+    const int ld = j->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    int t_all = tm.begin(st);
+    TRY(index_from_counts(ctx, j->table, j->counts.p, G, 0, G, C, &tm));
+    TRY(fill_table(ctx, j->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
+    // group joints: cells of one factor level, draws are local indices (R/functions.R:372-374)
+    for (int i = 0; i < 2; ++i)
+        TRY(run_joint(ctx, j->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
+                      j->jp[i].p, ld, j->scr, &tm, &j->contract_cells));
+    // batch joints: all cells, composition-sampled draws are global cell ids (R/functions.R:355-357)
+    if (j->has_batch)
+        for (int i = 0; i < 2; ++i)
+            TRY(run_joint(ctx, j->table, nullptr, C, j->boot[2 + i].p, j->n_boot, j->D[2 + i], (double)j->n_boot,
+                          j->jp[2 + i].p, ld, j->scr, &tm, &j->contract_cells));
+    int e0 = tm.begin(st);
+    int nl = 0;
+    RatioArgs r{};
+    r.p1 = j->jp[0].p;
+    r.p2 = j->jp[1].p;
+    r.ld = ld;
+    r.n_genes = G;
+    r.n = K;
+    r.prior = j->prior_y.p;
+    r.zero_index = j->zi.p;
+    r.n_zero = j->n_zero == 1 ? 1 : G;
+    r.idx = j->idx.p;
+    r.z = j->z.p;
+    r.post = (j->want_post || j->has_batch) ? j->post.p : nullptr;
+    r.ld_post = ldo;
+    SCDE_CUDA(launch_ratio_summary(r, st));
+    ++nl;
+    if (j->has_batch) {
+        static const int32_t mid_host = 0;
+        (void)mid_host;
+        // batch.effect is summarised with the default expectation = 0 (R/functions.R:362): H0 index = centre
+        RatioArgs b = r;
+        b.p1 = j->jp[2].p;
+        b.p2 = j->jp[3].p;
+        b.idx = j->bidx.p;
+        b.z = j->bz.p;
+        b.post = j->bpost.p;
+        b.zero_index = nullptr;  // centre of the grid: handled in-kernel as index n (1-based) when NULL
+        b.n_zero = 1;
+        SCDE_CUDA(launch_ratio_summary(b, st));
+        ++nl;
+        // batch adjustment: slide the two 2K-1 posteriors without prior weighting (R/functions.R:391)
+        RatioArgs c{};
+        c.p1 = j->post.p;
+        c.p2 = j->bpost.p;
+        c.ld = ldo;
+        c.n_genes = G;
+        c.n = nout;
+        c.prior = nullptr;
+        c.zero_index = j->zi_adj.p;
+        c.n_zero = j->n_zero == 1 ? 1 : G;
+        c.idx = j->aidx.p;
+        c.z = j->az.p;
+        c.post = j->want_post ? j->apost.p : nullptr;
+        c.ld_post = lda;
+        SCDE_CUDA(launch_ratio_summary(c, st));
+        ++nl;
+    }
+    tm.end(SCDE_B200_T_RATIO, e0, st, nl);
+    tm.end(SCDE_B200_T_TOTAL, t_all, st, 0);
+    j->ran = true;
+    return SCDE_B200_OK;
+}
+
+static int download_matrix(scde_b200_ctx *ctx, scde_b200_diff_job *j, const double *src, int ld_src, int cols, double *dst) {
+    cudaStream_t st = ctx->stream;
+    SCDE_CUDA(j->tbuf.ensure((size_t)j->G * cols));
+    SCDE_CUDA(launch_transpose_out(src, ld_src, j->G, cols, j->tbuf.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(dst, j->tbuf.p, sizeof(double) * (size_t)j->G * cols, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_out *o,
+                            scde_b200_stats *stats) {
+    CHECK_CTX(ctx);
+    if (!j || !j->ran) {
+        set_error("diff_download: job has not been run");
+        return SCDE_B200_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    const int G = j->G, K = j->K;
+    const int ld = j->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    if (o) {
+        if (o->idx) SCDE_CUDA(cudaMemcpyAsync(o->idx, j->idx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
+        if (o->z) SCDE_CUDA(cudaMemcpyAsync(o->z, j->z.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+        if (j->has_batch) {
+            if (o->batch_idx)
+                SCDE_CUDA(cudaMemcpyAsync(o->batch_idx, j->bidx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
+            if (o->batch_z) SCDE_CUDA(cudaMemcpyAsync(o->batch_z, j->bz.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+            if (o->adjusted_idx)
+                SCDE_CUDA(cudaMemcpyAsync(o->adjusted_idx, j->aidx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
+            if (o->adjusted_z)
+                SCDE_CUDA(cudaMemcpyAsync(o->adjusted_z, j->az.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+        }
+        SCDE_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; ++i) {
+            if (o->joint_posteriors[i]) TRY(download_matrix(ctx, j, j->jp[i].p, ld, K, o->joint_posteriors[i]));
+            if (j->has_batch && o->batch_joint_posteriors[i])
+                TRY(download_matrix(ctx, j, j->jp[2 + i].p, ld, K, o->batch_joint_posteriors[i]));
+        }
+        if (o->difference_posterior) {
+            if (!j->post.p) {
+                set_error("difference_posterior requested but the job was uploaded without want_posteriors");
+                return SCDE_B200_EINVAL;
+            }
+            TRY(download_matrix(ctx, j, j->post.p, ldo, nout, o->difference_posterior));
+        }
+        if (j->has_batch && o->batch_difference_posterior)
+            TRY(download_matrix(ctx, j, j->bpost.p, ldo, nout, o->batch_difference_posterior));
+        if (j->has_batch && o->adjusted_difference_posterior) {
+            if (!j->apost.p) {
+                set_error("adjusted posterior requested but the job was uploaded without want_posteriors");
+                return SCDE_B200_EINVAL;
+            }
+            TRY(download_matrix(ctx, j, j->apost.p, lda, nadj, o->adjusted_difference_posterior));
+        }
+    }
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        j->timer.collect(stats);
+        stats->table_rows = j->table.n_rows;
+        stats->contract_cells = j->contract_cells;
+    }
+    return SCDE_B200_OK;
+}
+
+void scde_b200_diff_free(scde_b200_ctx *ctx, scde_b200_diff_job *job) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete job;
+}
+
+int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_args *args, const scde_b200_diff_out *out,
+                                    scde_b200_stats *stats) {
+    CHECK_CTX(ctx);
+    if (!args || !out) return SCDE_B200_EINVAL;
+    const int want_post = out->difference_posterior || out->adjusted_difference_posterior;
+    scde_b200_diff_job *job = nullptr;
+    int r = scde_b200_diff_upload(ctx, args, want_post, &job);
+    if (r != SCDE_B200_OK) return r;
+    r = scde_b200_diff_run(ctx, job);
+    if (r == SCDE_B200_OK) r = scde_b200_diff_download(ctx, job, out, stats);
+    scde_b200_diff_free(ctx, job);
+    return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// common.cuh -- shared declarations for libscde_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace scde {
+
+// Row stride (in doubles) of the log-posterior table and of the joint-posterior matrices on the device.
+// The default grid has K = 401 points (R/functions.R:237-239); 416 = 2 x 208 keeps every row 128-byte aligned
+// and splits into the two 208-wide halves the tiled contraction kernel works on.
+constexpr int KP_TILED = 416;
+constexpr int WP_TILED = 104;  // bootstrap columns per pass of the tiled kernel (n.randomizations = 100 -> one pass)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// error reporting (api.cu)
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SCDE_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) return ::scde::cuda_fail(_e, #expr, __FILE__, __LINE__);   \
+    } while (0)
+
+// ---- lp_table.cu ---------------------------------------------------------------------------------
+struct CellPrep {  // per-cell grid vectors, each [n_cells][ld]
+    double *mu, *lcfp, *lcfpr, *theta;  // theta only for local-theta models
+    double *maxcfp;                     // [n_cells]
+    int ld;
+};
+// models: n_cells x 12 column-major with leading dimension ld_models (rows of the full model matrix);
+// cell c uses model row cell_row[c] (NULL = identity).
+cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
+                             const double *mag, int K, int local_theta, int sqlogit, CellPrep prep,
+                             cudaStream_t st);
+// One warp per table row r: cell = upper_bound(row_off, r) - 1, x = row_x[r].  Writes table[r*ld_table + k]
+// (k >= K zero-filled up to ld_table) and row_mode[r] (first argmax, before the clamp).
+cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
+                           const int32_t *row_off, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
+                           cudaStream_t st);
+
+// ---- dedup.cu ------------------------------------------------------------------------------------
+// counts: column-major with leading dimension ld_counts; genes [g0, g0+G) of n_cells columns.
+// Pass 1: n_unique[c].  Pass 2 (after an exclusive scan into row_off): row_x[row_off[c] + i] = i-th smallest
+// distinct count of cell c; ridx[g*ld_ridx + c] = row id of counts[g0+g, c].  err_flag: 1 = negative count,
+// 2 = more distinct values than the hash capacity.
+cudaError_t launch_dedup_count(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
+                               int32_t *n_unique, int32_t *err_flag, cudaStream_t st);
+cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, cudaStream_t st);  // out[n] = total
+cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
+                              const int32_t *row_off, int32_t *row_x, int32_t *ridx, int ld_ridx,
+                              int32_t *err_flag, cudaStream_t st);
+// (ucl, uci)-given form: ridx[g*ld_ridx + c] = ucl_off[c] + uci[g + G*c]
+cudaError_t launch_uci_to_ridx(const int32_t *uci, int G, int n_cells, const int32_t *ucl_off, int32_t *ridx,
+                               int ld_ridx, cudaStream_t st);
+
+// ---- boot_contract.cu ----------------------------------------------------------------------------
+// W = multiplicity of each cell among each boot's draws, pass-major: W[b / 104][cell][b % 104] with n_w_rows
+// (>= round_up(n_list, 8)) rows per pass, rows beyond n_list zero.  boot_idx: n_boot x D (draw order).
+cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_list, double *W, int n_w_rows,
+                           cudaStream_t st);
+struct ContractArgs {
+    const double *table;   // [rows][ld_table]
+    int ld_table;
+    const int32_t *ridx;   // [n_genes][ld_ridx]
+    int ld_ridx;
+    const int32_t *cell_ids;  // [n_list] ridx column per list entry (NULL = identity)
+    int n_list;
+    const double *W;  // pass-major [ceil(n_boot/104)][n_w_rows][104]
+    int n_w_rows;
+    int n_boot;    // columns of W that are real
+    double scale;  // jp += softmax / scale   (n_boot for the live path, 1 for the legacy / no-bootstrap forms)
+    int n_genes, K;
+    double *jp;  // [n_genes][ld_jp], must be zeroed by the caller
+    int ld_jp;
+};
+cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches);
+// requires K <= 416 and ld_table == 416
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches);
+bool contract_tiled_supported(const ContractArgs &a);
+// ensemble form (src/jpmatLogBoot.cpp:224-237)
+cudaError_t launch_ensemble(const ContractArgs &a, double *rownorm_scratch, int64_t n_rows, cudaStream_t st);
+// gathers for return_individual: modes[g + G*c] = mag[row_mode[ridx]], post[c][g + G*k] = table row (clamped)
+cudaError_t launch_gather_modes(const int32_t *ridx, int ld_ridx, int G, int n_cells, const int32_t *row_mode,
+                                const double *mag, double *modes, cudaStream_t st);
+cudaError_t launch_gather_post(const int32_t *ridx, int ld_ridx, int G, int n_cells, const double *table,
+                               int ld_table, int K, double sentinel, double minlogprob, double *post,
+                               cudaStream_t st);
+cudaError_t launch_transpose_out(const double *src, int ld_src, int G, int K, double *dst, cudaStream_t st);
+cudaError_t launch_transpose_in(const double *src, int G, int K, double *dst, int ld_dst, cudaStream_t st);
+cudaError_t launch_fp64_peak(double *sink, int iters, int blocks, cudaStream_t st);
+
+// ---- ratio_summary.cu ----------------------------------------------------------------------------
+struct RatioArgs {
+    const double *p1, *p2;  // [n_genes][ld] row-major (gene-major) device matrices
+    int ld;
+    int n_genes, n;       // n grid points per input row; output has 2n-1 lags
+    const double *prior;  // [n] or NULL
+    const int32_t *zero_index;  // device, 1-based
+    int n_zero;
+    int32_t *idx;     // [3][n_genes] (lb, mle, ub), 0-based   (column-major n_genes x 3)
+    double *z;        // [n_genes]
+    double *post;     // optional [n_genes][ld_post] gene-major normalised posterior
+    int ld_post;
+    double *raw;      // optional [n_genes][ld_post] un-normalised sliding product (matSlideMult)
+};
+cudaError_t launch_ratio_summary(const RatioArgs &a, cudaStream_t st);
+cudaError_t launch_magnitude(const int32_t *counts, int64_t n, int G, const double *corr_b, const double *corr_a,
+                             double *out, cudaStream_t st);
+
+}  // namespace scde

@@ -1,0 +1,144 @@
+// hostmath.cpp -- host-side pieces of the path that are not device work:
+//   * the bootstrap draw generator: glibc's TYPE_3 additive-feedback rand() restated so the library reproduces
+//     `srand(seed); rand()` (src/jpmatLogBoot.cpp:221,256 / :467,480) without touching libc's global state;
+//   * cZ = sign(Z) qnorm(p.adjust(pnorm(|Z|, lower = F), "BH"), lower = F)   (R/functions.R:5051), which needs every
+//     gene's Z and therefore runs after the per-shard results are gathered.
+#include "../../include/scde_b200.h"
+#include "hostmath.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+namespace scde {
+
+// glibc random_r(), TYPE_3: r[i] = r[i-3] + r[i-31] (mod 2^32), output r[i] >> 1; seeded with the Park-Miller
+// "minimal standard" LCG (16807) and 310 discarded outputs.
+GlibcRand::GlibcRand(uint32_t seed) {
+    if (seed == 0) seed = 1;
+    int32_t word = (int32_t)seed;
+    r_[0] = word;
+    for (int i = 1; i < 31; ++i) {
+        // word = 16807 * word % 2147483647 without overflow (Schrage)
+        long hi = word / 127773, lo = word % 127773;
+        word = (int32_t)(16807 * lo - 2836 * hi);
+        if (word < 0) word += 2147483647;
+        r_[i] = word;
+    }
+    f_ = 3;
+    b_ = 0;
+    for (int i = 0; i < 310; ++i) next();
+}
+
+int32_t GlibcRand::next() {
+    uint32_t v = (uint32_t)r_[f_] + (uint32_t)r_[b_];
+    r_[f_] = (int32_t)v;
+    if (++f_ == 31) f_ = 0;
+    if (++b_ == 31) b_ = 0;
+    return (int32_t)(v >> 1);
+}
+
+int GlibcRand::draw(int n) {  // while (n <= (rj = rand() / (RAND_MAX / n)));
+    const int div = 2147483647 / n;
+    int rj;
+    do {
+        rj = next() / div;
+    } while (n <= rj);
+    return rj;
+}
+
+static double qnorm_upper(double p) {  // Wichura AS 241 (PPND16), upper tail
+    if (std::isnan(p)) return p;
+    if (p < 0 || p > 1) return NAN;
+    if (p == 0) return INFINITY;
+    if (p == 1) return -INFINITY;
+    double p_ = 0.5 - p + 0.5;
+    double q = p_ - 0.5, r, val;
+    if (std::fabs(q) <= 0.425) {
+        r = .180625 - q * q;
+        return q * (((((((r * 2509.0809287301226727 + 33430.575583588128105) * r + 67265.770927008700853) * r +
+                         45921.953931549871457) * r + 13731.693765509461125) * r + 1971.5909503065514427) * r +
+                      133.14166789178437745) * r + 3.387132872796366608) /
+               (((((((r * 5226.495278852854561 + 28729.085735721942674) * r + 39307.89580009271061) * r +
+                    21213.794301586595867) * r + 5394.1960214247511077) * r + 687.1870074920579083) * r +
+                 42.313330701600911252) * r + 1.);
+    }
+    r = (q < 0) ? p_ : p;
+    r = std::sqrt(-std::log(r));
+    if (r <= 5.) {
+        r += -1.6;
+        val = (((((((r * 7.7454501427834140764e-4 + .0227238449892691845833) * r + .24178072517745061177) * r +
+                    1.27045825245236838258) * r + 3.64784832476320460504) * r + 5.7694972214606914055) * r +
+                 4.6303378461565452959) * r + 1.42343711074968357734) /
+              (((((((r * 1.05075007164441684324e-9 + 5.475938084995344946e-4) * r + .0151986665636164571966) * r +
+                   .14810397642748007459) * r + .68976733498510000455) * r + 1.6763848301838038494) * r +
+                2.05319162663775882187) * r + 1.);
+    } else {
+        r += -5.;
+        val = (((((((r * 2.01033439929228813265e-7 + 2.71155556874348757815e-5) * r + .0012426609473880784386) * r +
+                    .026532189526576123093) * r + .29656057182850489123) * r + 1.7848265399172913358) * r +
+                 5.4637849111641143699) * r + 6.6579046435011037772) /
+              (((((((r * 2.04426310338993978564e-15 + 1.4215117583164458887e-7) * r + 1.8463183175100546818e-5) * r +
+                   7.868691311456132591e-4) * r + .0148753612908506148525) * r + .13692988092273580531) * r +
+                .59983220655588793769) * r + 1.);
+    }
+    return q < 0.0 ? -val : val;
+}
+
+void bh_cz(const double *z, int n, double *cz) {
+    std::vector<double> p(n), pa(n);
+    for (int i = 0; i < n; ++i) p[i] = 0.5 * std::erfc(std::fabs(z[i]) * M_SQRT1_2);
+    std::vector<int> o(n);
+    std::iota(o.begin(), o.end(), 0);
+    // order(p, decreasing = TRUE), stable
+    std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return p[a] > p[b]; });
+    double cm = INFINITY;
+    for (int r = 0; r < n; ++r) {
+        double v = (double)n / (double)(n - r) * p[o[r]];
+        if (v < cm) cm = v;
+        pa[o[r]] = cm < 1 ? cm : 1;
+    }
+    for (int i = 0; i < n; ++i) {
+        double sgn = (z[i] > 0) - (z[i] < 0);
+        cz[i] = sgn * qnorm_upper(pa[i]);
+    }
+}
+
+}  // namespace scde
+
+extern "C" {
+
+int scde_b200_boot_indices(int32_t seed, int32_t n, int32_t n_boot, int32_t *out) {
+    if (n < 1 || n_boot < 0 || !out) return SCDE_B200_EINVAL;
+    scde::GlibcRand rng((uint32_t)seed);
+    for (int64_t i = 0; i < (int64_t)n_boot * n; ++i) out[i] = rng.draw(n);
+    return SCDE_B200_OK;
+}
+
+int scde_b200_batch_boot_indices(int32_t seed, int32_t n_levels, const int32_t *pool_offsets,
+                                 const int32_t *pool_cells, const int32_t *composition, int32_t n_boot,
+                                 int32_t *out) {
+    if (n_levels < 0 || !pool_offsets || !pool_cells || !composition || !out) return SCDE_B200_EINVAL;
+    for (int k = 0; k < n_levels; ++k)
+        if (composition[k] > 0 && pool_offsets[k + 1] - pool_offsets[k] < 1) return SCDE_B200_EINVAL;
+    scde::GlibcRand rng((uint32_t)seed);
+    int64_t o = 0;
+    for (int b = 0; b < n_boot; ++b)
+        for (int k = 0; k < n_levels; ++k) {
+            const int nsamp = composition[k];
+            if (nsamp <= 0) continue;
+            const int32_t *bi = pool_cells + pool_offsets[k];
+            const int npool = pool_offsets[k + 1] - pool_offsets[k];
+            for (int j = 0; j < nsamp; ++j) out[o++] = bi[rng.draw(npool)];
+        }
+    return SCDE_B200_OK;
+}
+
+int scde_b200_bh_cz(const double *z, int32_t n, double *cz) {
+    if (n < 0 || (n > 0 && (!z || !cz))) return SCDE_B200_EINVAL;
+    scde::bh_cz(z, n, cz);
+    return SCDE_B200_OK;
+}
+
+}  // extern "C"

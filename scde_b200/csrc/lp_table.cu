@@ -1,0 +1,336 @@
+// lp_table.cu -- per-cell log-posterior rows (the reference's `ucposteriors`, src/jpmatLogBoot.cpp:128-211).
+//
+// For every (cell c, distinct count x) one table row of K grid values:
+//   nb_k  = log NB(x; size = theta_k, prob = theta_k/(theta_k + mu~_k)) + log(1 - d_k)      (:166-188)
+//   f     = log Pois(x; exp(fail.r))                                                         (:190)
+//   v_k   = exp(nb_k - M) + exp(log d_k + f - M),  M = max(max_k nb_k, max_k log d_k + f)    (:191-193)
+//   lp_k  = log(v_k / sum_j v_j), -Inf replaced by a finite sentinel                         (:194-204)
+// with mu, d (drop-out probability) and theta from the cell's error-model row (:133-162) and the "snap" rule
+// mu~_k = x when mu_k < x < mu_{k+1} (:173,182).  The negative-binomial / Poisson log-densities follow
+// Loader's saddle-point algorithm as R's nmath evaluates them (stirlerr + bd0), so the table agrees with
+// the reference's Rf_dnbinom / Rf_dpois to rounding error instead of suffering lgamma cancellation.
+//
+// Layout: one warp per row, lanes stride the grid; reductions over the grid are warp shuffles.  The
+// k-independent pieces of the saddle-point formula (three stirlerr terms, two logs) are hoisted per row when
+// theta is constant.  FP64 throughout.
+#include "common.cuh"
+#include <cfloat>
+#include <cmath>
+
+namespace scde {
+namespace {
+
+constexpr double LN_SQRT_2PI = 0.918938533204672741780329736406;
+constexpr double LN_2PI = 1.837877066409345483560659472811;
+constexpr double MIN_THETA = 1.0e-2, MAX_THETA = 1.0e+3;  // src/jpmatLogBoot.cpp:7-8
+
+__constant__ double c_sferr_halves[31] = {
+    0.0,
+    0.1534264097200273452913848,   0.0810614667953272582196702,   0.0548141210519176538961390,
+    0.0413406959554092940938221,   0.03316287351993628748511048,  0.02767792568499833914878929,
+    0.02374616365629749597132920,  0.02079067210376509311152277,  0.01848845053267318523077934,
+    0.01664469118982119216319487,  0.01513497322191737887351255,  0.01387612882307074799874573,
+    0.01281046524292022692424986,  0.01189670994589177009505572,  0.01110455975820691732662991,
+    0.010411265261972096497478567, 0.009799416126158803298389475, 0.009255462182712732917728637,
+    0.008768700134139385462952823, 0.008330563433362871256469318, 0.007934114564314020547248100,
+    0.007573675487951840794972024, 0.007244554301320383179543912, 0.006942840107209529865664152,
+    0.006665247032707682442354394, 0.006408994188004207068439631, 0.006171712263039457647532867,
+    0.005951370112758847735624416, 0.005746216513010115682023589, 0.005554733551962801371038690};
+
+// log(n!) - log(sqrt(2 pi n) (n/e)^n)
+__device__ double d_stirlerr(double n) {
+    const double S0 = 0.083333333333333333333, S1 = 0.00277777777777777777778, S2 = 0.00079365079365079365079365,
+                 S3 = 0.000595238095238095238095238, S4 = 0.0008417508417508417508417508;
+    if (n <= 15.0) {
+        double nn = n + n;
+        if (nn == (double)(int)nn) return c_sferr_halves[(int)nn];
+        return lgamma(n + 1.) - (n + 0.5) * log(n) + n - LN_SQRT_2PI;
+    }
+    double nn = n * n;
+    if (n > 500) return (S0 - S1 / nn) / n;
+    if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+// x log(x/np) + np - x without cancellation near x == np
+__device__ double d_bd0(double x, double np) {
+    if (!isfinite(x) || !isfinite(np) || np == 0.0) return nan("");
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < DBL_MIN) return s;
+        double ej = 2 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            double s1 = s + ej / ((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+__device__ double d_dbinom_raw_log(double x, double n, double p, double q) {
+    if (p == 0) return (x == 0) ? 0.0 : -INFINITY;
+    if (q == 0) return (x == n) ? 0.0 : -INFINITY;
+    if (x == 0) {
+        if (n == 0) return 0.0;
+        return (p < 0.1) ? -d_bd0(n, n * q) - n * p : n * log(q);
+    }
+    if (x == n) return (q < 0.1) ? -d_bd0(n, n * p) - n * q : n * log(p);
+    if (x < 0 || x > n) return -INFINITY;
+    double lc = d_stirlerr(n) - d_stirlerr(x) - d_stirlerr(n - x) - d_bd0(x, n * p) - d_bd0(n - x, n * q);
+    double lf = LN_2PI + log(x) + log1p(-x / n);
+    return lc - 0.5 * lf;
+}
+
+// log dnbinom(x; size, prob), general form (used per grid point when theta varies along the grid)
+__device__ double d_dnbinom_log(double x, double size, double prob) {
+    if (isnan(x) || isnan(size) || isnan(prob)) return x + size + prob;
+    if (prob <= 0 || prob > 1 || size < 0) return nan("");
+    if (x < 0 || !isfinite(x)) return -INFINITY;
+    if (x == 0 && size == 0) return 0.0;
+    if (!isfinite(size)) size = DBL_MAX;
+    if (x == 0) return size * log(prob);
+    double ans = d_dbinom_raw_log(size, x + size, prob, 1 - prob);
+    double p = size / (size + x);
+    return log(p) + ans;
+}
+
+__device__ double d_dpois_log(double x, double lambda) {
+    if (isnan(x) || isnan(lambda)) return x + lambda;
+    if (lambda < 0) return nan("");
+    if (x < 0 || !isfinite(x)) return -INFINITY;
+    if (lambda == 0) return (x == 0) ? 0.0 : -INFINITY;
+    if (!isfinite(lambda)) return -INFINITY;
+    if (x <= lambda * DBL_MIN) return -lambda;
+    if (lambda < x * DBL_MIN) return -lambda + x * log(lambda) - lgamma(x + 1);
+    return -0.5 * log(2 * M_PI * x) + (-d_stirlerr(x) - d_bd0(x, lambda));
+}
+
+// Row-constant part of log dnbinom for fixed (x > 0, size): the same operations in the same order as
+// d_dnbinom_log, with the k-independent terms evaluated once.
+struct NbRow {
+    double x, size, n, nmx, c1, half_lf, logp;
+    bool regular;  // false -> fall back to the general function for every k
+};
+__device__ NbRow nb_row_prepare(double x, double size) {
+    NbRow r;
+    r.x = x;
+    r.size = size;
+    r.n = x + size;
+    r.nmx = r.n - size;
+    r.regular = (x > 0) && isfinite(x) && (size > 0) && isfinite(size) && !(size == r.n) && !(size > r.n);
+    if (r.regular) {
+        r.c1 = d_stirlerr(r.n) - d_stirlerr(size) - d_stirlerr(r.nmx);
+        r.half_lf = 0.5 * (LN_2PI + log(size) + log1p(-size / r.n));
+        r.logp = log(size / (size + x));
+    } else {
+        r.c1 = r.half_lf = r.logp = 0;
+    }
+    return r;
+}
+__device__ __forceinline__ double nb_row_eval(const NbRow &r, double prob) {
+    if (!r.regular || !(prob > 0) || prob > 1) return d_dnbinom_log(r.x, r.size, prob);
+    double q = 1 - prob;
+    if (q == 0) return r.logp + -INFINITY;  // size != n here
+    double lc = r.c1 - d_bd0(r.size, r.n * prob) - d_bd0(r.nmx, r.n * q);
+    return r.logp + (lc - r.half_lf);
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- per-cell grid vectors (src/jpmatLogBoot.cpp:133-162) ---------------------------------------
+__global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ cell_row,
+                                 int n_cells, const double *__restrict__ mag, int K, int local_theta, int sqlogit,
+                                 CellPrep prep) {
+    int c = blockIdx.x;
+    if (c >= n_cells) return;
+    int r = cell_row ? cell_row[c] : c;
+    auto M = [&](int col) { return models[(size_t)col * ldm + r]; };
+    const double corr_a = M(4), corr_b = M(3), conc_a = M(1), conc_b = M(0);
+    const double conc_a2 = sqlogit ? M(11) : 0.0;
+    double lmax = -INFINITY;
+    for (int k = threadIdx.x; k < prep.ld; k += blockDim.x) {
+        size_t o = (size_t)c * prep.ld + k;
+        if (k >= K) {  // padding: benign values
+            prep.mu[o] = 0;
+            prep.lcfp[o] = 0;
+            prep.lcfpr[o] = 0;
+            if (prep.theta) prep.theta[o] = 1;
+            continue;
+        }
+        double m = mag[k];
+        double t = m * corr_a;
+        t += corr_b;
+        prep.mu[o] = exp(t);
+        double cf;
+        if (sqlogit) {
+            cf = conc_a + m * conc_a2;
+            cf *= m;
+        } else {
+            cf = m * conc_a;
+        }
+        cf += conc_b;
+        cf = 1 / (exp(cf) + 1);
+        double cr = 1 - cf;
+        double l = log(cf);
+        prep.lcfp[o] = l;
+        prep.lcfpr[o] = log(cr);
+        lmax = fmax(lmax, l);
+        if (local_theta) {
+            double th = -1 * m + M(8);
+            th *= M(9);
+            th = pow(10.0, th) + 1;
+            th = pow(th, M(10));
+            th = (M(7) - M(6)) / th;
+            th += M(6);
+            th = exp(-1 * th);
+            if (!isfinite(th) || th < MIN_THETA) th = MIN_THETA;
+            if (th > MAX_THETA) th = MAX_THETA;
+            prep.theta[o] = th;
+        }
+    }
+    __shared__ double red[32];
+    lmax = warp_max(lmax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        v = warp_max(v);
+        if (threadIdx.x == 0) prep.maxcfp[c] = v;
+    }
+}
+
+// ---- table rows ----------------------------------------------------------------------------------
+constexpr int ROW_WARPS = 8;
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+lp_rows_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ cell_row, int n_cells,
+               const int32_t *__restrict__ row_off, const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep,
+               int K, int local_theta, double sentinel, double *__restrict__ table, int ld_table,
+               int32_t *__restrict__ row_mode) {
+    extern __shared__ double s_buf[];  // ROW_WARPS x K
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *nb = s_buf + (size_t)warp * K;
+    for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n_rows; row += (int64_t)gridDim.x * ROW_WARPS) {
+        // cell = last c with row_off[c] <= row
+        int lo = 0, hi = n_cells;  // invariant: row_off[lo] <= row < row_off[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (row_off[mid] <= row) lo = mid; else hi = mid;
+        }
+        const int c = lo;
+        const int mr = cell_row ? cell_row[c] : c;
+        const double x = (double)row_x[row];
+        const double *mu = prep.mu + (size_t)c * prep.ld;
+        const double *lcfp = prep.lcfp + (size_t)c * prep.ld;
+        const double *lcfpr = prep.lcfpr + (size_t)c * prep.ld;
+        const double *thv = local_theta ? prep.theta + (size_t)c * prep.ld : nullptr;
+        const double theta_c = models[(size_t)5 * ldm + mr];
+        const double lambda = exp(models[(size_t)2 * ldm + mr]);
+        NbRow nr;
+        if (!local_theta) nr = nb_row_prepare(x, theta_c);
+        double vmax = -INFINITY;
+        for (int k = lane; k < K; k += 32) {
+            double muv = mu[k];
+            if ((k < K - 1 && x > muv && x < mu[k + 1]) || (k == K - 1 && x > muv)) muv = x;
+            double v;
+            if (local_theta) {
+                double th = thv[k];
+                v = d_dnbinom_log(x, th, th / (th + muv));
+            } else if (x == 0) {
+                double prob = theta_c / (theta_c + muv);
+                v = (prob > 0 && prob <= 1 && theta_c >= 0 && isfinite(theta_c)) ? theta_c * log(prob)
+                                                                                 : d_dnbinom_log(x, theta_c, prob);
+            } else {
+                v = nb_row_eval(nr, theta_c / (theta_c + muv));
+            }
+            v += lcfpr[k];
+            nb[k] = v;
+            vmax = fmax(vmax, v);
+        }
+        vmax = warp_max(vmax);
+        const double fp = d_dpois_log(x, lambda);
+        double maxp = vmax;
+        const double alt = prep.maxcfp[c] + fp;
+        if (maxp < alt) maxp = alt;
+        double s = 0;
+        for (int k = lane; k < K; k += 32) {
+            double v = exp(nb[k] - maxp) + exp(lcfp[k] + fp - maxp);
+            nb[k] = v;
+            s += v;
+        }
+        s = warp_sum(s);
+        double best = -INFINITY;
+        int besti = 0x7fffffff;
+        double *out = table + (size_t)row * ld_table;
+        for (int k = lane; k < ld_table; k += 32) {
+            if (k < K) {
+                double v = log(nb[k] / s);
+                if (besti == 0x7fffffff || v > best) {  // first maximum within this lane's ascending k
+                    best = v;
+                    besti = k;
+                }
+                if (v < sentinel) v = sentinel;
+                out[k] = v;
+            } else {
+                out[k] = 0.0;
+            }
+        }
+        // first maximum across lanes: larger value wins, ties go to the smaller index
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti) || (besti == 0x7fffffff && oi != 0x7fffffff)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
+                             const double *mag, int K, int local_theta, int sqlogit, CellPrep prep,
+                             cudaStream_t st) {
+    if (n_cells <= 0) return cudaSuccess;
+    cell_prep_kernel<<<n_cells, 128, 0, st>>>(models, ld_models, cell_row, n_cells, mag, K, local_theta, sqlogit, prep);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
+                           const int32_t *row_off, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
+                           cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    size_t smem = (size_t)ROW_WARPS * K * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(lp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int64_t blocks = (n_rows + ROW_WARPS - 1) / ROW_WARPS;
+    const int64_t cap = 148 * 64;  // grid-stride beyond this
+    if (blocks > cap) blocks = cap;
+    lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, cell_row, n_cells, row_off, row_x,
+                                                                  n_rows, prep, K, local_theta, sentinel, table,
+                                                                  ld_table, row_mode);
+    return cudaGetLastError();
+}
+
+}  // namespace scde

@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- genes/sec of scde.expression.difference (100 randomizations) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement; the
+                                                             # reference itself cannot be built here)
+
+A "step" is one whole scde.expression.difference over one synthetic count matrix: device dedup of the counts,
+log-posterior table, the bootstrap joint posteriors of both groups, the sliding-product ratio posterior and the
+lb/mle/ub/Z summary.  Workload = BASELINE.json config 4 (30 000 genes x 10 000 cells, two groups, B = 100) on every
+rank: genes shard with no data-path exchange, so N ranks process N x 30 000 genes (weak scaling); per-shard Z / grid
+indices are all-gathered over NCCL at the end of every step and rank 0 applies the Benjamini-Hochberg correction.
+
+  value : genes/s with the counts, models, prior and draws already resident in HBM (device work only)
+  e2e   : genes/s through the C ABI call with host (pinned) buffers -- H2D of the counts and D2H of results inside
+  roofline : contraction kernel (the dominant one), dense-equivalent 2*K*C*B flops per gene against the FP64 DFMA
+             peak measured live on the same device (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline : oracle port of the reference loop nest, all host cores, bounded gene sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_GRID = 401
+N_BOOT = 100
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genes", type=int, default=30000)
+    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5])
+    ap.add_argument("--cpu-sample-genes-per-thread", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def workload_host(args, rank: int, device):
+    """Synthetic config-4-shaped inputs; counts in pinned host memory."""
+    from scde_b200 import synth
+
+    seed = synth.SEED_BASE + args.config + 1000 * rank
+    rng = np.random.Generator(np.random.PCG64(seed))
+    models = synth.make_models(rng, args.cells)
+    counts = synth.make_counts_torch(models, args.genes, seed, device)
+    prior = synth.make_prior(args.genes)
+    half = args.cells // 2
+    group = np.where(np.arange(args.cells) < half, 0, 1).astype(np.int32)
+    batch = None
+    if args.config == 5:
+        batch = (rng.uniform(size=args.cells) < 0.5).astype(np.int32)
+    return models, counts, prior, group, batch
+
+
+def cpu_arm(models, counts, prior, group, n_threads, genes_per_thread, n_boot=N_BOOT):
+    """Oracle port of the reference path on a contiguous gene sample: both group joints (gene-chunked over the host
+    threads as scde.posteriors does), ratio posterior and summary.  Returns (genes, seconds, detail)."""
+    from oracle import oracle as O
+
+    mm, lt, sq = O.pack_models(models)
+    mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+    G = min(counts.shape[0], n_threads * genes_per_thread)
+    sub = np.asfortranarray(counts[:G])
+    jps, t_table, t_boot = [], 0.0, 0.0
+    for lev in (0, 1):
+        ii = np.nonzero(group == lev)[0]
+        bi = O.boot_indices(1, len(ii), n_boot)
+        jp, times = O.posteriors_chunked(np.asfortranarray(mm[ii]), np.asfortranarray(sub[:, ii]), mag, n_boot, bi,
+                                         n_threads, return_times=True)
+        jps.append(jp)
+        t_table += times[0]
+        t_boot += times[1]
+    t0 = time.perf_counter()
+    bd = O.ratio_posterior(jps[0], jps[1], prior["y"].to_numpy())
+    res, idx = O.distribution_summary(bd, O.fold_change_grid(prior["x"].to_numpy()), 0.0)
+    t_ratio = time.perf_counter() - t0
+    return G, t_boot + t_ratio, {"t_table_s": t_table, "t_boot_s": t_boot, "t_ratio_s": t_ratio, "results": res, "idx": idx,
+                                "jp": jps}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from scde_b200 import synth
+
+    O.build()
+    n_threads = O.max_threads()
+    seed = synth.SEED_BASE + args.config
+    rng = np.random.Generator(np.random.PCG64(seed))
+    models = synth.make_models(rng, args.cells)
+    gpt = max(1, args.cpu_sample_genes_per_thread)
+    G = n_threads * gpt
+    counts = synth.make_counts_torch(models, G, seed, "cpu", pinned=False)
+    prior = synth.make_prior(args.genes)
+    group = np.where(np.arange(args.cells) < args.cells // 2, 0, 1).astype(np.int32)
+    for _ in range(min(args.warmup, 1)):
+        cpu_arm(models, counts, prior, group, n_threads, gpt)
+    tot_g, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        g, s, _d = cpu_arm(models, counts, prior, group, n_threads, gpt)
+        tot_g += g
+        tot_s += s
+    v = tot_g / tot_s
+    line = {
+        "impl": "reference", "metric": "genes/sec scde.expression.difference (100 boot)", "value": v, "unit": "genes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg{args.config}: {args.genes} genes x {args.cells} cells, 2 groups, B={N_BOOT}",
+                   "sampled_genes_per_step": G},
+        "cpu_baseline": {"value": v, "unit": "genes/s", "cores": n_threads, "kind": "port",
+                         "sample": f"{G} genes x {args.cells} cells per step ({gpt} per thread), bootstrap loop + ratio "
+                                   f"posterior + summary; per-chunk lp-table build excluded (favours the CPU arm)"},
+        "e2e": {"value": v, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from scde_b200 import _lib, api
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = _lib.Context(local_rank)
+    if args.kernel:
+        ctx.set_contract_kernel(args.kernel)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    models, counts, prior, group, batch = workload_host(args, rank, device)
+    mm, lt, sq = api.pack_models(models)
+    x, y = prior["x"].to_numpy(), prior["y"].to_numpy()
+    diffv = api.fold_change_grid(x)
+    zi = api._zero_index(diffv, 0.0)
+    G, C = counts.shape
+    n_groups = [int((group == 0).sum()), int((group == 1).sum())]
+
+    def make_job():
+        return api.DifferenceJob(ctx, counts, mm, x, y, group, N_BOOT, 1, batch_codes=batch,
+                                 n_batch_levels=2 if batch is not None else 0, zero_index=zi, local_theta=lt, sqlogit=sq)
+
+    def gather_and_correct(res):
+        """the one exchange of the path: per-shard Z and grid indices -> all ranks; BH over all genes on rank 0"""
+        z = torch.from_numpy(res["z"]).to(device, non_blocking=True)
+        idx = torch.from_numpy(np.ascontiguousarray(res["idx"])).to(device, non_blocking=True)
+        if world > 1:
+            zs = [torch.empty_like(z) for _ in range(world)]
+            ids = [torch.empty_like(idx) for _ in range(world)]
+            dist.all_gather(zs, z)
+            dist.all_gather(ids, idx)
+            z_all = torch.cat(zs).cpu().numpy()
+        else:
+            z_all = z.cpu().numpy()
+        if rank == 0:
+            cz = np.empty_like(z_all)
+            _lib.check(_lib.lib().scde_b200_bh_cz(_lib.p_f64(z_all), len(z_all), _lib.p_f64(cz)))
+            return z_all, cz
+        return z_all, None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        ctx.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    job = make_job()
+    fp64_peak = ctx.measure_fp64_peak()
+    stats_acc = []
+    for _ in range(args.warmup):
+        job.run()
+        gather_and_correct(job.download())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):  # torch's own ops (the final gather) go onto the library's stream as well
+        e0.record(ext)
+        for _ in range(args.steps):
+            job.run()
+            res = job.download()
+            stats_acc.append(res["stats"])
+            gather_and_correct(res)
+        e1.record(ext)
+    barrier()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    last = res
+    job.close()
+
+    # ---------------- end-to-end arm: host buffers through the one-shot C-ABI call ----------------
+    h2d = counts.nbytes + mm.nbytes + x.nbytes + y.nbytes + group.nbytes + 2 * N_BOOT * 4 * (n_groups[0] + n_groups[1]) // 2
+    d2h = G * (3 * 4 + 8)
+    import ctypes as Cc
+
+    def e2e_step():
+        a = _lib.DiffArgs()
+        a.n_genes, a.n_cells, a.n_grid = G, C, len(x)
+        a.counts, a.models = _lib.p_i32(counts), _lib.p_f64(mm)
+        a.prior_x, a.prior_y = _lib.p_f64(x), _lib.p_f64(y)
+        a.group = _lib.p_i32(group)
+        a.batch = _lib.p_i32(batch) if batch is not None else None
+        a.n_batch_levels = 2 if batch is not None else 0
+        a.n_boot, a.seed = N_BOOT, 1
+        zarr = _lib.i32(zi)
+        a.zero_index, a.n_zero = _lib.p_i32(zarr), 1
+        zadj = _lib.i32([2 * len(x) - 1])
+        a.zero_index_adjusted = _lib.p_i32(zadj)
+        a.local_theta, a.square_logit_conc = lt, sq
+        o = _lib.DiffOut()
+        out = {"idx": np.empty((G, 3), np.int32, order="F"), "z": np.empty(G)}
+        o.idx, o.z = _lib.p_i32(out["idx"]), _lib.p_f64(out["z"])
+        if batch is not None:
+            out["adjusted_idx"] = np.empty((G, 3), np.int32, order="F")
+            out["adjusted_z"] = np.empty(G)
+            o.adjusted_idx, o.adjusted_z = _lib.p_i32(out["adjusted_idx"]), _lib.p_f64(out["adjusted_z"])
+        st = _lib.Stats()
+        _lib.check(_lib.lib().scde_b200_expression_difference(ctx.handle, Cc.byref(a), Cc.byref(o), Cc.byref(st)))
+        return gather_and_correct(out)
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e2.record(ext)  # the stream is idle here, so this timestamps the start of the host call
+        for _ in range(e2e_steps):
+            e2e_step()
+        e3.record(ext)
+    barrier()
+    e2e_s = e2.elapsed_time(e3) * 1e-3 / e2e_steps
+
+    # ---------------- reduce timings over ranks (max) ----------------
+    tt = torch.tensor([ms_step, e2e_s * 1e3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms = float(tt[0]), float(tt[1])
+    total_genes = G * world
+    value = total_genes / (ms_step * 1e-3)
+    e2e_value = total_genes / (e2e_ms * 1e-3)
+
+    # ---------------- roofline of the contraction kernel ----------------
+    ms_c = float(np.mean([s["ms"]["contract"] for s in stats_acc]))
+    n_c = int(stats_acc[-1]["launches"]["contract"])
+    cells_per_gene = stats_acc[-1]["contract_cells"]  # sum of list lengths over the joints
+    flops_per_step = 2.0 * K_GRID * N_BOOT * cells_per_gene * G
+    achieved_tf = flops_per_step / (ms_c * 1e-3) / 1e12
+    gather_bytes = 8.0 * K_GRID * cells_per_gene * G
+    launches_per_step = int(sum(v for k, v in stats_acc[-1]["launches"].items() if k != "total"))
+    roof = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+            "kernel": "contract_tiled_kernel" if args.kernel != 1 else "contract_generic_kernel",
+            "launches_per_step": n_c, "avg_launch_ms": ms_c / max(1, n_c),
+            "flops_per_launch": flops_per_step / max(1, n_c),
+            "peak_source": "DFMA loop measured live on this device (scde_b200_measure_fp64_peak); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "gather_gbs": gather_bytes / (ms_c * 1e-3) / 1e9,
+            "stage_ms": {k: float(np.mean([s["ms"][k] for s in stats_acc])) for k in stats_acc[-1]["ms"]}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "genes/sec scde.expression.difference (100 boot)", "value": value, "unit": "genes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg{args.config}: {G} genes x {C} cells per GPU, 2 groups of {n_groups[0]}/{n_groups[1]}, "
+                               f"B={N_BOOT}, K={K_GRID}" + (", batch-corrected" if batch is not None else ""),
+                   "genes_total": total_genes, "sharding": "genes, one shard per rank, NCCL all_gather of Z/indices at the end",
+                   "l2": "inputs larger than L2 (counts %.1f GB, lp table %.1f GB)" % (
+                       counts.nbytes / 1e9, stats_acc[-1]["table_rows"] * 416 * 8 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "genes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof,
+    }
+
+    # ---------------- parity spot-check + CPU baseline on a bounded gene sample (rank 0) ----------------
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        O.build()
+        n_threads = O.max_threads()
+        gpt = max(1, args.cpu_sample_genes_per_thread)
+        g, s, det = cpu_arm(models, counts, prior, group, n_threads, gpt)
+        line["cpu_baseline"] = {"value": g / s, "unit": "genes/s", "cores": n_threads, "kind": "port",
+                                "sample": f"first {g} genes x {C} cells ({gpt} per thread), bootstrap loop + ratio posterior "
+                                          f"+ summary = {s:.1f} s; per-chunk lp-table build ({det['t_table_s']:.1f} s) "
+                                          f"excluded, which favours the CPU arm"}
+        if not args.no_parity and batch is None:
+            zc = det["results"][:, 4]
+            zg = last["z"][:g]
+            idx_equal = bool(np.array_equal(last["idx"][:g], det["idx"]))
+            line["parity"] = {"genes": int(g), "max_abs_dZ": float(np.max(np.abs(zc - zg))),
+                              "grid_indices_equal": idx_equal,
+                              "max_index_diff": int(np.max(np.abs(last["idx"][:g] - det["idx"])))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -278,7 +278,7 @@ def expression_magnitude(counts, corr_b, corr_a):
     return out
 
 
-def posteriors_chunked(models, counts, mag, nboot, boot_idx, nthreads):
+def posteriors_chunked(models, counts, mag, nboot, boot_idx, nthreads, return_times=False):
     """Gene-chunked CPU arm (R/functions.R:606-617 semantics with shared boot_idx)."""
     models = _f64(models)
     counts = _i32(counts)
@@ -286,9 +286,10 @@ def posteriors_chunked(models, counts, mag, nboot, boot_idx, nthreads):
     mag = _f64(mag)
     bi = np.ascontiguousarray(boot_idx, dtype=np.int32)
     jp = np.empty((G, len(mag)), dtype=np.float64, order="F")
+    times = np.zeros(2)
     lib().orc_posteriors_chunked(_d(models), C.c_int(Cn), _i(counts), C.c_int(G), _d(mag), C.c_int(len(mag)),
-                                 C.c_int(nboot), _i(bi), C.c_int(bi.shape[1]), C.c_int(nthreads), _d(jp))
-    return jp
+                                 C.c_int(nboot), _i(bi), C.c_int(bi.shape[1]), C.c_int(nthreads), _d(jp), _d(times))
+    return (jp, times) if return_times else jp
 
 
 def max_threads() -> int:

@@ -832,9 +832,17 @@ void orc_unique_counts(const int *counts, int G, int C, int *ucl_flat, int *ucl_
  * scde.posteriors chunks genes over n.cores (R/functions.R:606-617): every chunk rebuilds its own unique-count
  * lists and lp table and then runs the bootstrap loop (the reference forks one process per chunk; plain
  * pthreads here -- the image has no libgomp).  All chunks use the same boot_idx (the n.cores = 1 semantics,
- * SURVEY.md section 8(e)).  counts: G x C column-major; boot_idx: nboot x D cell ids; jp: G x K column-major. */
+ * SURVEY.md section 8(e)).  counts: G x C column-major; boot_idx: nboot x D cell ids; jp: G x K column-major;
+ * times (optional): seconds of the slowest worker in the table build and in the bootstrap loop. */
 #include <pthread.h>
+#include <time.h>
 #include <unistd.h>
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 typedef struct {
     const double *models;
@@ -843,6 +851,7 @@ typedef struct {
     const int *boot_idx;
     double *jp;
     int ncells, ngenes, K, nboot, D, g0, g1;
+    double t_table, t_boot; /* seconds spent building the chunk's lp table / in the bootstrap loop */
 } chunk_job_t;
 
 static void *chunk_worker(void *arg) {
@@ -854,9 +863,11 @@ static void *chunk_worker(void *arg) {
         memcpy(sub + (size_t)c * ng, jb->counts + (size_t)c * ngenes + jb->g0, sizeof(int) * ng);
     int *uf = (int *)malloc(sizeof(int) * (size_t)ng * ncells), *uo = (int *)malloc(sizeof(int) * (ncells + 1));
     int *ui = (int *)malloc(sizeof(int) * (size_t)ng * ncells);
+    double t0 = now_s();
     orc_unique_counts(sub, ng, ncells, uf, uo, ui);
     table_t t;
     table_build(&t, jb->models, ncells, uf, uo, jb->mag, K, 0, 0, 0);
+    double t1 = now_s();
     double *jpt = (double *)calloc((size_t)K * ng, sizeof(double));
     double *tjp = (double *)malloc(sizeof(double) * (size_t)K * ng);
     for (int b = 0; b < jb->nboot; b++) {
@@ -875,6 +886,8 @@ static void *chunk_worker(void *arg) {
     }
     for (int g = 0; g < ng; g++)
         for (int k = 0; k < K; k++) jb->jp[(size_t)k * ngenes + jb->g0 + g] = jpt[(size_t)g * K + k];
+    jb->t_table = t1 - t0;
+    jb->t_boot = now_s() - t1;
     free(jpt);
     free(tjp);
     table_free(&t);
@@ -886,7 +899,7 @@ static void *chunk_worker(void *arg) {
 }
 
 int orc_posteriors_chunked(const double *models, int ncells, const int *counts, int ngenes, const double *mag, int K,
-                           int nboot, const int *boot_idx, int D, int nthreads, double *jp) {
+                           int nboot, const int *boot_idx, int D, int nthreads, double *jp, double *times) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > ngenes) nthreads = ngenes > 0 ? ngenes : 1;
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
@@ -894,7 +907,7 @@ int orc_posteriors_chunked(const double *models, int ncells, const int *counts, 
     chunk_job_t *jobs = (chunk_job_t *)malloc(sizeof(chunk_job_t) * nthreads);
     for (int w = 0; w < nthreads; w++) {
         chunk_job_t jb = {models, counts, mag, boot_idx, jp, ncells, ngenes, K, nboot, D,
-                          (int)((long long)ngenes * w / nthreads), (int)((long long)ngenes * (w + 1) / nthreads)};
+                          (int)((long long)ngenes * w / nthreads), (int)((long long)ngenes * (w + 1) / nthreads), 0, 0};
         jobs[w] = jb;
         if (pthread_create(&th[w], NULL, chunk_worker, &jobs[w]) == 0)
             started[w] = 1;
@@ -903,6 +916,13 @@ int orc_posteriors_chunked(const double *models, int ncells, const int *counts, 
     }
     for (int w = 0; w < nthreads; w++)
         if (started[w]) pthread_join(th[w], NULL);
+    if (times) { /* slowest worker: [0] table build, [1] bootstrap loop */
+        times[0] = times[1] = 0;
+        for (int w = 0; w < nthreads; w++) {
+            if (jobs[w].t_table > times[0]) times[0] = jobs[w].t_table;
+            if (jobs[w].t_boot > times[1]) times[1] = jobs[w].t_boot;
+        }
+    }
     free(th);
     free(started);
     free(jobs);

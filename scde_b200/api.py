@@ -1,0 +1,490 @@
+"""Host-side mirror of scde's R API for the differential-expression posterior path.
+
+Same function names (dots -> underscores), argument meaning and error behaviour as the reference:
+
+    scde_expression_difference  <-  scde.expression.difference   R/functions.R:304-408
+    scde_posteriors             <-  scde.posteriors              R/functions.R:566-670
+    scde_expression_magnitude   <-  scde.expression.magnitude    R/functions.R:694-697
+    calculate_ratio_posterior   <-  calculate.ratio.posterior    R/functions.R:3491-3510
+    quick_distribution_summary  <-  quick.distribution.summary   R/functions.R:5039-5053
+    mat_slide_mult / jpmat_log_boot / jpmat_log_batch_boot  <-  the R wrappers at R/functions.R:3534-3546
+
+R data frames become pandas DataFrames (models: cells x coefficients; counts: genes x cells; prior: columns
+``x`` and ``y``), factors become pandas Categoricals / Series.  All numeric work happens in libscde_b200.so
+through the C ABI (``_lib``); this module only does what the R layer does: validation, reordering, packing,
+labelling.  ``n_cores`` is accepted for signature compatibility and ignored -- the GPU path must not go through
+a fork and always has the ``n.cores = 1`` semantics (Seed = 1, one draw set for all genes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from ._lib import check, f64, i32, lib, p_f64, p_i32
+
+MODEL_COLUMNS = ["conc.b", "conc.a", "fail.r", "corr.b", "corr.a", "corr.theta", "corr.ltheta.b", "corr.ltheta.t",
+                 "corr.ltheta.m", "corr.ltheta.s", "corr.ltheta.r", "conc.a2"]
+MIN_SLOPE = 1e-10  # R/functions.R:579
+
+
+def _stop(msg: str):
+    raise ValueError("ERROR: " + msg)
+
+
+# ------------------------------------------------------------------------------------------------
+# small R idioms
+def r_as_character_numeric(v: np.ndarray) -> np.ndarray:
+    """as.numeric(as.character(x)): R prints doubles with 15 significant digits (R/functions.R:3507,5040)."""
+    return np.array([float("%.15g" % t) for t in np.asarray(v, dtype=np.float64)], dtype=np.float64)
+
+
+def r_seq_length(lo: float, hi: float, n: int) -> np.ndarray:
+    """seq(lo, hi, length = n) as seq.default evaluates it: c(from, from + (1:(n-2)) * by, to)."""
+    if n == 1:
+        return np.array([lo], dtype=np.float64)
+    by = (hi - lo) / (n - 1)
+    out = lo + np.arange(n, dtype=np.float64) * by
+    out[0], out[-1] = lo, hi
+    return out
+
+
+def fold_change_grid(x: np.ndarray) -> np.ndarray:
+    """as.numeric(colnames(calculate.ratio.posterior(...))), log10 scale (R/functions.R:3506-3507)."""
+    x = np.asarray(x, dtype=np.float64)
+    return r_as_character_numeric(r_seq_length(x[0] - x[-1], x[-1] - x[0], 2 * len(x) - 1))
+
+
+def marginals_from_prior(prior) -> np.ndarray:
+    """R/functions.R:575-577."""
+    m = np.power(10.0, np.asarray(prior["x"], dtype=np.float64)) - 1.0
+    m[m < 0] = 0
+    with np.errstate(divide="ignore"):
+        return np.log(m)
+
+
+def pack_models(models: pd.DataFrame):
+    """12-column matrix with NaN for absent columns (R/functions.R:601-604) after the slope clamp (:579-583)."""
+    models = models.copy()
+    ca = np.asarray(models["corr.a"], dtype=np.float64)
+    bad = ca < MIN_SLOPE
+    if bad.any():
+        sys.stdout.write("WARNING: the following cells have negatively-correlated or 0-slope fits:  "
+                         + " ".join(map(str, models.index[bad])) + " . Setting slopes to 1e-10.\n")
+        ca = ca.copy()
+        ca[bad] = MIN_SLOPE
+        models["corr.a"] = ca
+    mm = np.full((len(models), 12), np.nan, dtype=np.float64, order="F")
+    for j, name in enumerate(MODEL_COLUMNS):
+        if name in models.columns:
+            mm[:, j] = np.asarray(models[name], dtype=np.float64)
+    return mm, int("corr.ltheta.b" in models.columns), int("conc.a2" in models.columns)
+
+
+def _counts_for_models(models: pd.DataFrame, counts) -> tuple[np.ndarray, list]:
+    """counts[, match(rownames(models), colnames(counts))] as an int32 Fortran matrix + gene names."""
+    if isinstance(counts, pd.DataFrame):
+        if not all(c in counts.columns for c in models.index):
+            _stop("provided count data does not cover all of the cells specified in the model matrix")
+        sub = counts.loc[:, list(models.index)]
+        return i32(sub.to_numpy()), list(sub.index)
+    arr = np.asarray(counts)
+    if arr.ndim != 2 or arr.shape[1] != len(models):
+        _stop("provided count data does not cover all of the cells specified in the model matrix")
+    return i32(arr), [str(i + 1) for i in range(arr.shape[0])]
+
+
+def _unique_index(counts: np.ndarray):
+    """ucl / uci (R/functions.R:631-632).  Sorted order instead of first appearance -- unobservable."""
+    G, Cn = counts.shape
+    flat, off = [], np.zeros(Cn + 1, dtype=np.int32)
+    uci = np.empty((G, Cn), dtype=np.int32, order="F")
+    for c in range(Cn):
+        u, inv = np.unique(counts[:, c], return_inverse=True)
+        flat.append(u.astype(np.int32))
+        uci[:, c] = inv
+        off[c + 1] = off[c] + len(u)
+    return (np.concatenate(flat) if flat else np.zeros(0, np.int32)), off, uci
+
+
+def _levels(f) -> tuple[np.ndarray, list]:
+    """integer codes (-1 = NA) and level names of an R-factor-like object."""
+    if isinstance(f, pd.Series):
+        f = f.values if isinstance(f.dtype, pd.CategoricalDtype) else pd.Categorical(f)
+    if not isinstance(f, pd.Categorical):
+        f = pd.Categorical(f)
+    return np.asarray(f.codes, dtype=np.int32), list(f.categories)
+
+
+def _named_factor(f, names: Sequence[str]):
+    """Align a (possibly named) factor to `names`; unnamed factors are taken positionally as R does."""
+    if isinstance(f, pd.Series) and not f.index.equals(pd.RangeIndex(len(f))):
+        f = f.reindex(list(names))
+    codes, lev = _levels(f)
+    if len(codes) != len(names):
+        _stop("factor length does not match the number of cells in the model matrix")
+    return codes, lev
+
+
+# ------------------------------------------------------------------------------------------------
+def scde_expression_magnitude(models: pd.DataFrame, counts) -> pd.DataFrame:
+    """(log(counts) - corr.b) / corr.a per cell; genes x cells (R/functions.R:694-697)."""
+    cm, genes = _counts_for_models(models, counts)
+    G, Cn = cm.shape
+    out = np.empty((G, Cn), dtype=np.float64, order="F")
+    ctx = _lib.default_context()
+    check(lib().scde_b200_expression_magnitude(ctx.handle, p_i32(cm), G, Cn,
+                                               p_f64(f64(models["corr.b"])), p_f64(f64(models["corr.a"])), p_f64(out)))
+    return pd.DataFrame(out, index=genes, columns=list(models.index))
+
+
+def scde_posteriors(models: pd.DataFrame, counts, prior, n_randomizations: int = 100, batch=None, composition=None,
+                    return_individual_posteriors: bool = False, return_individual_posterior_modes: bool = False,
+                    ensemble_posterior: bool = False, n_cores: int = 20, seed: int = 1, boot_idx=None, context=None):
+    """Joint posterior of the cells in `models` (scde.posteriors, R/functions.R:566-670).
+
+    Returns a genes x K DataFrame (columns = as.character(exp(marginals))) or, with the return_individual_* flags,
+    a dict with ``jp`` plus ``modes`` (genes x cells) and/or ``post`` (dict cell -> genes x K DataFrame).
+    `seed` / `boot_idx` expose what the reference fixes at Seed = 1 for n.cores = 1.
+    """
+    cm, genes = _counts_for_models(models, counts)
+    pools = comp = None
+    if batch is not None:
+        if composition is None:
+            _stop("group composition must be provided if the batch argument is passed")
+        bcodes, blev = _named_factor(batch, models.index)
+        pools = [np.nonzero(bcodes == l)[0].astype(np.int32) for l in range(len(blev))]
+        if isinstance(composition, (pd.Series, dict)):
+            comp = np.array([int(dict(composition).get(l, 0)) for l in blev], dtype=np.int32)
+        else:
+            comp = i32(composition)
+            if len(comp) != len(blev):
+                _stop("composition must have one entry per batch level")
+    mag = marginals_from_prior(prior)
+    mm, lt, sq = pack_models(models)
+    postflag = 0
+    if return_individual_posteriors:
+        postflag = 3 if return_individual_posterior_modes else 2
+    elif return_individual_posterior_modes:
+        postflag = 1
+    flat, off, uci = _unique_index(cm)
+    G, Cn = cm.shape
+    K = len(mag)
+    jp = np.empty((G, K), dtype=np.float64, order="F")
+    want_modes = postflag in (1, 3) if batch is None else postflag == 1
+    want_post = postflag in (2, 3)
+    modes = np.empty((G, Cn), dtype=np.float64, order="F") if want_modes else None
+    post = np.empty((Cn, K, G), dtype=np.float64) if want_post else None
+    bi = None if boot_idx is None else i32(boot_idx, order="C")
+    ctx = context or _lib.default_context()
+    if batch is None:
+        check(lib().scde_b200_log_boot_posterior(
+            ctx.handle, p_f64(mm), Cn, p_i32(flat), p_i32(off), p_i32(uci), G, p_f64(f64(mag)), K,
+            int(n_randomizations), int(seed), p_i32(bi), postflag, lt, sq, int(bool(ensemble_posterior)),
+            p_f64(jp), p_f64(modes), p_f64(post)))
+    else:
+        poff = np.zeros(len(pools) + 1, dtype=np.int32)
+        for k, p in enumerate(pools):
+            poff[k + 1] = poff[k] + len(p)
+        pcells = np.concatenate(pools).astype(np.int32) if pools else np.zeros(0, np.int32)
+        check(lib().scde_b200_log_boot_batch_posterior(
+            ctx.handle, p_f64(mm), Cn, p_i32(flat), p_i32(off), p_i32(uci), G, p_f64(f64(mag)), K, len(pools),
+            p_i32(poff), p_i32(pcells), p_i32(comp), int(n_randomizations), int(seed), p_i32(bi), postflag, lt, sq,
+            p_f64(jp), p_f64(modes), p_f64(post)))
+    with np.errstate(over="ignore"):
+        cols = ["%.15g" % v for v in np.exp(mag)]
+    jpd = pd.DataFrame(jp, index=genes, columns=cols)
+    if postflag == 0:
+        return jpd
+    out = {"jp": jpd}
+    if modes is not None:
+        out["modes"] = pd.DataFrame(modes, index=genes, columns=list(models.index))
+    if post is not None:
+        out["post"] = {cell: pd.DataFrame(post[i].T, index=genes, columns=cols) for i, cell in enumerate(models.index)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def mat_slide_mult(m1, m2, context=None) -> np.ndarray:
+    """matSlideMult (R/functions.R:3544, src/matSlideMult.cpp:5)."""
+    a, b = f64(m1), f64(m2)
+    if a.shape != b.shape or a.ndim != 2:
+        _stop("matSlideMult needs two matrices of the same shape")
+    G, n = a.shape
+    out = np.empty((G, 2 * n - 1), dtype=np.float64, order="F")
+    ctx = context or _lib.default_context()
+    check(lib().scde_b200_mat_slide_mult(ctx.handle, p_f64(a), p_f64(b), G, n, p_f64(out)))
+    return out
+
+
+def jpmat_log_boot(matl, nboot: int, seed: int, boot_idx=None, context=None) -> np.ndarray:
+    """jpmatLogBoot (R/functions.R:3534, src/jpmatLogBoot.cpp:11)."""
+    nrows, ncols = np.asarray(matl[0]).shape
+    stack = np.empty((len(matl), ncols, nrows), dtype=np.float64)
+    for i, m in enumerate(matl):
+        stack[i] = np.asarray(m, dtype=np.float64).T
+    jp = np.empty((nrows, ncols), dtype=np.float64, order="F")
+    bi = None if boot_idx is None else i32(boot_idx, order="C")
+    ctx = context or _lib.default_context()
+    check(lib().scde_b200_jpmat_log_boot(ctx.handle, p_f64(stack), len(matl), nrows, ncols, int(nboot), int(seed),
+                                         p_i32(bi), p_f64(jp)))
+    return jp
+
+
+def jpmat_log_batch_boot(matll, comp, nboot: int, seed: int, boot_idx=None, context=None) -> np.ndarray:
+    """jpmatLogBatchBoot (R/functions.R:3540, src/jpmatLogBoot.cpp:48)."""
+    flat = [m for pool in matll for m in pool]
+    off = np.zeros(len(matll) + 1, dtype=np.int32)
+    for k, pool in enumerate(matll):
+        off[k + 1] = off[k] + len(pool)
+    nrows, ncols = np.asarray(flat[0]).shape
+    stack = np.empty((len(flat), ncols, nrows), dtype=np.float64)
+    for i, m in enumerate(flat):
+        stack[i] = np.asarray(m, dtype=np.float64).T
+    jp = np.empty((nrows, ncols), dtype=np.float64, order="F")
+    bi = None if boot_idx is None else i32(boot_idx, order="C")
+    ctx = context or _lib.default_context()
+    check(lib().scde_b200_jpmat_log_batch_boot(ctx.handle, p_f64(stack), len(matll), p_i32(off), p_i32(i32(comp)), nrows,
+                                               ncols, int(nboot), int(seed), p_i32(bi), p_f64(jp)))
+    return jp
+
+
+def _zero_index(diffv: np.ndarray, expectation) -> np.ndarray:
+    """which.min(abs(mvs - expectation/log2(10))), 1-based (R/functions.R:3519,3524,5050)."""
+    ex = np.atleast_1d(np.asarray(expectation, dtype=np.float64)) / np.log2(10.0)
+    return np.array([int(np.argmin(np.abs(diffv - e))) + 1 for e in ex], dtype=np.int32)
+
+
+def _summary_frame(idx: np.ndarray, z: np.ndarray, diffv: np.ndarray, genes, cz: Optional[np.ndarray] = None):
+    """lb / mle / ub / ce / Z / cZ data frame from grid indices (R/functions.R:5045-5052)."""
+    dq = diffv[idx] / np.log10(2.0)  # G x 3
+    cq = np.zeros(len(z))
+    sel = dq[:, 0] > 0
+    cq[sel] = dq[sel, 0]
+    sel = dq[:, 2] < 0
+    cq[sel] = dq[sel, 2]
+    if cz is None:
+        cz = np.empty_like(z)
+        check(lib().scde_b200_bh_cz(p_f64(f64(z)), len(z), p_f64(cz)))
+    return pd.DataFrame({"lb": dq[:, 0], "mle": dq[:, 1], "ub": dq[:, 2], "ce": cq, "Z": z, "cZ": cz}, index=genes)
+
+
+def calculate_ratio_posterior(pmat1, pmat2, prior, n_cores: int = 15, skip_prior_adjustment: bool = False,
+                              context=None) -> pd.DataFrame:
+    """calculate.ratio.posterior (R/functions.R:3491-3510): genes x (2K-1), columns labelled by log10 ratio."""
+    genes = list(pmat1.index) if isinstance(pmat1, pd.DataFrame) else None
+    a, b = f64(np.asarray(pmat1)), f64(np.asarray(pmat2))
+    G, n = a.shape
+    x = np.asarray(prior["x"], dtype=np.float64)
+    py = None if skip_prior_adjustment else f64(prior["y"])
+    post = np.empty((G, 2 * n - 1), dtype=np.float64, order="F")
+    zi = np.array([n], dtype=np.int32)
+    ctx = context or _lib.default_context()
+    check(lib().scde_b200_ratio_posterior_summary(ctx.handle, p_f64(a), p_f64(b), G, n, p_f64(py), p_i32(zi), 1,
+                                                  None, None, p_f64(post)))
+    rv = r_seq_length(x[0] - x[-1], x[-1] - x[0], 2 * n - 1)
+    return pd.DataFrame(post, index=genes, columns=["%.15g" % v for v in rv])
+
+
+def quick_distribution_summary(pmat1, pmat2, prior, expectation=0.0, skip_prior_adjustment: bool = False,
+                               genes=None, context=None) -> pd.DataFrame:
+    """calculate.ratio.posterior + quick.distribution.summary fused on the device (no dense posterior)."""
+    if genes is None and isinstance(pmat1, pd.DataFrame):
+        genes = list(pmat1.index)
+    a, b = f64(np.asarray(pmat1)), f64(np.asarray(pmat2))
+    G, n = a.shape
+    diffv = fold_change_grid(np.asarray(prior["x"], dtype=np.float64))
+    py = None if skip_prior_adjustment else f64(prior["y"])
+    zi = _zero_index(diffv, expectation)
+    if len(zi) not in (1, G):
+        _stop("the expectation parameter must be either one number or a vector equal to the number of genes being tested")
+    idx = np.empty((G, 3), dtype=np.int32, order="F")
+    z = np.empty(G, dtype=np.float64)
+    ctx = context or _lib.default_context()
+    check(lib().scde_b200_ratio_posterior_summary(ctx.handle, p_f64(a), p_f64(b), G, n, p_f64(py), p_i32(zi), len(zi),
+                                                  p_i32(idx), p_f64(z), None))
+    return _summary_frame(idx, z, diffv, genes)
+
+
+# ------------------------------------------------------------------------------------------------
+class DifferenceJob:
+    """Device-resident scde.expression.difference: upload once, run, download (C ABI split form)."""
+
+    def __init__(self, ctx: _lib.Context, counts: np.ndarray, mm: np.ndarray, prior_x, prior_y, group_codes,
+                 n_boot: int, seed: int = 1, batch_codes=None, n_batch_levels: int = 0, zero_index=None,
+                 zero_index_adjusted=None, local_theta: int = 0, sqlogit: int = 0, boot_idx=(None,) * 4,
+                 gene_range=(0, 0), want_posteriors: bool = False):
+        self.ctx = ctx
+        self._keep = []  # host arrays must outlive the upload call
+
+        def keep(a):
+            self._keep.append(a)
+            return a
+
+        counts = keep(i32(counts))
+        G_all, Cn = counts.shape
+        K = len(prior_x)
+        a = _lib.DiffArgs()
+        a.n_genes, a.n_cells, a.n_grid = G_all, Cn, K
+        a.counts = p_i32(counts)
+        a.models = p_f64(keep(f64(mm)))
+        a.prior_x = p_f64(keep(f64(prior_x)))
+        a.prior_y = p_f64(keep(f64(prior_y)))
+        a.group = p_i32(keep(i32(group_codes)))
+        self.has_batch = batch_codes is not None and n_batch_levels > 1
+        a.batch = p_i32(keep(i32(batch_codes))) if batch_codes is not None else None
+        a.n_batch_levels = int(n_batch_levels)
+        a.n_boot, a.seed = int(n_boot), int(seed)
+        for i in range(4):
+            a.boot_idx[i] = p_i32(keep(i32(boot_idx[i], order="C"))) if boot_idx[i] is not None else None
+        zi = keep(i32(zero_index if zero_index is not None else [K]))
+        a.zero_index, a.n_zero = p_i32(zi), len(zi)
+        zia = keep(i32(zero_index_adjusted if zero_index_adjusted is not None else [2 * K - 1] * len(zi)))
+        a.zero_index_adjusted = p_i32(zia)
+        a.local_theta, a.square_logit_conc = int(local_theta), int(sqlogit)
+        a.gene_begin, a.gene_end = int(gene_range[0]), int(gene_range[1])
+        self.G = (gene_range[1] - gene_range[0]) if gene_range != (0, 0) else G_all
+        self.K = K
+        self.want_posteriors = bool(want_posteriors)
+        self._job = C.c_void_p()
+        check(lib().scde_b200_diff_upload(ctx.handle, C.byref(a), int(want_posteriors), C.byref(self._job)))
+        self._keep.clear()
+
+    def run(self):
+        """Queue all device work on the context stream (asynchronous)."""
+        check(lib().scde_b200_diff_run(self.ctx.handle, self._job))
+
+    def download(self, joint_posteriors: bool = False):
+        G, K = self.G, self.K
+        o = _lib.DiffOut()
+        res = {"idx": np.empty((G, 3), np.int32, order="F"), "z": np.empty(G)}
+        o.idx, o.z = p_i32(res["idx"]), p_f64(res["z"])
+        if self.has_batch:
+            for k in ("batch", "adjusted"):
+                res[k + "_idx"] = np.empty((G, 3), np.int32, order="F")
+                res[k + "_z"] = np.empty(G)
+            o.batch_idx, o.batch_z = p_i32(res["batch_idx"]), p_f64(res["batch_z"])
+            o.adjusted_idx, o.adjusted_z = p_i32(res["adjusted_idx"]), p_f64(res["adjusted_z"])
+        if self.want_posteriors:
+            res["difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
+            o.difference_posterior = p_f64(res["difference_posterior"])
+            if self.has_batch:
+                res["batch_difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
+                res["adjusted_difference_posterior"] = np.empty((G, 4 * K - 3), order="F")
+                o.batch_difference_posterior = p_f64(res["batch_difference_posterior"])
+                o.adjusted_difference_posterior = p_f64(res["adjusted_difference_posterior"])
+        if joint_posteriors or self.want_posteriors:
+            res["joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
+            for i in range(2):
+                o.joint_posteriors[i] = p_f64(res["joint_posteriors"][i])
+            if self.has_batch:
+                res["batch_joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
+                for i in range(2):
+                    o.batch_joint_posteriors[i] = p_f64(res["batch_joint_posteriors"][i])
+        st = _lib.Stats()
+        check(lib().scde_b200_diff_download(self.ctx.handle, self._job, C.byref(o), C.byref(st)))
+        res["stats"] = st.as_dict()
+        return res
+
+    def close(self):
+        if self._job:
+            lib().scde_b200_diff_free(self.ctx.handle, self._job)
+            self._job = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None, batch=None,
+                               n_randomizations: int = 150, n_cores: int = 10, batch_models=None,
+                               return_posteriors: bool = False, expectation=0, verbose: int = 0, seed: int = 1,
+                               context=None, boot_idx=(None,) * 4):
+    """scde.expression.difference (R/functions.R:304-408).
+
+    Returns the ``lb mle ub ce Z cZ`` data frame (genes as rows), or a dict shaped like the reference's list when
+    `batch` and/or `return_posteriors` are given (keys: ``results``, ``batch.adjusted``, ``batch.effect``,
+    ``difference.posterior``, ``batch.adjusted.difference.posterior``, ``joint.posteriors``).
+    """
+    cm, genes = _counts_for_models(models, counts)
+    if batch_models is not None and batch_models is not models:
+        raise NotImplementedError("batch.models different from models is not supported by the fused device path")
+    if groups is None:
+        groups = models.attrs.get("groups")
+        if groups is None:
+            _stop("groups factor is not provided, and models structure is lacking groups attribute")
+        groups = pd.Categorical(groups)
+    gcodes, glev = _named_factor(groups, models.index)
+    if len(glev) != 2:
+        _stop("wrong number of levels in the grouping factor (" + " ".join(map(str, glev)) + "), but must be two.")
+    correct_batch = False
+    bcodes, blev = None, []
+    if batch is not None:
+        bcodes, blev = _named_factor(batch, models.index)
+        if len(blev) > 1:
+            correct_batch = True
+        elif verbose:
+            sys.stdout.write("WARNING: only one batch level detected. Nothing to correct for.")
+    if correct_batch and verbose:
+        sys.stdout.write("controlling for batch effects. interaction:\n")
+        sys.stdout.write(str(pd.crosstab(pd.Series(gcodes, name="groups"), pd.Series(bcodes, name="batch"))) + "\n")
+    elif verbose:
+        sys.stdout.write("comparing groups:\n")
+        sys.stdout.write(str(pd.Series([glev[c] for c in gcodes if c >= 0]).value_counts().sort_index()) + "\n")
+    mm, lt, sq = pack_models(models)
+    x = np.asarray(prior["x"], dtype=np.float64)
+    diffv = fold_change_grid(x)
+    zi = _zero_index(diffv, expectation)
+    G = cm.shape[0]
+    if len(zi) not in (1, G):
+        _stop("the expectation parameter must be either one number or a vector equal to the number of genes being tested")
+    adiffv = r_as_character_numeric(r_seq_length(diffv[0] - diffv[-1], diffv[-1] - diffv[0], 2 * len(diffv) - 1))
+    zia = _zero_index(adiffv, expectation)
+    ctx = context or _lib.default_context()
+    job = DifferenceJob(ctx, cm, mm, x, np.asarray(prior["y"], dtype=np.float64), gcodes, n_randomizations, seed,
+                        batch_codes=bcodes if correct_batch else None, n_batch_levels=len(blev) if correct_batch else 0,
+                        zero_index=zi, zero_index_adjusted=zia, local_theta=lt, sqlogit=sq, boot_idx=boot_idx,
+                        want_posteriors=return_posteriors)
+    try:
+        if verbose:
+            sys.stdout.write("calculating difference posterior\n")
+        job.run()
+        res = job.download()
+    finally:
+        job.close()
+    if verbose:
+        sys.stdout.write("summarizing differences\n")
+    bdiffp_rep = _summary_frame(res["idx"], res["z"], diffv, genes)
+    with np.errstate(over="ignore"):
+        kcols = ["%.15g" % v for v in np.exp(marginals_from_prior(prior))]
+
+    def _posts():
+        d = {"difference.posterior": pd.DataFrame(res["difference_posterior"], index=genes,
+                                                  columns=["%.15g" % v for v in diffv]),
+             "joint.posteriors": {glev[i]: pd.DataFrame(res["joint_posteriors"][i], index=genes, columns=kcols)
+                                  for i in range(2)}}
+        return d
+
+    if correct_batch:
+        out = {"batch.adjusted": _summary_frame(res["adjusted_idx"], res["adjusted_z"], adiffv, genes),
+               "results": bdiffp_rep,
+               "batch.effect": _summary_frame(res["batch_idx"], res["batch_z"], diffv, genes)}
+        if return_posteriors:
+            out.update(_posts())
+            out["batch.adjusted.difference.posterior"] = pd.DataFrame(
+                res["adjusted_difference_posterior"], index=genes, columns=["%.15g" % v for v in adiffv])
+        out["stats"] = res["stats"]
+        return out
+    if return_posteriors:
+        out = {"results": bdiffp_rep}
+        out.update(_posts())
+        out["stats"] = res["stats"]
+        return out
+    bdiffp_rep.attrs["stats"] = res["stats"]
+    return bdiffp_rep

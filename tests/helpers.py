@@ -1,0 +1,56 @@
+"""Shared test inputs: the es.mef.small / o.ifm fixtures (tests/golden) prepared as tests/tests.R:8-38 does."""
+from __future__ import annotations
+
+import functools
+import os
+
+import numpy as np
+import pandas as pd
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@functools.lru_cache(maxsize=None)
+def es_mef_raw():
+    d = np.load(os.path.join(GOLD, "es_mef_small.npz"))
+    return pd.DataFrame(d["counts"], index=[str(g) for g in d["genes"]], columns=[str(c) for c in d["cells"]])
+
+
+@functools.lru_cache(maxsize=None)
+def o_ifm():
+    d = np.load(os.path.join(GOLD, "o_ifm.npz"))
+    df = pd.DataFrame(d["values"], index=[str(c) for c in d["cells"]], columns=[str(c) for c in d["columns"]])
+    df.attrs["groups"] = [str(g) for g in d["groups"]]
+    return df
+
+
+@functools.lru_cache(maxsize=None)
+def knn_models():
+    d = np.load(os.path.join(GOLD, "knn.npz"))
+    return pd.DataFrame(d["values"], index=[str(c) for c in d["cells"]], columns=[str(c) for c in d["columns"]])
+
+
+@functools.lru_cache(maxsize=None)
+def es_mef_inputs(variant: str = "tests"):
+    """(counts DataFrame, models DataFrame, prior DataFrame, groups Categorical).
+
+    variant "tests":    the filter of tests/tests.R:19-21,33-38 (rowSums > 0, colSums > 1e4, corr.a > 0), default prior;
+    variant "vignette": clean.counts(min.lib.size = 1000, min.reads = 1, min.detected = 1) and max.quantile = 0.999
+                        -- the settings the printed vignette rows were produced with.
+    """
+    from scde_b200.prior import clean_counts, scde_expression_prior
+
+    cd = es_mef_raw()
+    ifm = o_ifm()
+    if variant == "tests":
+        cd = cd[cd.sum(axis=1) > 0]
+        cd = cd.loc[:, cd.sum(axis=0) > 1e4]
+        ifm = ifm[ifm["corr.a"] > 0]
+        prior = scde_expression_prior(ifm, cd, length_out=400)
+    else:
+        cd = clean_counts(cd, min_lib_size=1000, min_reads=1, min_detected=1)
+        ifm = ifm[ifm["corr.a"] > 0]
+        prior = scde_expression_prior(ifm, cd, length_out=400, max_quantile=0.999)
+    cd = cd.loc[:, list(ifm.index)]
+    groups = pd.Categorical([("ESC" if n.startswith("ESC") else "MEF") for n in ifm.index], categories=["ESC", "MEF"])
+    return cd, ifm, prior, groups

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical inputs
+(same bootstrap draws).  Tolerances (BASELINE.json north star): bootstrap indices bit-exact; log-posteriors within
+1e-6 relative; lb/ub within one grid step (asserted exactly here and reported if not); mle index exact; Z within 1e-6."""
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import helpers
+from oracle import oracle as O
+from scde_b200 import _lib, api, synth
+
+pytestmark = pytest.mark.gpu
+
+LOGP_RTOL = 1e-6
+
+
+def _logp_close(a, b, rtol=LOGP_RTOL, floor=1e-290):
+    """|log a - log b| <= rtol * |log b| wherever both are above the underflow floor; absolute 1e-300 elsewhere."""
+    a, b = np.asarray(a), np.asarray(b)
+    big = (a > floor) & (b > floor)
+    la, lb = np.log(a[big]), np.log(b[big])
+    ok_big = np.all(np.abs(la - lb) <= rtol * np.maximum(np.abs(lb), 1.0))
+    ok_small = np.all(np.abs(a[~big] - b[~big]) <= 1e-280)
+    worst = float(np.max(np.abs(la - lb) / np.maximum(np.abs(lb), 1.0))) if big.any() else 0.0
+    return bool(ok_big and ok_small), worst
+
+
+def _small_problem(G=97, Cn=23, seed=5, batch=False):
+    w = synth.make_workload(3, n_genes=G, n_cells=Cn, batch=batch, seed=seed)
+    return w
+
+
+def _oracle_inputs(w):
+    mm, lt, sq = O.pack_models(w.models)
+    mag = O.marginals_from_prior_x(w.prior["x"].to_numpy())
+    return mm, lt, sq, mag
+
+
+# ------------------------------------------------------------------------------------------------
+def test_cell_table_matches_oracle(ctx):
+    ifm = helpers.o_ifm()
+    cd, _, prior, _ = helpers.es_mef_inputs("tests")
+    mm, lt, sq = O.pack_models(ifm)
+    mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+    for cell in (0, 7, 39):
+        uc = np.unique(cd.to_numpy()[:, cell]).astype(np.int32)
+        want, wmodes = O.cell_table(mm[cell], uc, mag, ncells_for_clamp=20)
+        got = np.empty((len(uc), len(mag)))
+        gmodes = np.empty(len(uc), np.int32)
+        _lib.check(_lib.lib().scde_b200_cell_table(ctx.handle, _lib.p_f64(_lib.f64(mm[cell])), _lib.p_i32(uc), len(uc),
+                                                   _lib.p_f64(_lib.f64(mag)), len(mag), 0, 0, 20, _lib.p_f64(got),
+                                                   _lib.p_i32(gmodes)))
+        want = want.T
+        sent = want < -1e300
+        assert np.array_equal(sent, got < -1e300)
+        assert np.array_equal(want[sent], got[sent])  # the clamp value itself
+        np.testing.assert_allclose(got[~sent], want[~sent], rtol=1e-9, atol=1e-9)
+        assert np.array_equal(gmodes, wmodes)
+
+
+def test_cell_table_local_theta(ctx):
+    knn = helpers.knn_models()
+    mm, lt, sq = O.pack_models(knn)
+    assert lt == 1 and sq == 1
+    mag = O.marginals_from_prior_x(np.linspace(0, 4.8, 401))
+    uc = np.array([0, 1, 2, 3, 7, 19, 150, 2048, 99999], dtype=np.int32)
+    for cell in (0, 31, 63):
+        want, wmodes = O.cell_table(mm[cell], uc, mag, localtheta=1, sqlogit=1, ncells_for_clamp=64)
+        got = np.empty((len(uc), len(mag)))
+        gmodes = np.empty(len(uc), np.int32)
+        _lib.check(_lib.lib().scde_b200_cell_table(ctx.handle, _lib.p_f64(_lib.f64(mm[cell])), _lib.p_i32(uc), len(uc),
+                                                   _lib.p_f64(_lib.f64(mag)), len(mag), 1, 1, 64, _lib.p_f64(got),
+                                                   _lib.p_i32(gmodes)))
+        want = want.T
+        sent = want < -1e300
+        assert np.array_equal(sent, got < -1e300)
+        np.testing.assert_allclose(got[~sent], want[~sent], rtol=1e-9, atol=1e-9)
+        assert np.array_equal(gmodes, wmodes)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("G,Cn,B", [(97, 23, 100), (5, 1, 7), (33, 40, 150), (1, 9, 100)])
+def test_posteriors_match_oracle(ctx, kernel, G, Cn, B):
+    w = _small_problem(G, Cn)
+    mm, lt, sq, mag = _oracle_inputs(w)
+    flat, off, uci = O.unique_counts(w.counts)
+    bi = O.boot_indices(1, Cn, B)
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, B, boot_idx=bi)["jp"]
+    ctx.set_contract_kernel(kernel)
+    try:
+        got = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=B, context=ctx)
+    finally:
+        ctx.set_contract_kernel(0)
+    ok, worst = _logp_close(got.to_numpy(), want)
+    assert ok, f"log-posterior mismatch, worst relative {worst:.3e}"
+    np.testing.assert_allclose(got.to_numpy().sum(axis=1), 1.0, rtol=1e-12)
+
+
+def test_posteriors_variants(ctx):
+    w = _small_problem(41, 12)
+    mm, lt, sq, mag = _oracle_inputs(w)
+    flat, off, uci = O.unique_counts(w.counts)
+    # no bootstrap
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, 0)["jp"]
+    got = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=0, context=ctx)
+    assert _logp_close(got.to_numpy(), want)[0]
+    # ensemble
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, 10, ensemble=1)["jp"]
+    got = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=10, ensemble_posterior=True, context=ctx)
+    np.testing.assert_allclose(got.to_numpy(), want, rtol=1e-9, atol=1e-300)
+    # modes + individual posteriors
+    ow = O.log_boot_posterior(mm, flat, off, uci, mag, 20, returnpost=3)
+    gw = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=20, return_individual_posteriors=True,
+                             return_individual_posterior_modes=True, context=ctx)
+    assert _logp_close(gw["jp"].to_numpy(), ow["jp"])[0]
+    np.testing.assert_array_equal(gw["modes"].to_numpy(), ow["modes"])
+    for i, cell in enumerate(w.models.index):
+        a, b = gw["post"][cell].to_numpy(), ow["post"][i]
+        sent = b < -1e300
+        assert np.array_equal(a[sent], b[sent])
+        np.testing.assert_allclose(a[~sent], b[~sent], rtol=1e-9, atol=1e-9)
+
+
+def test_batch_posteriors_match_oracle(ctx):
+    w = _small_problem(53, 31, batch=True)
+    mm, lt, sq, mag = _oracle_inputs(w)
+    flat, off, uci = O.unique_counts(w.counts)
+    bcodes = np.asarray(w.batch.codes)
+    pools = [np.nonzero(bcodes == l)[0].astype(np.int32) for l in range(2)]
+    comp = np.array([5, 0], dtype=np.int32)  # a zero-count composition level
+    want = O.log_boot_batch_posterior(mm, flat, off, uci, mag, pools, comp, 40, seed=1)["jp"]
+    got = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=40, batch=w.batch,
+                              composition={"batch1": 5, "batch2": 0}, context=ctx)
+    assert _logp_close(got.to_numpy(), want)[0]
+    comp = np.bincount(bcodes[:15], minlength=2).astype(np.int32)
+    want = O.log_boot_batch_posterior(mm, flat, off, uci, mag, pools, comp, 100, seed=1)["jp"]
+    got = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=100, batch=w.batch, composition=comp,
+                              context=ctx)
+    assert _logp_close(got.to_numpy(), want)[0]
+
+
+def test_mat_slide_mult_bit_exact(ctx):
+    rng = np.random.default_rng(3)
+    for G, n in [(7, 5), (64, 401), (3, 801), (1, 1)]:
+        a, b = rng.random((G, n)), rng.random((G, n)) * 1e-3
+        want = O.mat_slide_mult(a, b)
+        got = api.mat_slide_mult(a, b, context=ctx)
+        assert np.array_equal(got, want)  # separately rounded multiply/add in ascending j: bit-identical
+        ref = np.stack([np.correlate(a[g], b[g], "full") for g in range(G)])
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+
+
+def test_legacy_jpmat_log_boot(ctx):
+    rng = np.random.default_rng(11)
+    matl = [np.log(rng.dirichlet(np.ones(37), size=19)) for _ in range(6)]
+    bi = O.boot_indices(3, 6, 25)
+    want = O.jpmat_log_boot(matl, 25, seed=3)
+    got = api.jpmat_log_boot(matl, 25, 3, context=ctx)
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    got2 = api.jpmat_log_boot(matl, 25, 3, boot_idx=bi, context=ctx)
+    assert np.array_equal(got, got2)
+    matll = [matl[:2], matl[2:]]
+    want = O.jpmat_log_batch_boot(matll, [3, 2], 25, seed=4)
+    got = api.jpmat_log_batch_boot(matll, [3, 2], 25, 4, context=ctx)
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+
+
+def _compare_summaries(got: pd.DataFrame, want: np.ndarray, widx, gidx, what):
+    assert np.array_equal(gidx[:, 1], widx[:, 1]), f"{what}: mle grid index differs"
+    assert np.max(np.abs(gidx[:, [0, 2]] - widx[:, [0, 2]])) <= 1, f"{what}: bound differs by more than one grid step"
+    assert np.array_equal(gidx, widx), f"{what}: bounds differ (within one step)"
+    np.testing.assert_allclose(got["Z"].to_numpy(), want[:, 4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["cZ"].to_numpy(), want[:, 5], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got[["lb", "mle", "ub", "ce"]].to_numpy(), want[:, :4], rtol=1e-12, atol=1e-300)
+
+
+def test_expression_difference_small(ctx):
+    w = _small_problem(211, 30)
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1)
+    job_res = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                             return_posteriors=True, context=ctx)
+    got = job_res["results"]
+    ok, worst = _logp_close(job_res["difference.posterior"].to_numpy(), want["difference.posterior"])
+    assert ok, worst
+    for i, lev in enumerate(["g1", "g2"]):
+        assert _logp_close(job_res["joint.posteriors"][lev].to_numpy(), want["joint.posteriors"][i])[0]
+    diffv = api.fold_change_grid(w.prior["x"].to_numpy())
+    gidx = np.stack([np.searchsorted(diffv, got[c].to_numpy() * np.log10(2.0) - 1e-9) for c in ("lb", "mle", "ub")], 1)
+    _compare_summaries(got, want["results"], want["idx"], gidx, "results")
+
+
+def test_expression_difference_batch_small(ctx):
+    w = _small_problem(101, 26, batch=True)
+    codes = np.asarray(w.groups.codes)
+    bcodes = np.asarray(w.batch.codes)
+    ex = 0.5
+    want = O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=60, seed=1,
+                                   batch_codes=bcodes, expectation=ex)
+    got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=w.batch,
+                                         n_randomizations=60, return_posteriors=True, expectation=ex, context=ctx)
+    assert _logp_close(got["batch.adjusted.difference.posterior"].to_numpy(),
+                       want["batch.adjusted.difference.posterior"])[0]
+    for key in ("results", "batch.effect", "batch.adjusted"):
+        np.testing.assert_allclose(got[key]["Z"].to_numpy(), want[key][:, 4], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got[key][["lb", "mle", "ub", "ce"]].to_numpy(), want[key][:, :4], rtol=1e-12,
+                                   atol=1e-300)
+        np.testing.assert_allclose(got[key]["cZ"].to_numpy(), want[key][:, 5], rtol=1e-6, atol=1e-9)
+
+
+def test_expression_magnitude(ctx):
+    cd, ifm, prior, groups = helpers.es_mef_inputs("tests")
+    sub = cd.iloc[:500]
+    got = api.scde_expression_magnitude(ifm, sub)
+    with np.errstate(divide="ignore"):
+        want = O.expression_magnitude(sub.to_numpy(), ifm["corr.b"].to_numpy(), ifm["corr.a"].to_numpy())
+    assert np.array_equal(np.isneginf(got.to_numpy()), np.isneginf(want))
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got.to_numpy()[fin], want[fin], rtol=1e-14)
+
+
+def test_es_mef_small_subset_full_path(ctx):
+    """cfg1 (bundled data): a 1500-gene slice through the whole path against the oracle, both kernels agreeing."""
+    cd, ifm, prior, groups = helpers.es_mef_inputs("tests")
+    sub = cd.iloc[2000:3500]
+    codes = np.asarray(groups.codes)
+    want = O.expression_difference(ifm, sub.to_numpy(), prior["x"].to_numpy(), prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1)
+    got = api.scde_expression_difference(ifm, sub, prior, groups=groups, n_randomizations=100, context=ctx)
+    np.testing.assert_allclose(got["Z"].to_numpy(), want["results"][:, 4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got[["lb", "mle", "ub", "ce"]].to_numpy(), want["results"][:, :4], rtol=1e-12, atol=1e-300)
+    ctx.set_contract_kernel(1)
+    try:
+        got1 = api.scde_expression_difference(ifm, sub, prior, groups=groups, n_randomizations=100, context=ctx)
+    finally:
+        ctx.set_contract_kernel(0)
+    np.testing.assert_allclose(got1["Z"].to_numpy(), got["Z"].to_numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_error_paths(ctx):
+    w = _small_problem(10, 6)
+    with pytest.raises(ValueError):
+        api.scde_expression_difference(w.models, w.counts[:, :3], w.prior, groups=w.groups, context=ctx)
+    bad = w.counts.copy()
+    bad[0, 0] = -4
+    with pytest.raises(_lib.ScdeB200Error):
+        api.scde_expression_difference(w.models, bad, w.prior, groups=w.groups, n_randomizations=5, context=ctx)
+    with pytest.raises(ValueError):
+        api.scde_expression_difference(w.models, w.counts, w.prior,
+                                       groups=pd.Categorical(["a", "b", "c", "a", "b", "c"]), context=ctx)
+
+
+def test_full_size_properties(ctx):
+    """cfg3-sized shapes are too slow for the oracle; check size-independent properties instead: rows of the joint
+    posterior sum to one, swapping the groups mirrors the summary, and an oracle spot-check on a gene subset."""
+    w = synth.make_workload(3, n_genes=3000, n_cells=600)
+    res = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                         return_posteriors=True, context=ctx)
+    for lev in ("g1", "g2"):
+        np.testing.assert_allclose(res["joint.posteriors"][lev].to_numpy().sum(axis=1), 1.0, rtol=1e-11)
+    np.testing.assert_allclose(res["difference.posterior"].to_numpy().sum(axis=1), 1.0, rtol=1e-11)
+    swapped = pd.Categorical(np.where(np.asarray(w.groups.codes) == 0, "g2", "g1"), categories=["g1", "g2"])
+    # same cells per level, levels exchanged -> the ratio posterior is mirrored (draws are per level size: equal halves)
+    res2 = api.scde_expression_difference(w.models, w.counts, w.prior, groups=swapped, n_randomizations=100,
+                                          return_posteriors=True, context=ctx)
+    a = res["difference.posterior"].to_numpy()
+    b = res2["difference.posterior"].to_numpy()[:, ::-1]
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(res["results"]["Z"].to_numpy(), -res2["results"]["Z"].to_numpy(), rtol=1e-6, atol=1e-9)
+    # oracle spot-check on 24 genes with the same draws
+    sel = np.arange(0, 3000, 125)
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, w.counts[sel], w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1)
+    ok, worst = _logp_close(a[sel], want["difference.posterior"])
+    assert ok, worst
+    # cZ is global over genes, so compare Z only
+    np.testing.assert_allclose(res["results"]["Z"].to_numpy()[sel], want["results"][:, 4], rtol=1e-6, atol=1e-9)

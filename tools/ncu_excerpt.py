@@ -1,0 +1,20 @@
+"""Prints the metrics we track from an .ncu-rep (read here, on the CPU box): python tools/ncu_excerpt.py rep [title]"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+h, units = rows[0], rows[1]
+keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'lts__t_sector_hit_rate.pct',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed']
+keys += [n for n in h if 'issue_stalled' in n and 'per_issue_active' in n and 'not_issued' not in n]
+print("#", " ".join(sys.argv[2:]) if len(sys.argv) > 2 else rep)
+for r in rows[2:]:
+    print('----')
+    for n in keys:
+        if n in h:
+            i = h.index(n)
+            print(f"{n}: {r[i]} {units[i]}")

@@ -115,7 +115,7 @@ struct scde_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int n_sm = 148;
-    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled
+    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled (DMMA), 3 tiled (DFMA register tiles)
 };
 
 namespace {
@@ -228,14 +228,14 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     a.ld_jp = ld_jp;
     bool tiled = contract_tiled_supported(a);
     if (ctx->contract_kernel == 1) tiled = false;
-    if (ctx->contract_kernel == 2 && !tiled) {
+    if (ctx->contract_kernel >= 2 && !tiled) {
         set_error("tiled contraction kernel forced but unsupported for K=%d", t.K);
         return SCDE_B200_EINVAL;
     }
     e0 = tm ? tm->begin(st) : -1;
     int nl = 0;
     if (tiled)
-        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, st, &nl));
+        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, ctx->contract_kernel == 3 ? 1 : 0, st, &nl));
     else
         SCDE_CUDA(launch_contract_generic(a, st, &nl));
     if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
@@ -334,7 +334,7 @@ int scde_b200_synchronize(scde_b200_ctx *ctx) {
 }
 
 int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which) {
-    if (!ctx || which < 0 || which > 2) return SCDE_B200_EINVAL;
+    if (!ctx || which < 0 || which > 3) return SCDE_B200_EINVAL;
     ctx->contract_kernel = which;
     return SCDE_B200_OK;
 }

@@ -373,6 +373,275 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contra
 }
 
 // ------------------------------------------------------------------------------------------------
+// tiled kernel, DMMA form (the default).  Same cluster / TMA ring / soft-max structure as above, but the inner
+// product runs on mma.sync.aligned.m8n8k4.f64: M = 8 grid points, N = 8 boots, K = 4 cells per instruction.  The FP64
+// rate of DMMA equals that of DFMA on B200 (37 vs 36.5 TFLOP/s measured, tools/microbench.cu), but one DMMA replaces
+// eight DFMA warp-instructions and its fragments are one double per lane, so a warp issues 15 LDS.64 + 26 DMMA per four
+// cells instead of 36 LDS + 208 DFMA -- the register-tile version was limited by shared-memory instruction issue
+// (LDS.128 sustains one per two cycles per SM) and by issue slots, not by the FP64 pipe (profiles/r01a_*).
+//
+// Tiles per CTA: 26 (grid) x 13 (boots).  Sub-partition s (= warp & 3) owns grid tiles 6s..6s+5 completely -- two per
+// warp slot -- and half of a shared grid tile (24 for s = 0,1; 25 for s = 2,3): boot tiles 0..6 for even s, 6..12 for
+// odd s, where the duplicated boot tile 6 of the odd warps is computed but masked out.  That is 85 tiles per
+// sub-partition, i.e. the FP64 pipe of every sub-partition carries the same load.
+// Shared-memory rows are padded to 216 doubles so the four cells of an A fragment fall into disjoint bank halves
+// (216 * 2 words = 16 mod 32), as the 104-double W rows already do: every fragment load is conflict-free.
+constexpr int M_AS = 216;                                   // padded row stride of the A stage (doubles)
+constexpr int M_STAGE_DOUBLES = T_S * M_AS + T_S * T_WP;    // 2560
+constexpr int M_NT = 13;                                    // boot tiles
+
+struct MmaSmem {
+    double stage[T_NS][M_STAGE_DOUBLES];
+    double red[T_WARPS][T_WP];
+    double xmax[2][T_WP];
+    double xsum[2][T_WP];
+    uint64_t full[T_NS];
+    uint64_t empty[T_NS];
+};
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// NEX: extra tiles of the shared grid tile (0 or 7); NX0: first boot tile of the extras (0 or 6)
+template <int NEX, int NX0>
+__device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int warp, int lane, uint32_t rank,
+                                        int n_my_genes, int spg) {
+    const int g = lane >> 2, t = lane & 3;
+    const int smsp = warp & 3, slot = warp >> 2;
+    const int m0 = smsp * 6 + slot * 2;   // first of the two full grid tiles
+    const int mx = 24 + (smsp >> 1);      // shared grid tile (slot 2 only)
+    const int kbase = rank * T_KH;
+    const uint32_t peer = rank ^ 1u;
+    const int64_t total_stages = (int64_t)n_my_genes * spg;
+    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
+
+    // ---- producer (warp 0; it always runs the NEX == 0 instantiation) ----
+    int64_t pq = 0;
+    int p_gi = 0, p_cb = 0;
+    int32_t next_row = 0;
+    auto prefetch_row = [&](int gi, int cb) -> int32_t {
+        if (lane < T_S && gi < n_my_genes) {
+            int cell = cb * T_S + lane;
+            if (cell >= p.n_list) cell = p.n_list - 1;
+            int col = p.cell_ids ? p.cell_ids[cell] : cell;
+            int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
+            return p.ridx[gene * p.ld_ridx + col];
+        }
+        return 0;
+    };
+    auto issue_stage = [&]() {
+        const int sl = (int)(pq % T_NS);
+        const uint32_t fill = (uint32_t)(pq / T_NS);
+        if (fill > 0) mbar_wait(&sm.empty[sl], (fill - 1) & 1u);
+        double *dstA = sm.stage[sl];
+        double *dstW = dstA + T_S * M_AS;
+        if (lane == 0) mbar_arrive_expect_tx(&sm.full[sl], T_STAGE_BYTES);
+        __syncwarp();
+        if (lane < T_S) {
+            bulk_g2s(dstA + lane * M_AS, p.table + (int64_t)next_row * KP_TILED + kbase, T_KH * 8u, &sm.full[sl]);
+        } else if (lane == T_S) {
+            bulk_g2s(dstW, p.W + (int64_t)p_cb * T_S * T_WP, T_STAGE_W * 8u, &sm.full[sl]);
+        }
+        ++pq;
+        if (++p_cb == spg) {
+            p_cb = 0;
+            ++p_gi;
+        }
+        next_row = prefetch_row(p_gi, p_cb);
+    };
+    if constexpr (NEX == 0) {
+        if (warp == 0) {
+            next_row = prefetch_row(0, 0);
+            for (int i = 0; i < T_PD && pq < total_stages; ++i) issue_stage();
+        }
+    }
+
+    // validity of this thread's grid points
+    const bool kv0 = (kbase + (m0 + 0) * 8 + g) < p.K;
+    const bool kv1 = (kbase + (m0 + 1) * 8 + g) < p.K;
+    const bool kvx = (kbase + mx * 8 + g) < p.K;
+
+    int64_t q = 0;
+    for (int gi = 0; gi < n_my_genes; ++gi) {
+        const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
+        double acc[2][M_NT][2];
+        double ex[NEX > 0 ? NEX : 1][2];
+#pragma unroll
+        for (int nt = 0; nt < M_NT; ++nt) {
+            acc[0][nt][0] = acc[0][nt][1] = 0.0;
+            acc[1][nt][0] = acc[1][nt][1] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < (NEX > 0 ? NEX : 1); ++j) ex[j][0] = ex[j][1] = 0.0;
+
+        for (int cb = 0; cb < spg; ++cb, ++q) {
+            if constexpr (NEX == 0) {
+                if (warp == 0 && pq < total_stages) issue_stage();
+            }
+            const int sl = (int)(q % T_NS);
+            mbar_wait(&sm.full[sl], (uint32_t)(q / T_NS) & 1u);
+            const double *sA = sm.stage[sl];
+            const double *sW = sA + T_S * M_AS;
+#pragma unroll
+            for (int ks = 0; ks < T_S / 4; ++ks) {
+                const double *ap = sA + (ks * 4 + t) * M_AS + g;
+                const double *wp = sW + (ks * 4 + t) * T_WP + g;
+                const double a0 = ap[(m0 + 0) * 8];
+                const double a1 = ap[(m0 + 1) * 8];
+                double a2 = 0.0;
+                if constexpr (NEX > 0) a2 = ap[mx * 8];
+#pragma unroll
+                for (int nt = 0; nt < M_NT; ++nt) {
+                    const double b = wp[nt * 8];
+                    dmma(acc[0][nt], a0, b);
+                    dmma(acc[1][nt], a1, b);
+                    if constexpr (NEX > 0) {
+                        if (nt >= NX0 && nt < NX0 + NEX) dmma(ex[nt - NX0], a2, b);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[sl]);
+        }
+
+        // ---------------- fused soft-max over the grid and average over boots ----------------
+        // thread holds, per tile, C[m = g][n = 2t + i]: grid point (tile*8 + g), boot (nt*8 + 2t + i)
+        // (1) per-boot maximum over this CTA's grid points
+#pragma unroll
+        for (int nt = 0; nt < M_NT; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double m = -INFINITY;
+                if (kv0) m = fmax(m, acc[0][nt][i]);
+                if (kv1) m = fmax(m, acc[1][nt][i]);
+                if constexpr (NEX > 0) {
+                    if (nt >= NX0 && nt < NX0 + NEX && !(NX0 > 0 && nt == NX0) && kvx) m = fmax(m, ex[nt - NX0][i]);
+                }
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                if (g == 0) sm.red[warp][nt * 8 + 2 * t + i] = m;
+            }
+        }
+        named_bar_sync(1, T_THREADS);
+        if (threadIdx.x < T_WP) {
+            double m = sm.red[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < T_WARPS; ++w) m = fmax(m, sm.red[w][threadIdx.x]);
+            sm.xmax[0][threadIdx.x] = m;
+            st_peer_f64(&sm.xmax[1][threadIdx.x], peer, m);
+        }
+        cluster_arrive();
+        cluster_wait();
+        // (2) exponentials and per-boot sums
+#pragma unroll
+        for (int nt = 0; nt < M_NT; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int b = nt * 8 + 2 * t + i;
+                const double M = fmax(sm.xmax[0][b], sm.xmax[1][b]);
+                double e0 = kv0 ? exp(acc[0][nt][i] - M) : 0.0;
+                double e1 = kv1 ? exp(acc[1][nt][i] - M) : 0.0;
+                acc[0][nt][i] = e0;
+                acc[1][nt][i] = e1;
+                double s = e0 + e1;
+                if constexpr (NEX > 0) {
+                    if (nt >= NX0 && nt < NX0 + NEX) {
+                        const bool ok = kvx && !(NX0 > 0 && nt == NX0);
+                        double e2 = ok ? exp(ex[nt - NX0][i] - M) : 0.0;
+                        ex[nt - NX0][i] = e2;
+                        s += e2;
+                    }
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (g == 0) sm.red[warp][b] = s;
+            }
+        }
+        named_bar_sync(1, T_THREADS);
+        if (threadIdx.x < T_WP) {
+            double s = sm.red[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < T_WARPS; ++w) s += sm.red[w][threadIdx.x];
+            sm.xsum[0][threadIdx.x] = s;
+            st_peer_f64(&sm.xsum[1][threadIdx.x], peer, s);
+        }
+        cluster_arrive();
+        cluster_wait();
+        // (3) jp[g, k] += sum_b e[k, b] / (S_b * scale)
+        double r0 = 0.0, r1 = 0.0, rx = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < M_NT; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int b = nt * 8 + 2 * t + i;
+                if (b < p.n_boot_pass) {
+                    const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
+                    const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
+                    const double den = (s0 + s1) * p.scale;
+                    r0 += acc[0][nt][i] / den;
+                    r1 += acc[1][nt][i] / den;
+                    if constexpr (NEX > 0) {
+                        if (nt >= NX0 && nt < NX0 + NEX) rx += ex[nt - NX0][i] / den;
+                    }
+                }
+            }
+        }
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        if constexpr (NEX > 0) {
+            rx += __shfl_xor_sync(0xffffffffu, rx, 1);
+            rx += __shfl_xor_sync(0xffffffffu, rx, 2);
+        }
+        if (t == 0) {
+            // jp is zero-filled by the caller; the shared grid tile receives two partial sums (commutative, so the
+            // result does not depend on their order)
+            double *out = p.jp + gene * p.ld_jp + kbase;
+            if (kv0) atomicAdd(out + (m0 + 0) * 8 + g, r0);
+            if (kv1) atomicAdd(out + (m0 + 1) * 8 + g, r1);
+            if constexpr (NEX > 0) {
+                if (kvx) atomicAdd(out + mx * 8 + g, rx);
+            }
+        }
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contract_mma_kernel(const TiledParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MmaSmem &sm = *reinterpret_cast<MmaSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_NS; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], T_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_arrive();
+    cluster_wait();
+    const int n_my_genes = ((int)cid < p.n_genes) ? (p.n_genes - (int)cid + (int)ncl - 1) / (int)ncl : 0;
+    const int spg = (p.n_list + T_S - 1) / T_S;
+    const int smsp = warp & 3, slot = warp >> 2;
+    if (slot < 2)
+        run_mma<0, 0>(p, sm, warp, lane, rank, n_my_genes, spg);
+    else if ((smsp & 1) == 0)
+        run_mma<7, 0>(p, sm, warp, lane, rank, n_my_genes, spg);
+    else
+        run_mma<7, 6>(p, sm, warp, lane, rank, n_my_genes, spg);
+    cluster_arrive();
+    cluster_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic kernel: one CTA per gene, threads stride the grid, boots in chunks of G_BC accumulators.
 // Any K, any B.  When the grid fits one sweep (K <= 512) T is computed once per boot chunk; for larger grids the
 // max / sum / accumulate phases each recompute it (this kernel is the fallback and the on-device cross-check,
@@ -658,12 +927,14 @@ bool contract_tiled_supported(const ContractArgs &a) {
            a.n_w_rows >= round_up(a.n_list, 8);
 }
 
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches) {
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, int variant, cudaStream_t st, int *n_launches) {
     if (a.n_genes <= 0) return cudaSuccess;
     static bool attr_set = false;
-    const int smem = (int)sizeof(TiledSmem);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(contract_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(TiledSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -687,7 +958,10 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t 
         p.jp = a.jp;
         p.ld_jp = a.ld_jp;
         p.accumulate = ps > 0;
-        contract_tiled_kernel<<<2 * clusters, T_THREADS, smem, st>>>(p);
+        if (variant == 1)
+            contract_tiled_kernel<<<2 * clusters, T_THREADS, sizeof(TiledSmem), st>>>(p);
+        else
+            contract_mma_kernel<<<2 * clusters, T_THREADS, sizeof(MmaSmem), st>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) ++*n_launches;

@@ -79,7 +79,8 @@ struct ContractArgs {
 };
 cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches);
 // requires K <= 416 and ld_table == 416
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches);
+// variant 0 = DMMA tiles (default), 1 = DFMA register tiles
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, int variant, cudaStream_t st, int *n_launches);
 bool contract_tiled_supported(const ContractArgs &a);
 // ensemble form (src/jpmatLogBoot.cpp:224-237)
 cudaError_t launch_ensemble(const ContractArgs &a, double *rownorm_scratch, int64_t n_rows, cudaStream_t st);

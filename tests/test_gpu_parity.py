@@ -80,7 +80,7 @@ def test_cell_table_local_theta(ctx):
         assert np.array_equal(gmodes, wmodes)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("G,Cn,B", [(97, 23, 100), (5, 1, 7), (33, 40, 150), (1, 9, 100)])
 def test_posteriors_match_oracle(ctx, kernel, G, Cn, B):
     w = _small_problem(G, Cn)

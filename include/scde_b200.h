@@ -240,8 +240,7 @@ SCDE_B200_API int scde_b200_cell_table(scde_b200_ctx *ctx, const double *model_r
 /* Measured FP64 FMA throughput of this device (TFLOP/s) from a register-resident DFMA loop; the roofline
  * denominator for the contraction kernel (MEASURED_PEAKS.json has no FP64 entry). */
 SCDE_B200_API int scde_b200_measure_fp64_peak(scde_b200_ctx *ctx, double *tflops);
-/* 0 = pick automatically; 1 = force the generic contraction kernel; 2 = force the tiled sm_100a kernel (DMMA tiles);
- * 3 = force the tiled kernel's DFMA register-tile variant */
+/* 0 = pick automatically; 1 = force the generic contraction kernel; 2 = force the tiled sm_100a kernel */
 SCDE_B200_API int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which);
 
 #ifdef __cplusplus

@@ -111,11 +111,17 @@ struct StageTimer {
 
 using namespace scde;
 
+namespace {
+struct DiffWorkspace;
+}
+
 struct scde_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int n_sm = 148;
-    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled (DMMA), 3 tiled (DFMA register tiles)
+    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled (DMMA tiles)
+    DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
+    bool ws_busy = false;
 };
 
 namespace {
@@ -126,8 +132,9 @@ struct LpTable {
     int n_cells = 0, n_genes = 0, K = 0, ld = 0, ld_ridx = 0;
     int64_t n_rows = 0;
     double sentinel = 0;
-    DBuf<int32_t> row_off, row_x, row_mode, ridx, n_unique, err;
-    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp;
+    DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err;
+    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2;
+    bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
 };
 
 #define CHECK_CTX(ctx)                                                  \
@@ -151,12 +158,21 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     SCDE_CUDA(t.maxcfp.ensure(t.n_cells));
     SCDE_CUDA(t.table.ensure((size_t)t.n_rows * t.ld));
     SCDE_CUDA(t.row_mode.ensure((size_t)t.n_rows));
-    CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld};
+    SCDE_CUDA(t.row_cell.ensure((size_t)t.n_rows));
+    const bool fast = t.fast_theta && !local_theta && t.K <= KP_TILED;
+    if (fast) {
+        SCDE_CUDA(t.cfp.ensure(cl));
+        SCDE_CUDA(t.l1.ensure(cl));
+        SCDE_CUDA(t.l2.ensure(cl));
+    }
+    CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
+                  fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr};
     int e0 = tm ? tm->begin(st) : -1;
     SCDE_CUDA(launch_cell_prep(models_dev, ld_models, nullptr, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
-    SCDE_CUDA(launch_lp_rows(models_dev, ld_models, nullptr, t.n_cells, t.row_off.p, t.row_x.p, t.n_rows, prep, t.K,
-                             local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, st));
-    if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, 2);
+    SCDE_CUDA(launch_row_cell(t.row_off.p, t.n_cells, t.row_cell.p, st));
+    SCDE_CUDA(launch_lp_rows(models_dev, ld_models, nullptr, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep,
+                             t.K, local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, st));
+    if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, 3);
     return SCDE_B200_OK;
 }
 
@@ -199,6 +215,18 @@ struct JointScratch {
     DBuf<int32_t> idx;
 };
 
+// The big allocations of scde.expression.difference (counts shard, index matrix, lp table, joint posteriors, ratio
+// posteriors).  They live in the context and are reused by successive jobs, so a one-shot call does not pay a
+// cudaMalloc/cudaFree of tens of GB every time; one job per context at a time.
+struct DiffWorkspace {
+    DBuf<int32_t> counts;  // [C][G] (column-major shard)
+    LpTable table;
+    JointScratch scr;
+    DBuf<double> jp[4];
+    DBuf<double> post, bpost, apost;  // [G][ld] gene-major ratio posteriors
+    DBuf<double> tbuf;                // transposition scratch for downloads
+};
+
 // jp_dev[G][ld_jp] = joint posterior of the listed cells under the draws boot_idx_dev (n_boot x D, device).
 int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev, int n_list,
               const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
@@ -206,7 +234,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     cudaStream_t st = ctx->stream;
     const int n_w_rows = round_up(n_list, 8);
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
-    SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WP_TILED));
+    SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WS_TILED));
     int e0 = tm ? tm->begin(st) : -1;
     SCDE_CUDA(launch_build_w(boot_idx_dev, n_boot, D, n_list, scr.W.p, n_w_rows, st));
     SCDE_CUDA(cudaMemsetAsync(jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
@@ -235,12 +263,22 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     e0 = tm ? tm->begin(st) : -1;
     int nl = 0;
     if (tiled)
-        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, ctx->contract_kernel == 3 ? 1 : 0, st, &nl));
+        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, st, &nl));
     else
         SCDE_CUDA(launch_contract_generic(a, st, &nl));
     if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
     if (contract_cells) *contract_cells += n_list;
     return SCDE_B200_OK;
+}
+
+// constant-theta fast path is valid when every cell's corr.theta is finite and positive (host check on the
+// caller's model matrix, n_cells x 12 column-major with leading dimension ld)
+bool theta_all_regular(const double *models, int ld, int n_cells) {
+    for (int c = 0; c < n_cells; ++c) {
+        const double th = models[(size_t)5 * ld + c];
+        if (!(th > 0) || !std::isfinite(th)) return false;
+    }
+    return true;
 }
 
 std::vector<int32_t> gen_boot(int seed, int n, int n_boot) {
@@ -322,6 +360,7 @@ void scde_b200_destroy(scde_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->ws;
     delete ctx;
 }
 
@@ -334,7 +373,7 @@ int scde_b200_synchronize(scde_b200_ctx *ctx) {
 }
 
 int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which) {
-    if (!ctx || which < 0 || which > 3) return SCDE_B200_EINVAL;
+    if (!ctx || which < 0 || which > 2) return SCDE_B200_EINVAL;
     ctx->contract_kernel = which;
     return SCDE_B200_OK;
 }
@@ -382,6 +421,7 @@ int scde_b200_cell_table(scde_b200_ctx *ctx, const double *model_row12, const in
     t.ld = table_ld(n_grid);
     t.n_rows = n_counts;
     t.sentinel = -DBL_MAX / n_cells_for_clamp / 1.1;
+    t.fast_theta = !local_theta && theta_all_regular(model_row12, 1, 1);
     DBuf<double> d_models, d_mag;
     TRY(upload(d_models, model_row12, 12, st));
     TRY(upload(d_mag, magnitudes, (size_t)n_grid, st));
@@ -442,6 +482,7 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     t.n_rows = ucl_offsets[n_cells];
     const double minlogprob = -DBL_MAX / n_cells / 1.1;  // src/jpmatLogBoot.cpp:127,372
     t.sentinel = -DBL_MAX / (double)(D > n_cells ? D : n_cells) / 1.1;
+    t.fast_theta = !local_theta && theta_all_regular(models, n_cells, n_cells);
     DBuf<double> d_models, d_mag, d_jp, d_out, d_rs;
     DBuf<int32_t> d_uci, d_boot;
     TRY(upload(d_models, models, (size_t)n_cells * 12, st));
@@ -771,19 +812,15 @@ struct scde_b200_diff_job {
     int local_theta = 0, sqlogit = 0, want_post = 0, has_batch = 0;
     int n_group[2] = {0, 0};
     int n_zero = 1;
-    DBuf<int32_t> counts;  // [C][G] (column-major shard)
+    DiffWorkspace *ws = nullptr;
+    scde_b200_ctx *owner = nullptr;
     DBuf<double> models, mag, prior_y;
     DBuf<int32_t> cell_ids[2];  // group cell lists
     DBuf<int32_t> boot[4];
     int D[4] = {0, 0, 0, 0};
     DBuf<int32_t> zi, zi_adj;
-    LpTable table;
-    JointScratch scr;
-    DBuf<double> jp[4];
-    DBuf<double> post, bpost, apost;  // [G][ld] gene-major ratio posteriors
     DBuf<int32_t> idx, bidx, aidx;
     DBuf<double> z, bz, az;
-    DBuf<double> tbuf;  // transposition scratch for downloads
     StageTimer timer;
     int64_t contract_cells = 0;
     bool ran = false;
@@ -825,8 +862,17 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
         return SCDE_B200_EINVAL;
     }
     cudaStream_t st = ctx->stream;
+    if (ctx->ws_busy) {
+        set_error("another expression_difference job is alive on this context (free it first)");
+        return SCDE_B200_EINVAL;
+    }
+    if (!ctx->ws) ctx->ws = new DiffWorkspace();
     scde_b200_diff_job *j = new scde_b200_diff_job();
+    j->ws = ctx->ws;
+    j->owner = ctx;
+    ctx->ws_busy = true;
     auto fail = [&](int r) {
+        ctx->ws_busy = false;
         delete j;
         return r;
     };
@@ -851,8 +897,8 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
     j->n_levels = has_batch ? a->n_batch_levels : 0;
     j->n_zero = a->n_zero;
     // counts shard: rows [g0, g1) of every column
-    JCUDA(j->counts.ensure((size_t)G * C));
-    JCUDA(cudaMemcpy2DAsync(j->counts.p, sizeof(int32_t) * G, a->counts + g0, sizeof(int32_t) * (size_t)a->n_genes,
+    JCUDA(j->ws->counts.ensure((size_t)G * C));
+    JCUDA(cudaMemcpy2DAsync(j->ws->counts.p, sizeof(int32_t) * G, a->counts + g0, sizeof(int32_t) * (size_t)a->n_genes,
                             sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
     JTRY(upload(j->models, a->models, (size_t)C * 12, st));
     JTRY(upload(j->prior_y, a->prior_y, (size_t)K, st));
@@ -927,21 +973,22 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
         JCUDA(cudaStreamSynchronize(st));
     }
     const int ld = table_ld(K), nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
-    for (int i = 0; i < (has_batch ? 4 : 2); ++i) JCUDA(j->jp[i].ensure((size_t)G * ld));
+    for (int i = 0; i < (has_batch ? 4 : 2); ++i) JCUDA(j->ws->jp[i].ensure((size_t)G * ld));
     JCUDA(j->idx.ensure((size_t)3 * G));
     JCUDA(j->z.ensure((size_t)G));
-    if (want_posteriors || has_batch) JCUDA(j->post.ensure((size_t)G * ldo));
+    if (want_posteriors || has_batch) JCUDA(j->ws->post.ensure((size_t)G * ldo));
     if (has_batch) {
-        JCUDA(j->bpost.ensure((size_t)G * ldo));
+        JCUDA(j->ws->bpost.ensure((size_t)G * ldo));
         JCUDA(j->bidx.ensure((size_t)3 * G));
         JCUDA(j->bz.ensure((size_t)G));
         JCUDA(j->aidx.ensure((size_t)3 * G));
         JCUDA(j->az.ensure((size_t)G));
-        if (want_posteriors) JCUDA(j->apost.ensure((size_t)G * lda));
+        if (want_posteriors) JCUDA(j->ws->apost.ensure((size_t)G * lda));
     }
-    j->table.K = K;
-    j->table.ld = ld;
-    j->table.sentinel = -DBL_MAX / C / 1.1;
+    j->ws->table.K = K;
+    j->ws->table.ld = ld;
+    j->ws->table.sentinel = -DBL_MAX / C / 1.1;
+    j->ws->table.fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
     JCUDA(cudaStreamSynchronize(st));
     *out = j;
     return SCDE_B200_OK;
@@ -957,24 +1004,24 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     tm.reset();
     j->contract_cells = 0;
     const int G = j->G, C = j->C, K = j->K;
-    const int ld = j->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
     int t_all = tm.begin(st);
-    TRY(index_from_counts(ctx, j->table, j->counts.p, G, 0, G, C, &tm));
-    TRY(fill_table(ctx, j->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
+    TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
+    TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
     // group joints: cells of one factor level, draws are local indices (R/functions.R:372-374)
     for (int i = 0; i < 2; ++i)
-        TRY(run_joint(ctx, j->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
-                      j->jp[i].p, ld, j->scr, &tm, &j->contract_cells));
+        TRY(run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
+                      j->ws->jp[i].p, ld, j->ws->scr, &tm, &j->contract_cells));
     // batch joints: all cells, composition-sampled draws are global cell ids (R/functions.R:355-357)
     if (j->has_batch)
         for (int i = 0; i < 2; ++i)
-            TRY(run_joint(ctx, j->table, nullptr, C, j->boot[2 + i].p, j->n_boot, j->D[2 + i], (double)j->n_boot,
-                          j->jp[2 + i].p, ld, j->scr, &tm, &j->contract_cells));
+            TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot[2 + i].p, j->n_boot, j->D[2 + i], (double)j->n_boot,
+                          j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, &j->contract_cells));
     int e0 = tm.begin(st);
     int nl = 0;
     RatioArgs r{};
-    r.p1 = j->jp[0].p;
-    r.p2 = j->jp[1].p;
+    r.p1 = j->ws->jp[0].p;
+    r.p2 = j->ws->jp[1].p;
     r.ld = ld;
     r.n_genes = G;
     r.n = K;
@@ -983,7 +1030,7 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     r.n_zero = j->n_zero == 1 ? 1 : G;
     r.idx = j->idx.p;
     r.z = j->z.p;
-    r.post = (j->want_post || j->has_batch) ? j->post.p : nullptr;
+    r.post = (j->want_post || j->has_batch) ? j->ws->post.p : nullptr;
     r.ld_post = ldo;
     SCDE_CUDA(launch_ratio_summary(r, st));
     ++nl;
@@ -992,19 +1039,19 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
         (void)mid_host;
         // batch.effect is summarised with the default expectation = 0 (R/functions.R:362): H0 index = centre
         RatioArgs b = r;
-        b.p1 = j->jp[2].p;
-        b.p2 = j->jp[3].p;
+        b.p1 = j->ws->jp[2].p;
+        b.p2 = j->ws->jp[3].p;
         b.idx = j->bidx.p;
         b.z = j->bz.p;
-        b.post = j->bpost.p;
+        b.post = j->ws->bpost.p;
         b.zero_index = nullptr;  // centre of the grid: handled in-kernel as index n (1-based) when NULL
         b.n_zero = 1;
         SCDE_CUDA(launch_ratio_summary(b, st));
         ++nl;
         // batch adjustment: slide the two 2K-1 posteriors without prior weighting (R/functions.R:391)
         RatioArgs c{};
-        c.p1 = j->post.p;
-        c.p2 = j->bpost.p;
+        c.p1 = j->ws->post.p;
+        c.p2 = j->ws->bpost.p;
         c.ld = ldo;
         c.n_genes = G;
         c.n = nout;
@@ -1013,7 +1060,7 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
         c.n_zero = j->n_zero == 1 ? 1 : G;
         c.idx = j->aidx.p;
         c.z = j->az.p;
-        c.post = j->want_post ? j->apost.p : nullptr;
+        c.post = j->want_post ? j->ws->apost.p : nullptr;
         c.ld_post = lda;
         SCDE_CUDA(launch_ratio_summary(c, st));
         ++nl;
@@ -1026,9 +1073,9 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
 
 static int download_matrix(scde_b200_ctx *ctx, scde_b200_diff_job *j, const double *src, int ld_src, int cols, double *dst) {
     cudaStream_t st = ctx->stream;
-    SCDE_CUDA(j->tbuf.ensure((size_t)j->G * cols));
-    SCDE_CUDA(launch_transpose_out(src, ld_src, j->G, cols, j->tbuf.p, st));
-    SCDE_CUDA(cudaMemcpyAsync(dst, j->tbuf.p, sizeof(double) * (size_t)j->G * cols, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(j->ws->tbuf.ensure((size_t)j->G * cols));
+    SCDE_CUDA(launch_transpose_out(src, ld_src, j->G, cols, j->ws->tbuf.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(dst, j->ws->tbuf.p, sizeof(double) * (size_t)j->G * cols, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));
     return SCDE_B200_OK;
 }
@@ -1042,7 +1089,7 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
     }
     cudaStream_t st = ctx->stream;
     const int G = j->G, K = j->K;
-    const int ld = j->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
     if (o) {
         if (o->idx) SCDE_CUDA(cudaMemcpyAsync(o->idx, j->idx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
         if (o->z) SCDE_CUDA(cudaMemcpyAsync(o->z, j->z.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
@@ -1057,31 +1104,31 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
         }
         SCDE_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < 2; ++i) {
-            if (o->joint_posteriors[i]) TRY(download_matrix(ctx, j, j->jp[i].p, ld, K, o->joint_posteriors[i]));
+            if (o->joint_posteriors[i]) TRY(download_matrix(ctx, j, j->ws->jp[i].p, ld, K, o->joint_posteriors[i]));
             if (j->has_batch && o->batch_joint_posteriors[i])
-                TRY(download_matrix(ctx, j, j->jp[2 + i].p, ld, K, o->batch_joint_posteriors[i]));
+                TRY(download_matrix(ctx, j, j->ws->jp[2 + i].p, ld, K, o->batch_joint_posteriors[i]));
         }
         if (o->difference_posterior) {
-            if (!j->post.p) {
+            if (!j->ws->post.p) {
                 set_error("difference_posterior requested but the job was uploaded without want_posteriors");
                 return SCDE_B200_EINVAL;
             }
-            TRY(download_matrix(ctx, j, j->post.p, ldo, nout, o->difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->post.p, ldo, nout, o->difference_posterior));
         }
         if (j->has_batch && o->batch_difference_posterior)
-            TRY(download_matrix(ctx, j, j->bpost.p, ldo, nout, o->batch_difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->bpost.p, ldo, nout, o->batch_difference_posterior));
         if (j->has_batch && o->adjusted_difference_posterior) {
-            if (!j->apost.p) {
+            if (!j->ws->apost.p) {
                 set_error("adjusted posterior requested but the job was uploaded without want_posteriors");
                 return SCDE_B200_EINVAL;
             }
-            TRY(download_matrix(ctx, j, j->apost.p, lda, nadj, o->adjusted_difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->apost.p, lda, nadj, o->adjusted_difference_posterior));
         }
     }
     SCDE_CUDA(cudaStreamSynchronize(st));
     if (stats) {
         j->timer.collect(stats);
-        stats->table_rows = j->table.n_rows;
+        stats->table_rows = j->ws->table.n_rows;
         stats->contract_cells = j->contract_cells;
     }
     return SCDE_B200_OK;
@@ -1089,6 +1136,7 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
 
 void scde_b200_diff_free(scde_b200_ctx *ctx, scde_b200_diff_job *job) {
     if (ctx) cudaSetDevice(ctx->device);
+    if (job && job->owner) job->owner->ws_busy = false;
     delete job;
 }
 

@@ -8,24 +8,22 @@
 // 1e-6 relative tolerance on log-posteriors leaves no room for a reduced-precision tensor-core split in this round;
 // tcgen05 has no FP64 kind).
 //
-// contract_tiled_kernel (the sm_100a hot kernel)
+// contract_mma_kernel (the sm_100a hot kernel)
 //   * one 2-CTA cluster per gene; CTA r owns grid points [208 r, 208 r + 208) and all 104 (100 + pad) boots, so
 //     its 208 x 104 FP64 accumulator tile (173 KB) lives entirely in the register file (12 warps x 168 regs);
 //   * operands are staged through shared memory by the TMA engine: per stage of 8 cells, 8 bulk copies of one
 //     gathered 1664-byte table row half each plus one bulk copy of the 8 matching W rows, completion signalled on
-//     an mbarrier (cp.async.bulk ... mbarrier::complete_tx); an 8-deep ring keeps ~150 KB in flight per SM;
-//   * warps are laid out so that every SM sub-partition holds the same number of accumulators
-//     (three warps with 4x13, 4x13 and 5x13 register tiles = 52 grid points x 104 boots each) -- the FP64 pipe is
-//     per sub-partition, so an unbalanced split would idle a quarter of it;
-//   * lanes are 4 (grid) x 8 (boots): a warp reads 16..20 consecutive doubles of the table row and all 104 W
-//     values per cell, i.e. ~9 shared-memory wavefronts for 52..65 DFMA warp-instructions;
+//     an mbarrier (cp.async.bulk ... mbarrier::complete_tx); an 8-deep ring keeps ~160 KB in flight per SM;
+//   * the product runs on FP64 tensor-core tiles (mma.sync m8n8k4.f64), laid out so that every SM sub-partition
+//     carries the same number of tiles (85 of the 338 per CTA);
 //   * the soft-max over the grid is fused: per-boot max and sum are reduced with warp shuffles, across warps
 //     through shared memory and across the two CTAs through distributed shared memory, then every thread adds
-//     exp(T - max)/(sum * B) over its boots and writes jp -- T never leaves the chip.
+//     exp(T - max)/(sum * B) over its boots and adds into jp -- T never leaves the chip.
 // contract_generic_kernel handles any K / any B (used for K > 416 and as an on-device cross-check).
 #include "common.cuh"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace scde {
 namespace {
@@ -95,13 +93,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // W build: multiplicities from the draw lists
 __global__ void build_w_kernel(const int32_t *__restrict__ boot_idx, int n_boot, int D, int n_list, double *W,
                                int n_w_rows) {
-    // W is pass-major: W[pass][cell][104], boot b = 104*pass + column.  One CTA per boot, so atomics from
+    // W is pass-major: W[pass][cell][108] (104 boots + 4 zero pad), boot b = 104*pass + column.  One CTA per boot, so atomics from
     // different CTAs never touch the same element.
     const int b = blockIdx.x;
-    double *Wp = W + ((size_t)(b / WP_TILED) * n_w_rows) * WP_TILED + (b % WP_TILED);
+    double *Wp = W + ((size_t)(b / WP_TILED) * n_w_rows) * WS_TILED + (b % WP_TILED);
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         int c = boot_idx[(size_t)b * D + j];
-        if (c >= 0 && c < n_list) atomicAdd(&Wp[(size_t)c * WP_TILED], 1.0);
+        if (c >= 0 && c < n_list) atomicAdd(&Wp[(size_t)c * WS_TILED], 1.0);
     }
 }
 
@@ -114,20 +112,8 @@ constexpr int T_NS = 8;         // ring depth
 constexpr int T_PD = T_NS - 2;  // prefetch distance: the slot refilled at iteration i was consumed at i-2
 constexpr int T_WARPS = 12;
 constexpr int T_THREADS = T_WARPS * 32;
-constexpr int T_STAGE_A = T_S * T_KH;                      // doubles
-constexpr int T_STAGE_W = T_S * T_WP;                      // doubles
-constexpr int T_STAGE_DOUBLES = T_STAGE_A + T_STAGE_W;     // 2496
-constexpr uint32_t T_STAGE_BYTES = T_STAGE_DOUBLES * 8u;   // 19968
-constexpr int T_NB = 13;                                   // boots per thread
-
-struct TiledSmem {
-    double stage[T_NS][T_STAGE_DOUBLES];
-    double red[T_WARPS][T_WP];
-    double xmax[2][T_WP];  // [0] this CTA's value, [1] written by the peer
-    double xsum[2][T_WP];
-    uint64_t full[T_NS];
-    uint64_t empty[T_NS];
-};
+constexpr int T_WS = WS_TILED;  // row stride of W in global and shared memory (108 doubles, see below)
+constexpr uint32_t T_STAGE_BYTES = (T_S * T_KH + T_S * T_WS) * 8u;  // bytes the TMA engine delivers per stage (20224)
 
 struct TiledParams {
     const double *table;
@@ -135,260 +121,38 @@ struct TiledParams {
     int64_t ld_ridx;
     const int32_t *cell_ids;
     int n_list;
-    const double *W;  // this pass: rows [n_w_rows][ldw], columns [0, 104)
-    int64_t ldw;
+    const double *W;  // this pass: rows [n_w_rows][108], columns [0, 104) real
     int n_boot_pass;  // real boots in this pass (<= 104)
     double scale;
     int n_genes, K;
-    double *jp;
+    double *jp;  // zero-filled by the caller; every pass adds into it
     int64_t ld_jp;
-    int accumulate;
+    int pd;     // prefetch distance in stages (1 .. T_NS - 1)
+    int debug;  // timing experiments only (SCDE_B200_DEBUG_CONTRACT): 1 = no DMMA, 2 = no table-row copies, 4 = no epilogue
 };
 
-template <int TK>
-__device__ __forceinline__ void consume_stage(const double *__restrict__ sA, const double *__restrict__ sW,
-                                              double (&acc)[TK][T_NB], int a_off, int a4_off, int lb) {
-#pragma unroll 2
-    for (int c = 0; c < T_S; ++c) {
-        const double *a = sA + c * T_KH + a_off;
-        const double2 a01 = *reinterpret_cast<const double2 *>(a);
-        const double2 a23 = *reinterpret_cast<const double2 *>(a + 2);
-        double av[TK];
-        av[0] = a01.x;
-        av[1] = a01.y;
-        av[2] = a23.x;
-        av[3] = a23.y;
-        if (TK == 5) av[TK - 1] = sA[c * T_KH + a4_off];
-        const double *w = sW + c * T_WP + 2 * lb;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const double2 wv = *reinterpret_cast<const double2 *>(w + 16 * j);
-#pragma unroll
-            for (int i = 0; i < TK; ++i) {
-                acc[i][2 * j] = fma(av[i], wv.x, acc[i][2 * j]);
-                acc[i][2 * j + 1] = fma(av[i], wv.y, acc[i][2 * j + 1]);
-            }
-        }
-        const double w12 = sW[c * T_WP + 96 + lb];
-#pragma unroll
-        for (int i = 0; i < TK; ++i) acc[i][12] = fma(av[i], w12, acc[i][12]);
-    }
-}
-
-// boot column of accumulator slot j for boot-lane lb
-__device__ __forceinline__ int boot_of(int j, int lb) { return j < 12 ? 16 * (j >> 1) + 2 * lb + (j & 1) : 96 + lb; }
-
-template <int TK>
-__device__ __forceinline__ void run_tiles(const TiledParams &p, TiledSmem &sm, int warp, int lane, uint32_t rank,
-                                          int n_my_genes, int spg, int kw) {
-    const int lk = lane & 3, lb = lane >> 2;
-    const int a_off = kw + lk * 4;    // first of the thread's 4 consecutive grid points (CTA-relative)
-    const int a4_off = kw + 16 + lk;  // fifth grid point of the 5-wide tiles
-    const int kbase = rank * T_KH;
-    const uint32_t peer = rank ^ 1u;
-    const int64_t total_stages = (int64_t)n_my_genes * spg;
-    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
-
-    // ---- producer state (warp 0 only): lanes 0..7 gather table rows, lane 8 copies the W rows ----
-    int64_t pq = 0;             // next stage to issue
-    int p_gi = 0, p_cb = 0;     // its (gene ordinal, cell block)
-    int32_t next_row = 0;       // row index prefetched for stage pq (lane j: cell p_cb*8 + j)
-    auto prefetch_row = [&](int gi, int cb) -> int32_t {
-        if (lane < T_S && gi < n_my_genes) {
-            int cell = cb * T_S + lane;
-            if (cell >= p.n_list) cell = p.n_list - 1;  // padded cells re-read a valid row; their W rows are zero
-            int col = p.cell_ids ? p.cell_ids[cell] : cell;
-            int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
-            return p.ridx[gene * p.ld_ridx + col];
-        }
-        return 0;
-    };
-    auto issue_stage = [&]() {  // issues stage pq using next_row, then prefetches the following stage's rows
-        const int slot = (int)(pq % T_NS);
-        const uint32_t fill = (uint32_t)(pq / T_NS);
-        if (fill > 0) mbar_wait(&sm.empty[slot], (fill - 1) & 1u);
-        double *dstA = sm.stage[slot];
-        double *dstW = dstA + T_STAGE_A;
-        if (lane == 0) mbar_arrive_expect_tx(&sm.full[slot], T_STAGE_BYTES);
-        __syncwarp();
-        if (lane < T_S) {
-            bulk_g2s(dstA + lane * T_KH, p.table + (int64_t)next_row * KP_TILED + kbase, T_KH * 8u, &sm.full[slot]);
-        } else if (lane == T_S) {
-            bulk_g2s(dstW, p.W + (int64_t)p_cb * T_S * p.ldw, T_STAGE_W * 8u, &sm.full[slot]);
-        }
-        ++pq;
-        if (++p_cb == spg) {
-            p_cb = 0;
-            ++p_gi;
-        }
-        next_row = prefetch_row(p_gi, p_cb);
-    };
-    if constexpr (TK == 4) {  // warp 0 always runs the 4-wide instantiation
-        if (warp == 0) {
-            next_row = prefetch_row(0, 0);
-            for (int i = 0; i < T_PD && pq < total_stages; ++i) issue_stage();
-        }
-    }
-
-    int64_t q = 0;  // stage being consumed
-    for (int gi = 0; gi < n_my_genes; ++gi) {
-        const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
-        double acc[TK][T_NB];
-#pragma unroll
-        for (int i = 0; i < TK; ++i)
-#pragma unroll
-            for (int j = 0; j < T_NB; ++j) acc[i][j] = 0.0;
-
-        for (int cb = 0; cb < spg; ++cb, ++q) {
-            if constexpr (TK == 4) {
-                if (warp == 0 && pq < total_stages) issue_stage();
-            }
-            const int slot = (int)(q % T_NS);
-            mbar_wait(&sm.full[slot], (uint32_t)(q / T_NS) & 1u);
-            const double *sA = sm.stage[slot];
-            consume_stage<TK>(sA, sA + T_STAGE_A, acc, a_off, a4_off, lb);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[slot]);
-        }
-
-        // ---------------- fused soft-max over the grid and average over boots ----------------
-        bool kvalid[TK];
-#pragma unroll
-        for (int i = 0; i < TK; ++i) {
-            int kk = (i < 4) ? a_off + i : a4_off;
-            kvalid[i] = (kbase + kk) < p.K;
-        }
-        // (1) per-boot maximum over this CTA's grid points
-#pragma unroll
-        for (int j = 0; j < T_NB; ++j) {
-            double m = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < TK; ++i)
-                if (kvalid[i]) m = fmax(m, acc[i][j]);
-            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            if (lk == 0) sm.red[warp][boot_of(j, lb)] = m;
-        }
-        named_bar_sync(1, T_THREADS);
-        if (threadIdx.x < T_WP) {
-            double m = sm.red[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < T_WARPS; ++w) m = fmax(m, sm.red[w][threadIdx.x]);
-            sm.xmax[0][threadIdx.x] = m;
-            st_peer_f64(&sm.xmax[1][threadIdx.x], peer, m);
-        }
-        cluster_arrive();
-        cluster_wait();
-        // (2) exponentials and per-boot sums
-#pragma unroll
-        for (int j = 0; j < T_NB; ++j) {
-            const int b = boot_of(j, lb);
-            const double M = fmax(sm.xmax[0][b], sm.xmax[1][b]);
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < TK; ++i) {
-                double e = kvalid[i] ? exp(acc[i][j] - M) : 0.0;
-                acc[i][j] = e;
-                s += e;
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (lk == 0) sm.red[warp][b] = s;
-        }
-        named_bar_sync(1, T_THREADS);
-        if (threadIdx.x < T_WP) {
-            double s = sm.red[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < T_WARPS; ++w) s += sm.red[w][threadIdx.x];
-            sm.xsum[0][threadIdx.x] = s;
-            st_peer_f64(&sm.xsum[1][threadIdx.x], peer, s);
-        }
-        cluster_arrive();
-        cluster_wait();
-        // (3) jp[g, k] += sum_b e[k, b] / (S_b * scale)
-        double r[TK];
-#pragma unroll
-        for (int i = 0; i < TK; ++i) r[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < T_NB; ++j) {
-            const int b = boot_of(j, lb);
-            if (b < p.n_boot_pass) {
-                // rank-0 value first so both CTAs add in the same order
-                const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
-                const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
-                const double den = (s0 + s1) * p.scale;
-#pragma unroll
-                for (int i = 0; i < TK; ++i) r[i] += acc[i][j] / den;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < TK; ++i) {
-            r[i] += __shfl_xor_sync(0xffffffffu, r[i], 4);
-            r[i] += __shfl_xor_sync(0xffffffffu, r[i], 8);
-            r[i] += __shfl_xor_sync(0xffffffffu, r[i], 16);
-        }
-        if (lb == 0) {
-            double *out = p.jp + gene * p.ld_jp + kbase;
-#pragma unroll
-            for (int i = 0; i < TK; ++i) {
-                int kk = (i < 4) ? a_off + i : a4_off;
-                if (kvalid[i]) {
-                    if (p.accumulate) out[kk] += r[i]; else out[kk] = r[i];
-                }
-            }
-        }
-    }
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contract_tiled_kernel(const TiledParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TiledSmem &sm = *reinterpret_cast<TiledSmem *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < T_NS; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], T_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // both CTAs must be resident before any DSMEM store
-    cluster_arrive();
-    cluster_wait();
-
-    const int n_my_genes = ((int)cid < p.n_genes) ? (p.n_genes - (int)cid + (int)ncl - 1) / (int)ncl : 0;
-    const int spg = (p.n_list + T_S - 1) / T_S;
-    // warp -> sub-partition (warp & 3) and slot (warp >> 2): slots 0,1 own 16 grid points, slot 2 owns 20
-    const int smsp = warp & 3, slot = warp >> 2;
-    const int kw = smsp * 52 + slot * 16;
-    if (slot == 2)
-        run_tiles<5>(p, sm, warp, lane, rank, n_my_genes, spg, kw);
-    else
-        run_tiles<4>(p, sm, warp, lane, rank, n_my_genes, spg, kw);
-    // keep this CTA's shared memory alive until the peer's last DSMEM store has landed
-    cluster_arrive();
-    cluster_wait();
-}
-
 // ------------------------------------------------------------------------------------------------
-// tiled kernel, DMMA form (the default).  Same cluster / TMA ring / soft-max structure as above, but the inner
-// product runs on mma.sync.aligned.m8n8k4.f64: M = 8 grid points, N = 8 boots, K = 4 cells per instruction.  The FP64
-// rate of DMMA equals that of DFMA on B200 (37 vs 36.5 TFLOP/s measured, tools/microbench.cu), but one DMMA replaces
-// eight DFMA warp-instructions and its fragments are one double per lane, so a warp issues 15 LDS.64 + 26 DMMA per four
-// cells instead of 36 LDS + 208 DFMA -- the register-tile version was limited by shared-memory instruction issue
-// (LDS.128 sustains one per two cycles per SM) and by issue slots, not by the FP64 pipe (profiles/r01a_*).
+// tiled kernel.  The inner product runs on mma.sync.aligned.m8n8k4.f64: M = 8 grid points, N = 8 boots, K = 4 cells
+// per instruction.  The FP64 rate of DMMA equals that of DFMA on B200 (37 vs 36.5 TFLOP/s measured,
+// tools/microbench.cu), but one DMMA replaces eight DFMA warp-instructions and its fragments are one double per lane,
+// so a warp issues 15 LDS.64 + 26 DMMA per four cells instead of 36 LDS + 208 DFMA -- the first version of this kernel
+// (DFMA register tiles, 54 % of the FP64 peak) was limited by shared-memory instruction issue (LDS.128 sustains one
+// per two cycles per SM) and by issue slots, not by the FP64 pipe (profiles/r01a_*).
 //
 // Tiles per CTA: 26 (grid) x 13 (boots).  Sub-partition s (= warp & 3) owns grid tiles 6s..6s+5 completely -- two per
-// warp slot -- and half of a shared grid tile (24 for s = 0,1; 25 for s = 2,3): boot tiles 0..6 for even s, 6..12 for
-// odd s, where the duplicated boot tile 6 of the odd warps is computed but masked out.  That is 85 tiles per
-// sub-partition, i.e. the FP64 pipe of every sub-partition carries the same load.
-// Shared-memory rows are padded to 216 doubles so the four cells of an A fragment fall into disjoint bank halves
-// (216 * 2 words = 16 mod 32), as the 104-double W rows already do: every fragment load is conflict-free.
-constexpr int M_AS = 216;                                   // padded row stride of the A stage (doubles)
-constexpr int M_STAGE_DOUBLES = T_S * M_AS + T_S * T_WP;    // 2560
+// warp -- and half of a shared grid tile (24 for s = 0,1; 25 for s = 2,3): boot tiles 0..6 for even s (split 2/2/3 over
+// its warps), 7..12 for odd s (2/2/2).  Every sub-partition carries 85 or 84 tiles and every warp 28 or 29, so neither
+// the FP64 pipes nor the warps sharing one drift apart (a 26/26/33 split cost ~10 %: the heavy warp fell behind its
+// siblings until they stalled on the ring).
+// A 64-bit shared load is served one half-warp at a time; a half-warp of a fragment load reads 4 cells x 4 consecutive
+// doubles, so the row stride has to be 4 (or 12) mod 16 doubles for the four cells to land in disjoint bank quarters:
+// table rows are padded to 212 doubles in shared memory and W rows to 108 doubles in global and shared memory
+// (strides of 208 / 104 or 216 make every fragment load a 2-way bank conflict -- 750 M conflicts per launch measured).
+constexpr int M_AS = 212;                                   // padded row stride of the A stage (doubles)
+constexpr int M_STAGE_DOUBLES = T_S * M_AS + T_S * T_WS;    // 2560
 constexpr int M_NT = 13;                                    // boot tiles
+
+constexpr int M_IDX_CAP = 5120;  // cells per gene whose table-row ids are staged in shared memory (else read from L2)
 
 struct MmaSmem {
     double stage[T_NS][M_STAGE_DOUBLES];
@@ -397,6 +161,7 @@ struct MmaSmem {
     double xsum[2][T_WP];
     uint64_t full[T_NS];
     uint64_t empty[T_NS];
+    int32_t idx[2][M_IDX_CAP];  // table-row ids of the current and the next gene of this cluster
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -405,59 +170,71 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// NEX: extra tiles of the shared grid tile (0 or 7); NX0: first boot tile of the extras (0 or 6)
-template <int NEX, int NX0>
+constexpr int M_NEX = 3;  // at most three tiles of the shared grid tile per warp
+
 __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int warp, int lane, uint32_t rank,
                                         int n_my_genes, int spg) {
     const int g = lane >> 2, t = lane & 3;
     const int smsp = warp & 3, slot = warp >> 2;
     const int m0 = smsp * 6 + slot * 2;   // first of the two full grid tiles
-    const int mx = 24 + (smsp >> 1);      // shared grid tile (slot 2 only)
+    const int mx = 24 + (smsp >> 1);      // shared grid tile
+    // boot tiles of the shared grid tile owned by this warp: even sub-partitions split 0..6 as 2/2/3, odd ones 7..12
+    // as 2/2/2, so the three warps of a sub-partition carry 28/28/29 (or 28/28/28) tiles
+    const int nx0 = (smsp & 1) ? 7 + 2 * slot : 2 * slot;
+    const int nex = ((smsp & 1) == 0 && slot == 2) ? 3 : 2;
     const int kbase = rank * T_KH;
     const uint32_t peer = rank ^ 1u;
     const int64_t total_stages = (int64_t)n_my_genes * spg;
     const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
 
-    // ---- producer (warp 0; it always runs the NEX == 0 instantiation) ----
-    int64_t pq = 0;
-    int p_gi = 0, p_cb = 0;
-    int32_t next_row = 0;
-    auto prefetch_row = [&](int gi, int cb) -> int32_t {
-        if (lane < T_S && gi < n_my_genes) {
-            int cell = cb * T_S + lane;
-            if (cell >= p.n_list) cell = p.n_list - 1;
-            int col = p.cell_ids ? p.cell_ids[cell] : cell;
-            int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
-            return p.ridx[gene * p.ld_ridx + col];
-        }
-        return 0;
+    // ---- producer duty ----
+    // Stage q + T_PD is issued at consumer iteration q by warp (q mod 12): the duty (an empty-slot wait, nine TMA bulk
+    // copies) rotates, so no warp becomes the straggler of its sub-partition (a fixed producer warp cost 25 % of the
+    // kernel: it was also a consumer and fell a third of a stage behind every stage).  The gathered row ids of the
+    // current and the next gene sit in shared memory (filled cooperatively once per gene), so issuing a stage does not
+    // wait on a dependent global load.
+    const int PD = p.pd;
+    const bool idx_in_smem = (spg >= PD + 1) && (p.n_list <= M_IDX_CAP);
+    auto fill_idx = [&](int gi) {  // all threads: row ids of this cluster's gi-th gene -> sm.idx[gi & 1]
+        if (!idx_in_smem || gi >= n_my_genes) return;
+        const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
+        const int32_t *src = p.ridx + gene * p.ld_ridx;
+        int32_t *dst = sm.idx[gi & 1];
+        for (int c = threadIdx.x; c < p.n_list; c += T_THREADS) dst[c] = src[p.cell_ids ? p.cell_ids[c] : c];
     };
-    auto issue_stage = [&]() {
-        const int sl = (int)(pq % T_NS);
-        const uint32_t fill = (uint32_t)(pq / T_NS);
+    auto issue_stage = [&](int64_t qp) {  // one warp: issue stage qp
+        const int gi = (int)(qp / spg), cb = (int)(qp - (int64_t)gi * spg);
+        const int sl = (int)(qp % T_NS);
+        const uint32_t fill = (uint32_t)(qp / T_NS);
+        int32_t row = 0;
+        if (lane < T_S) {
+            int cell = cb * T_S + lane;
+            if (cell >= p.n_list) cell = p.n_list - 1;  // padded cells re-read a valid row; their W rows are zero
+            if (idx_in_smem) {
+                row = sm.idx[gi & 1][cell];
+            } else {
+                const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
+                row = p.ridx[gene * p.ld_ridx + (p.cell_ids ? p.cell_ids[cell] : cell)];
+            }
+        }
         if (fill > 0) mbar_wait(&sm.empty[sl], (fill - 1) & 1u);
         double *dstA = sm.stage[sl];
         double *dstW = dstA + T_S * M_AS;
-        if (lane == 0) mbar_arrive_expect_tx(&sm.full[sl], T_STAGE_BYTES);
+        const bool no_rows = (p.debug & 2) != 0;
+        if (lane == 0) mbar_arrive_expect_tx(&sm.full[sl], no_rows ? T_S * T_WS * 8u : T_STAGE_BYTES);
         __syncwarp();
         if (lane < T_S) {
-            bulk_g2s(dstA + lane * M_AS, p.table + (int64_t)next_row * KP_TILED + kbase, T_KH * 8u, &sm.full[sl]);
+            if (!no_rows)
+                bulk_g2s(dstA + lane * M_AS, p.table + (int64_t)row * KP_TILED + kbase, T_KH * 8u, &sm.full[sl]);
         } else if (lane == T_S) {
-            bulk_g2s(dstW, p.W + (int64_t)p_cb * T_S * T_WP, T_STAGE_W * 8u, &sm.full[sl]);
+            bulk_g2s(dstW, p.W + (int64_t)cb * T_S * T_WS, T_S * T_WS * 8u, &sm.full[sl]);
         }
-        ++pq;
-        if (++p_cb == spg) {
-            p_cb = 0;
-            ++p_gi;
-        }
-        next_row = prefetch_row(p_gi, p_cb);
     };
-    if constexpr (NEX == 0) {
-        if (warp == 0) {
-            next_row = prefetch_row(0, 0);
-            for (int i = 0; i < T_PD && pq < total_stages; ++i) issue_stage();
-        }
-    }
+    fill_idx(0);
+    fill_idx(1);
+    named_bar_sync(1, T_THREADS);
+    if (warp == 0)
+        for (int64_t i = 0; i < PD && i < total_stages; ++i) issue_stage(i);
 
     // validity of this thread's grid points
     const bool kv0 = (kbase + (m0 + 0) * 8 + g) < p.K;
@@ -468,45 +245,50 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
     for (int gi = 0; gi < n_my_genes; ++gi) {
         const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
         double acc[2][M_NT][2];
-        double ex[NEX > 0 ? NEX : 1][2];
+        double ex[M_NEX][2];
 #pragma unroll
         for (int nt = 0; nt < M_NT; ++nt) {
             acc[0][nt][0] = acc[0][nt][1] = 0.0;
             acc[1][nt][0] = acc[1][nt][1] = 0.0;
         }
 #pragma unroll
-        for (int j = 0; j < (NEX > 0 ? NEX : 1); ++j) ex[j][0] = ex[j][1] = 0.0;
+        for (int j = 0; j < M_NEX; ++j) ex[j][0] = ex[j][1] = 0.0;
 
+        if (gi > 0) {  // row ids of the next gene (its buffer was last used by gene gi-1, whose stages are all issued)
+            fill_idx(gi + 1);
+            named_bar_sync(1, T_THREADS);
+        }
         for (int cb = 0; cb < spg; ++cb, ++q) {
-            if constexpr (NEX == 0) {
-                if (warp == 0 && pq < total_stages) issue_stage();
-            }
+            if (q + PD < total_stages && warp == (int)(q % T_WARPS)) issue_stage(q + PD);
             const int sl = (int)(q % T_NS);
             mbar_wait(&sm.full[sl], (uint32_t)(q / T_NS) & 1u);
             const double *sA = sm.stage[sl];
             const double *sW = sA + T_S * M_AS;
+            if (!(p.debug & 1))
 #pragma unroll
             for (int ks = 0; ks < T_S / 4; ++ks) {
                 const double *ap = sA + (ks * 4 + t) * M_AS + g;
-                const double *wp = sW + (ks * 4 + t) * T_WP + g;
+                const double *wp = sW + (ks * 4 + t) * T_WS + g;
                 const double a0 = ap[(m0 + 0) * 8];
                 const double a1 = ap[(m0 + 1) * 8];
-                double a2 = 0.0;
-                if constexpr (NEX > 0) a2 = ap[mx * 8];
+                const double a2 = ap[mx * 8];
+                const double bx0 = wp[(nx0 + 0) * 8], bx1 = wp[(nx0 + 1) * 8];
+                const double bx2 = wp[(nx0 + (nex > 2 ? 2 : 1)) * 8];
 #pragma unroll
                 for (int nt = 0; nt < M_NT; ++nt) {
                     const double b = wp[nt * 8];
                     dmma(acc[0][nt], a0, b);
                     dmma(acc[1][nt], a1, b);
-                    if constexpr (NEX > 0) {
-                        if (nt >= NX0 && nt < NX0 + NEX) dmma(ex[nt - NX0], a2, b);
-                    }
+                    if (nt == 3) dmma(ex[0], a2, bx0);
+                    if (nt == 7) dmma(ex[1], a2, bx1);
+                    if (nt == 11 && nex > 2) dmma(ex[2], a2, bx2);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[sl]);
         }
 
+        if (p.debug & 4) continue;
         // ---------------- fused soft-max over the grid and average over boots ----------------
         // thread holds, per tile, C[m = g][n = 2t + i]: grid point (tile*8 + g), boot (nt*8 + 2t + i)
         // (1) per-boot maximum over this CTA's grid points
@@ -517,13 +299,25 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
                 double m = -INFINITY;
                 if (kv0) m = fmax(m, acc[0][nt][i]);
                 if (kv1) m = fmax(m, acc[1][nt][i]);
-                if constexpr (NEX > 0) {
-                    if (nt >= NX0 && nt < NX0 + NEX && !(NX0 > 0 && nt == NX0) && kvx) m = fmax(m, ex[nt - NX0][i]);
-                }
                 m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
                 m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
                 m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
                 if (g == 0) sm.red[warp][nt * 8 + 2 * t + i] = m;
+            }
+        }
+        // the warp's tiles of the shared grid tile: boots (nx0 + j) * 8 + 2t + i; merged into red[] by the g == 0 lanes
+#pragma unroll
+        for (int j = 0; j < M_NEX; ++j) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double m = (kvx && j < nex) ? ex[j][i] : -INFINITY;
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                if (g == 0 && j < nex) {
+                    double *slotp = &sm.red[warp][(nx0 + j) * 8 + 2 * t + i];
+                    *slotp = fmax(*slotp, m);
+                }
             }
         }
         named_bar_sync(1, T_THREADS);
@@ -548,18 +342,25 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
                 acc[0][nt][i] = e0;
                 acc[1][nt][i] = e1;
                 double s = e0 + e1;
-                if constexpr (NEX > 0) {
-                    if (nt >= NX0 && nt < NX0 + NEX) {
-                        const bool ok = kvx && !(NX0 > 0 && nt == NX0);
-                        double e2 = ok ? exp(ex[nt - NX0][i] - M) : 0.0;
-                        ex[nt - NX0][i] = e2;
-                        s += e2;
-                    }
-                }
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
                 s += __shfl_xor_sync(0xffffffffu, s, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 16);
                 if (g == 0) sm.red[warp][b] = s;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < M_NEX; ++j) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int b = (nx0 + (j < nex ? j : 0)) * 8 + 2 * t + i;
+                const double M = fmax(sm.xmax[0][b], sm.xmax[1][b]);
+                double e2 = (kvx && j < nex) ? exp(ex[j][i] - M) : 0.0;
+                ex[j][i] = e2;
+                double s = e2;
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (g == 0 && j < nex) sm.red[warp][b] += s;
             }
         }
         named_bar_sync(1, T_THREADS);
@@ -585,9 +386,18 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
                     const double den = (s0 + s1) * p.scale;
                     r0 += acc[0][nt][i] / den;
                     r1 += acc[1][nt][i] / den;
-                    if constexpr (NEX > 0) {
-                        if (nt >= NX0 && nt < NX0 + NEX) rx += ex[nt - NX0][i] / den;
-                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < M_NEX; ++j) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int b = (nx0 + (j < nex ? j : 0)) * 8 + 2 * t + i;
+                if (j < nex && b < p.n_boot_pass) {
+                    const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
+                    const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
+                    rx += ex[j][i] / ((s0 + s1) * p.scale);
                 }
             }
         }
@@ -595,19 +405,16 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
         r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
         r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
         r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
-        if constexpr (NEX > 0) {
-            rx += __shfl_xor_sync(0xffffffffu, rx, 1);
-            rx += __shfl_xor_sync(0xffffffffu, rx, 2);
-        }
+        rx += __shfl_xor_sync(0xffffffffu, rx, 1);
+        rx += __shfl_xor_sync(0xffffffffu, rx, 2);
         if (t == 0) {
-            // jp is zero-filled by the caller; the shared grid tile receives two partial sums (commutative, so the
-            // result does not depend on their order)
+            // jp is zero-filled by the caller.  The shared grid tile receives one partial sum per owning warp: the
+            // order of these (up to six) atomic adds is not fixed, so jp at those 8 + 8 grid points may differ in the
+            // last bit from run to run (same as any other summation order)
             double *out = p.jp + gene * p.ld_jp + kbase;
             if (kv0) atomicAdd(out + (m0 + 0) * 8 + g, r0);
             if (kv1) atomicAdd(out + (m0 + 1) * 8 + g, r1);
-            if constexpr (NEX > 0) {
-                if (kvx) atomicAdd(out + mx * 8 + g, rx);
-            }
+            if (kvx) atomicAdd(out + mx * 8 + g, rx);
         }
     }
 }
@@ -630,13 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contra
     cluster_wait();
     const int n_my_genes = ((int)cid < p.n_genes) ? (p.n_genes - (int)cid + (int)ncl - 1) / (int)ncl : 0;
     const int spg = (p.n_list + T_S - 1) / T_S;
-    const int smsp = warp & 3, slot = warp >> 2;
-    if (slot < 2)
-        run_mma<0, 0>(p, sm, warp, lane, rank, n_my_genes, spg);
-    else if ((smsp & 1) == 0)
-        run_mma<7, 0>(p, sm, warp, lane, rank, n_my_genes, spg);
-    else
-        run_mma<7, 6>(p, sm, warp, lane, rank, n_my_genes, spg);
+    run_mma(p, sm, warp, lane, rank, n_my_genes, spg);
     cluster_arrive();
     cluster_wait();
 }
@@ -657,7 +458,7 @@ struct GenericParams {
     int64_t ld_ridx;
     const int32_t *cell_ids;
     int n_list;
-    const double *W;  // pass-major [pass][n_w_rows][104]
+    const double *W;  // pass-major [pass][n_w_rows][108]
     int64_t n_w_rows;
     int n_boot;
     double scale;
@@ -672,7 +473,7 @@ __device__ __forceinline__ void generic_accumulate(const GenericParams &p, int64
     for (int i = 0; i < G_KPT; ++i)
 #pragma unroll
         for (int j = 0; j < G_BC; ++j) acc[i][j] = 0.0;
-    const double *Wc = p.W + ((int64_t)(b0 / WP_TILED) * p.n_w_rows) * WP_TILED + (b0 % WP_TILED);
+    const double *Wc = p.W + ((int64_t)(b0 / WP_TILED) * p.n_w_rows) * WS_TILED + (b0 % WP_TILED);
     for (int c = 0; c < p.n_list; ++c) {
         const int col = p.cell_ids ? p.cell_ids[c] : c;
         const int64_t row = p.ridx[g * p.ld_ridx + col];
@@ -683,7 +484,7 @@ __device__ __forceinline__ void generic_accumulate(const GenericParams &p, int64
             int k = k0 + i * G_THREADS;
             av[i] = k < p.K ? a[k] : 0.0;
         }
-        const double *w = Wc + (int64_t)c * WP_TILED;
+        const double *w = Wc + (int64_t)c * WS_TILED;
 #pragma unroll
         for (int j = 0; j < G_BC; ++j) {
             double wv = (b0 + j < p.n_boot) ? w[j] : 0.0;
@@ -915,7 +716,7 @@ __global__ void fp64_peak_kernel(double *sink, int iters) {
 cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_list, double *W, int n_w_rows,
                            cudaStream_t st) {
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
-    cudaError_t e = cudaMemsetAsync(W, 0, sizeof(double) * (size_t)(passes > 0 ? passes : 1) * n_w_rows * WP_TILED, st);
+    cudaError_t e = cudaMemsetAsync(W, 0, sizeof(double) * (size_t)(passes > 0 ? passes : 1) * n_w_rows * WS_TILED, st);
     if (e != cudaSuccess) return e;
     if (n_boot <= 0 || D <= 0) return cudaSuccess;
     build_w_kernel<<<n_boot, 256, 0, st>>>(boot_idx, n_boot, D, n_list, W, n_w_rows);
@@ -927,14 +728,12 @@ bool contract_tiled_supported(const ContractArgs &a) {
            a.n_w_rows >= round_up(a.n_list, 8);
 }
 
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, int variant, cudaStream_t st, int *n_launches) {
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches) {
     if (a.n_genes <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(TiledSmem));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem));
+        cudaError_t e = cudaFuncSetAttribute(contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(MmaSmem));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -949,19 +748,20 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, int variant, 
         p.ld_ridx = a.ld_ridx;
         p.cell_ids = a.cell_ids;
         p.n_list = a.n_list;
-        p.W = a.W + (size_t)ps * a.n_w_rows * WP_TILED;
-        p.ldw = WP_TILED;
+        p.W = a.W + (size_t)ps * a.n_w_rows * WS_TILED;
         p.n_boot_pass = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;
         p.scale = a.scale;
         p.n_genes = a.n_genes;
         p.K = a.K;
         p.jp = a.jp;
         p.ld_jp = a.ld_jp;
-        p.accumulate = ps > 0;
-        if (variant == 1)
-            contract_tiled_kernel<<<2 * clusters, T_THREADS, sizeof(TiledSmem), st>>>(p);
-        else
-            contract_mma_kernel<<<2 * clusters, T_THREADS, sizeof(MmaSmem), st>>>(p);
+        const char *dbg = getenv("SCDE_B200_DEBUG_CONTRACT");
+        p.debug = dbg ? atoi(dbg) : 0;
+        const char *pde = getenv("SCDE_B200_CONTRACT_PD");
+        p.pd = pde ? atoi(pde) : T_PD;
+        if (p.pd < 1) p.pd = 1;
+        if (p.pd > T_NS - 1) p.pd = T_NS - 1;
+        contract_mma_kernel<<<2 * clusters, T_THREADS, sizeof(MmaSmem), st>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) ++*n_launches;

@@ -11,6 +11,7 @@ namespace scde {
 // and splits into the two 208-wide halves the tiled contraction kernel works on.
 constexpr int KP_TILED = 416;
 constexpr int WP_TILED = 104;  // bootstrap columns per pass of the tiled kernel (n.randomizations = 100 -> one pass)
+constexpr int WS_TILED = 108;  // row stride of the multiplicity matrix W (104 + 4 pad: bank-conflict-free fragment loads)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -29,6 +30,9 @@ struct CellPrep {  // per-cell grid vectors, each [n_cells][ld]
     double *mu, *lcfp, *lcfpr, *theta;  // theta only for local-theta models
     double *maxcfp;                     // [n_cells]
     int ld;
+    // constant-theta fast path (NULL = use the general saddle-point kernel): drop-out probability and the
+    // negative binomial's log p_k = -log1p(mu_k/theta), log q_k = -log1p(theta/mu_k)
+    double *cfp, *l1, *l2;
 };
 // models: n_cells x 12 column-major with leading dimension ld_models (rows of the full model matrix);
 // cell c uses model row cell_row[c] (NULL = identity).
@@ -37,8 +41,10 @@ cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t 
                              cudaStream_t st);
 // One warp per table row r: cell = upper_bound(row_off, r) - 1, x = row_x[r].  Writes table[r*ld_table + k]
 // (k >= K zero-filled up to ld_table) and row_mode[r] (first argmax, before the clamp).
+// row_cell[r] = cell of table row r (from row_off)
+cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_cell, cudaStream_t st);
 cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                           const int32_t *row_off, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           const int32_t *row_off, const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
                            cudaStream_t st);
 
@@ -58,7 +64,7 @@ cudaError_t launch_uci_to_ridx(const int32_t *uci, int G, int n_cells, const int
                                int ld_ridx, cudaStream_t st);
 
 // ---- boot_contract.cu ----------------------------------------------------------------------------
-// W = multiplicity of each cell among each boot's draws, pass-major: W[b / 104][cell][b % 104] with n_w_rows
+// W = multiplicity of each cell among each boot's draws, pass-major: W[b / 104][cell][108] (column b % 104) with n_w_rows
 // (>= round_up(n_list, 8)) rows per pass, rows beyond n_list zero.  boot_idx: n_boot x D (draw order).
 cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_list, double *W, int n_w_rows,
                            cudaStream_t st);
@@ -69,7 +75,7 @@ struct ContractArgs {
     int ld_ridx;
     const int32_t *cell_ids;  // [n_list] ridx column per list entry (NULL = identity)
     int n_list;
-    const double *W;  // pass-major [ceil(n_boot/104)][n_w_rows][104]
+    const double *W;  // pass-major [ceil(n_boot/104)][n_w_rows][108]
     int n_w_rows;
     int n_boot;    // columns of W that are real
     double scale;  // jp += softmax / scale   (n_boot for the live path, 1 for the legacy / no-bootstrap forms)
@@ -79,8 +85,7 @@ struct ContractArgs {
 };
 cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches);
 // requires K <= 416 and ld_table == 416
-// variant 0 = DMMA tiles (default), 1 = DFMA register tiles
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, int variant, cudaStream_t st, int *n_launches);
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches);
 bool contract_tiled_supported(const ContractArgs &a);
 // ensemble form (src/jpmatLogBoot.cpp:224-237)
 cudaError_t launch_ensemble(const ContractArgs &a, double *rownorm_scratch, int64_t n_rows, cudaStream_t st);

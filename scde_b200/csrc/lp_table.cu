@@ -169,6 +169,7 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, con
             prep.lcfp[o] = 0;
             prep.lcfpr[o] = 0;
             if (prep.theta) prep.theta[o] = 1;
+            if (prep.cfp) prep.cfp[o] = prep.l1[o] = prep.l2[o] = 0;
             continue;
         }
         double m = mag[k];
@@ -189,6 +190,12 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, con
         prep.lcfp[o] = l;
         prep.lcfpr[o] = log(cr);
         lmax = fmax(lmax, l);
+        if (prep.cfp) {  // constant-theta fast path: log p_k, log q_k of the NB parametrisation and the drop-out prob
+            const double th0 = M(5), muk = exp(t);
+            prep.cfp[o] = cf;
+            prep.l1[o] = -log1p(muk / th0);
+            prep.l2[o] = -log1p(th0 / muk);
+        }
         if (local_theta) {
             double th = -1 * m + M(8);
             th *= M(9);
@@ -215,6 +222,12 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, con
 
 // ---- table rows ----------------------------------------------------------------------------------
 constexpr int ROW_WARPS = 8;
+
+__global__ void row_cell_kernel(const int32_t *__restrict__ row_off, int n_cells, int32_t *__restrict__ row_cell) {
+    const int c = blockIdx.x;
+    if (c >= n_cells) return;
+    for (int r = row_off[c] + threadIdx.x; r < row_off[c + 1]; r += blockDim.x) row_cell[r] = c;
+}
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 lp_rows_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ cell_row, int n_cells,
@@ -304,6 +317,109 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, const int32_t *__rest
     }
 }
 
+// ---- table rows, constant-theta fast path ---------------------------------------------------------
+// With size = theta fixed along the grid the saddle-point form collapses: bd0(s, n p) + bd0(x, n q) =
+// s log(s/n) + x log(x/n) - s log p - x log q (the linear terms cancel because p + q = 1), so
+//     log NB(x; s, p_k) = R(x, s) + s * L1_k + x * L2_k,     L1_k = log p_k, L2_k = log q_k  (per cell, per grid point)
+// with the row constant R = log(s/(s+x)) + stirlerr(n) - stirlerr(s) - stirlerr(n-s) - (log 2 pi + log s + log1p(-s/n))/2
+//                           - s log(s/n) - x log1p(-s/n).
+// Per element that is two FMAs, one exp (the drop-out term is cfp_k * exp(f - M)) and one log instead of two
+// divisions, three logs and two exps; the grid values live in registers (K <= 416 -> 13 per lane).
+constexpr int FAST_J = KP_TILED / 32;  // 13
+
+__global__ void __launch_bounds__(ROW_WARPS * 32, 3)
+lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
+                    const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, double sentinel,
+                    double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n_rows; row += (int64_t)gridDim.x * ROW_WARPS) {
+        const int c = row_cell[row];
+        const double x = (double)row_x[row];
+        const double s = models[(size_t)5 * ldm + c];
+        const double lambda = exp(models[(size_t)2 * ldm + c]);
+        const size_t base = (size_t)c * prep.ld;
+        const double *mu = prep.mu + base, *l1 = prep.l1 + base, *l2 = prep.l2 + base;
+        const double *lcfpr = prep.lcfpr + base, *cfp = prep.cfp + base;
+        // row constants
+        double R = 0.0, l1s = 0.0, l2s = 0.0;
+        if (x > 0) {
+            const double n = x + s, nmx = n - s;
+            const double c1 = d_stirlerr(n) - d_stirlerr(s) - d_stirlerr(nmx);
+            const double half_lf = 0.5 * (LN_2PI + log(s) + log1p(-s / n));
+            R = log(s / (s + x)) + (c1 - half_lf) - (s * log(s / n) + nmx * log1p(-s / n));
+            l1s = -log1p(x / s);  // "snap": mu~ = x
+            l2s = -log1p(s / x);
+        }
+        const double fp = d_dpois_log(x, lambda);
+        double nb[FAST_J];
+        double vmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < FAST_J; ++j) {
+            const int k = lane + 32 * j;
+            double v = -INFINITY;
+            if (k < K) {
+                const double muv = mu[k];
+                const bool snap = (k < K - 1) ? (x > muv && x < mu[k + 1]) : (x > muv);
+                if (x > 0) {
+                    const double a1 = snap ? l1s : l1[k];
+                    const double a2 = snap ? l2s : l2[k];
+                    v = fma(x, a2, fma(s, a1, R));
+                } else {
+                    v = s * l1[k];
+                }
+                v += lcfpr[k];
+                vmax = fmax(vmax, v);
+            }
+            nb[j] = v;
+        }
+        vmax = warp_max(vmax);
+        double maxp = vmax;
+        const double alt = prep.maxcfp[c] + fp;
+        if (maxp < alt) maxp = alt;
+        const double E = exp(fp - maxp);
+        double sum = 0;
+#pragma unroll
+        for (int j = 0; j < FAST_J; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                const double v = exp(nb[j] - maxp) + cfp[k] * E;
+                nb[j] = v;
+                sum += v;
+            }
+        }
+        sum = warp_sum(sum);
+        const double lsum = log(sum);
+        double best = -INFINITY;
+        int besti = 0x7fffffff;
+        double *out = table + (size_t)row * ld_table;
+#pragma unroll
+        for (int j = 0; j < FAST_J; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                double v = log(nb[j]) - lsum;
+                if (besti == 0x7fffffff || v > best) {
+                    best = v;
+                    besti = k;
+                }
+                if (v < sentinel) v = sentinel;
+                out[k] = v;
+            } else if (k < ld_table) {
+                out[k] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti) || (besti == 0x7fffffff && oi != 0x7fffffff)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
@@ -314,19 +430,30 @@ cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t 
     return cudaGetLastError();
 }
 
+cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_cell, cudaStream_t st) {
+    if (n_cells <= 0) return cudaSuccess;
+    row_cell_kernel<<<n_cells, 128, 0, st>>>(row_off, n_cells, row_cell);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                           const int32_t *row_off, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           const int32_t *row_off, const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
                            cudaStream_t st) {
     if (n_rows <= 0) return cudaSuccess;
+    int64_t blocks = (n_rows + ROW_WARPS - 1) / ROW_WARPS;
+    const int64_t cap = 148 * 64;  // grid-stride beyond this
+    if (blocks > cap) blocks = cap;
+    if (prep.cfp && row_cell_map && !local_theta && !cell_row && K <= KP_TILED && ld_table >= K) {
+        lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x, n_rows,
+                                                                        prep, K, sentinel, table, ld_table, row_mode);
+        return cudaGetLastError();
+    }
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(lp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    int64_t blocks = (n_rows + ROW_WARPS - 1) / ROW_WARPS;
-    const int64_t cap = 148 * 64;  // grid-stride beyond this
-    if (blocks > cap) blocks = cap;
     lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, cell_row, n_cells, row_off, row_x,
                                                                   n_rows, prep, K, local_theta, sentinel, table,
                                                                   ld_table, row_mode);

@@ -104,6 +104,26 @@ int main() {
         // per warp instruction: 8*8*4 FMAs = 512 flops
         printf(", \"dmma_m8n8k4_tflops\": %.3f", 512.0 * 8 * iters * (double)(thr / 32) * blocks / (ms * 1e-3) / 1e12);
     }
+    {   // DMMA at the contraction kernel's occupancies: (warps per SM, independent tiles per warp)
+        const int iters = 4000;
+#define DMMA_CASE(TILES, THR)                                                                                     \
+        for (int rep = 0; rep < 3; ++rep) {                                                                       \
+            cudaEventRecord(e0);                                                                                  \
+            dmma_kernel<TILES><<<sms, THR>>>(sink, iters);                                                        \
+            cudaEventRecord(e1);                                                                                  \
+            CK(cudaEventSynchronize(e1));                                                                         \
+            cudaEventElapsedTime(&ms, e0, e1);                                                                    \
+        }                                                                                                         \
+        printf(", \"dmma_tflops_%dwarps_%dtiles\": %.3f", THR / 32, TILES,                                         \
+               512.0 * TILES * iters * (double)(THR / 32) * sms / (ms * 1e-3) / 1e12);
+        DMMA_CASE(26, 384)
+        DMMA_CASE(33, 384)
+        DMMA_CASE(21, 512)
+        DMMA_CASE(13, 768)
+        DMMA_CASE(42, 256)
+        DMMA_CASE(26, 128)
+        DMMA_CASE(8, 1024)
+    }
     for (int mode = 0; mode < 3; ++mode) {
         const int iters = 20000, blocks = sms, thr = 512;
         for (int rep = 0; rep < 2; ++rep) {

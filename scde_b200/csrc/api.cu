@@ -232,7 +232,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
               const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
               JointScratch &scr, StageTimer *tm, int64_t *contract_cells) {
     cudaStream_t st = ctx->stream;
-    const int n_w_rows = round_up(n_list, 8);
+    const int n_w_rows = round_up(n_list, 16);
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
     SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WS_TILED));
     int e0 = tm ? tm->begin(st) : -1;

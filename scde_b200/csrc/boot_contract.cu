@@ -107,9 +107,12 @@ __global__ void build_w_kernel(const int32_t *__restrict__ boot_idx, int n_boot,
 // tiled kernel
 constexpr int T_KH = 208;       // grid points per CTA
 constexpr int T_WP = WP_TILED;  // boots per pass (104)
-constexpr int T_S = 8;          // cells per stage
-constexpr int T_NS = 8;         // ring depth
-constexpr int T_PD = T_NS - 2;  // prefetch distance: the slot refilled at iteration i was consumed at i-2
+#ifndef SCDE_TS
+#define SCDE_TS 8
+#endif
+constexpr int T_S = SCDE_TS;        // cells per stage
+constexpr int T_NS = 64 / T_S;      // ring depth (64 cells of operands resident: 160 KB)
+constexpr int T_PD = T_NS - (T_S >= 16 ? 1 : 2);  // prefetch distance
 constexpr int T_WARPS = 12;
 constexpr int T_THREADS = T_WARPS * 32;
 constexpr int T_WS = WS_TILED;  // row stride of W in global and shared memory (108 doubles, see below)
@@ -264,7 +267,20 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
             mbar_wait(&sm.full[sl], (uint32_t)(q / T_NS) & 1u);
             const double *sA = sm.stage[sl];
             const double *sW = sA + T_S * M_AS;
-            if (!(p.debug & 1))
+            if (p.debug & 8) {  // timing experiment: DMMA stream without the fragment loads
+#pragma unroll
+                for (int ks = 0; ks < T_S / 4; ++ks) {
+                    const double a0 = 1.0 + ks, b = 1e-9 * lane;
+#pragma unroll
+                    for (int nt = 0; nt < M_NT; ++nt) {
+                        dmma(acc[0][nt], a0, b);
+                        dmma(acc[1][nt], a0, b);
+                        if (nt == 3) dmma(ex[0], a0, b);
+                        if (nt == 7) dmma(ex[1], a0, b);
+                        if (nt == 11 && nex > 2) dmma(ex[2], a0, b);
+                    }
+                }
+            } else if (!(p.debug & 1))
 #pragma unroll
             for (int ks = 0; ks < T_S / 4; ++ks) {
                 const double *ap = sA + (ks * 4 + t) * M_AS + g;
@@ -383,9 +399,9 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
                 if (b < p.n_boot_pass) {
                     const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
                     const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
-                    const double den = (s0 + s1) * p.scale;
-                    r0 += acc[0][nt][i] / den;
-                    r1 += acc[1][nt][i] / den;
+                    const double inv = 1.0 / ((s0 + s1) * p.scale);  // e * (1/den): e is often denormal, which
+                    r0 += acc[0][nt][i] * inv;                        // sends a true division down its slow path
+                    r1 += acc[1][nt][i] * inv;
                 }
             }
         }
@@ -397,7 +413,7 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
                 if (j < nex && b < p.n_boot_pass) {
                     const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
                     const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
-                    rx += ex[j][i] / ((s0 + s1) * p.scale);
+                    rx += ex[j][i] * (1.0 / ((s0 + s1) * p.scale));
                 }
             }
         }
@@ -725,7 +741,7 @@ cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_lis
 
 bool contract_tiled_supported(const ContractArgs &a) {
     return a.K <= KP_TILED && a.ld_table == KP_TILED && a.n_list >= 1 && a.n_boot >= 1 &&
-           a.n_w_rows >= round_up(a.n_list, 8);
+           a.n_w_rows >= round_up(a.n_list, 16);
 }
 
 cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches) {

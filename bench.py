@@ -320,19 +320,23 @@ def main():
     # ---------------- roofline of the contraction kernel ----------------
     ms_c = float(np.mean([s["ms"]["contract"] for s in stats_acc]))
     n_c = int(stats_acc[-1]["launches"]["contract"])
-    cells_per_gene = stats_acc[-1]["contract_cells"]  # sum of list lengths over the joints
-    flops_per_step = 2.0 * K_GRID * N_BOOT * cells_per_gene * G
-    achieved_tf = flops_per_step / (ms_c * 1e-3) / 1e12
-    gather_bytes = 8.0 * K_GRID * cells_per_gene * G
+    entries = stats_acc[-1]["contract_cells"]  # (gene, cell) pairs the kernel visited, over all joints of one step
+    n_joint_cells = (n_groups[0] + n_groups[1]) * (2 if batch is not None else 1)  # batch joints draw |group| cells too
+    dense_entries = float(G) * n_joint_cells if batch is None else float(G) * (n_groups[0] + n_groups[1] + 2 * C)
+    flops_exec = 2.0 * K_GRID * N_BOOT * entries          # what the kernel has to multiply-add (K = 401, B = 100)
+    flops_dense = 2.0 * K_GRID * N_BOOT * dense_entries   # 2*K*C*B per gene, every cell visited
+    achieved_tf = flops_exec / (ms_c * 1e-3) / 1e12
     launches_per_step = int(sum(v for k, v in stats_acc[-1]["launches"].items() if k != "total"))
     roof = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
-            "kernel": "contract_tiled_kernel" if args.kernel != 1 else "contract_generic_kernel",
+            "kernel": "contract_mma_kernel" if args.kernel != 1 else "contract_generic_kernel",
             "launches_per_step": n_c, "avg_launch_ms": ms_c / max(1, n_c),
-            "flops_per_launch": flops_per_step / max(1, n_c),
+            "flops_per_launch": flops_exec / max(1, n_c),
+            "entries_visited_frac": entries / dense_entries,
+            "dense_equivalent_tflops": flops_dense / (ms_c * 1e-3) / 1e12,
             "peak_source": "DFMA loop measured live on this device (scde_b200_measure_fp64_peak); "
                            "MEASURED_PEAKS.json has no FP64 entry",
-            "gather_gbs": gather_bytes / (ms_c * 1e-3) / 1e9,
+            "gather_gbs": 8.0 * (K_GRID + N_BOOT) * entries / (ms_c * 1e-3) / 1e9,
             "stage_ms": {k: float(np.mean([s["ms"][k] for s in stats_acc])) for k in stats_acc[-1]["ms"]}}
 
     if rank != 0:

@@ -209,7 +209,7 @@ typedef struct {
     float ms[SCDE_B200_T_COUNT];
     int32_t launches[SCDE_B200_T_COUNT];
     int64_t table_rows;      /* rows in the log-posterior table */
-    int64_t contract_cells;  /* sum over joints of cells (draw-list rows) contracted per gene */
+    int64_t contract_cells;  /* list entries (gene x cell pairs) the contraction visited, summed over all joints */
 } scde_b200_stats;
 
 /* One-shot: host buffers in, host buffers out (uploads, runs, downloads). */

@@ -132,9 +132,12 @@ struct LpTable {
     int n_cells = 0, n_genes = 0, K = 0, ld = 0, ld_ridx = 0;
     int64_t n_rows = 0;
     double sentinel = 0;
-    DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err;
+    DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
     DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2;
     bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
+    // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
+    // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
+    bool zero_base = false;
 };
 
 #define CHECK_CTX(ctx)                                                  \
@@ -167,12 +170,27 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     }
     CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
                   fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr};
+    if (t.zero_base) {
+        SCDE_CUDA(t.zero_row.ensure((size_t)t.n_cells));
+        SCDE_CUDA(t.based.ensure((size_t)t.n_cells));
+    }
     int e0 = tm ? tm->begin(st) : -1;
-    SCDE_CUDA(launch_cell_prep(models_dev, ld_models, nullptr, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
+    int nl = 3;
+    SCDE_CUDA(launch_cell_prep(models_dev, ld_models, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
     SCDE_CUDA(launch_row_cell(t.row_off.p, t.n_cells, t.row_cell.p, st));
-    SCDE_CUDA(launch_lp_rows(models_dev, ld_models, nullptr, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep,
-                             t.K, local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, st));
-    if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, 3);
+    if (t.zero_base) {
+        SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, st));
+        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, st));
+        nl += 3;
+    } else {
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, st));
+    }
+    if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, nl);
     return SCDE_B200_OK;
 }
 
@@ -211,8 +229,9 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 }
 
 struct JointScratch {
-    DBuf<double> W;
-    DBuf<int32_t> idx;
+    DBuf<double> W, Z, zpart;
+    DBuf<int32_t> lst_row, lst_cell, lst_len, order;
+    DBuf<unsigned long long> total;  // running sum of list lengths over the joints of one run
 };
 
 // The big allocations of scde.expression.difference (counts shard, index matrix, lp table, joint posteriors, ratio
@@ -230,25 +249,40 @@ struct DiffWorkspace {
 // jp_dev[G][ld_jp] = joint posterior of the listed cells under the draws boot_idx_dev (n_boot x D, device).
 int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev, int n_list,
               const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
-              JointScratch &scr, StageTimer *tm, int64_t *contract_cells) {
+              JointScratch &scr, StageTimer *tm, bool count_entries) {
     cudaStream_t st = ctx->stream;
-    const int n_w_rows = round_up(n_list, 16);
+    const int n_w_rows = round_up(n_list + 1, 16);  // at least one all-zero row after the cells (list padding)
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
+    const int ld_lst = round_up(n_list, 8);
     SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WS_TILED));
+    SCDE_CUDA(scr.lst_row.ensure((size_t)t.n_genes * ld_lst));
+    SCDE_CUDA(scr.lst_cell.ensure((size_t)t.n_genes * ld_lst));
+    SCDE_CUDA(scr.lst_len.ensure((size_t)t.n_genes));
+    SCDE_CUDA(scr.order.ensure((size_t)t.n_genes));
+    SCDE_CUDA(scr.total.ensure(1));
+    const bool zb = t.zero_base && t.ld <= KP_TILED;
+    if (zb) {
+        SCDE_CUDA(scr.Z.ensure((size_t)passes * WP_TILED * t.ld));
+        SCDE_CUDA(scr.zpart.ensure(base_sum_scratch_doubles(n_boot, t.ld)));
+    }
     int e0 = tm ? tm->begin(st) : -1;
     SCDE_CUDA(launch_build_w(boot_idx_dev, n_boot, D, n_list, scr.W.p, n_w_rows, st));
     SCDE_CUDA(cudaMemsetAsync(jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
-    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
+    GeneLists lists{scr.lst_row.p, scr.lst_cell.p, scr.lst_len.p, scr.order.p, ld_lst};
+    SCDE_CUDA(launch_build_lists(t.ridx.p, t.ld_ridx, cell_ids_dev, n_list, t.n_genes, zb ? t.zero_row.p : nullptr,
+                                 zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st));
+    if (zb)
+        SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
+                                  scr.Z.p, scr.zpart.p, st));
+    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, zb ? 5 : 3);
     ContractArgs a;
     a.table = t.table.p;
     a.ld_table = t.ld;
-    a.ridx = t.ridx.p;
-    a.ld_ridx = t.ld_ridx;
-    a.cell_ids = cell_ids_dev;
-    a.n_list = n_list;
+    a.lists = lists;
     a.W = scr.W.p;
     a.n_w_rows = n_w_rows;
     a.n_boot = n_boot;
+    a.Z = zb ? scr.Z.p : nullptr;
     a.scale = scale;
     a.n_genes = t.n_genes;
     a.K = t.K;
@@ -267,7 +301,6 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     else
         SCDE_CUDA(launch_contract_generic(a, st, &nl));
     if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
-    if (contract_cells) *contract_cells += n_list;
     return SCDE_B200_OK;
 }
 
@@ -483,6 +516,7 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     const double minlogprob = -DBL_MAX / n_cells / 1.1;  // src/jpmatLogBoot.cpp:127,372
     t.sentinel = -DBL_MAX / (double)(D > n_cells ? D : n_cells) / 1.1;
     t.fast_theta = !local_theta && theta_all_regular(models, n_cells, n_cells);
+    t.zero_base = !post_flag && !ensemble && t.ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
     DBuf<double> d_models, d_mag, d_jp, d_out, d_rs;
     DBuf<int32_t> d_uci, d_boot;
     TRY(upload(d_models, models, (size_t)n_cells * 12, st));
@@ -497,19 +531,9 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     SCDE_CUDA(d_jp.ensure((size_t)n_genes * ld_jp));
     JointScratch scr;
     if (ensemble) {
-        ContractArgs a{};
-        a.table = t.table.p;
-        a.ld_table = t.ld;
-        a.ridx = t.ridx.p;
-        a.ld_ridx = t.ld_ridx;
-        a.cell_ids = nullptr;
-        a.n_list = n_cells;
-        a.n_genes = n_genes;
-        a.K = n_grid;
-        a.jp = d_jp.p;
-        a.ld_jp = ld_jp;
         SCDE_CUDA(d_rs.ensure((size_t)t.n_rows));
-        SCDE_CUDA(launch_ensemble(a, d_rs.p, t.n_rows, st));
+        SCDE_CUDA(launch_ensemble(t.table.p, t.ld, t.ridx.p, t.ld_ridx, n_cells, n_genes, n_grid, d_jp.p, ld_jp, d_rs.p,
+                                  t.n_rows, st));
     } else {
         std::vector<int32_t> gen;
         int nb = n_boot, dd = D;
@@ -524,7 +548,7 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
         }
         TRY(validate_index(boot_idx, (size_t)nb * dd, 0, n_cells, "boot_idx"));
         TRY(upload(d_boot, boot_idx, (size_t)nb * dd, st));
-        TRY(run_joint(ctx, t, nullptr, n_cells, d_boot.p, nb, dd, scale, d_jp.p, ld_jp, scr, nullptr, nullptr));
+        TRY(run_joint(ctx, t, nullptr, n_cells, d_boot.p, nb, dd, scale, d_jp.p, ld_jp, scr, nullptr, false));
     }
     SCDE_CUDA(d_out.ensure((size_t)n_genes * n_grid));
     SCDE_CUDA(launch_transpose_out(d_jp.p, ld_jp, n_genes, n_grid, d_out.p, st));
@@ -640,7 +664,7 @@ static int jpmat_common(scde_b200_ctx *ctx, const double *matl, int n_mat, int n
     JointScratch scr;
     if (n_boot > 0) {
         // not divided by n_boot: src/jpmatLogBoot.cpp:36-38
-        TRY(run_joint(ctx, t, nullptr, n_mat, d_boot.p, n_boot, D, 1.0, d_jp.p, t.ld, scr, nullptr, nullptr));
+        TRY(run_joint(ctx, t, nullptr, n_mat, d_boot.p, n_boot, D, 1.0, d_jp.p, t.ld, scr, nullptr, false));
     } else {
         SCDE_CUDA(cudaMemsetAsync(d_jp.p, 0, sizeof(double) * (size_t)n_rows * t.ld, st));
     }
@@ -989,6 +1013,7 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
     j->ws->table.ld = ld;
     j->ws->table.sentinel = -DBL_MAX / C / 1.1;
     j->ws->table.fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
+    j->ws->table.zero_base = ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
     JCUDA(cudaStreamSynchronize(st));
     *out = j;
     return SCDE_B200_OK;
@@ -1003,6 +1028,8 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     StageTimer &tm = j->timer;
     tm.reset();
     j->contract_cells = 0;
+    SCDE_CUDA(j->ws->scr.total.ensure(1));
+    SCDE_CUDA(cudaMemsetAsync(j->ws->scr.total.p, 0, sizeof(unsigned long long), st));
     const int G = j->G, C = j->C, K = j->K;
     const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
     int t_all = tm.begin(st);
@@ -1011,12 +1038,12 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     // group joints: cells of one factor level, draws are local indices (R/functions.R:372-374)
     for (int i = 0; i < 2; ++i)
         TRY(run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
-                      j->ws->jp[i].p, ld, j->ws->scr, &tm, &j->contract_cells));
+                      j->ws->jp[i].p, ld, j->ws->scr, &tm, true));
     // batch joints: all cells, composition-sampled draws are global cell ids (R/functions.R:355-357)
     if (j->has_batch)
         for (int i = 0; i < 2; ++i)
             TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot[2 + i].p, j->n_boot, j->D[2 + i], (double)j->n_boot,
-                          j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, &j->contract_cells));
+                          j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, true));
     int e0 = tm.begin(st);
     int nl = 0;
     RatioArgs r{};
@@ -1129,7 +1156,9 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
     if (stats) {
         j->timer.collect(stats);
         stats->table_rows = j->ws->table.n_rows;
-        stats->contract_cells = j->contract_cells;
+        unsigned long long tot = 0;
+        SCDE_CUDA(cudaMemcpy(&tot, j->ws->scr.total.p, sizeof(tot), cudaMemcpyDeviceToHost));
+        stats->contract_cells = (int64_t)tot;  // list entries contracted, summed over genes and joints
     }
     return SCDE_B200_OK;
 }

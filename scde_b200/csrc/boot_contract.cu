@@ -11,9 +11,9 @@
 // contract_mma_kernel (the sm_100a hot kernel)
 //   * one 2-CTA cluster per gene; CTA r owns grid points [208 r, 208 r + 208) and all 104 (100 + pad) boots, so
 //     its 208 x 104 FP64 accumulator tile (173 KB) lives entirely in the register file (12 warps x 168 regs);
-//   * operands are staged through shared memory by the TMA engine: per stage of 8 cells, 8 bulk copies of one
-//     gathered 1664-byte table row half each plus one bulk copy of the 8 matching W rows, completion signalled on
-//     an mbarrier (cp.async.bulk ... mbarrier::complete_tx); an 8-deep ring keeps ~160 KB in flight per SM;
+//   * operands are staged through shared memory by the TMA engine: per stage of 8 list entries, 8 bulk copies of one
+//     gathered 1664-byte table row half each plus 8 bulk copies of the matching 864-byte W rows, completion signalled
+//     on an mbarrier (cp.async.bulk ... mbarrier::complete_tx); a 10-deep ring keeps ~160 KB in flight per SM;
 //   * the product runs on FP64 tensor-core tiles (mma.sync m8n8k4.f64), laid out so that every SM sub-partition
 //     carries the same number of tiles (85 of the 338 per CTA);
 //   * the soft-max over the grid is fused: per-boot max and sum are reduced with warp shuffles, across warps
@@ -93,8 +93,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // W build: multiplicities from the draw lists
 __global__ void build_w_kernel(const int32_t *__restrict__ boot_idx, int n_boot, int D, int n_list, double *W,
                                int n_w_rows) {
-    // W is pass-major: W[pass][cell][108] (104 boots + 4 zero pad), boot b = 104*pass + column.  One CTA per boot, so atomics from
-    // different CTAs never touch the same element.
+    // W is pass-major: W[pass][cell][108] (104 boots + 4 zero pad), boot b = 104*pass + column.  One CTA per boot, so
+    // atomics from different CTAs never touch the same element.
     const int b = blockIdx.x;
     double *Wp = W + ((size_t)(b / WP_TILED) * n_w_rows) * WS_TILED + (b % WP_TILED);
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
@@ -104,15 +104,118 @@ __global__ void build_w_kernel(const int32_t *__restrict__ boot_idx, int n_boot,
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-gene entry lists.  Entry e of gene g = (table row, W row).  Dense form: every cell of the joint.  Zero-base form:
+// only the cells whose count is non-zero (or whose zero-count row cannot serve as a base); the zero-count rows of all
+// other cells are summed once per randomization into Z (base_sum kernels) and the table holds differences to them.
+// One warp per gene, order-preserving ballot compaction, lists padded to a multiple of 8 with (pad_row, zero W row).
+__global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_ridx, const int32_t *__restrict__ cell_ids,
+                                   int n_list, int n_genes, const int32_t *__restrict__ zero_row,
+                                   const int32_t *__restrict__ based, int pad_row, int32_t *__restrict__ lst_row,
+                                   int32_t *__restrict__ lst_cell, int32_t *__restrict__ lst_len, int64_t ld_lst,
+                                   unsigned long long *total_entries) {
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_genes) return;
+    const int lane = threadIdx.x & 31;
+    int pos = 0;
+    for (int base = 0; base < n_list; base += 32) {
+        const int c = base + lane;
+        bool keep = false;
+        int32_t r = 0;
+        if (c < n_list) {
+            const int col = cell_ids ? cell_ids[c] : c;
+            r = ridx[g * ld_ridx + col];
+            keep = !zero_row || !based[col] || r != zero_row[col];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int o = pos + __popc(m & ((1u << lane) - 1));
+            lst_row[g * ld_lst + o] = r;
+            lst_cell[g * ld_lst + o] = c;
+        }
+        pos += __popc(m);
+    }
+    const int padded = (pos + 7) & ~7;
+    if (pos + lane < padded) {
+        lst_row[g * ld_lst + pos + lane] = pad_row;
+        lst_cell[g * ld_lst + pos + lane] = n_list;  // a W row that is all zero
+    }
+    if (lane == 0) {
+        lst_len[g] = pos;
+        if (total_entries) atomicAdd(total_entries, (unsigned long long)pos);
+    }
+}
+
+// heaviest genes first: one CTA, bitonic sort of (0xFFFF - len) << 16 | gene
+__global__ void sort_genes_kernel(const int32_t *__restrict__ len, int n_genes, int n_pow2, int32_t *__restrict__ order) {
+    extern __shared__ uint32_t s_key[];
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x)
+        s_key[i] = i < n_genes ? ((uint32_t)(0xFFFF - min(len[i], 0xFFFF)) << 16) | (uint32_t)i : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint32_t a = s_key[i], b = s_key[l];
+                    if ((a > b) == ((i & k) == 0)) {
+                        s_key[i] = b;
+                        s_key[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n_genes; i += blockDim.x) order[i] = (int32_t)(s_key[i] & 0xFFFFu);
+}
+
+__global__ void iota_kernel(int32_t *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+// Z partials: part[chunk][pass*104 + b][k] = sum over the chunk's based cells of W[cell][b] * table[zero_row][k]
+constexpr int Z_CHUNKS = 32, Z_BC = 8;
+__global__ void __launch_bounds__(KP_TILED)
+base_sum_partial_kernel(const double *__restrict__ table, int64_t ld_table, const int32_t *__restrict__ zero_row,
+                        const int32_t *__restrict__ based, const int32_t *__restrict__ cell_ids, int n_list,
+                        const double *__restrict__ W, int64_t n_w_rows, int n_bcols, double *__restrict__ part) {
+    const int k = threadIdx.x;                 // blockDim.x == ld_table (<= 416 by construction of the caller)
+    const int b0 = blockIdx.x * Z_BC;          // column among passes*104
+    const int chunk = blockIdx.y;
+    const int per = (n_list + Z_CHUNKS - 1) / Z_CHUNKS;
+    const int c0 = chunk * per, c1 = min(n_list, c0 + per);
+    const int pass = b0 / WP_TILED, bb = b0 % WP_TILED;
+    const double *Wp = W + ((int64_t)pass * n_w_rows) * WS_TILED + bb;
+    double acc[Z_BC];
+#pragma unroll
+    for (int j = 0; j < Z_BC; ++j) acc[j] = 0.0;
+    for (int c = c0; c < c1; ++c) {
+        const int col = cell_ids ? cell_ids[c] : c;
+        if (!based[col]) continue;
+        const double a = table[(int64_t)zero_row[col] * ld_table + k];
+        const double *w = Wp + (int64_t)c * WS_TILED;
+#pragma unroll
+        for (int j = 0; j < Z_BC; ++j) acc[j] = fma(a, w[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < Z_BC; ++j)
+        part[((int64_t)chunk * n_bcols + b0 + j) * ld_table + k] = acc[j];
+}
+__global__ void base_sum_reduce_kernel(const double *__restrict__ part, int64_t n, double *__restrict__ Z) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < Z_CHUNKS; ++c) s += part[(int64_t)c * n + i];  // fixed order: deterministic
+    Z[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // tiled kernel
 constexpr int T_KH = 208;       // grid points per CTA
 constexpr int T_WP = WP_TILED;  // boots per pass (104)
-#ifndef SCDE_TS
-#define SCDE_TS 8
-#endif
-constexpr int T_S = SCDE_TS;        // cells per stage
-constexpr int T_NS = 64 / T_S;      // ring depth (64 cells of operands resident: 160 KB)
-constexpr int T_PD = T_NS - (T_S >= 16 ? 1 : 2);  // prefetch distance
+constexpr int T_S = 8;          // list entries (cells) per stage
+constexpr int T_NS = 10;        // ring depth
+constexpr int T_PD = 8;         // prefetch distance in stages
 constexpr int T_WARPS = 12;
 constexpr int T_THREADS = T_WARPS * 32;
 constexpr int T_WS = WS_TILED;  // row stride of W in global and shared memory (108 doubles, see below)
@@ -120,27 +223,25 @@ constexpr uint32_t T_STAGE_BYTES = (T_S * T_KH + T_S * T_WS) * 8u;  // bytes the
 
 struct TiledParams {
     const double *table;
-    const int32_t *ridx;
-    int64_t ld_ridx;
-    const int32_t *cell_ids;
-    int n_list;
+    const int32_t *lst_row, *lst_cell, *lst_len, *order;
+    int64_t ld_lst;
     const double *W;  // this pass: rows [n_w_rows][108], columns [0, 104) real
+    const double *Z;  // this pass: [104][416] initial value of T (zero-base form) or NULL
     int n_boot_pass;  // real boots in this pass (<= 104)
     double scale;
     int n_genes, K;
     double *jp;  // zero-filled by the caller; every pass adds into it
     int64_t ld_jp;
-    int pd;     // prefetch distance in stages (1 .. T_NS - 1)
     int debug;  // timing experiments only (SCDE_B200_DEBUG_CONTRACT): 1 = no DMMA, 2 = no table-row copies, 4 = no epilogue
 };
 
 // ------------------------------------------------------------------------------------------------
-// tiled kernel.  The inner product runs on mma.sync.aligned.m8n8k4.f64: M = 8 grid points, N = 8 boots, K = 4 cells
-// per instruction.  The FP64 rate of DMMA equals that of DFMA on B200 (37 vs 36.5 TFLOP/s measured,
-// tools/microbench.cu), but one DMMA replaces eight DFMA warp-instructions and its fragments are one double per lane,
-// so a warp issues 15 LDS.64 + 26 DMMA per four cells instead of 36 LDS + 208 DFMA -- the first version of this kernel
-// (DFMA register tiles, 54 % of the FP64 peak) was limited by shared-memory instruction issue (LDS.128 sustains one
-// per two cycles per SM) and by issue slots, not by the FP64 pipe (profiles/r01a_*).
+// The inner product runs on mma.sync.aligned.m8n8k4.f64: M = 8 grid points, N = 8 boots, K = 4 cells per instruction.
+// The FP64 rate of DMMA equals that of DFMA on B200 (37 vs 36.5 TFLOP/s measured, tools/microbench.cu), but one DMMA
+// replaces eight DFMA warp-instructions and its fragments are one double per lane, so a warp issues 19 LDS.64 + 29 DMMA
+// per four cells instead of 36 LDS + 208 DFMA -- the first version of this kernel (DFMA register tiles, 54 % of the
+// FP64 peak) was limited by shared-memory instruction issue (LDS.128 sustains one per two cycles per SM) and by issue
+// slots, not by the FP64 pipe (profiles/r01a_*).
 //
 // Tiles per CTA: 26 (grid) x 13 (boots).  Sub-partition s (= warp & 3) owns grid tiles 6s..6s+5 completely -- two per
 // warp -- and half of a shared grid tile (24 for s = 0,1; 25 for s = 2,3): boot tiles 0..6 for even s (split 2/2/3 over
@@ -154,8 +255,7 @@ struct TiledParams {
 constexpr int M_AS = 212;                                   // padded row stride of the A stage (doubles)
 constexpr int M_STAGE_DOUBLES = T_S * M_AS + T_S * T_WS;    // 2560
 constexpr int M_NT = 13;                                    // boot tiles
-
-constexpr int M_IDX_CAP = 5120;  // cells per gene whose table-row ids are staged in shared memory (else read from L2)
+constexpr int M_NEX = 3;                                    // at most three tiles of the shared grid tile per warp
 
 struct MmaSmem {
     double stage[T_NS][M_STAGE_DOUBLES];
@@ -164,7 +264,6 @@ struct MmaSmem {
     double xsum[2][T_WP];
     uint64_t full[T_NS];
     uint64_t empty[T_NS];
-    int32_t idx[2][M_IDX_CAP];  // table-row ids of the current and the next gene of this cluster
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -173,10 +272,8 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-constexpr int M_NEX = 3;  // at most three tiles of the shared grid tile per warp
-
 __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int warp, int lane, uint32_t rank,
-                                        int n_my_genes, int spg) {
+                                        int n_my_genes) {
     const int g = lane >> 2, t = lane & 3;
     const int smsp = warp & 3, slot = warp >> 2;
     const int m0 = smsp * 6 + slot * 2;   // first of the two full grid tiles
@@ -187,39 +284,39 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
     const int nex = ((smsp & 1) == 0 && slot == 2) ? 3 : 2;
     const int kbase = rank * T_KH;
     const uint32_t peer = rank ^ 1u;
-    const int64_t total_stages = (int64_t)n_my_genes * spg;
     const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
+    auto gene_of = [&](int gi) -> int64_t {
+        const int64_t o = (int64_t)cid + (int64_t)gi * ncl;
+        return p.order ? p.order[o] : o;
+    };
+    auto stages_of = [&](int gi) -> int { return (p.lst_len[gene_of(gi)] + T_S - 1) / T_S; };
 
     // ---- producer duty ----
-    // Stage q + T_PD is issued at consumer iteration q by warp (q mod 12): the duty (an empty-slot wait, nine TMA bulk
-    // copies) rotates, so no warp becomes the straggler of its sub-partition (a fixed producer warp cost 25 % of the
-    // kernel: it was also a consumer and fell a third of a stage behind every stage).  The gathered row ids of the
-    // current and the next gene sit in shared memory (filled cooperatively once per gene), so issuing a stage does not
-    // wait on a dependent global load.
-    const int PD = p.pd;
-    const bool idx_in_smem = (spg >= PD + 1) && (p.n_list <= M_IDX_CAP);
-    auto fill_idx = [&](int gi) {  // all threads: row ids of this cluster's gi-th gene -> sm.idx[gi & 1]
-        if (!idx_in_smem || gi >= n_my_genes) return;
-        const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
-        const int32_t *src = p.ridx + gene * p.ld_ridx;
-        int32_t *dst = sm.idx[gi & 1];
-        for (int c = threadIdx.x; c < p.n_list; c += T_THREADS) dst[c] = src[p.cell_ids ? p.cell_ids[c] : c];
-    };
-    auto issue_stage = [&](int64_t qp) {  // one warp: issue stage qp
-        const int gi = (int)(qp / spg), cb = (int)(qp - (int64_t)gi * spg);
-        const int sl = (int)(qp % T_NS);
-        const uint32_t fill = (uint32_t)(qp / T_NS);
-        int32_t row = 0;
-        if (lane < T_S) {
-            int cell = cb * T_S + lane;
-            if (cell >= p.n_list) cell = p.n_list - 1;  // padded cells re-read a valid row; their W rows are zero
-            if (idx_in_smem) {
-                row = sm.idx[gi & 1][cell];
-            } else {
-                const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
-                row = p.ridx[gene * p.ld_ridx + (p.cell_ids ? p.cell_ids[cell] : cell)];
-            }
+    // Consumption is a stream of stages q = 0, 1, 2, ... over this cluster's genes; stage q + T_PD is issued at consumer
+    // iteration q by warp (q mod 12): the duty (an empty-slot wait, sixteen TMA bulk copies) rotates, so no warp becomes
+    // the straggler of its sub-partition (a fixed producer warp cost 25 % of the kernel: it was also a consumer and fell
+    // a third of a stage behind every stage).  Every warp keeps its own cursor (gene ordinal, stage within gene) over
+    // the stages it will issue -- they are 12 apart -- and fetches the list entries of its next duty into registers
+    // right after the current one, so issuing never waits on a dependent global load.
+    int p_gi = 0, p_cb = T_PD + warp, p_spg = n_my_genes > 0 ? stages_of(0) : 0;
+    int32_t p_ent = 0;  // lanes 0..7: table row of entry `lane`; lanes 8..15: W row of entry `lane - 8`
+    auto normalize = [&]() {
+        while (p_gi < n_my_genes && p_cb >= p_spg) {
+            p_cb -= p_spg;
+            ++p_gi;
+            p_spg = p_gi < n_my_genes ? stages_of(p_gi) : 0;
         }
+    };
+    auto fetch_entries = [&](int gi, int cb) -> int32_t {
+        if (lane < 2 * T_S && gi < n_my_genes) {
+            const int64_t o = gene_of(gi) * p.ld_lst + (int64_t)cb * T_S + (lane & (T_S - 1));
+            return lane < T_S ? p.lst_row[o] : p.lst_cell[o];
+        }
+        return 0;
+    };
+    auto issue = [&](int64_t stage_no, int32_t ent) {  // one warp: TMA copies of stage `stage_no` (entries in `ent`)
+        const int sl = (int)(stage_no % T_NS);
+        const uint32_t fill = (uint32_t)(stage_no / T_NS);
         if (fill > 0) mbar_wait(&sm.empty[sl], (fill - 1) & 1u);
         double *dstA = sm.stage[sl];
         double *dstW = dstA + T_S * M_AS;
@@ -228,16 +325,26 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
         __syncwarp();
         if (lane < T_S) {
             if (!no_rows)
-                bulk_g2s(dstA + lane * M_AS, p.table + (int64_t)row * KP_TILED + kbase, T_KH * 8u, &sm.full[sl]);
-        } else if (lane == T_S) {
-            bulk_g2s(dstW, p.W + (int64_t)cb * T_S * T_WS, T_S * T_WS * 8u, &sm.full[sl]);
+                bulk_g2s(dstA + lane * M_AS, p.table + (int64_t)ent * KP_TILED + kbase, T_KH * 8u, &sm.full[sl]);
+        } else if (lane < 2 * T_S) {
+            bulk_g2s(dstW + (lane - T_S) * T_WS, p.W + (int64_t)ent * T_WS, T_WS * 8u, &sm.full[sl]);
         }
     };
-    fill_idx(0);
-    fill_idx(1);
-    named_bar_sync(1, T_THREADS);
-    if (warp == 0)
-        for (int64_t i = 0; i < PD && i < total_stages; ++i) issue_stage(i);
+    if (warp == 0) {  // prologue: stages 0 .. T_PD-1
+        int gi = 0, cb = 0, spg = p_spg;
+        for (int i = 0; i < T_PD; ++i) {
+            while (gi < n_my_genes && cb >= spg) {
+                cb -= spg;
+                ++gi;
+                spg = gi < n_my_genes ? stages_of(gi) : 0;
+            }
+            if (gi >= n_my_genes) break;
+            issue(i, fetch_entries(gi, cb));
+            ++cb;
+        }
+    }
+    normalize();
+    p_ent = fetch_entries(p_gi, p_cb);
 
     // validity of this thread's grid points
     const bool kv0 = (kbase + (m0 + 0) * 8 + g) < p.K;
@@ -246,41 +353,46 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
 
     int64_t q = 0;
     for (int gi = 0; gi < n_my_genes; ++gi) {
-        const int64_t gene = (int64_t)cid + (int64_t)gi * ncl;
+        const int64_t gene = gene_of(gi);
+        const int spg = (p.lst_len[gene] + T_S - 1) / T_S;
         double acc[2][M_NT][2];
         double ex[M_NEX][2];
+        if (p.Z) {  // zero-base form: T starts from the per-randomization sum of the zero-count rows
 #pragma unroll
-        for (int nt = 0; nt < M_NT; ++nt) {
-            acc[0][nt][0] = acc[0][nt][1] = 0.0;
-            acc[1][nt][0] = acc[1][nt][1] = 0.0;
+            for (int nt = 0; nt < M_NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double *z = p.Z + (int64_t)(nt * 8 + 2 * t + i) * KP_TILED + kbase + g;
+                    acc[0][nt][i] = z[(m0 + 0) * 8];
+                    acc[1][nt][i] = z[(m0 + 1) * 8];
+                }
+#pragma unroll
+            for (int j = 0; j < M_NEX; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    ex[j][i] = p.Z[(int64_t)((nx0 + (j < nex ? j : 0)) * 8 + 2 * t + i) * KP_TILED + kbase + mx * 8 + g];
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < M_NT; ++nt) {
+                acc[0][nt][0] = acc[0][nt][1] = 0.0;
+                acc[1][nt][0] = acc[1][nt][1] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < M_NEX; ++j) ex[j][0] = ex[j][1] = 0.0;
         }
-#pragma unroll
-        for (int j = 0; j < M_NEX; ++j) ex[j][0] = ex[j][1] = 0.0;
 
-        if (gi > 0) {  // row ids of the next gene (its buffer was last used by gene gi-1, whose stages are all issued)
-            fill_idx(gi + 1);
-            named_bar_sync(1, T_THREADS);
-        }
         for (int cb = 0; cb < spg; ++cb, ++q) {
-            if (q + PD < total_stages && warp == (int)(q % T_WARPS)) issue_stage(q + PD);
+            if (warp == (int)(q % T_WARPS) && p_gi < n_my_genes) {
+                issue(q + T_PD, p_ent);
+                p_cb += T_WARPS;
+                normalize();
+                p_ent = fetch_entries(p_gi, p_cb);
+            }
             const int sl = (int)(q % T_NS);
             mbar_wait(&sm.full[sl], (uint32_t)(q / T_NS) & 1u);
             const double *sA = sm.stage[sl];
             const double *sW = sA + T_S * M_AS;
-            if (p.debug & 8) {  // timing experiment: DMMA stream without the fragment loads
-#pragma unroll
-                for (int ks = 0; ks < T_S / 4; ++ks) {
-                    const double a0 = 1.0 + ks, b = 1e-9 * lane;
-#pragma unroll
-                    for (int nt = 0; nt < M_NT; ++nt) {
-                        dmma(acc[0][nt], a0, b);
-                        dmma(acc[1][nt], a0, b);
-                        if (nt == 3) dmma(ex[0], a0, b);
-                        if (nt == 7) dmma(ex[1], a0, b);
-                        if (nt == 11 && nex > 2) dmma(ex[2], a0, b);
-                    }
-                }
-            } else if (!(p.debug & 1))
+            if (!(p.debug & 1))
 #pragma unroll
             for (int ks = 0; ks < T_S / 4; ++ks) {
                 const double *ap = sA + (ks * 4 + t) * M_AS + g;
@@ -397,6 +509,7 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
             for (int i = 0; i < 2; ++i) {
                 const int b = nt * 8 + 2 * t + i;
                 if (b < p.n_boot_pass) {
+                    // rank-0 value first so both CTAs add in the same order
                     const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
                     const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
                     const double inv = 1.0 / ((s0 + s1) * p.scale);  // e * (1/den): e is often denormal, which
@@ -449,11 +562,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contra
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // both CTAs must be resident before any DSMEM store
     cluster_arrive();
     cluster_wait();
     const int n_my_genes = ((int)cid < p.n_genes) ? (p.n_genes - (int)cid + (int)ncl - 1) / (int)ncl : 0;
-    const int spg = (p.n_list + T_S - 1) / T_S;
-    run_mma(p, sm, warp, lane, rank, n_my_genes, spg);
+    run_mma(p, sm, warp, lane, rank, n_my_genes);
+    // keep this CTA's shared memory alive until the peer's last DSMEM store has landed
     cluster_arrive();
     cluster_wait();
 }
@@ -470,12 +584,11 @@ constexpr int G_KPT = 2;  // grid points per thread per sweep -> 512 grid points
 struct GenericParams {
     const double *table;
     int64_t ld_table;
-    const int32_t *ridx;
-    int64_t ld_ridx;
-    const int32_t *cell_ids;
-    int n_list;
+    const int32_t *lst_row, *lst_cell, *lst_len;
+    int64_t ld_lst;
     const double *W;  // pass-major [pass][n_w_rows][108]
     int64_t n_w_rows;
+    const double *Z;  // [passes*104][ld_table] or NULL
     int n_boot;
     double scale;
     int K;
@@ -485,14 +598,19 @@ struct GenericParams {
 
 __device__ __forceinline__ void generic_accumulate(const GenericParams &p, int64_t g, int b0, int k0,
                                                    double (&acc)[G_KPT][G_BC]) {
+    const int pass = b0 / WP_TILED, bb = b0 % WP_TILED;
 #pragma unroll
     for (int i = 0; i < G_KPT; ++i)
 #pragma unroll
-        for (int j = 0; j < G_BC; ++j) acc[i][j] = 0.0;
-    const double *Wc = p.W + ((int64_t)(b0 / WP_TILED) * p.n_w_rows) * WS_TILED + (b0 % WP_TILED);
-    for (int c = 0; c < p.n_list; ++c) {
-        const int col = p.cell_ids ? p.cell_ids[c] : c;
-        const int64_t row = p.ridx[g * p.ld_ridx + col];
+        for (int j = 0; j < G_BC; ++j) {
+            const int k = k0 + i * G_THREADS;
+            acc[i][j] = (p.Z && k < p.K) ? p.Z[((int64_t)pass * WP_TILED + bb + j) * p.ld_table + k] : 0.0;
+        }
+    const double *Wc = p.W + ((int64_t)pass * p.n_w_rows) * WS_TILED + bb;
+    const int len = p.lst_len[g];
+    for (int e = 0; e < len; ++e) {
+        const int64_t row = p.lst_row[g * p.ld_lst + e];
+        const int c = p.lst_cell[g * p.ld_lst + e];
         const double *a = p.table + row * p.ld_table;
         double av[G_KPT];
 #pragma unroll
@@ -739,9 +857,53 @@ cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_lis
     return cudaGetLastError();
 }
 
+cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
+                               const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
+                               unsigned long long *total_entries, cudaStream_t st) {
+    if (n_genes <= 0) return cudaSuccess;
+    const int wpb = 8;
+    build_lists_kernel<<<(n_genes + wpb - 1) / wpb, wpb * 32, 0, st>>>(ridx, ld_ridx, cell_ids, n_list, n_genes, zero_row,
+                                                                      based, pad_row, out.row, out.cell, out.len, out.ld,
+                                                                      total_entries);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // processing order: heaviest genes first when the packed 16+16-bit sort key applies, else identity
+    if (zero_row && n_genes <= 32768 && n_list < 65535) {
+        int n2 = 32;
+        while (n2 < n_genes) n2 <<= 1;
+        const size_t smem = sizeof(uint32_t) * n2;
+        e = cudaFuncSetAttribute(sort_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sort_genes_kernel<<<1, 1024, smem, st>>>(out.len, n_genes, n2, out.order);
+    } else {
+        iota_kernel<<<(n_genes + 255) / 256, 256, 0, st>>>(out.order, n_genes);
+    }
+    return cudaGetLastError();
+}
+
+size_t base_sum_scratch_doubles(int n_boot, int ld_table) {
+    const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
+    return (size_t)Z_CHUNKS * passes * WP_TILED * ld_table;
+}
+
+cudaError_t launch_base_sum(const double *table, int ld_table, const int32_t *zero_row, const int32_t *based,
+                            const int32_t *cell_ids, int n_list, const double *W, int n_w_rows, int n_boot, double *Z,
+                            double *scratch, cudaStream_t st) {
+    const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
+    const int n_bcols = passes * WP_TILED;
+    if (ld_table > KP_TILED) return cudaErrorInvalidValue;
+    dim3 grid(n_bcols / Z_BC, Z_CHUNKS);
+    base_sum_partial_kernel<<<grid, ld_table, 0, st>>>(table, ld_table, zero_row, based, cell_ids, n_list, W, n_w_rows,
+                                                      n_bcols, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int64_t n = (int64_t)n_bcols * ld_table;
+    base_sum_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, n, Z);
+    return cudaGetLastError();
+}
+
 bool contract_tiled_supported(const ContractArgs &a) {
-    return a.K <= KP_TILED && a.ld_table == KP_TILED && a.n_list >= 1 && a.n_boot >= 1 &&
-           a.n_w_rows >= round_up(a.n_list, 16);
+    return a.K <= KP_TILED && a.ld_table == KP_TILED && a.n_boot >= 1 && (a.lists.ld % 8) == 0;
 }
 
 cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches) {
@@ -760,11 +922,13 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t 
     for (int ps = 0; ps < passes; ++ps) {
         TiledParams p;
         p.table = a.table;
-        p.ridx = a.ridx;
-        p.ld_ridx = a.ld_ridx;
-        p.cell_ids = a.cell_ids;
-        p.n_list = a.n_list;
+        p.lst_row = a.lists.row;
+        p.lst_cell = a.lists.cell;
+        p.lst_len = a.lists.len;
+        p.order = a.lists.order;
+        p.ld_lst = a.lists.ld;
         p.W = a.W + (size_t)ps * a.n_w_rows * WS_TILED;
+        p.Z = a.Z ? a.Z + (size_t)ps * WP_TILED * KP_TILED : nullptr;
         p.n_boot_pass = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;
         p.scale = a.scale;
         p.n_genes = a.n_genes;
@@ -773,10 +937,6 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t 
         p.ld_jp = a.ld_jp;
         const char *dbg = getenv("SCDE_B200_DEBUG_CONTRACT");
         p.debug = dbg ? atoi(dbg) : 0;
-        const char *pde = getenv("SCDE_B200_CONTRACT_PD");
-        p.pd = pde ? atoi(pde) : T_PD;
-        if (p.pd < 1) p.pd = 1;
-        if (p.pd > T_NS - 1) p.pd = T_NS - 1;
         contract_mma_kernel<<<2 * clusters, T_THREADS, sizeof(MmaSmem), st>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -795,12 +955,13 @@ cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int 
     GenericParams p;
     p.table = a.table;
     p.ld_table = a.ld_table;
-    p.ridx = a.ridx;
-    p.ld_ridx = a.ld_ridx;
-    p.cell_ids = a.cell_ids;
-    p.n_list = a.n_list;
+    p.lst_row = a.lists.row;
+    p.lst_cell = a.lists.cell;
+    p.lst_len = a.lists.len;
+    p.ld_lst = a.lists.ld;
     p.W = a.W;
     p.n_w_rows = a.n_w_rows;
+    p.Z = a.Z;
     p.n_boot = a.n_boot;
     p.scale = a.scale;
     p.K = a.K;
@@ -811,20 +972,19 @@ cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_ensemble(const ContractArgs &a, double *rownorm_scratch, int64_t n_rows, cudaStream_t st) {
-    if (a.n_genes <= 0) return cudaSuccess;
+cudaError_t launch_ensemble(const double *table, int ld_table, const int32_t *ridx, int ld_ridx, int n_cells, int n_genes,
+                            int K, double *jp, int ld_jp, double *rownorm_scratch, int64_t n_rows, cudaStream_t st) {
+    if (n_genes <= 0) return cudaSuccess;
     int wpb = 8;
-    row_expsum_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(a.table, a.ld_table, a.K, n_rows,
-                                                                               rownorm_scratch);
+    row_expsum_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(table, ld_table, K, n_rows, rownorm_scratch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    size_t smem = sizeof(double) * a.K;
+    size_t smem = sizeof(double) * K;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    ensemble_kernel<<<a.n_genes, 256, smem, st>>>(a.table, a.ld_table, a.ridx, a.ld_ridx, a.cell_ids, a.n_list, a.K,
-                                                  rownorm_scratch, a.jp, a.ld_jp);
+    ensemble_kernel<<<n_genes, 256, smem, st>>>(table, ld_table, ridx, ld_ridx, nullptr, n_cells, K, rownorm_scratch, jp, ld_jp);
     return cudaGetLastError();
 }
 

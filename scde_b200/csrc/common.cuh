@@ -34,19 +34,23 @@ struct CellPrep {  // per-cell grid vectors, each [n_cells][ld]
     // negative binomial's log p_k = -log1p(mu_k/theta), log q_k = -log1p(theta/mu_k)
     double *cfp, *l1, *l2;
 };
-// models: n_cells x 12 column-major with leading dimension ld_models (rows of the full model matrix);
-// cell c uses model row cell_row[c] (NULL = identity).
-cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                             const double *mag, int K, int local_theta, int sqlogit, CellPrep prep,
-                             cudaStream_t st);
-// One warp per table row r: cell = upper_bound(row_off, r) - 1, x = row_x[r].  Writes table[r*ld_table + k]
-// (k >= K zero-filled up to ld_table) and row_mode[r] (first argmax, before the clamp).
+// models: n_cells x 12 column-major with leading dimension ld_models
+cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, const double *mag, int K,
+                             int local_theta, int sqlogit, CellPrep prep, cudaStream_t st);
 // row_cell[r] = cell of table row r (from row_off)
 cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_cell, cudaStream_t st);
-cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                           const int32_t *row_off, const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
-                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
-                           cudaStream_t st);
+// zero_row[c] = the row of cell c whose count is 0, or -1
+cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st);
+// based[c] = 1 when cell c has a zero-count row and that row holds no "log 0" sentinel (it can be subtracted)
+cudaError_t launch_based_flags(const double *table, int ld_table, int K, double sentinel, const int32_t *zero_row,
+                               int n_cells, int32_t *based, cudaStream_t st);
+// One warp per table row.  Writes table[r*ld_table + k] (k >= K zero-filled up to ld_table) and row_mode[r] (first
+// argmax, before the clamp).  which: 0 = every row, plain values; 1 = only the zero-count rows (plain values);
+// 2 = every row except the zero-count ones, stored as the difference to the cell's zero-count row when based[cell].
+cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
+                           const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
+                           const int32_t *zero_row, const int32_t *based, cudaStream_t st);
 
 // ---- dedup.cu ------------------------------------------------------------------------------------
 // counts: column-major with leading dimension ld_counts; genes [g0, g0+G) of n_cells columns.
@@ -68,17 +72,33 @@ cudaError_t launch_uci_to_ridx(const int32_t *uci, int G, int n_cells, const int
 // (>= round_up(n_list, 8)) rows per pass, rows beyond n_list zero.  boot_idx: n_boot x D (draw order).
 cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_list, double *W, int n_w_rows,
                            cudaStream_t st);
+// Per-gene entry lists: entry e of gene g is (table row lists.row[g*ld + e], W row lists.cell[g*ld + e]); lists.len[g]
+// entries, padded to a multiple of 8 with entries that contribute nothing.  order[] = processing order of the genes.
+struct GeneLists {
+    int32_t *row, *cell, *len, *order;
+    int ld;  // multiple of 8, >= round_up(longest list, 8)
+};
+// zero_row == NULL: dense lists (every cell of the joint).  Otherwise the zero-base form: only cells whose row differs
+// from the cell's zero-count row (or whose cell is not `based`) are listed, and the genes are ordered heaviest first.
+cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
+                               const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
+                               unsigned long long *total_entries /* += sum of list lengths, may be NULL */,
+                               cudaStream_t st);
+// Z[pass*104 + b][k] = sum over based cells of the joint of W[cell][b] * table[zero_row[cell]][k]; scratch holds
+// base_sum_scratch_doubles() doubles.  Two deterministic passes (partials per cell chunk, then a fixed-order reduction).
+size_t base_sum_scratch_doubles(int n_boot, int ld_table);
+cudaError_t launch_base_sum(const double *table, int ld_table, const int32_t *zero_row, const int32_t *based,
+                            const int32_t *cell_ids, int n_list, const double *W, int n_w_rows, int n_boot, double *Z,
+                            double *scratch, cudaStream_t st);
 struct ContractArgs {
     const double *table;   // [rows][ld_table]
     int ld_table;
-    const int32_t *ridx;   // [n_genes][ld_ridx]
-    int ld_ridx;
-    const int32_t *cell_ids;  // [n_list] ridx column per list entry (NULL = identity)
-    int n_list;
-    const double *W;  // pass-major [ceil(n_boot/104)][n_w_rows][108]
+    GeneLists lists;
+    const double *W;  // pass-major [ceil(n_boot/104)][n_w_rows][108]; rows >= (number of cells) are zero
     int n_w_rows;
-    int n_boot;    // columns of W that are real
-    double scale;  // jp += softmax / scale   (n_boot for the live path, 1 for the legacy / no-bootstrap forms)
+    int n_boot;       // columns of W that are real
+    const double *Z;  // [ceil(n_boot/104)*104][ld_table] initial value of T, or NULL (dense lists)
+    double scale;     // jp += softmax / scale   (n_boot for the live path, 1 for the legacy / no-bootstrap forms)
     int n_genes, K;
     double *jp;  // [n_genes][ld_jp], must be zeroed by the caller
     int ld_jp;
@@ -87,8 +107,9 @@ cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int 
 // requires K <= 416 and ld_table == 416
 cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches);
 bool contract_tiled_supported(const ContractArgs &a);
-// ensemble form (src/jpmatLogBoot.cpp:224-237)
-cudaError_t launch_ensemble(const ContractArgs &a, double *rownorm_scratch, int64_t n_rows, cudaStream_t st);
+// ensemble form (src/jpmatLogBoot.cpp:224-237), all cells of the table
+cudaError_t launch_ensemble(const double *table, int ld_table, const int32_t *ridx, int ld_ridx, int n_cells, int n_genes,
+                            int K, double *jp, int ld_jp, double *rownorm_scratch, int64_t n_rows, cudaStream_t st);
 // gathers for return_individual: modes[g + G*c] = mag[row_mode[ridx]], post[c][g + G*k] = table row (clamped)
 cudaError_t launch_gather_modes(const int32_t *ridx, int ld_ridx, int G, int n_cells, const int32_t *row_mode,
                                 const double *mag, double *modes, cudaStream_t st);

@@ -26,8 +26,10 @@ __device__ bool build_set(const int32_t *__restrict__ col, int G, uint32_t *s_ta
     for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) s_tab[i] = EMPTY;
     if (threadIdx.x == 0) *s_count = 0;
     __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        int32_t xi = col[g];
+    // g == -1 stands for the count 0, which every cell gets a table row for whether or not a gene has it (the zero-count
+    // row is the base of the zero-base contraction)
+    for (int g = (int)threadIdx.x - 1; g < G; g += blockDim.x) {
+        int32_t xi = g < 0 ? 0 : col[g];
         if (xi < 0) {
             atomicOr(err_flag, 1);
             continue;
@@ -154,9 +156,9 @@ __global__ void uci_to_ridx_kernel(const int32_t *__restrict__ uci, int G, int n
 }
 
 int pick_log2cap(int G) {
-    // capacity > distinct values is required; distinct <= G.  Cap at 2^15 slots (128 KB of shared memory).
+    // capacity > distinct values is required; distinct <= G + 1 (the forced 0).  Cap at 2^15 slots (128 KB).
     int l = 5;
-    while ((1 << l) <= G && l < 15) ++l;
+    while ((1 << l) <= G + 1 && l < 15) ++l;
     if ((1 << l) < 2 * G && l < 15) ++l;  // keep the load factor below 1/2 when that is free
     return l;
 }

@@ -152,12 +152,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- per-cell grid vectors (src/jpmatLogBoot.cpp:133-162) ---------------------------------------
-__global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ cell_row,
-                                 int n_cells, const double *__restrict__ mag, int K, int local_theta, int sqlogit,
-                                 CellPrep prep) {
+__global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, int n_cells,
+                                 const double *__restrict__ mag, int K, int local_theta, int sqlogit, CellPrep prep) {
     int c = blockIdx.x;
     if (c >= n_cells) return;
-    int r = cell_row ? cell_row[c] : c;
+    int r = c;
     auto M = [&](int col) { return models[(size_t)col * ldm + r]; };
     const double corr_a = M(4), corr_b = M(3), conc_a = M(1), conc_b = M(0);
     const double conc_a2 = sqlogit ? M(11) : 0.0;
@@ -223,6 +222,35 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, con
 // ---- table rows ----------------------------------------------------------------------------------
 constexpr int ROW_WARPS = 8;
 
+__global__ void zero_rows_kernel(const int32_t *__restrict__ row_off, const int32_t *__restrict__ row_x, int n_cells,
+                                 int32_t *__restrict__ zero_row) {
+    const int c = blockIdx.x;
+    if (c >= n_cells) return;
+    __shared__ int found;
+    if (threadIdx.x == 0) found = -1;
+    __syncthreads();
+    for (int r = row_off[c] + threadIdx.x; r < row_off[c + 1]; r += blockDim.x)
+        if (row_x[r] == 0) found = r;  // a cell's distinct counts contain 0 at most once
+    __syncthreads();
+    if (threadIdx.x == 0) zero_row[c] = found;
+}
+
+__global__ void based_flags_kernel(const double *__restrict__ table, int ld_table, int K, double sentinel,
+                                   const int32_t *__restrict__ zero_row, int n_cells, int32_t *__restrict__ based) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_cells) return;
+    const int lane = threadIdx.x & 31;
+    const int zr = zero_row[c];
+    bool ok = zr >= 0;
+    if (ok)
+        for (int k = lane; k < K; k += 32) {
+            const double v = table[(size_t)zr * ld_table + k];
+            ok = ok && (v > sentinel) && isfinite(v);
+        }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) based[c] = ok ? 1 : 0;
+}
+
 __global__ void row_cell_kernel(const int32_t *__restrict__ row_off, int n_cells, int32_t *__restrict__ row_cell) {
     const int c = blockIdx.x;
     if (c >= n_cells) return;
@@ -230,22 +258,27 @@ __global__ void row_cell_kernel(const int32_t *__restrict__ row_off, int n_cells
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-lp_rows_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ cell_row, int n_cells,
-               const int32_t *__restrict__ row_off, const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep,
-               int K, int local_theta, double sentinel, double *__restrict__ table, int ld_table,
-               int32_t *__restrict__ row_mode) {
+lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
+               const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, int local_theta, double sentinel,
+               double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
+               const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
     extern __shared__ double s_buf[];  // ROW_WARPS x K
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *nb = s_buf + (size_t)warp * K;
-    for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n_rows; row += (int64_t)gridDim.x * ROW_WARPS) {
-        // cell = last c with row_off[c] <= row
-        int lo = 0, hi = n_cells;  // invariant: row_off[lo] <= row < row_off[hi]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (row_off[mid] <= row) lo = mid; else hi = mid;
+    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    for (int64_t item = (int64_t)blockIdx.x * ROW_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ROW_WARPS) {
+        int64_t row = item;
+        int c;
+        if (which == 1) {
+            c = (int)item;
+            row = zero_row[c];
+            if (row < 0) continue;
+        } else {
+            c = row_cell[row];
+            if (which == 2 && zero_row[c] == row) continue;
         }
-        const int c = lo;
-        const int mr = cell_row ? cell_row[c] : c;
+        const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
+        const int mr = c;
         const double x = (double)row_x[row];
         const double *mu = prep.mu + (size_t)c * prep.ld;
         const double *lcfp = prep.lcfp + (size_t)c * prep.ld;
@@ -297,7 +330,7 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, const int32_t *__rest
                     besti = k;
                 }
                 if (v < sentinel) v = sentinel;
-                out[k] = v;
+                out[k] = zr ? v - zr[k] : v;
             } else {
                 out[k] = 0.0;
             }
@@ -330,10 +363,22 @@ constexpr int FAST_J = KP_TILED / 32;  // 13
 __global__ void __launch_bounds__(ROW_WARPS * 32, 3)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
                     const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, double sentinel,
-                    double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode) {
+                    double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
+                    const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < n_rows; row += (int64_t)gridDim.x * ROW_WARPS) {
-        const int c = row_cell[row];
+    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    for (int64_t item = (int64_t)blockIdx.x * ROW_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ROW_WARPS) {
+        int64_t row = item;
+        int c;
+        if (which == 1) {
+            c = (int)item;
+            row = zero_row[c];
+            if (row < 0) continue;
+        } else {
+            c = row_cell[row];
+            if (which == 2 && zero_row[c] == row) continue;
+        }
+        const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
         const double x = (double)row_x[row];
         const double s = models[(size_t)5 * ldm + c];
         const double lambda = exp(models[(size_t)2 * ldm + c]);
@@ -402,7 +447,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                     besti = k;
                 }
                 if (v < sentinel) v = sentinel;
-                out[k] = v;
+                out[k] = zr ? v - zr[k] : v;
             } else if (k < ld_table) {
                 out[k] = 0.0;
             }
@@ -422,11 +467,10 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
 
 }  // namespace
 
-cudaError_t launch_cell_prep(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                             const double *mag, int K, int local_theta, int sqlogit, CellPrep prep,
-                             cudaStream_t st) {
+cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, const double *mag, int K,
+                             int local_theta, int sqlogit, CellPrep prep, cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
-    cell_prep_kernel<<<n_cells, 128, 0, st>>>(models, ld_models, cell_row, n_cells, mag, K, local_theta, sqlogit, prep);
+    cell_prep_kernel<<<n_cells, 128, 0, st>>>(models, ld_models, n_cells, mag, K, local_theta, sqlogit, prep);
     return cudaGetLastError();
 }
 
@@ -436,17 +480,32 @@ cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_ce
     return cudaGetLastError();
 }
 
-cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *cell_row, int n_cells,
-                           const int32_t *row_off, const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
-                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode,
-                           cudaStream_t st) {
-    if (n_rows <= 0) return cudaSuccess;
-    int64_t blocks = (n_rows + ROW_WARPS - 1) / ROW_WARPS;
+cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st) {
+    if (n_cells <= 0) return cudaSuccess;
+    zero_rows_kernel<<<n_cells, 128, 0, st>>>(row_off, row_x, n_cells, zero_row);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_based_flags(const double *table, int ld_table, int K, double sentinel, const int32_t *zero_row,
+                               int n_cells, int32_t *based, cudaStream_t st) {
+    if (n_cells <= 0) return cudaSuccess;
+    based_flags_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(table, ld_table, K, sentinel, zero_row, n_cells, based);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
+                           const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+                           int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
+                           const int32_t *zero_row, const int32_t *based, cudaStream_t st) {
+    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    if (n_items <= 0) return cudaSuccess;
+    int64_t blocks = (n_items + ROW_WARPS - 1) / ROW_WARPS;
     const int64_t cap = 148 * 64;  // grid-stride beyond this
     if (blocks > cap) blocks = cap;
-    if (prep.cfp && row_cell_map && !local_theta && !cell_row && K <= KP_TILED && ld_table >= K) {
-        lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x, n_rows,
-                                                                        prep, K, sentinel, table, ld_table, row_mode);
+    if (prep.cfp && !local_theta && K <= KP_TILED && ld_table >= K) {
+        lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x,
+                                                                        n_rows, prep, K, sentinel, table, ld_table,
+                                                                        row_mode, which, zero_row, based);
         return cudaGetLastError();
     }
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);
@@ -454,9 +513,9 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, const int32_t *c
         cudaError_t e = cudaFuncSetAttribute(lp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, cell_row, n_cells, row_off, row_x,
-                                                                  n_rows, prep, K, local_theta, sentinel, table,
-                                                                  ld_table, row_mode);
+    lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, n_cells, row_cell_map, row_x, n_rows,
+                                                                  prep, K, local_theta, sentinel, table, ld_table,
+                                                                  row_mode, which, zero_row, based);
     return cudaGetLastError();
 }
 

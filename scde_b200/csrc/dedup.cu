@@ -90,13 +90,17 @@ dedup_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int 
 }
 
 __global__ void __launch_bounds__(DEDUP_THREADS)
-dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells, int log2cap,
+dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells, int log2cap_max,
                   const int32_t *__restrict__ row_off, int32_t *__restrict__ row_x, int32_t *__restrict__ ridx,
                   int ld_ridx, int32_t *err_flag) {
     extern __shared__ uint32_t s_tab[];
     __shared__ int s_count;
     const int c = blockIdx.x;
     const int32_t *col = counts + (size_t)c * ldc + g0;
+    // the count pass told us how many distinct values this cell has: size the set (and the sort) for that, not for G
+    const int n_distinct = row_off[c + 1] - row_off[c];
+    int log2cap = 5;
+    while ((1 << log2cap) < 2 * n_distinct + 2 && log2cap < log2cap_max) ++log2cap;
     if (!build_set(col, G, s_tab, log2cap, err_flag, &s_count)) return;
     const int U = s_count;
     bitonic_sort(s_tab, 1u << log2cap);

@@ -266,7 +266,11 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *nb = s_buf + (size_t)warp * K;
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
-    for (int64_t item = (int64_t)blockIdx.x * ROW_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ROW_WARPS) {
+    // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
+    // one) and the per-cell grid vectors stay in L1
+    const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+    const int64_t item_end = min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
+    for (int64_t item = (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
         int64_t row = item;
         int c;
         if (which == 1) {
@@ -367,7 +371,11 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
-    for (int64_t item = (int64_t)blockIdx.x * ROW_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ROW_WARPS) {
+    // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
+    // one) and the per-cell grid vectors stay in L1
+    const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+    const int64_t item_end = min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
+    for (int64_t item = (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
         int64_t row = item;
         int c;
         if (which == 1) {

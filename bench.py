@@ -252,14 +252,21 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ext):  # torch's own ops (the final gather) go onto the library's stream as well
-        e0.record(ext)
-        for _ in range(args.steps):
-            job.run()
-            res = job.download()
-            stats_acc.append(res["stats"])
-            gather_and_correct(res)
-        e1.record(ext)
+    # The library's work runs on its own stream (`ext`); the end-of-path exchange (all_gather of Z / indices over NCCL,
+    # BH on rank 0) of step i runs on torch's stream and overlaps the device work of step i+1, as a pipelined caller
+    # would do.  Both streams are drained before the closing event.
+    prev = None
+    e0.record(ext)
+    for _ in range(args.steps):
+        job.run()                       # asynchronous after its one internal sync (table size)
+        if prev is not None:
+            gather_and_correct(prev)    # host + NCCL work hidden behind the kernels just queued
+        prev = job.download()           # waits for this step's device work
+        stats_acc.append(prev["stats"])
+    gather_and_correct(prev)
+    torch.cuda.current_stream(device).synchronize()
+    e1.record(ext)
+    res = prev
     barrier()
     ms_step = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()

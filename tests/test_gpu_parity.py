@@ -300,3 +300,87 @@ def test_full_size_properties(ctx):
     assert ok, worst
     # cZ is global over genes, so compare Z only
     _z_close(res["results"]["Z"].to_numpy()[sel], want["results"][:, 4])
+
+
+def test_es_mef_small_all_genes_against_committed_golden(ctx):
+    """cfg1 on the real data, every gene: the CUDA path against the oracle output committed in tests/golden (vignette
+    variant: G = 12142, max.quantile = 0.999, Seed = 1, 100 randomizations)."""
+    import os
+    d = np.load(os.path.join(helpers.GOLD, "es_mef_vignette_oracle.npz"))
+    cd, ifm, prior, groups = helpers.es_mef_inputs("vignette")
+    assert [str(g) for g in d["genes"]] == list(cd.index)
+    got = api.scde_expression_difference(ifm, cd, prior, groups=groups, n_randomizations=100, context=ctx)
+    want = d["results"]
+    diffv = api.fold_change_grid(prior["x"].to_numpy())
+    step = (diffv[1] - diffv[0]) / np.log10(2.0)
+    dq = got[["lb", "mle", "ub"]].to_numpy() - want[:, :3]
+    n_off = int(np.sum(np.abs(dq) > 1e-9))
+    assert np.max(np.abs(dq)) <= step * 1.0001, "a bound or mle moved by more than one grid step"
+    assert n_off == 0, f"{n_off} of {dq.size} lb/mle/ub grid indices differ from the oracle (each by one step)"
+    _z_close(got["Z"].to_numpy(), want[:, 4])
+    _z_close(got["cZ"].to_numpy(), want[:, 5])
+    top = list(got.sort_values("Z", ascending=False).index[:6])
+    assert len(set(top) & {"Dppa5a", "Pou5f1", "Gm13242", "Tdh", "Ift46", "4930509G22Rik"}) >= 5  # vignette rows
+
+
+def test_knn_models_local_theta_full_path(ctx):
+    """12-column models (local theta fit + conc.a2, data/knn.rda) through scde.posteriors with per-cell modes -- the
+    pagoda.varnorm call shape (R/functions.R:1425)."""
+    knn = helpers.knn_models().iloc[:12]
+    rng = np.random.default_rng(8)
+    counts = np.asfortranarray(rng.negative_binomial(0.6, 0.02, size=(60, 12)).astype(np.int32))
+    counts[rng.random(counts.shape) < 0.4] = 0
+    prior = synth.make_prior(60)
+    mm, lt, sq = O.pack_models(knn)
+    mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+    flat, off, uci = O.unique_counts(counts)
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, 30, seed=1, returnpost=1, localtheta=lt, sqlogit=sq)
+    got = api.scde_posteriors(knn, counts, prior, n_randomizations=30, return_individual_posterior_modes=True, context=ctx)
+    ok, worst = _logp_close(got["jp"].to_numpy(), want["jp"])
+    assert ok, worst
+    np.testing.assert_array_equal(got["modes"].to_numpy(), want["modes"])
+
+
+def test_na_group_cells_and_per_gene_expectation(ctx):
+    w = _small_problem(40, 18)
+    codes = np.asarray(w.groups.codes).copy()
+    codes[[2, 11]] = -1  # NA: in neither group
+    groups = pd.Categorical.from_codes(codes, categories=["g1", "g2"])
+    ex = np.linspace(-1.5, 1.5, 40)
+    want = O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=50, seed=1, expectation=ex)
+    got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=groups, n_randomizations=50, expectation=ex,
+                                         context=ctx)
+    _z_close(got["Z"].to_numpy(), want["results"][:, 4])
+    np.testing.assert_allclose(got[["lb", "mle", "ub", "ce"]].to_numpy(), want["results"][:, :4], rtol=1e-12, atol=1e-300)
+
+
+def test_zero_base_equals_dense_form(ctx, monkeypatch):
+    """The zero-base contraction (visit only non-zero-count cells) against the dense form on the same device."""
+    w = synth.make_workload(3, n_genes=300, n_cells=120, seed=4)
+    a = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                       return_posteriors=True, context=ctx)
+    monkeypatch.setenv("SCDE_B200_NO_ZERO_BASE", "1")
+    b = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                       return_posteriors=True, context=ctx)
+    monkeypatch.delenv("SCDE_B200_NO_ZERO_BASE")
+    assert a["stats"]["contract_cells"] < 0.8 * b["stats"]["contract_cells"]
+    for lev in ("g1", "g2"):
+        ok, worst = _logp_close(a["joint.posteriors"][lev].to_numpy(), b["joint.posteriors"][lev].to_numpy(), rtol=1e-9)
+        assert ok, worst
+    assert np.array_equal(a["results"][["lb", "mle", "ub"]].to_numpy(), b["results"][["lb", "mle", "ub"]].to_numpy())
+
+
+def test_batch_config5_shape_against_oracle_subset(ctx):
+    w = synth.make_workload(5, n_genes=400, n_cells=300)
+    codes = np.asarray(w.groups.codes)
+    bcodes = np.asarray(w.batch.codes)
+    got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=w.batch, n_randomizations=100,
+                                         context=ctx)
+    sel = np.arange(0, 400, 25)
+    want = O.expression_difference(w.models, w.counts[sel], w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1,
+                                   batch_codes=bcodes)
+    for key in ("results", "batch.effect", "batch.adjusted"):
+        _z_close(got[key]["Z"].to_numpy()[sel], want[key][:, 4])
+        np.testing.assert_allclose(got[key][["lb", "mle", "ub"]].to_numpy()[sel], want[key][:, :3], rtol=1e-12, atol=1e-300)

@@ -488,3 +488,59 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
         return out
     bdiffp_rep.attrs["stats"] = res["stats"]
     return bdiffp_rep
+
+
+def scde_test_gene_expression_difference(gene, models: pd.DataFrame, counts: pd.DataFrame, prior, groups=None, batch=None,
+                                         batch_models=None, n_randomizations: int = 1000, show_plots: bool = False,
+                                         return_details: bool = False, verbose: bool = False, expectation=0,
+                                         n_cores: int = 1, seed: int = 1, context=None):
+    """Numeric core of scde.test.gene.expression.difference (R/functions.R:783-947; plotting is out of scope).
+
+    One gene, n.randomizations = 1e3 by default, individual posteriors kept (`return.details`).  Goes through the same
+    C-ABI entry points as the reference's R code does: two (or four) scde_posteriors calls, calculate.ratio.posterior,
+    quick.distribution.summary.
+    """
+    if gene not in counts.index:
+        _stop(f"specified gene ({gene}) is not found in the count data")
+    if batch_models is not None and batch_models is not models:
+        raise NotImplementedError("batch.models different from models")
+    sub = counts.loc[[gene], list(models.index)]
+    if groups is None:
+        groups = models.attrs.get("groups")
+        if groups is None:
+            _stop("groups factor is not provided, and models structure is lacking groups attribute")
+        groups = pd.Categorical(groups)
+    gcodes, glev = _named_factor(groups, models.index)
+    if len(glev) != 2:
+        _stop("wrong number of levels in the grouping factor (" + " ".join(map(str, glev)) + "), but must be two.")
+    ctx = context or _lib.default_context()
+    jpl = []
+    for lev in range(2):
+        ii = np.nonzero(gcodes == lev)[0]
+        jpl.append(scde_posteriors(models.iloc[ii], sub.iloc[:, ii], prior, n_randomizations=n_randomizations,
+                                   return_individual_posteriors=True, seed=seed, context=ctx))
+    diffv = fold_change_grid(np.asarray(prior["x"], dtype=np.float64))
+    bdiffp = calculate_ratio_posterior(jpl[0]["jp"], jpl[1]["jp"], prior, context=ctx)
+    rep = quick_distribution_summary(jpl[0]["jp"], jpl[1]["jp"], prior, expectation=expectation, genes=[gene], context=ctx)
+    correct_batch = False
+    if batch is not None:
+        bcodes, blev = _named_factor(batch, models.index)
+        correct_batch = len(blev) > 1
+    if correct_batch:
+        bjpl = []
+        for lev in range(2):
+            ii = np.nonzero(gcodes == lev)[0]
+            comp = np.bincount(bcodes[ii][bcodes[ii] >= 0], minlength=len(blev)).astype(np.int32)
+            bjpl.append(scde_posteriors(models, sub, prior, n_randomizations=n_randomizations, batch=batch,
+                                        composition=comp, seed=seed, context=ctx))
+        bb = calculate_ratio_posterior(bjpl[0], bjpl[1], prior, context=ctx)
+        uni = {"x": diffv, "y": np.full(len(diffv), 1.0 / len(diffv))}
+        abd = calculate_ratio_posterior(bdiffp, bb, uni, skip_prior_adjustment=True, context=ctx)
+        arep = quick_distribution_summary(bdiffp, bb, uni, expectation=expectation, skip_prior_adjustment=True,
+                                          genes=[gene], context=ctx)
+        if return_details:
+            return {"results": arep, "difference.posterior": abd, "results.nobatchcorrection": rep}
+        return arep
+    if return_details:
+        return {"results": rep, "difference.posterior": bdiffp, "posteriors": {glev[i]: jpl[i] for i in range(2)}}
+    return rep

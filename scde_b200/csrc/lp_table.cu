@@ -361,14 +361,14 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const in
 // with the row constant R = log(s/(s+x)) + stirlerr(n) - stirlerr(s) - stirlerr(n-s) - (log 2 pi + log s + log1p(-s/n))/2
 //                           - s log(s/n) - x log1p(-s/n).
 // Per element that is two FMAs, one exp (the drop-out term is cfp_k * exp(f - M)) and one log instead of two
-// divisions, three logs and two exps; the grid values live in registers (K <= 416 -> 13 per lane).
-constexpr int FAST_J = KP_TILED / 32;  // 13
+// divisions, three logs and two exps.
 
-__global__ void __launch_bounds__(ROW_WARPS * 32, 3)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
                     const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
+    __shared__ double s_rows[ROW_WARPS * KP_TILED];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
     // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
@@ -404,26 +404,25 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
             l2s = -log1p(s / x);
         }
         const double fp = d_dpois_log(x, lambda);
-        double nb[FAST_J];
+        // three sweeps over the grid through a per-warp shared-memory row (partially unrolled: fully unrolling 13
+        // inlined exp/log bodies made the kernel instruction-cache bound, "no instruction" was its top stall)
+        double *nb = s_rows + warp * KP_TILED;
         double vmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < FAST_J; ++j) {
-            const int k = lane + 32 * j;
-            double v = -INFINITY;
-            if (k < K) {
-                const double muv = mu[k];
-                const bool snap = (k < K - 1) ? (x > muv && x < mu[k + 1]) : (x > muv);
-                if (x > 0) {
-                    const double a1 = snap ? l1s : l1[k];
-                    const double a2 = snap ? l2s : l2[k];
-                    v = fma(x, a2, fma(s, a1, R));
-                } else {
-                    v = s * l1[k];
-                }
-                v += lcfpr[k];
-                vmax = fmax(vmax, v);
+#pragma unroll 4
+        for (int k = lane; k < K; k += 32) {
+            const double muv = mu[k];
+            const bool snap = (k < K - 1) ? (x > muv && x < mu[k + 1]) : (x > muv);
+            double v;
+            if (x > 0) {
+                const double a1 = snap ? l1s : l1[k];
+                const double a2 = snap ? l2s : l2[k];
+                v = fma(x, a2, fma(s, a1, R));
+            } else {
+                v = s * l1[k];
             }
-            nb[j] = v;
+            v += lcfpr[k];
+            vmax = fmax(vmax, v);
+            nb[k] = v;
         }
         vmax = warp_max(vmax);
         double maxp = vmax;
@@ -431,35 +430,28 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         if (maxp < alt) maxp = alt;
         const double E = exp(fp - maxp);
         double sum = 0;
-#pragma unroll
-        for (int j = 0; j < FAST_J; ++j) {
-            const int k = lane + 32 * j;
-            if (k < K) {
-                const double v = exp(nb[j] - maxp) + cfp[k] * E;
-                nb[j] = v;
-                sum += v;
-            }
+#pragma unroll 4
+        for (int k = lane; k < K; k += 32) {
+            const double v = exp(nb[k] - maxp) + cfp[k] * E;
+            nb[k] = v;
+            sum += v;
         }
         sum = warp_sum(sum);
         const double lsum = log(sum);
         double best = -INFINITY;
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
-#pragma unroll
-        for (int j = 0; j < FAST_J; ++j) {
-            const int k = lane + 32 * j;
-            if (k < K) {
-                double v = log(nb[j]) - lsum;
-                if (besti == 0x7fffffff || v > best) {
-                    best = v;
-                    besti = k;
-                }
-                if (v < sentinel) v = sentinel;
-                out[k] = zr ? v - zr[k] : v;
-            } else if (k < ld_table) {
-                out[k] = 0.0;
+#pragma unroll 4
+        for (int k = lane; k < K; k += 32) {
+            double v = log(nb[k]) - lsum;
+            if (besti == 0x7fffffff || v > best) {
+                best = v;
+                besti = k;
             }
+            if (v < sentinel) v = sentinel;
+            out[k] = zr ? v - zr[k] : v;
         }
+        for (int k = K + lane; k < ld_table; k += 32) out[k] = 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -469,6 +461,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                 besti = oi;
             }
         }
+        __syncwarp();
         if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
     }
 }

@@ -384,3 +384,23 @@ def test_batch_config5_shape_against_oracle_subset(ctx):
     for key in ("results", "batch.effect", "batch.adjusted"):
         _z_close(got[key]["Z"].to_numpy()[sel], want[key][:, 4])
         np.testing.assert_allclose(got[key][["lb", "mle", "ub"]].to_numpy()[sel], want[key][:, :3], rtol=1e-12, atol=1e-300)
+
+
+def test_single_gene_test_tdh(ctx):
+    """scde.test.gene.expression.difference("Tdh", ...) numeric core: G = 1, 1000 randomizations, individual posteriors
+    (tests/tests.R:46, vignettes/diffexp.md:139: lb 5.73 mle 8.04 ub 10.30 Z 7.15 with another libc's rand())."""
+    cd, ifm, prior, groups = helpers.es_mef_inputs("vignette")
+    got = api.scde_test_gene_expression_difference("Tdh", ifm, cd, prior, groups=groups, return_details=True, context=ctx)
+    codes = np.asarray(groups.codes)
+    want = O.expression_difference(ifm, cd.loc[["Tdh"]].to_numpy(), prior["x"].to_numpy(), prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=1000, seed=1)
+    r = got["results"]
+    np.testing.assert_allclose(r[["lb", "mle", "ub", "ce"]].to_numpy(), want["results"][:, :4], rtol=1e-12)
+    _z_close(r["Z"].to_numpy(), want["results"][:, 4])
+    assert abs(r["Z"].iloc[0] - r["cZ"].iloc[0]) < 1e-12  # one gene: BH leaves Z unchanged
+    ok, worst = _logp_close(got["difference.posterior"].to_numpy(), want["difference.posterior"])
+    assert ok, worst
+    step = 0.0397793
+    assert abs(r["lb"].iloc[0] - 5.728235) <= 5 * step and abs(r["ub"].iloc[0] - 10.30287) <= 5 * step
+    assert abs(r["Z"].iloc[0] - 7.151425) < 0.05
+    assert set(got["posteriors"]) == {"ESC", "MEF"} and len(got["posteriors"]["ESC"]["post"]) == 20

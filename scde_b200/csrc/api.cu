@@ -229,7 +229,7 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 }
 
 struct JointScratch {
-    DBuf<double> W, Z, zpart;
+    DBuf<double> W, Z, zpart, T;
     DBuf<int32_t> lst_row, lst_cell, lst_len, order;
     DBuf<unsigned long long> total;  // running sum of list lengths over the joints of one run
 };
@@ -296,8 +296,10 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     }
     e0 = tm ? tm->begin(st) : -1;
     int nl = 0;
-    if (tiled)
-        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, st, &nl));
+    if (tiled) {
+        SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
+        SCDE_CUDA(launch_contract_tiled(a, ctx->n_sm, scr.T.p, st, &nl));
+    }
     else
         SCDE_CUDA(launch_contract_generic(a, st, &nl));
     if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);

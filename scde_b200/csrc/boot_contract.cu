@@ -8,17 +8,17 @@
 // 1e-6 relative tolerance on log-posteriors leaves no room for a reduced-precision tensor-core split in this round;
 // tcgen05 has no FP64 kind).
 //
-// contract_mma_kernel (the sm_100a hot kernel)
-//   * one 2-CTA cluster per gene; CTA r owns grid points [208 r, 208 r + 208) and all 104 (100 + pad) boots, so
-//     its 208 x 104 FP64 accumulator tile (173 KB) lives entirely in the register file (12 warps x 168 regs);
+// contract_mma_kernel (the sm_100a hot kernel) + softmax_avg_kernel
+//   * persistent, one CTA per SM; a work item is (gene, grid half): the CTA owns grid points [208 h, 208 h + 208) x all
+//     104 (100 + pad) boots, so its 208 x 104 FP64 accumulator tile (173 KB) lives entirely in the register file
+//     (12 warps x 168 regs);
 //   * operands are staged through shared memory by the TMA engine: per stage of 8 list entries, 8 bulk copies of one
 //     gathered 1664-byte table row half each plus 8 bulk copies of the matching 864-byte W rows, completion signalled
-//     on an mbarrier (cp.async.bulk ... mbarrier::complete_tx); a 10-deep ring keeps ~160 KB in flight per SM;
+//     on an mbarrier (cp.async.bulk ... mbarrier::complete_tx); a 10-deep ring keeps ~200 KB in flight per SM;
 //   * the product runs on FP64 tensor-core tiles (mma.sync m8n8k4.f64), laid out so that every SM sub-partition
-//     carries the same number of tiles (85 of the 338 per CTA);
-//   * the soft-max over the grid is fused: per-boot max and sum are reduced with warp shuffles, across warps
-//     through shared memory and across the two CTAs through distributed shared memory, then every thread adds
-//     exp(T - max)/(sum * B) over its boots and adds into jp -- T never leaves the chip.
+//     carries the same number of tiles (85 of the 338 per CTA) and every warp 28 or 29;
+//   * items are independent: warps never synchronise with each other except through the ring's mbarriers;
+//   * softmax_avg_kernel then does the log-sum-exp over the grid with warp shuffles and the average over boots.
 // contract_generic_kernel handles any K / any B (used for K > 416 and as an on-device cross-check).
 #include "common.cuh"
 #include <cfloat>
@@ -217,6 +217,7 @@ constexpr int T_S = 8;          // list entries (cells) per stage
 constexpr int T_NS = 10;        // ring depth
 constexpr int T_PD = 8;         // prefetch distance in stages
 constexpr int T_WARPS = 12;
+constexpr int TILED_MAX_GENES_PER_LAUNCH = 32768;  // bounds the T scratch (346 KB per gene) to 11.3 GB
 constexpr int T_THREADS = T_WARPS * 32;
 constexpr int T_WS = WS_TILED;  // row stride of W in global and shared memory (108 doubles, see below)
 constexpr uint32_t T_STAGE_BYTES = (T_S * T_KH + T_S * T_WS) * 8u;  // bytes the TMA engine delivers per stage (20224)
@@ -227,12 +228,9 @@ struct TiledParams {
     int64_t ld_lst;
     const double *W;  // this pass: rows [n_w_rows][108], columns [0, 104) real
     const double *Z;  // this pass: [104][416] initial value of T (zero-base form) or NULL
-    int n_boot_pass;  // real boots in this pass (<= 104)
-    double scale;
-    int n_genes, K;
-    double *jp;  // zero-filled by the caller; every pass adds into it
-    int64_t ld_jp;
-    int debug;  // timing experiments only (SCDE_B200_DEBUG_CONTRACT): 1 = no DMMA, 2 = no table-row copies, 4 = no epilogue
+    double *T;        // [n_pos][104][416]: T[b, k] of the gene at position `pos` of `order` (this launch's chunk)
+    int n_pos;        // genes in this launch: positions [0, n_pos) of `order`
+    int debug;  // timing experiments only (SCDE_B200_DEBUG_CONTRACT): 1 = no DMMA, 2 = no table-row copies
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -259,9 +257,6 @@ constexpr int M_NEX = 3;                                    // at most three til
 
 struct MmaSmem {
     double stage[T_NS][M_STAGE_DOUBLES];
-    double red[T_WARPS][T_WP];
-    double xmax[2][T_WP];
-    double xsum[2][T_WP];
     uint64_t full[T_NS];
     uint64_t empty[T_NS];
 };
@@ -272,8 +267,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int warp, int lane, uint32_t rank,
-                                        int n_my_genes) {
+// Work items are (gene position, grid half): item i = 2 * pos + half; CTA c walks items c, c + gridDim.x, ... (the two
+// halves of a gene run on neighbouring CTAs at the same time, so their W rows and list entries meet in L2).  There
+// is no synchronisation between items: a warp stores its accumulator tiles to T and moves on, the soft-max over the
+// grid and the average over boots happen in softmax_avg_kernel.  (An earlier version fused them here with a 2-CTA
+// cluster and distributed shared memory; its two cluster barriers and two CTA barriers per gene re-synchronised all
+// warps 60 000 times per launch and cost ~8 % of the kernel, more than writing T once and reading it back: 21 GB of the
+// 6.4 TB/s HBM per joint.)
+__device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int warp, int lane) {
     const int g = lane >> 2, t = lane & 3;
     const int smsp = warp & 3, slot = warp >> 2;
     const int m0 = smsp * 6 + slot * 2;   // first of the two full grid tiles
@@ -282,39 +283,37 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
     // as 2/2/2, so the three warps of a sub-partition carry 28/28/29 (or 28/28/28) tiles
     const int nx0 = (smsp & 1) ? 7 + 2 * slot : 2 * slot;
     const int nex = ((smsp & 1) == 0 && slot == 2) ? 3 : 2;
-    const int kbase = rank * T_KH;
-    const uint32_t peer = rank ^ 1u;
-    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
-    auto gene_of = [&](int gi) -> int64_t {
-        const int64_t o = (int64_t)cid + (int64_t)gi * ncl;
-        return p.order ? p.order[o] : o;
-    };
-    auto stages_of = [&](int gi) -> int { return (p.lst_len[gene_of(gi)] + T_S - 1) / T_S; };
+    const int n_items = 2 * p.n_pos;
+    const int n_my = ((int)blockIdx.x < n_items) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto item_of = [&](int i) -> int { return (int)blockIdx.x + i * (int)gridDim.x; };
+    auto gene_of = [&](int item) -> int64_t { return p.order ? p.order[item >> 1] : (item >> 1); };
+    auto stages_of = [&](int i) -> int { return (p.lst_len[gene_of(item_of(i))] + T_S - 1) / T_S; };
 
     // ---- producer duty ----
-    // Consumption is a stream of stages q = 0, 1, 2, ... over this cluster's genes; stage q + T_PD is issued at consumer
+    // Consumption is a stream of stages q = 0, 1, 2, ... over this CTA's items; stage q + T_PD is issued at consumer
     // iteration q by warp (q mod 12): the duty (an empty-slot wait, sixteen TMA bulk copies) rotates, so no warp becomes
     // the straggler of its sub-partition (a fixed producer warp cost 25 % of the kernel: it was also a consumer and fell
-    // a third of a stage behind every stage).  Every warp keeps its own cursor (gene ordinal, stage within gene) over
+    // a third of a stage behind every stage).  Every warp keeps its own cursor (item ordinal, stage within item) over
     // the stages it will issue -- they are 12 apart -- and fetches the list entries of its next duty into registers
     // right after the current one, so issuing never waits on a dependent global load.
-    int p_gi = 0, p_cb = T_PD + warp, p_spg = n_my_genes > 0 ? stages_of(0) : 0;
+    int p_i = 0, p_cb = T_PD + warp, p_spg = n_my > 0 ? stages_of(0) : 0;
     int32_t p_ent = 0;  // lanes 0..7: table row of entry `lane`; lanes 8..15: W row of entry `lane - 8`
+    int p_kbase = 0;    // grid half of the cursor's item
     auto normalize = [&]() {
-        while (p_gi < n_my_genes && p_cb >= p_spg) {
+        while (p_i < n_my && p_cb >= p_spg) {
             p_cb -= p_spg;
-            ++p_gi;
-            p_spg = p_gi < n_my_genes ? stages_of(p_gi) : 0;
+            ++p_i;
+            p_spg = p_i < n_my ? stages_of(p_i) : 0;
         }
     };
-    auto fetch_entries = [&](int gi, int cb) -> int32_t {
-        if (lane < 2 * T_S && gi < n_my_genes) {
-            const int64_t o = gene_of(gi) * p.ld_lst + (int64_t)cb * T_S + (lane & (T_S - 1));
+    auto fetch_entries = [&](int i, int cb) -> int32_t {
+        if (lane < 2 * T_S && i < n_my) {
+            const int64_t o = gene_of(item_of(i)) * p.ld_lst + (int64_t)cb * T_S + (lane & (T_S - 1));
             return lane < T_S ? p.lst_row[o] : p.lst_cell[o];
         }
         return 0;
     };
-    auto issue = [&](int64_t stage_no, int32_t ent) {  // one warp: TMA copies of stage `stage_no` (entries in `ent`)
+    auto issue = [&](int64_t stage_no, int32_t ent, int kbase) {  // one warp: TMA copies of stage `stage_no`
         const int sl = (int)(stage_no % T_NS);
         const uint32_t fill = (uint32_t)(stage_no / T_NS);
         if (fill > 0) mbar_wait(&sm.empty[sl], (fill - 1) & 1u);
@@ -331,30 +330,27 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
         }
     };
     if (warp == 0) {  // prologue: stages 0 .. T_PD-1
-        int gi = 0, cb = 0, spg = p_spg;
-        for (int i = 0; i < T_PD; ++i) {
-            while (gi < n_my_genes && cb >= spg) {
+        int i = 0, cb = 0, spg = p_spg;
+        for (int st = 0; st < T_PD; ++st) {
+            while (i < n_my && cb >= spg) {
                 cb -= spg;
-                ++gi;
-                spg = gi < n_my_genes ? stages_of(gi) : 0;
+                ++i;
+                spg = i < n_my ? stages_of(i) : 0;
             }
-            if (gi >= n_my_genes) break;
-            issue(i, fetch_entries(gi, cb));
+            if (i >= n_my) break;
+            issue(st, fetch_entries(i, cb), (item_of(i) & 1) * T_KH);
             ++cb;
         }
     }
     normalize();
-    p_ent = fetch_entries(p_gi, p_cb);
-
-    // validity of this thread's grid points
-    const bool kv0 = (kbase + (m0 + 0) * 8 + g) < p.K;
-    const bool kv1 = (kbase + (m0 + 1) * 8 + g) < p.K;
-    const bool kvx = (kbase + mx * 8 + g) < p.K;
+    p_ent = fetch_entries(p_i, p_cb);
+    p_kbase = p_i < n_my ? (item_of(p_i) & 1) * T_KH : 0;
 
     int64_t q = 0;
-    for (int gi = 0; gi < n_my_genes; ++gi) {
-        const int64_t gene = gene_of(gi);
-        const int spg = (p.lst_len[gene] + T_S - 1) / T_S;
+    for (int it = 0; it < n_my; ++it) {
+        const int item = item_of(it);
+        const int kbase = (item & 1) * T_KH;
+        const int spg = (p.lst_len[gene_of(item)] + T_S - 1) / T_S;
         double acc[2][M_NT][2];
         double ex[M_NEX][2];
         if (p.Z) {  // zero-base form: T starts from the per-randomization sum of the zero-count rows
@@ -382,11 +378,12 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
         }
 
         for (int cb = 0; cb < spg; ++cb, ++q) {
-            if (warp == (int)(q % T_WARPS) && p_gi < n_my_genes) {
-                issue(q + T_PD, p_ent);
+            if (warp == (int)(q % T_WARPS) && p_i < n_my) {
+                issue(q + T_PD, p_ent, p_kbase);
                 p_cb += T_WARPS;
                 normalize();
-                p_ent = fetch_entries(p_gi, p_cb);
+                p_ent = fetch_entries(p_i, p_cb);
+                p_kbase = p_i < n_my ? (item_of(p_i) & 1) * T_KH : 0;
             }
             const int sl = (int)(q % T_NS);
             mbar_wait(&sm.full[sl], (uint32_t)(q / T_NS) & 1u);
@@ -416,144 +413,28 @@ __device__ __forceinline__ void run_mma(const TiledParams &p, MmaSmem &sm, int w
             if (lane == 0) mbar_arrive(&sm.empty[sl]);
         }
 
-        if (p.debug & 4) continue;
-        // ---------------- fused soft-max over the grid and average over boots ----------------
-        // thread holds, per tile, C[m = g][n = 2t + i]: grid point (tile*8 + g), boot (nt*8 + 2t + i)
-        // (1) per-boot maximum over this CTA's grid points
+        // store the accumulator tiles: thread holds C[m = g][n = 2t + i] of each tile, i.e. T[boot nt*8+2t+i][grid tile*8+g]
+        double *Tg = p.T + (int64_t)(item >> 1) * (T_WP * KP_TILED) + kbase + g;
 #pragma unroll
-        for (int nt = 0; nt < M_NT; ++nt) {
+        for (int nt = 0; nt < M_NT; ++nt)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                double m = -INFINITY;
-                if (kv0) m = fmax(m, acc[0][nt][i]);
-                if (kv1) m = fmax(m, acc[1][nt][i]);
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                if (g == 0) sm.red[warp][nt * 8 + 2 * t + i] = m;
+                double *row = Tg + (int64_t)(nt * 8 + 2 * t + i) * KP_TILED;
+                row[(m0 + 0) * 8] = acc[0][nt][i];
+                row[(m0 + 1) * 8] = acc[1][nt][i];
             }
-        }
-        // the warp's tiles of the shared grid tile: boots (nx0 + j) * 8 + 2t + i; merged into red[] by the g == 0 lanes
 #pragma unroll
-        for (int j = 0; j < M_NEX; ++j) {
+        for (int j = 0; j < M_NEX; ++j)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                double m = (kvx && j < nex) ? ex[j][i] : -INFINITY;
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                if (g == 0 && j < nex) {
-                    double *slotp = &sm.red[warp][(nx0 + j) * 8 + 2 * t + i];
-                    *slotp = fmax(*slotp, m);
-                }
-            }
-        }
-        named_bar_sync(1, T_THREADS);
-        if (threadIdx.x < T_WP) {
-            double m = sm.red[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < T_WARPS; ++w) m = fmax(m, sm.red[w][threadIdx.x]);
-            sm.xmax[0][threadIdx.x] = m;
-            st_peer_f64(&sm.xmax[1][threadIdx.x], peer, m);
-        }
-        cluster_arrive();
-        cluster_wait();
-        // (2) exponentials and per-boot sums
-#pragma unroll
-        for (int nt = 0; nt < M_NT; ++nt) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int b = nt * 8 + 2 * t + i;
-                const double M = fmax(sm.xmax[0][b], sm.xmax[1][b]);
-                double e0 = kv0 ? exp(acc[0][nt][i] - M) : 0.0;
-                double e1 = kv1 ? exp(acc[1][nt][i] - M) : 0.0;
-                acc[0][nt][i] = e0;
-                acc[1][nt][i] = e1;
-                double s = e0 + e1;
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if (g == 0) sm.red[warp][b] = s;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < M_NEX; ++j) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int b = (nx0 + (j < nex ? j : 0)) * 8 + 2 * t + i;
-                const double M = fmax(sm.xmax[0][b], sm.xmax[1][b]);
-                double e2 = (kvx && j < nex) ? exp(ex[j][i] - M) : 0.0;
-                ex[j][i] = e2;
-                double s = e2;
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if (g == 0 && j < nex) sm.red[warp][b] += s;
-            }
-        }
-        named_bar_sync(1, T_THREADS);
-        if (threadIdx.x < T_WP) {
-            double s = sm.red[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < T_WARPS; ++w) s += sm.red[w][threadIdx.x];
-            sm.xsum[0][threadIdx.x] = s;
-            st_peer_f64(&sm.xsum[1][threadIdx.x], peer, s);
-        }
-        cluster_arrive();
-        cluster_wait();
-        // (3) jp[g, k] += sum_b e[k, b] / (S_b * scale)
-        double r0 = 0.0, r1 = 0.0, rx = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < M_NT; ++nt) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int b = nt * 8 + 2 * t + i;
-                if (b < p.n_boot_pass) {
-                    // rank-0 value first so both CTAs add in the same order
-                    const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
-                    const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
-                    const double inv = 1.0 / ((s0 + s1) * p.scale);  // e * (1/den): e is often denormal, which
-                    r0 += acc[0][nt][i] * inv;                        // sends a true division down its slow path
-                    r1 += acc[1][nt][i] * inv;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < M_NEX; ++j) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int b = (nx0 + (j < nex ? j : 0)) * 8 + 2 * t + i;
-                if (j < nex && b < p.n_boot_pass) {
-                    const double s0 = rank == 0 ? sm.xsum[0][b] : sm.xsum[1][b];
-                    const double s1 = rank == 0 ? sm.xsum[1][b] : sm.xsum[0][b];
-                    rx += ex[j][i] * (1.0 / ((s0 + s1) * p.scale));
-                }
-            }
-        }
-        r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
-        r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
-        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
-        rx += __shfl_xor_sync(0xffffffffu, rx, 1);
-        rx += __shfl_xor_sync(0xffffffffu, rx, 2);
-        if (t == 0) {
-            // jp is zero-filled by the caller.  The shared grid tile receives one partial sum per owning warp: the
-            // order of these (up to six) atomic adds is not fixed, so jp at those 8 + 8 grid points may differ in the
-            // last bit from run to run (same as any other summation order)
-            double *out = p.jp + gene * p.ld_jp + kbase;
-            if (kv0) atomicAdd(out + (m0 + 0) * 8 + g, r0);
-            if (kv1) atomicAdd(out + (m0 + 1) * 8 + g, r1);
-            if (kvx) atomicAdd(out + mx * 8 + g, rx);
-        }
+            for (int i = 0; i < 2; ++i)
+                if (j < nex) Tg[(int64_t)((nx0 + j) * 8 + 2 * t + i) * KP_TILED + mx * 8] = ex[j][i];
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contract_mma_kernel(const TiledParams p) {
+__global__ void __launch_bounds__(T_THREADS, 1) contract_mma_kernel(const TiledParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MmaSmem &sm = *reinterpret_cast<MmaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t cid = cluster_id_x(), ncl = n_clusters_x();
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_NS; ++s) {
             mbar_init(&sm.full[s], 1);
@@ -562,14 +443,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1) contra
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // both CTAs must be resident before any DSMEM store
-    cluster_arrive();
-    cluster_wait();
-    const int n_my_genes = ((int)cid < p.n_genes) ? (p.n_genes - (int)cid + (int)ncl - 1) / (int)ncl : 0;
-    run_mma(p, sm, warp, lane, rank, n_my_genes);
-    // keep this CTA's shared memory alive until the peer's last DSMEM store has landed
-    cluster_arrive();
-    cluster_wait();
+    run_mma(p, sm, warp, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax_avg_kernel: jp[gene, k] (+)= sum_b exp(T[b, k] - max_k T[b, :]) / (sum_k exp(...) * scale)
+// (src/jpmatLogBoot.cpp:264-269).  One CTA per gene.  Phase A: one warp per boot row -- log-sum-exp pieces by warp
+// shuffles, exponentials written back over T (the 346 KB tile is L2-resident).  Phase B: one thread per grid point adds
+// the boots in ascending order, as the reference does.
+constexpr int SM_THREADS = 256;
+__global__ void __launch_bounds__(SM_THREADS)
+softmax_avg_kernel(double *__restrict__ T, const int32_t *__restrict__ order, int K, int n_boot_pass, double scale,
+                   double *__restrict__ jp, int64_t ld_jp, int accumulate) {
+    __shared__ double s_inv[T_WP];
+    const int pos = blockIdx.x;
+    const int64_t gene = order ? order[pos] : pos;
+    double *Tg = T + (int64_t)pos * (T_WP * KP_TILED);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < n_boot_pass; b += SM_THREADS / 32) {
+        double *row = Tg + (int64_t)b * KP_TILED;
+        double v[KP_TILED / 32];
+        double m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KP_TILED / 32; ++j) {
+            const int k = lane + 32 * j;
+            v[j] = k < K ? row[k] : -INFINITY;
+            m = fmax(m, v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP_TILED / 32; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                const double e = exp(v[j] - m);
+                row[k] = e;
+                sum += e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) s_inv[b] = 1.0 / (sum * scale);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += SM_THREADS) {
+        double r = 0.0;
+        for (int b = 0; b < n_boot_pass; ++b) r += Tg[(int64_t)b * KP_TILED + k] * s_inv[b];
+        double *out = jp + gene * ld_jp + k;
+        *out = accumulate ? *out + r : r;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -906,7 +829,12 @@ bool contract_tiled_supported(const ContractArgs &a) {
     return a.K <= KP_TILED && a.ld_table == KP_TILED && a.n_boot >= 1 && (a.lists.ld % 8) == 0;
 }
 
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches) {
+size_t contract_tiled_scratch_doubles(int n_genes) {
+    const int chunk = n_genes < TILED_MAX_GENES_PER_LAUNCH ? n_genes : TILED_MAX_GENES_PER_LAUNCH;
+    return (size_t)chunk * WP_TILED * KP_TILED;
+}
+
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches) {
     if (a.n_genes <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
@@ -915,32 +843,34 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int clusters = n_sm / 2;
-    if (clusters < 1) clusters = 1;
-    if (clusters > a.n_genes) clusters = a.n_genes;
     const int passes = (a.n_boot + WP_TILED - 1) / WP_TILED;
-    for (int ps = 0; ps < passes; ++ps) {
-        TiledParams p;
-        p.table = a.table;
-        p.lst_row = a.lists.row;
-        p.lst_cell = a.lists.cell;
-        p.lst_len = a.lists.len;
-        p.order = a.lists.order;
-        p.ld_lst = a.lists.ld;
-        p.W = a.W + (size_t)ps * a.n_w_rows * WS_TILED;
-        p.Z = a.Z ? a.Z + (size_t)ps * WP_TILED * KP_TILED : nullptr;
-        p.n_boot_pass = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;
-        p.scale = a.scale;
-        p.n_genes = a.n_genes;
-        p.K = a.K;
-        p.jp = a.jp;
-        p.ld_jp = a.ld_jp;
-        const char *dbg = getenv("SCDE_B200_DEBUG_CONTRACT");
-        p.debug = dbg ? atoi(dbg) : 0;
-        contract_mma_kernel<<<2 * clusters, T_THREADS, sizeof(MmaSmem), st>>>(p);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (n_launches) ++*n_launches;
+    const char *dbg = getenv("SCDE_B200_DEBUG_CONTRACT");
+    for (int g0 = 0; g0 < a.n_genes; g0 += TILED_MAX_GENES_PER_LAUNCH) {
+        const int n_pos = (a.n_genes - g0) < TILED_MAX_GENES_PER_LAUNCH ? (a.n_genes - g0) : TILED_MAX_GENES_PER_LAUNCH;
+        for (int ps = 0; ps < passes; ++ps) {
+            TiledParams p;
+            p.table = a.table;
+            p.lst_row = a.lists.row;
+            p.lst_cell = a.lists.cell;
+            p.lst_len = a.lists.len;
+            p.order = a.lists.order + g0;
+            p.ld_lst = a.lists.ld;
+            p.W = a.W + (size_t)ps * a.n_w_rows * WS_TILED;
+            p.Z = a.Z ? a.Z + (size_t)ps * WP_TILED * KP_TILED : nullptr;
+            p.T = t_scratch;
+            p.n_pos = n_pos;
+            p.debug = dbg ? atoi(dbg) : 0;
+            int grid = n_sm < 2 * n_pos ? n_sm : 2 * n_pos;
+            contract_mma_kernel<<<grid, T_THREADS, sizeof(MmaSmem), st>>>(p);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            const int nb = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;
+            softmax_avg_kernel<<<n_pos, SM_THREADS, 0, st>>>(t_scratch, a.lists.order + g0, a.K, nb, a.scale, a.jp, a.ld_jp,
+                                                             ps > 0);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            if (n_launches) *n_launches += 2;
+        }
     }
     return cudaSuccess;
 }

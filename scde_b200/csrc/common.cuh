@@ -104,8 +104,10 @@ struct ContractArgs {
     int ld_jp;
 };
 cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches);
-// requires K <= 416 and ld_table == 416
-cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, cudaStream_t st, int *n_launches);
+// requires K <= 416 and ld_table == 416; t_scratch holds contract_tiled_scratch_doubles(n_genes) doubles (the raw
+// T[boot, grid] tiles between the contraction and the soft-max kernel)
+size_t contract_tiled_scratch_doubles(int n_genes);
+cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches);
 bool contract_tiled_supported(const ContractArgs &a);
 // ensemble form (src/jpmatLogBoot.cpp:224-237), all cells of the table
 cudaError_t launch_ensemble(const double *table, int ld_table, const int32_t *ridx, int ld_ridx, int n_cells, int n_genes,

@@ -133,7 +133,7 @@ struct LpTable {
     int64_t n_rows = 0;
     double sentinel = 0;
     DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
-    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2;
+    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc;
     bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
     // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
     // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
@@ -167,7 +167,9 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
         SCDE_CUDA(t.cfp.ensure(cl));
         SCDE_CUDA(t.l1.ensure(cl));
         SCDE_CUDA(t.l2.ensure(cl));
+        SCDE_CUDA(t.rowc.ensure((size_t)4 * t.n_rows));
     }
+    void *rowc = fast ? (void *)t.rowc.p : nullptr;
     CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
                   fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr};
     if (t.zero_base) {
@@ -178,17 +180,21 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     int nl = 3;
     SCDE_CUDA(launch_cell_prep(models_dev, ld_models, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
     SCDE_CUDA(launch_row_cell(t.row_off.p, t.n_cells, t.row_cell.p, st));
+    if (fast) {
+        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_cell.p, t.row_x.p, t.n_rows, rowc, st));
+        ++nl;
+    }
     if (t.zero_base) {
         SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, rowc, st));
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, rowc, st));
         nl += 3;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, rowc, st));
     }
     if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, nl);
     return SCDE_B200_OK;

@@ -50,7 +50,10 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, cudaStream_t st);
+                           const int32_t *zero_row, const int32_t *based, void *row_const, cudaStream_t st);
+// per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
+cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
+                              int64_t n_rows, void *row_const, cudaStream_t st);
 
 // ---- dedup.cu ------------------------------------------------------------------------------------
 // counts: column-major with leading dimension ld_counts; genes [g0, g0+G) of n_cells columns.

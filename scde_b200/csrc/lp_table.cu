@@ -363,9 +363,32 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const in
 // Per element that is two FMAs, one exp (the drop-out term is cfp_k * exp(f - M)) and one log instead of two
 // divisions, three logs and two exps.
 
+// Row constants, one THREAD per row (the warp-per-row kernel below would execute this scalar code once per warp, i.e.
+// 32 times more instruction issues): R(x, s), the "snap" pair log p / log q at mu~ = x, and the Poisson term.
+__global__ void row_const_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_cell,
+                                 const int32_t *__restrict__ row_x, int64_t n_rows, double4 *__restrict__ rowc) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int c = row_cell[row];
+    const double x = (double)row_x[row];
+    const double s = models[(size_t)5 * ldm + c];
+    const double lambda = exp(models[(size_t)2 * ldm + c]);
+    double R = 0.0, l1s = 0.0, l2s = 0.0;
+    if (x > 0) {
+        const double n = x + s, nmx = n - s;
+        const double c1 = d_stirlerr(n) - d_stirlerr(s) - d_stirlerr(nmx);
+        const double half_lf = 0.5 * (LN_2PI + log(s) + log1p(-s / n));
+        R = log(s / (s + x)) + (c1 - half_lf) - (s * log(s / n) + nmx * log1p(-s / n));
+        l1s = -log1p(x / s);  // "snap": mu~ = x
+        l2s = -log1p(s / x);
+    }
+    rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
+}
+
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
-                    const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, double sentinel,
+                    const int32_t *__restrict__ row_x, const double4 *__restrict__ rowc, int64_t n_rows, CellPrep prep,
+                    int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
     __shared__ double s_rows[ROW_WARPS * KP_TILED];
@@ -389,21 +412,11 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
         const double x = (double)row_x[row];
         const double s = models[(size_t)5 * ldm + c];
-        const double lambda = exp(models[(size_t)2 * ldm + c]);
         const size_t base = (size_t)c * prep.ld;
         const double *mu = prep.mu + base, *l1 = prep.l1 + base, *l2 = prep.l2 + base;
         const double *lcfpr = prep.lcfpr + base, *cfp = prep.cfp + base;
-        // row constants
-        double R = 0.0, l1s = 0.0, l2s = 0.0;
-        if (x > 0) {
-            const double n = x + s, nmx = n - s;
-            const double c1 = d_stirlerr(n) - d_stirlerr(s) - d_stirlerr(nmx);
-            const double half_lf = 0.5 * (LN_2PI + log(s) + log1p(-s / n));
-            R = log(s / (s + x)) + (c1 - half_lf) - (s * log(s / n) + nmx * log1p(-s / n));
-            l1s = -log1p(x / s);  // "snap": mu~ = x
-            l2s = -log1p(s / x);
-        }
-        const double fp = d_dpois_log(x, lambda);
+        const double4 rc = rowc[row];  // row constants from row_const_kernel
+        const double R = rc.x, l1s = rc.y, l2s = rc.z, fp = rc.w;
         // three sweeps over the grid through a per-warp shared-memory row (partially unrolled: fully unrolling 13
         // inlined exp/log bodies made the kernel instruction-cache bound, "no instruction" was its top stall)
         double *nb = s_rows + warp * KP_TILED;
@@ -481,6 +494,14 @@ cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_ce
     return cudaGetLastError();
 }
 
+cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
+                              int64_t n_rows, void *row_const, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    row_const_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(models, ld_models, row_cell, row_x, n_rows,
+                                                                       (double4 *)row_const);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
     zero_rows_kernel<<<n_cells, 128, 0, st>>>(row_off, row_x, n_cells, zero_row);
@@ -497,16 +518,17 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, cudaStream_t st) {
+                           const int32_t *zero_row, const int32_t *based, void *row_const, cudaStream_t st) {
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
     if (n_items <= 0) return cudaSuccess;
     int64_t blocks = (n_items + ROW_WARPS - 1) / ROW_WARPS;
     const int64_t cap = 148 * 64;  // grid-stride beyond this
     if (blocks > cap) blocks = cap;
-    if (prep.cfp && !local_theta && K <= KP_TILED && ld_table >= K) {
+    if (prep.cfp && row_const && !local_theta && K <= KP_TILED && ld_table >= K) {
         lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x,
-                                                                        n_rows, prep, K, sentinel, table, ld_table,
-                                                                        row_mode, which, zero_row, based);
+                                                                        (const double4 *)row_const, n_rows, prep, K,
+                                                                        sentinel, table, ld_table, row_mode, which,
+                                                                        zero_row, based);
         return cudaGetLastError();
     }
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);

@@ -404,3 +404,48 @@ def test_single_gene_test_tdh(ctx):
     assert abs(r["lb"].iloc[0] - 5.728235) <= 5 * step and abs(r["ub"].iloc[0] - 10.30287) <= 5 * step
     assert abs(r["Z"].iloc[0] - 7.151425) < 0.05
     assert set(got["posteriors"]) == {"ESC", "MEF"} and len(got["posteriors"]["ESC"]["post"]) == 20
+
+
+@pytest.mark.parametrize("length_out", [200, 500])
+def test_other_grid_sizes(ctx, length_out):
+    """K = 201 (tiled kernel, half-empty tiles) and K = 501 (> 416: generic contraction kernel, general table stride)."""
+    w = _small_problem(45, 14)
+    prior = synth.make_prior(45, length_out=length_out)
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, w.counts, prior["x"].to_numpy(), prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=30, seed=1)
+    got = api.scde_expression_difference(w.models, w.counts, prior, groups=w.groups, n_randomizations=30,
+                                         return_posteriors=True, context=ctx)
+    ok, worst = _logp_close(got["difference.posterior"].to_numpy(), want["difference.posterior"])
+    assert ok, worst
+    _z_close(got["results"]["Z"].to_numpy(), want["results"][:, 4])
+    np.testing.assert_allclose(got["results"][["lb", "mle", "ub"]].to_numpy(), want["results"][:, :3], rtol=1e-12, atol=1e-300)
+
+
+def test_all_zero_and_constant_genes(ctx):
+    """Genes whose counts are all zero (empty entry list: T is the base sum alone) and genes with one non-zero cell."""
+    w = _small_problem(30, 16)
+    counts = w.counts.copy()
+    counts[0, :] = 0
+    counts[1, :] = 0
+    counts[1, 5] = 7
+    counts[2, :] = 3
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1)
+    got = api.scde_expression_difference(w.models, counts, w.prior, groups=w.groups, n_randomizations=100,
+                                         return_posteriors=True, context=ctx)
+    for i, lev in enumerate(["g1", "g2"]):
+        ok, worst = _logp_close(got["joint.posteriors"][lev].to_numpy(), want["joint.posteriors"][i])
+        assert ok, (lev, worst)
+    _z_close(got["results"]["Z"].to_numpy(), want["results"][:, 4])
+
+
+def test_single_randomization_and_single_cell_groups(ctx):
+    w = _small_problem(12, 2)
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=1, seed=1)
+    got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=1, context=ctx)
+    _z_close(got["Z"].to_numpy(), want["results"][:, 4])
+    np.testing.assert_allclose(got[["lb", "mle", "ub"]].to_numpy(), want["results"][:, :3], rtol=1e-12, atol=1e-300)

@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--genes", type=int, default=30000)
     ap.add_argument("--cells", type=int, default=10000)
     ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5])
-    ap.add_argument("--cpu-sample-genes-per-thread", type=int, default=4)
+    ap.add_argument("--cpu-sample-genes-per-thread", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")

@@ -40,6 +40,33 @@ __global__ void dmma_kernel(double *sink, int iters) {
     if (s == 123.456) sink[0] = s;
 }
 
+// DMMA and DFMA issued from the same warp: do the FP64 tensor sub-pipe and the FP64 vector pipe run concurrently?
+template <int TILES, int CHAINS>
+__global__ void dmma_dfma_kernel(double *sink, int iters) {
+    double c[TILES][2], f[CHAINS];
+#pragma unroll
+    for (int i = 0; i < TILES; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) f[i] = threadIdx.x * 1e-9 + i;
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    const double x = 1.0000000001, y = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < TILES; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int j = 0; j < CHAINS / TILES; ++j) f[i * (CHAINS / TILES) + j] = fma(f[i * (CHAINS / TILES) + j], x, y);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < TILES; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += f[i];
+    if (s == 123.456) sink[0] = s;
+}
+
 // LDS.128 patterns: mode 0 = all lanes same address (broadcast), 1 = 8 distinct 16B chunks (lane>>2), 2 = 32 distinct
 __global__ void lds_kernel(double *sink, int iters, int mode) {
     __shared__ double2 buf[1024];
@@ -123,6 +150,23 @@ int main() {
         DMMA_CASE(42, 256)
         DMMA_CASE(26, 128)
         DMMA_CASE(8, 1024)
+    }
+    {   // both FP64 pipes at once, from the same warps: per loop trip TILES DMMA (512 flop each) + CHAINS DFMA (64 flop each)
+        const int iters = 4000;
+#define MIX_CASE(TILES, CHAINS)                                                                                    \
+        for (int rep = 0; rep < 3; ++rep) {                                                                       \
+            cudaEventRecord(e0);                                                                                  \
+            dmma_dfma_kernel<TILES, CHAINS><<<sms, 384>>>(sink, iters);                                           \
+            cudaEventRecord(e1);                                                                                  \
+            CK(cudaEventSynchronize(e1));                                                                         \
+            cudaEventElapsedTime(&ms, e0, e1);                                                                    \
+        }                                                                                                         \
+        printf(", \"mix_dmma%d_dfma%d_tflops\": %.3f", TILES, CHAINS,                                              \
+               (512.0 * TILES + 64.0 * CHAINS) * iters * 12.0 * sms / (ms * 1e-3) / 1e12);
+        MIX_CASE(16, 16)
+        MIX_CASE(16, 32)
+        MIX_CASE(16, 64)
+        MIX_CASE(16, 128)
     }
     for (int mode = 0; mode < 3; ++mode) {
         const int iters = 20000, blocks = sms, thr = 512;

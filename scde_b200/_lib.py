@@ -67,7 +67,7 @@ EXPORTED = [
     "scde_b200_jpmat_log_batch_boot", "scde_b200_mat_slide_mult", "scde_b200_ratio_posterior_summary",
     "scde_b200_bh_cz", "scde_b200_expression_difference", "scde_b200_diff_upload", "scde_b200_diff_run",
     "scde_b200_diff_download", "scde_b200_diff_free", "scde_b200_expression_magnitude", "scde_b200_cell_table",
-    "scde_b200_measure_fp64_peak", "scde_b200_set_contract_kernel",
+    "scde_b200_measure_fp64_peak", "scde_b200_set_contract_kernel", "scde_b200_probe_contract_i8",
 ]
 
 _lib = None

@@ -119,7 +119,8 @@ struct scde_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int n_sm = 148;
-    int contract_kernel = 0;  // 0 auto, 1 generic, 2 tiled (DMMA tiles)
+    int contract_kernel = 0;  // 0 auto (tcgen05 int8 where supported), 1 generic, 2 tiled FP64 (DMMA), 3 tcgen05 int8
+    DBuf<int32_t> flags;      // device status word of the int8 path: 1 = a multiplicity > 127, 2 = kernel watchdog
     DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
     bool ws_busy = false;
 };
@@ -134,6 +135,8 @@ struct LpTable {
     double sentinel = 0;
     DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
     DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc;
+    DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
+    bool want_q = false, has_q = false;
     bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
     // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
     // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
@@ -196,9 +199,18 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
                                  local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, rowc, st));
     }
+    t.has_q = false;
+    if (t.want_q && t.zero_base && t.ld == KP_TILED) {
+        SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
+        SCDE_CUDA(launch_quantize_rows(t.table.p, t.ld, t.K, t.n_rows, t.q.p, st));
+        t.has_q = true;
+        ++nl;
+    }
     if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, nl);
     return SCDE_B200_OK;
 }
+
+inline bool want_i8(const scde_b200_ctx *ctx) { return ctx->contract_kernel == 0 || ctx->contract_kernel == 3; }
 
 // unique-count indices from raw counts (device, column-major, leading dimension ldc, genes [g0, g0+G))
 int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev, int64_t ldc, int g0, int G, int C,
@@ -236,6 +248,7 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 
 struct JointScratch {
     DBuf<double> W, Z, zpart, T;
+    DBuf<int8_t> W8;
     DBuf<int32_t> lst_row, lst_cell, lst_len, order;
     DBuf<unsigned long long> total;  // running sum of list lengths over the joints of one run
 };
@@ -259,7 +272,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     cudaStream_t st = ctx->stream;
     const int n_w_rows = round_up(n_list + 1, 16);  // at least one all-zero row after the cells (list padding)
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
-    const int ld_lst = round_up(n_list, 8);
+    const int ld_lst = round_up(n_list, 32);
     SCDE_CUDA(scr.W.ensure((size_t)passes * n_w_rows * WS_TILED));
     SCDE_CUDA(scr.lst_row.ensure((size_t)t.n_genes * ld_lst));
     SCDE_CUDA(scr.lst_cell.ensure((size_t)t.n_genes * ld_lst));
@@ -280,7 +293,41 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     if (zb)
         SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
                                   scr.Z.p, scr.zpart.p, st));
-    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, zb ? 5 : 3);
+    const bool i8 = zb && t.has_q && want_i8(ctx) && contract_i8_supported(t.K, t.ld, ld_lst);
+    if (ctx->contract_kernel == 3 && !i8) {
+        set_error("tcgen05 int8 contraction forced but unsupported here (K=%d, zero-base form %d)", t.K, (int)zb);
+        return SCDE_B200_EINVAL;
+    }
+    if (i8) {
+        SCDE_CUDA(scr.W8.ensure((size_t)passes * n_w_rows * Q_WB));
+        SCDE_CUDA(ctx->flags.ensure(1));
+        SCDE_CUDA(launch_w_to_i8(scr.W.p, n_w_rows, n_boot, scr.W8.p, ctx->flags.p, st));
+    }
+    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, (zb ? 5 : 3) + (i8 ? 1 : 0));
+    if (i8) {
+        ContractI8Args q{};
+        q.qtable = t.q.p;
+        q.ldq = q_row_bytes(t.K);
+        q.lists = lists;
+        q.W8 = scr.W8.p;
+        q.n_w_rows = n_w_rows;
+        q.n_boot = n_boot;
+        q.Z = scr.Z.p;
+        q.scale = scale;
+        q.sentinel = t.sentinel;
+        q.n_genes = t.n_genes;
+        q.K = t.K;
+        q.jp = jp_dev;
+        q.ld_jp = ld_jp;
+        q.err = ctx->flags.p;
+        q.swap_strides = getenv("SCDE_B200_I8_SWAP") ? 1 : 0;
+        e0 = tm ? tm->begin(st) : -1;
+        int nl = 0;
+        SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
+        SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, scr.T.p, st, &nl));
+        if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
+        return SCDE_B200_OK;
+    }
     ContractArgs a;
     a.table = t.table.p;
     a.ld_table = t.ld;
@@ -309,6 +356,26 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     else
         SCDE_CUDA(launch_contract_generic(a, st, &nl));
     if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
+    return SCDE_B200_OK;
+}
+
+// status word of the int8 contraction path (see scde_b200_ctx::flags)
+int reset_flags(scde_b200_ctx *ctx) {
+    SCDE_CUDA(ctx->flags.ensure(1));
+    SCDE_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int32_t), ctx->stream));
+    return SCDE_B200_OK;
+}
+// after the stream has been synchronised: 0 = fine, 1 = rerun on the FP64 kernel (a multiplicity above 127), < 0 error
+int read_flags(scde_b200_ctx *ctx, int *rerun) {
+    *rerun = 0;
+    if (!ctx->flags.p) return SCDE_B200_OK;
+    int32_t f = 0;
+    SCDE_CUDA(cudaMemcpy(&f, ctx->flags.p, sizeof(f), cudaMemcpyDeviceToHost));
+    if (f & 2) {
+        set_error("tcgen05 contraction kernel aborted (pipeline watchdog); use scde_b200_set_contract_kernel(ctx, 2)");
+        return SCDE_B200_ECUDA;
+    }
+    if (f & 1) *rerun = 1;
     return SCDE_B200_OK;
 }
 
@@ -414,7 +481,7 @@ int scde_b200_synchronize(scde_b200_ctx *ctx) {
 }
 
 int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which) {
-    if (!ctx || which < 0 || which > 2) return SCDE_B200_EINVAL;
+    if (!ctx || which < 0 || which > 3) return SCDE_B200_EINVAL;
     ctx->contract_kernel = which;
     return SCDE_B200_OK;
 }
@@ -481,7 +548,7 @@ int scde_b200_cell_table(scde_b200_ctx *ctx, const double *model_row12, const in
 }
 
 // --------------------------------------------------------------------------------------------
-static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
+static int log_boot_impl(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
                            const int32_t *ucl_offsets, const int32_t *uci, int32_t n_genes, const double *magnitudes,
                            int32_t n_grid, int32_t n_boot, const int32_t *boot_idx, int32_t D, int32_t return_individual,
                            int32_t local_theta, int32_t square_logit_conc, int32_t ensemble, int32_t modes_flag,
@@ -525,6 +592,8 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     t.sentinel = -DBL_MAX / (double)(D > n_cells ? D : n_cells) / 1.1;
     t.fast_theta = !local_theta && theta_all_regular(models, n_cells, n_cells);
     t.zero_base = !post_flag && !ensemble && t.ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
+    t.want_q = want_i8(ctx) && n_boot > 0;
+    TRY(reset_flags(ctx));
     DBuf<double> d_models, d_mag, d_jp, d_out, d_rs;
     DBuf<int32_t> d_uci, d_boot;
     TRY(upload(d_models, models, (size_t)n_cells * 12, st));
@@ -579,6 +648,27 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     }
     SCDE_CUDA(cudaStreamSynchronize(st));
     return SCDE_B200_OK;
+}
+
+static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
+                           const int32_t *ucl_offsets, const int32_t *uci, int32_t n_genes, const double *magnitudes,
+                           int32_t n_grid, int32_t n_boot, const int32_t *boot_idx, int32_t D, int32_t return_individual,
+                           int32_t local_theta, int32_t square_logit_conc, int32_t ensemble, int32_t modes_flag,
+                           int32_t post_flag, double *jp, double *modes, double *post) {
+    int r = log_boot_impl(ctx, models, n_cells, ucl_flat, ucl_offsets, uci, n_genes, magnitudes, n_grid, n_boot, boot_idx, D,
+                          return_individual, local_theta, square_logit_conc, ensemble, modes_flag, post_flag, jp, modes, post);
+    if (r != SCDE_B200_OK) return r;
+    int rerun = 0;
+    TRY(read_flags(ctx, &rerun));
+    if (rerun) {  // a cell drawn more than 127 times in one randomization: outside the int8 operand range
+        const int keep = ctx->contract_kernel;
+        ctx->contract_kernel = 2;
+        r = log_boot_impl(ctx, models, n_cells, ucl_flat, ucl_offsets, uci, n_genes, magnitudes, n_grid, n_boot, boot_idx, D,
+                          return_individual, local_theta, square_logit_conc, ensemble, modes_flag, post_flag, jp, modes,
+                          post);
+        ctx->contract_kernel = keep;
+    }
+    return r;
 }
 
 int scde_b200_log_boot_posterior(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *ucl_flat,
@@ -835,6 +925,62 @@ int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, in
     return SCDE_B200_OK;
 }
 
+int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
+                                const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row, const int32_t *lst_cell,
+                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t swap_strides,
+                                double *t_out) {
+    CHECK_CTX(ctx);
+    if (!qtable || !w8 || !lst_row || !lst_cell || !lst_len || !t_out || n_rows < 1 || n_genes < 1 || n_w_rows < 1 ||
+        !contract_i8_supported(n_grid, KP_TILED, ld_lst) || n_genes > contract_tiled_max_genes()) {
+        set_error("probe_contract_i8: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    for (int g = 0; g < n_genes; ++g) {
+        if (lst_len[g] < 0 || lst_len[g] > ld_lst) {
+            set_error("probe_contract_i8: lst_len[%d] out of range", g);
+            return SCDE_B200_EINVAL;
+        }
+    }
+    TRY(validate_index(lst_row, (size_t)n_genes * ld_lst, 0, n_rows, "lst_row"));
+    TRY(validate_index(lst_cell, (size_t)n_genes * ld_lst, 0, n_w_rows, "lst_cell"));
+    cudaStream_t st = ctx->stream;
+    DBuf<int8_t> d_q, d_w;
+    DBuf<int32_t> d_row, d_cell, d_len;
+    DBuf<double> d_t;
+    const int ldq = q_row_bytes(n_grid);
+    TRY(upload(d_q, qtable, (size_t)n_rows * ldq, st));
+    TRY(upload(d_w, w8, (size_t)n_w_rows * Q_WB, st));
+    TRY(upload(d_row, lst_row, (size_t)n_genes * ld_lst, st));
+    TRY(upload(d_cell, lst_cell, (size_t)n_genes * ld_lst, st));
+    TRY(upload(d_len, lst_len, (size_t)n_genes, st));
+    const size_t nt = (size_t)n_genes * WP_TILED * KP_TILED;
+    SCDE_CUDA(d_t.ensure(nt));
+    SCDE_CUDA(cudaMemsetAsync(d_t.p, 0, sizeof(double) * nt, st));
+    TRY(reset_flags(ctx));
+    ContractI8Args q{};
+    q.qtable = d_q.p;
+    q.ldq = ldq;
+    q.lists = GeneLists{d_row.p, d_cell.p, d_len.p, nullptr, ld_lst};
+    q.W8 = d_w.p;
+    q.n_w_rows = n_w_rows;
+    q.n_boot = WP_TILED;
+    q.Z = nullptr;
+    q.scale = 1.0;
+    q.sentinel = -1.0e300;
+    q.n_genes = n_genes;
+    q.K = n_grid;
+    q.jp = nullptr;
+    q.ld_jp = 0;
+    q.err = ctx->flags.p;
+    q.swap_strides = swap_strides;
+    SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, d_t.p, st, nullptr));
+    SCDE_CUDA(cudaMemcpyAsync(t_out, d_t.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    int rerun = 0;
+    TRY(read_flags(ctx, &rerun));
+    return SCDE_B200_OK;
+}
+
 }  // extern "C"
 
 // ============================================================================================
@@ -1022,6 +1168,7 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
     j->ws->table.sentinel = -DBL_MAX / C / 1.1;
     j->ws->table.fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
     j->ws->table.zero_base = ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
+    j->ws->table.want_q = want_i8(ctx);
     JCUDA(cudaStreamSynchronize(st));
     *out = j;
     return SCDE_B200_OK;
@@ -1040,6 +1187,8 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     SCDE_CUDA(cudaMemsetAsync(j->ws->scr.total.p, 0, sizeof(unsigned long long), st));
     const int G = j->G, C = j->C, K = j->K;
     const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    j->ws->table.want_q = want_i8(ctx);
+    TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
     TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
     TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
@@ -1125,6 +1274,19 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
     cudaStream_t st = ctx->stream;
     const int G = j->G, K = j->K;
     const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
+    {
+        SCDE_CUDA(cudaStreamSynchronize(st));
+        int rerun = 0;
+        TRY(read_flags(ctx, &rerun));
+        if (rerun) {  // a multiplicity above 127: repeat the run on the FP64 contraction kernel
+            const int keep = ctx->contract_kernel;
+            ctx->contract_kernel = 2;
+            const int r = scde_b200_diff_run(ctx, j);
+            ctx->contract_kernel = keep;
+            if (r != SCDE_B200_OK) return r;
+            SCDE_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     if (o) {
         if (o->idx) SCDE_CUDA(cudaMemcpyAsync(o->idx, j->idx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
         if (o->z) SCDE_CUDA(cudaMemcpyAsync(o->z, j->z.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));

@@ -107,7 +107,7 @@ __global__ void build_w_kernel(const int32_t *__restrict__ boot_idx, int n_boot,
 // per-gene entry lists.  Entry e of gene g = (table row, W row).  Dense form: every cell of the joint.  Zero-base form:
 // only the cells whose count is non-zero (or whose zero-count row cannot serve as a base); the zero-count rows of all
 // other cells are summed once per randomization into Z (base_sum kernels) and the table holds differences to them.
-// One warp per gene, order-preserving ballot compaction, lists padded to a multiple of 8 with (pad_row, zero W row).
+// One warp per gene, order-preserving ballot compaction, lists padded to a multiple of 32 with (pad_row, zero W row).
 __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_ridx, const int32_t *__restrict__ cell_ids,
                                    int n_list, int n_genes, const int32_t *__restrict__ zero_row,
                                    const int32_t *__restrict__ based, int pad_row, int32_t *__restrict__ lst_row,
@@ -134,7 +134,7 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
         }
         pos += __popc(m);
     }
-    const int padded = (pos + 7) & ~7;
+    const int padded = (pos + 31) & ~31;  // whole stages of both tiled kernels (8 and 32 entries)
     if (pos + lane < padded) {
         lst_row[g * ld_lst + pos + lane] = pad_row;
         lst_cell[g * ld_lst + pos + lane] = n_list;  // a W row that is all zero
@@ -873,6 +873,15 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, double *t_scr
         }
     }
     return cudaSuccess;
+}
+
+int contract_tiled_max_genes() { return TILED_MAX_GENES_PER_LAUNCH; }
+
+cudaError_t launch_softmax_avg(double *T, const int32_t *order, int K, int n_boot_pass, double scale, double *jp,
+                               int ld_jp, int accumulate, int n_pos, cudaStream_t st) {
+    if (n_pos <= 0) return cudaSuccess;
+    softmax_avg_kernel<<<n_pos, SM_THREADS, 0, st>>>(T, order, K, n_boot_pass, scale, jp, ld_jp, accumulate);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches) {

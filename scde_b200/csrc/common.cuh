@@ -124,6 +124,45 @@ cudaError_t launch_gather_post(const int32_t *ridx, int ld_ridx, int G, int n_ce
 cudaError_t launch_transpose_out(const double *src, int ld_src, int G, int K, double *dst, cudaStream_t st);
 cudaError_t launch_transpose_in(const double *src, int G, int K, double *dst, int ld_dst, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *sink, int iters, int blocks, cudaStream_t st);
+// the soft-max over the grid and the average over boots that follows either tiled contraction kernel: T is
+// [n_pos][104][416] raw T[boot, grid] of the genes order[0 .. n_pos); jp[gene][k] (+)= sum_b softmax_k(T[b, :]) / scale
+cudaError_t launch_softmax_avg(double *T, const int32_t *order, int K, int n_boot_pass, double scale, double *jp,
+                               int ld_jp, int accumulate, int n_pos, cudaStream_t st);
+int contract_tiled_max_genes();  // genes per launch of a tiled kernel (bounds the T scratch)
+
+// ---- contract_i8.cu ------------------------------------------------------------------------------
+// Fixed-point form of the table for the tcgen05 (kind::i8) contraction: value = 2^-Q_FRAC * sum_{p < Q_NV} 256^p d_p with
+// signed 8-bit digits d_p, plus one indicator plane for the "log 0" sentinel.  A row is stored
+// [grid chunk of Q_CW points][plane][w] so the Q_NP planes of one chunk are one contiguous run.
+constexpr int Q_NV = 5;           // value planes
+constexpr int Q_NP = Q_NV + 1;    // + sentinel indicator plane
+constexpr int Q_FRAC = 29;        // fractional bits (|value| <= 1000 < 2^10 fits 5 digits)
+constexpr int Q_CW = 80;          // grid points per chunk: Q_NP * Q_CW = 480 of the 512 tensor-memory columns
+constexpr int Q_WB = 128;         // bytes per int8 W row: 104 boots + zero padding = M of the MMA
+int q_row_bytes(int K);           // Q_NP * round_up(K, 16)
+// planes of every row of an FP64 table (ld_table >= round_up(K, 16), columns K.. zero)
+cudaError_t launch_quantize_rows(const double *table, int ld_table, int K, int64_t n_rows, int8_t *qtable,
+                                 cudaStream_t st);
+// W8[pass][row][128] = (int8) W[pass][row][0..104); *flag |= 1 if a multiplicity exceeds 127
+cudaError_t launch_w_to_i8(const double *W, int n_w_rows, int n_boot, int8_t *W8, int32_t *flag, cudaStream_t st);
+struct ContractI8Args {
+    const int8_t *qtable;
+    int ldq;
+    GeneLists lists;   // ld a multiple of 32, lists padded to a multiple of 32 with zero-W entries
+    const int8_t *W8;  // pass-major [ceil(n_boot/104)][n_w_rows][128]
+    int n_w_rows;
+    int n_boot;
+    const double *Z;   // [ceil(n_boot/104)*104][416] or NULL
+    double scale;
+    double sentinel;   // the "log 0" value of the FP64 table
+    int n_genes, K;
+    double *jp;
+    int ld_jp;
+    int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired
+    int swap_strides;  // descriptor probe (0 in production)
+};
+bool contract_i8_supported(int K, int ld_table, int ld_lst);
+cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches);
 
 // ---- ratio_summary.cu ----------------------------------------------------------------------------
 struct RatioArgs {

@@ -1,0 +1,160 @@
+"""Probe of the tcgen05 (kind::i8) contraction kernel on random integer operands, checked exactly with numpy.
+
+    python tools/probe_i8.py [--genes 7] [--cells 90] [--rows 300] [--grid 401] [--swap 0|1|both]
+
+Prints, per descriptor variant, whether T matches and (if not) where it differs.  Used by tests/test_gpu_i8.py."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+NP, NV, CW, WB, FRAC = 6, 5, 80, 128, 29
+WP, KP = 104, 416
+
+
+def make_problem(n_genes, n_cells, n_rows, n_grid, seed=0, max_w=5, sentinel_frac=0.01, full_lists=False):
+    rng = np.random.default_rng(seed)
+    kp = (n_grid + 15) // 16 * 16
+    planes = rng.integers(-128, 128, size=(n_rows, NP, kp), dtype=np.int64)
+    planes[:, NV, :] = rng.random((n_rows, kp)) < sentinel_frac
+    planes[:, :, n_grid:] = 0
+    # [row][chunk][plane][w]
+    q = np.zeros((n_rows, NP * kp), dtype=np.int8)
+    n_chunks = (kp + CW - 1) // CW
+    for c in range(n_chunks):
+        w = min(CW, kp - c * CW)
+        for p in range(NP):
+            q[:, NP * CW * c + p * w: NP * CW * c + (p + 1) * w] = planes[:, p, c * CW: c * CW + w]
+    n_w_rows = (n_cells + 1 + 15) // 16 * 16
+    w8 = np.zeros((n_w_rows, WB), dtype=np.int8)
+    w8[:n_cells, :WP] = rng.integers(0, max_w + 1, size=(n_cells, WP))
+    ld = (n_cells + 31) // 32 * 32
+    lst_row = np.zeros((n_genes, ld), dtype=np.int32)
+    lst_cell = np.full((n_genes, ld), n_cells, dtype=np.int32)  # zero W row
+    lst_len = np.zeros(n_genes, dtype=np.int32)
+    for g in range(n_genes):
+        n = n_cells if full_lists else int(rng.integers(0, n_cells + 1))
+        if g == 0:
+            n = n_cells
+        if g == 1 and n_genes > 2:
+            n = 0
+        lst_len[g] = n
+        lst_row[g, :n] = rng.integers(0, n_rows, size=n)
+        lst_cell[g, :n] = rng.permutation(n_cells)[:n]
+    return dict(planes=planes, q=q, w8=w8, lst_row=lst_row, lst_cell=lst_cell, lst_len=lst_len, n_grid=n_grid, kp=kp,
+                n_w_rows=n_w_rows, ld=ld)
+
+
+def expected(pr):
+    G = pr["lst_len"].shape[0]
+    kp = pr["kp"]
+    S = np.zeros((G, NP, WP, kp), dtype=np.int64)
+    for g in range(G):
+        n = pr["lst_len"][g]
+        rows, cells = pr["lst_row"][g, :n], pr["lst_cell"][g, :n]
+        W = pr["w8"][cells, :WP].astype(np.int64)  # [n][104]
+        for p in range(NP):
+            S[g, p] = W.T @ pr["planes"][rows, p, :]
+    val = np.zeros((G, WP, kp), dtype=np.int64)
+    for p in range(NV - 1, -1, -1):
+        val = val * 256 + S[:, p]
+    return val, S[:, NV]
+
+
+def run(ctx, pr, swap):
+    from scde_b200 import _lib
+
+    L = _lib.lib()
+    G = pr["lst_len"].shape[0]
+    out = np.zeros((G, WP, KP), dtype=np.float64)
+    i8p, i32p, f64p = C.POINTER(C.c_int8), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.scde_b200_probe_contract_i8.argtypes = [C.c_void_p, i8p, C.c_int32, C.c_int32, i8p, C.c_int32, i32p, i32p, i32p,
+                                              C.c_int32, C.c_int32, C.c_int32, f64p]
+    q, w8 = np.ascontiguousarray(pr["q"]), np.ascontiguousarray(pr["w8"])
+    r = L.scde_b200_probe_contract_i8(ctx._h, q.ctypes.data_as(i8p), q.shape[0], pr["n_grid"], w8.ctypes.data_as(i8p),
+                                      pr["n_w_rows"], pr["lst_row"].ctypes.data_as(i32p),
+                                      pr["lst_cell"].ctypes.data_as(i32p), pr["lst_len"].ctypes.data_as(i32p), G,
+                                      pr["ld"], int(swap), out.ctypes.data_as(f64p))
+    _lib.check(r)
+    return out
+
+
+def compare(pr, out):
+    val, ns = expected(pr)
+    kp = pr["kp"]
+    want = val.astype(np.float64) * 2.0 ** -FRAC
+    got = out[:, :, :kp]
+    clean = ns == 0
+    ok_clean = got[clean] == want[clean]
+    sent_ok = np.allclose(got[~clean], want[~clean] - 1e300 * ns[~clean], rtol=1e-12) if (~clean).any() else True
+    return bool(ok_clean.all()) and bool(sent_ok), got, want, clean
+
+
+def report(pr, out, label):
+    ok, got, want, clean = compare(pr, out)
+    print(f"[{label}] match={ok}")
+    if ok:
+        return True
+    bad = (got != want) & clean
+    print(f"   mismatching clean elements: {bad.sum()} of {clean.sum()}")
+    G = got.shape[0]
+    for g in range(min(G, 4)):
+        bg = bad[g]
+        print(f"   gene {g} len {pr['lst_len'][g]}: bad boots {np.unique(np.nonzero(bg)[0])[:12]} ... "
+              f"bad grid {np.unique(np.nonzero(bg)[1])[:24]} ...")
+        if bg.any():
+            b, k = np.argwhere(bg)[0]
+            print(f"      first bad (b={b}, k={k}): got {got[g, b, k] * 2.0 ** FRAC:.0f} want {want[g, b, k] * 2.0 ** FRAC:.0f}")
+    # does the output equal the expectation under some permutation of chunks/planes?  print a few raw values
+    g = 0
+    print("   got[0, 0, :8] * 2^29 =", (got[g, 0, :8] * 2.0 ** FRAC).astype(np.int64))
+    print("   want[0, 0, :8] * 2^29 =", (want[g, 0, :8] * 2.0 ** FRAC).astype(np.int64))
+    return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genes", type=int, default=7)
+    ap.add_argument("--cells", type=int, default=90)
+    ap.add_argument("--rows", type=int, default=300)
+    ap.add_argument("--grid", type=int, default=401)
+    ap.add_argument("--swap", default="both")
+    ap.add_argument("--simple", action="store_true", help="planes: only plane 0 non-zero, W = identity-like")
+    a = ap.parse_args()
+    from scde_b200 import _lib
+
+    ctx = _lib.Context(0)
+    pr = make_problem(a.genes, a.cells, a.rows, a.grid)
+    if a.simple:
+        pr["planes"][:, 1:, :] = 0
+        pr = dict(pr)
+        # rebuild q from modified planes
+        kp = pr["kp"]
+        q = np.zeros_like(pr["q"])
+        for c in range((kp + CW - 1) // CW):
+            w = min(CW, kp - c * CW)
+            for p in range(NP):
+                q[:, NP * CW * c + p * w: NP * CW * c + (p + 1) * w] = pr["planes"][:, p, c * CW: c * CW + w]
+        pr["q"] = q
+    variants = [0, 1] if a.swap == "both" else [int(a.swap)]
+    good = []
+    for sw in variants:
+        try:
+            out = run(ctx, pr, sw)
+        except Exception as e:  # noqa: BLE001
+            print(f"[swap={sw}] error: {e}")
+            continue
+        if report(pr, out, f"swap={sw}"):
+            good.append(sw)
+    print("matching variants:", good)
+    return 0 if good else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

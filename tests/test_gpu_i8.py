@@ -1,0 +1,115 @@
+"""The tcgen05 (kind::i8) contraction kernel: exact integer checks of the kernel alone (random operands through the probe
+entry of the C ABI), and the fixed-point path against the FP64 kernel / the oracle at the 1e-6 contract."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from scde_b200 import _lib, api, synth
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import probe_i8 as P  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("genes,cells,rows,grid", [
+    (7, 90, 300, 401),     # the default grid: five 80-point chunks + one 16-point chunk
+    (3, 700, 900, 401),    # lists of 22 stages: the 10-slot ring wraps twice within an item
+    (400, 40, 64, 401),    # 2400 items on 148 CTAs: many items per CTA, accumulator hand-over every item
+    (5, 33, 50, 201),      # chunks 80 + 80 + 48 (two MMAs of N = 144 in the last one)
+    (5, 33, 50, 80),       # a single full chunk
+    (5, 33, 50, 16),       # a single narrow chunk (one MMA of N = 96)
+    (4, 64, 40, 96),       # 80 + 16
+    (2, 1, 3, 401),        # one-entry lists
+])
+def test_kernel_exact_on_random_integers(ctx, genes, cells, rows, grid):
+    pr = P.make_problem(genes, cells, rows, grid, seed=genes + cells)
+    out = P.run(ctx, pr, 0)
+    ok, got, want, clean = P.compare(pr, out)
+    assert ok, f"{int(((got != want) & clean).sum())} of {int(clean.sum())} elements differ"
+
+
+def test_kernel_extreme_digits(ctx):
+    """all digits at -128 / 127 and multiplicities at 127: the int32 accumulators hold |sum| <= 128 * 127 * entries"""
+    pr = P.make_problem(3, 200, 16, 401, seed=5, max_w=127, sentinel_frac=0.0, full_lists=True)
+    pr["planes"][:, :P.NV, :] = np.where(np.random.default_rng(1).random(pr["planes"][:, :P.NV, :].shape) < 0.5, -128, 127)
+    kp = pr["kp"]
+    q = np.zeros_like(pr["q"])
+    for c in range((kp + P.CW - 1) // P.CW):
+        w = min(P.CW, kp - c * P.CW)
+        for p in range(P.NP):
+            q[:, P.NP * P.CW * c + p * w: P.NP * P.CW * c + (p + 1) * w] = pr["planes"][:, p, c * P.CW: c * P.CW + w]
+    pr["q"] = q
+    out = P.run(ctx, pr, 0)
+    ok, got, want, clean = P.compare(pr, out)
+    assert ok
+
+
+def _err(a, b, floor=1e-290):
+    big = (a > floor) & (b > floor)
+    la, lb = np.log(a[big]), np.log(b[big])
+    return float(np.max(np.abs(la - lb) / np.maximum(np.abs(lb), 1.0)))
+
+
+@pytest.mark.parametrize("G,Cn", [(200, 64), (60, 400)])
+def test_fixed_point_path_vs_fp64_kernel(ctx, G, Cn):
+    """same inputs, same draws: joint posteriors of the fixed-point path within 1e-6 (relative, log scale) of the FP64
+    kernel, grid indices of the summary identical, and the run is reproducible bit for bit"""
+    w = synth.make_workload(3, n_genes=G, n_cells=Cn, seed=11)
+    res = {}
+    for kernel in (2, 3, 3):
+        ctx.set_contract_kernel(kernel)
+        try:
+            r = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                               return_posteriors=True, context=ctx)
+        finally:
+            ctx.set_contract_kernel(0)
+        res.setdefault(kernel, []).append(r)
+    a, b, b2 = res[2][0], res[3][0], res[3][1]
+    for lev in ("g1", "g2"):
+        e = _err(b["joint.posteriors"][lev].to_numpy(), a["joint.posteriors"][lev].to_numpy())
+        assert e < 1e-6, e
+        assert np.array_equal(b["joint.posteriors"][lev].to_numpy(), b2["joint.posteriors"][lev].to_numpy())
+    assert np.array_equal(a["results"][["lb", "mle", "ub"]].to_numpy(), b["results"][["lb", "mle", "ub"]].to_numpy())
+    za, zb = a["results"]["Z"].to_numpy(), b["results"]["Z"].to_numpy()
+    assert np.all(np.abs(za - zb) <= np.where(za < -6.0, 2e-4, 1e-6 * np.maximum(1.0, np.abs(za)) + 1e-9))
+
+
+def test_large_counts_sentinel_plane(ctx):
+    """counts in the tens of thousands put the reference's "log 0" clamp (-DBL_MAX/n/1.1) on the low end of the grid: the
+    indicator plane has to reproduce the FP64 path's hard exclusion of those grid points"""
+    w = synth.make_workload(3, n_genes=80, n_cells=30, seed=3)
+    counts = np.array(w.counts, copy=True)
+    rng = np.random.default_rng(0)
+    counts[:40] = rng.integers(0, 60000, size=counts[:40].shape)
+    counts[40:60, ::3] = 0
+    mm, lt, sq = api.pack_models(w.models)
+    mag = api.marginals_from_prior(w.prior)
+    flat, off, uci = O.unique_counts(counts)
+    bi = O.boot_indices(1, counts.shape[1], 100)
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, 100, boot_idx=bi)["jp"]
+    ctx.set_contract_kernel(3)
+    try:
+        got = api.scde_posteriors(w.models, counts, w.prior, n_randomizations=100, context=ctx).to_numpy()
+    finally:
+        ctx.set_contract_kernel(0)
+    assert _err(got, want) < 1e-6
+    assert np.all(got[want == 0.0] < 1e-280)
+
+
+def test_multiplicity_above_127_falls_back_to_fp64(ctx):
+    """a cell drawn 150 times in every randomization does not fit the int8 operand: the library reruns on the FP64 kernel"""
+    w = synth.make_workload(3, n_genes=20, n_cells=150, seed=2)
+    bi = np.zeros((10, 150), dtype=np.int32)  # every draw hits cell 0
+    res = {}
+    for kernel in (0, 2):
+        ctx.set_contract_kernel(kernel)
+        try:
+            res[kernel] = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=10, boot_idx=bi,
+                                              context=ctx).to_numpy()
+        finally:
+            ctx.set_contract_kernel(0)
+    assert np.array_equal(res[0], res[2])

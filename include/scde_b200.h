@@ -248,10 +248,11 @@ SCDE_B200_API int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t whic
 /* Probe of the tcgen05 contraction kernel alone, on caller-made operands (tests): qtable[n_rows][6 * round_up(n_grid, 16)]
  * int8 in the layout [chunk of 80 grid points][plane 0..5][w], w8[n_w_rows][128] int8, entry lists as (row, W row) with
  * ld_lst a multiple of 32 and entries beyond lst_len[g] up to the next multiple of 32 pointing at an all-zero W row.
+ * layout: 0 = 128-byte-swizzle operand layout (production), 1 = interleave layout (cross-check).
  * t_out[n_genes][104][416] = 2^-29 * sum_p 256^p (sum_e plane_p[row_e][k] * w8[cell_e][b]) - 1e300 * (plane-5 sum). */
 SCDE_B200_API int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
                                 const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row, const int32_t *lst_cell,
-                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t swap_strides,
+                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t layout,
                                 double *t_out);
 
 #ifdef __cplusplus

@@ -320,7 +320,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.jp = jp_dev;
         q.ld_jp = ld_jp;
         q.err = ctx->flags.p;
-        q.swap_strides = getenv("SCDE_B200_I8_SWAP") ? 1 : 0;
+        q.layout = getenv("SCDE_B200_I8_INTERLEAVE") ? 1 : 0;
         e0 = tm ? tm->begin(st) : -1;
         int nl = 0;
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
@@ -927,7 +927,7 @@ int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, in
 
 int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
                                 const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row, const int32_t *lst_cell,
-                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t swap_strides,
+                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t layout,
                                 double *t_out) {
     CHECK_CTX(ctx);
     if (!qtable || !w8 || !lst_row || !lst_cell || !lst_len || !t_out || n_rows < 1 || n_genes < 1 || n_w_rows < 1 ||
@@ -972,7 +972,7 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.jp = nullptr;
     q.ld_jp = 0;
     q.err = ctx->flags.p;
-    q.swap_strides = swap_strides;
+    q.layout = layout;
     SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, d_t.p, st, nullptr));
     SCDE_CUDA(cudaMemcpyAsync(t_out, d_t.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));

@@ -159,7 +159,7 @@ struct ContractI8Args {
     double *jp;
     int ld_jp;
     int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired
-    int swap_strides;  // descriptor probe (0 in production)
+    int layout;        // shared-memory operand layout: 0 = 128-byte swizzle (production), 1 = interleave (cross-check)
 };
 bool contract_i8_supported(int K, int ld_table, int ld_lst);
 cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches);

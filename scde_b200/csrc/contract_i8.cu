@@ -42,21 +42,22 @@ using namespace ptx;
 constexpr int Q_ES = 32;                         // list entries per stage = K of one tcgen05.mma.kind::i8
 constexpr int Q_NS = 10;                         // ring depth
 constexpr int Q_A_BYTES = Q_ES * Q_WB;           // W tile of a stage: 4096
-constexpr int Q_B_BYTES = Q_ES * Q_NP * Q_CW;    // table tile of a stage: 15360
-constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;
+constexpr int Q_B_BYTES = Q_ES * 512;            // table tile of a stage: 480 bytes per entry, padded to 4 x 128
+constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;  // 20480, a multiple of the 1024-byte swizzle atom
 constexpr int Q_PRODUCER_WARPS = 4, Q_EPILOGUE_WARPS = 4;
 constexpr int Q_THREADS = (Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS + 1) * 32;  // + the MMA warp
 constexpr int Q_TMEM_COLS = 512;
 constexpr long long Q_WATCHDOG_CYCLES = 4000000000ll;  // a barrier wait longer than ~2 s aborts the kernel (err = 2)
+constexpr int Q_LAYOUT_SW128 = 0, Q_LAYOUT_INTERLEAVE = 1;
 
 struct I8Smem {
-    alignas(128) uint8_t stage[Q_NS][Q_STAGE_BYTES];
     uint64_t full[Q_NS];
     uint64_t empty[Q_NS];
     uint64_t acc_full, acc_empty;
     uint32_t tmem_base;
     volatile int abort;
 };
+constexpr size_t Q_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)Q_NS * Q_STAGE_BYTES + sizeof(I8Smem);
 
 struct I8Params {
     const int8_t *qtable;  // [rows][ldq]: row = [chunk][plane][w_chunk]
@@ -70,7 +71,6 @@ struct I8Params {
     int n_pos;         // genes in this launch: positions [0, n_pos) of `order`
     int n_chunks;      // grid chunks per gene; all but the last are Q_CW wide
     int w_last;        // width of the last chunk (multiple of 16, <= Q_CW)
-    int swap_strides;  // probe: exchange the two stride fields of the shared-memory descriptors
     int32_t *err;      // device flag: 2 = watchdog abort
 };
 
@@ -106,9 +106,199 @@ __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
     return it;
 }
 
+// ---- producers ------------------------------------------------------------------------------------------------------
+// Warp w gathers entries 8w .. 8w+7 (one k-group of the MMA) of every stage.  List entries are read one coalesced load
+// per four stages and three groups ahead (a load issued at stage 4t is first used at stage 4t + 8), so the gather never
+// waits on the list: with a one-stage look-ahead the kernel ran at the latency of that dependent load (long-scoreboard
+// stalls were 66 % of the producers' cycles, profiles/r01p).
+//
+// SW128 layout (canonical 128-byte-swizzle layout of an MN-major operand): the bytes of one entry are split into runs of
+// 128 (8 pieces of 16 bytes), a run of entry kk sits at [run][k-group][kk][128 B] and its piece j at 16 * (j ^ kk).
+// Lane (r = lane >> 3, j = lane & 7) copies piece j of entries r and r + 4: a warp instruction moves four 128-byte runs of
+// global memory into four 128-byte lines of shared memory -- coalesced on both sides, no bank conflicts.
+// INTERLEAVE layout (no swizzle): piece j of entry kk at [k-group][j][kk][16 B]; lane (kk = lane & 7, q = lane >> 3) copies
+// pieces q, q + 4, ...  Verified first; kept as a cross-check (its shared-memory side serialises: the four pieces of one
+// 64-byte global run land 128 bytes apart, i.e. in the same banks).
+template <int LAYOUT>
+__device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
+    int64_t q = 0;
+    const int l7 = lane & 7, l3 = lane >> 3;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const int64_t gene = p.order ? p.order[it.pos] : it.pos;
+        const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
+        const int npieces = Q_NP * (it.w >> 4);
+        const int8_t *qbase = p.qtable + (int64_t)it.chunk * (Q_NP * Q_CW);
+        const int64_t lbase = gene * p.ld_lst + warp * 8 + l7;
+        // entries of stages 4t + l3 (t = group): registers of groups t, t+1, t+2
+        int32_t er[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
+        auto load_group = [&](int t, int32_t &row, int32_t &cell) {
+            const int s = 4 * t + l3;
+            row = 0;
+            cell = 0;
+            if (s < nst) {
+                row = p.lst_row[lbase + (int64_t)s * Q_ES];
+                cell = p.lst_cell[lbase + (int64_t)s * Q_ES];
+            }
+        };
+        load_group(0, er[0], ec[0]);
+        load_group(1, er[1], ec[1]);
+        load_group(2, er[2], ec[2]);
+        for (int s = 0; s < nst; ++s, ++q) {
+            if (s > 0 && (s & 3) == 0) {
+                er[0] = er[1];
+                ec[0] = ec[1];
+                er[1] = er[2];
+                ec[1] = ec[2];
+                load_group((s >> 2) + 2, er[2], ec[2]);
+            }
+            const int slot = (int)(q % Q_NS);
+            const uint32_t fill = (uint32_t)(q / Q_NS);
+            const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
+            const uint32_t sB = sA + Q_A_BYTES;
+            const int g4 = (s & 3) << 3;
+            if (LAYOUT == Q_LAYOUT_SW128) {
+                const int32_t row0 = __shfl_sync(0xffffffffu, er[0], g4 | l3), row1 = __shfl_sync(0xffffffffu, er[0], g4 | (l3 + 4));
+                const int32_t cel0 = __shfl_sync(0xffffffffu, ec[0], g4 | l3), cel1 = __shfl_sync(0xffffffffu, ec[0], g4 | (l3 + 4));
+                if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
+                const int8_t *src0 = qbase + (int64_t)row0 * p.ldq + l7 * 16;
+                const int8_t *src1 = qbase + (int64_t)row1 * p.ldq + l7 * 16;
+                // entry kk = l3 (and l3 + 4): line (kk) of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
+                const uint32_t d0 = (uint32_t)warp * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
+                const uint32_t d1 = (uint32_t)warp * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
+                for (int run = 0; run * 8 + l7 < npieces; ++run) {
+                    cp_async16(sB + (uint32_t)run * 4096u + d0, src0 + run * 128);
+                    cp_async16(sB + (uint32_t)run * 4096u + d1, src1 + run * 128);
+                }
+                cp_async16(sA + d0, p.W8 + (int64_t)cel0 * Q_WB + l7 * 16);
+                cp_async16(sA + d1, p.W8 + (int64_t)cel1 * Q_WB + l7 * 16);
+            } else {
+                const int32_t row = __shfl_sync(0xffffffffu, er[0], g4 | l7);
+                const int32_t cell = __shfl_sync(0xffffffffu, ec[0], g4 | l7);
+                if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
+                const int8_t *src = qbase + (int64_t)row * p.ldq;
+                const uint32_t dB = sB + (uint32_t)warp * (uint32_t)(npieces * 128) + (uint32_t)l7 * 16u;
+                for (int j = l3; j < npieces; j += 4) cp_async16(dB + (uint32_t)j * 128u, src + j * 16);
+                const int8_t *wsrc = p.W8 + (int64_t)cell * Q_WB;
+                const uint32_t dA = sA + (uint32_t)warp * 1024u + (uint32_t)l7 * 16u;
+                cp_async16(dA + (uint32_t)l3 * 128u, wsrc + l3 * 16);
+                cp_async16(dA + (uint32_t)(l3 + 4) * 128u, wsrc + (l3 + 4) * 16);
+            }
+            cp_async_mbar_arrive_noinc(&sm.full[slot]);
+        }
+    }
+}
+
+// ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t stage0, uint32_t tmem, int n_items) {
+    int64_t q = 0;
+    uint32_t n_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        const Item it = decode_item(p, item);
+        const int64_t gene = p.order ? p.order[it.pos] : it.pos;
+        const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
+        const int ntot = Q_NP * it.w;  // accumulator columns of this item (480 for a full chunk)
+        // N <= 256 per instruction.  SW128: the second MMA has to start on a 128-byte run of the entry -> 256 + 224;
+        // INTERLEAVE: any multiple of 16 -> two halves
+        int n1, n2;
+        if (LAYOUT == Q_LAYOUT_SW128) {
+            n1 = ntot > 256 ? 256 : ntot;
+            n2 = ntot - n1;
+        } else {
+            n1 = ntot > 256 ? ntot / 2 : ntot;
+            n2 = ntot - n1;
+        }
+        const uint32_t idesc1 = umma_idesc_s8_mn(128, n1), idesc2 = umma_idesc_s8_mn(128, n2 > 0 ? n2 : 16);
+        const uint32_t stride_k_b = (uint32_t)(Q_NP * (it.w >> 4)) * 128u;  // INTERLEAVE: bytes between 8-entry groups of B
+        if (n_done > 0) {  // the epilogue has drained the previous item's accumulators
+            if (!wait_or_abort(sm, &sm.acc_empty, (n_done - 1) & 1u)) return;
+            tc_fence_after_sync();
+        }
+        for (int s = 0; s < nst; ++s, ++q) {
+            const int slot = (int)(q % Q_NS);
+            if (!wait_or_abort(sm, &sm.full[slot], (uint32_t)(q / Q_NS) & 1u)) return;
+            fence_proxy_async_smem();
+            tc_fence_after_sync();
+            const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
+            const uint32_t sB = sA + Q_A_BYTES;
+            if (LAYOUT == Q_LAYOUT_SW128) {
+                const uint64_t da = umma_desc_sw128(sA, 4096u, 1024u);
+                umma_s8(tmem, da, umma_desc_sw128(sB, 4096u, 1024u), idesc1, s > 0);
+                if (n2 > 0) umma_s8(tmem + 256u, da, umma_desc_sw128(sB + 2u * 4096u, 4096u, 1024u), idesc2, s > 0);
+            } else {
+                const uint64_t da = umma_desc_nosw(sA, 128u, 1024u, false);
+                umma_s8(tmem, da, umma_desc_nosw(sB, 128u, stride_k_b, false), idesc1, s > 0);
+                if (n2 > 0)
+                    umma_s8(tmem + (uint32_t)n1, da, umma_desc_nosw(sB + (uint32_t)(n1 >> 4) * 128u, 128u, stride_k_b, false),
+                            idesc2, s > 0);
+            }
+            umma_commit(&sm.empty[slot]);  // frees the slot once these MMAs have read it
+        }
+        if (nst > 0)
+            umma_commit(&sm.acc_full);
+        else
+            mbar_arrive(&sm.acc_full);
+    }
+}
+
+// ---- epilogue: warp (4 + qd) owns tensor-memory lanes 32 qd .. 32 qd + 31 ----------------------------------------------
+__device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t tmem, int n_items, int warp, int lane) {
+    const int qd = warp & 3;
+    const int b = qd * 32 + lane;  // boot of this thread
+    const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
+    const double scale = 1.0 / (double)(1ll << Q_FRAC);
+    uint32_t n_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        const Item it = decode_item(p, item);
+        const int64_t gene = p.order ? p.order[it.pos] : it.pos;
+        const bool empty_list = p.lst_len[gene] <= 0;
+        if (!wait_or_abort(sm, &sm.acc_full, n_done & 1u)) return;
+        tc_fence_after_sync();
+        double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + it.chunk * Q_CW;
+        const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + it.chunk * Q_CW : nullptr;
+        for (int i0 = 0; i0 < it.w; i0 += 8) {
+            uint32_t r[Q_NP][8];
+            if (!empty_list) {
+#pragma unroll
+                for (int pl = 0; pl < Q_NP; ++pl) tmem_ld_32x32b_x8(tlane + (uint32_t)(pl * it.w + i0), r[pl]);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int pl = 0; pl < Q_NP; ++pl)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[pl][j] = 0u;
+            }
+            if (b < WP_TILED) {
+                double out[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    long long s = 0;
+#pragma unroll
+                    for (int pl = Q_NV - 1; pl >= 0; --pl) s = s * 256 + (long long)(int32_t)r[pl][j];
+                    double t = (double)s * scale;
+                    if (Zrow) t += Zrow[i0 + j];
+                    const int32_t ns = (int32_t)r[Q_NV][j];  // draws that hit a "log 0" entry at this grid point
+                    if (ns != 0) t = fma((double)ns, p.sentinel, t);
+                    out[j] = t;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j += 2)
+                    *reinterpret_cast<double2 *>(Trow + i0 + j) = make_double2(out[j], out[j + 1]);
+            }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&sm.acc_empty);
+    }
+}
+
+template <int LAYOUT>
 __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Params p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // stage buffers on a 1024-byte boundary (the swizzle pattern is a function of the shared-memory address bits)
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw + (stage0 - raw) + (size_t)Q_NS * Q_STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_NS; ++s) {
@@ -127,141 +317,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Param
     const uint32_t tmem = sm.tmem_base;
     const int n_items = p.n_pos * p.n_chunks;
 
-    if (warp < Q_PRODUCER_WARPS) {
-        // ================= producers: warp w gathers entries 8w .. 8w+7 of every stage =================
-        const int kk = lane & 7, pq = lane >> 3;
-        int64_t q = 0;
-        bool ok = true;
-        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
-            const Item it = decode_item(p, item);
-            const int64_t gene = p.order ? p.order[it.pos] : it.pos;
-            const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
-            const int npieces = Q_NP * (it.w >> 4);
-            const int8_t *qbase = p.qtable + (int64_t)it.chunk * (Q_NP * Q_CW);
-            const int64_t lbase = gene * p.ld_lst + warp * 8 + kk;
-            int32_t row = 0, cell = 0;
-            if (nst > 0) {
-                row = p.lst_row[lbase];
-                cell = p.lst_cell[lbase];
-            }
-            for (int s = 0; s < nst; ++s, ++q) {
-                int32_t nrow = 0, ncell = 0;
-                if (s + 1 < nst) {  // next stage's entry, fetched before this stage's wait
-                    nrow = p.lst_row[lbase + (int64_t)(s + 1) * Q_ES];
-                    ncell = p.lst_cell[lbase + (int64_t)(s + 1) * Q_ES];
-                }
-                const int slot = (int)(q % Q_NS);
-                const uint32_t fill = (uint32_t)(q / Q_NS);
-                if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) {
-                    ok = false;
-                    break;
-                }
-                const uint32_t sA = smem_u32(sm.stage[slot]);
-                const uint32_t sB = sA + Q_A_BYTES;
-                const int8_t *src = qbase + (int64_t)row * p.ldq;
-                const uint32_t dB = sB + (uint32_t)warp * (uint32_t)(npieces * 128) + (uint32_t)kk * 16u;
-                for (int j = pq; j < npieces; j += 4) cp_async16(dB + (uint32_t)j * 128u, src + j * 16);
-                const int8_t *wsrc = p.W8 + (int64_t)cell * Q_WB;
-                const uint32_t dA = sA + (uint32_t)warp * 1024u + (uint32_t)kk * 16u;
-                cp_async16(dA + (uint32_t)pq * 128u, wsrc + pq * 16);
-                cp_async16(dA + (uint32_t)(pq + 4) * 128u, wsrc + (pq + 4) * 16);
-                cp_async_mbar_arrive_noinc(&sm.full[slot]);
-                row = nrow;
-                cell = ncell;
-            }
-        }
-    } else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS) {
-        // ================= epilogue: warp (4 + qd) owns tensor-memory lanes 32 qd .. 32 qd + 31 =================
-        const int qd = warp & 3;
-        const int b = qd * 32 + lane;  // boot of this thread
-        const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
-        const double scale = 1.0 / (double)(1ll << Q_FRAC);
-        uint32_t n_done = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-            const Item it = decode_item(p, item);
-            const int64_t gene = p.order ? p.order[it.pos] : it.pos;
-            const bool empty_list = p.lst_len[gene] <= 0;
-            if (!wait_or_abort(sm, &sm.acc_full, n_done & 1u)) break;
-            tc_fence_after_sync();
-            double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + it.chunk * Q_CW;
-            const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + it.chunk * Q_CW : nullptr;
-            for (int i0 = 0; i0 < it.w; i0 += 8) {
-                uint32_t r[Q_NP][8];
-                if (!empty_list) {
-#pragma unroll
-                    for (int pl = 0; pl < Q_NP; ++pl) tmem_ld_32x32b_x8(tlane + (uint32_t)(pl * it.w + i0), r[pl]);
-                    tmem_wait_ld();
-                } else {
-#pragma unroll
-                    for (int pl = 0; pl < Q_NP; ++pl)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) r[pl][j] = 0u;
-                }
-                if (b < WP_TILED) {
-                    double out[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        long long s = 0;
-#pragma unroll
-                        for (int pl = Q_NV - 1; pl >= 0; --pl) s = s * 256 + (long long)(int32_t)r[pl][j];
-                        double t = (double)s * scale;
-                        if (Zrow) t += Zrow[i0 + j];
-                        const int32_t ns = (int32_t)r[Q_NV][j];  // draws that hit a "log 0" entry at this grid point
-                        if (ns != 0) t = fma((double)ns, p.sentinel, t);
-                        out[j] = t;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2)
-                        *reinterpret_cast<double2 *>(Trow + i0 + j) = make_double2(out[j], out[j + 1]);
-                }
-            }
-            tc_fence_before_sync();
-            mbar_arrive(&sm.acc_empty);
-        }
-    } else if (lane == 0) {
-        // ================= MMA issuer =================
-        int64_t q = 0;
-        uint32_t n_done = 0;
-        const bool swap = p.swap_strides != 0;
-        bool ok = true;
-        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++n_done) {
-            const Item it = decode_item(p, item);
-            const int64_t gene = p.order ? p.order[it.pos] : it.pos;
-            const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
-            const int ntot = Q_NP * it.w;                  // accumulator columns of this item
-            const int nmma = ntot > 256 ? 2 : 1;           // N <= 256 per instruction
-            const int nn = ntot / nmma;                    // 240 (w = 80); always a multiple of 16
-            const uint32_t idesc = umma_idesc_s8_mn(128, nn);
-            const uint32_t stride_k_b = (uint32_t)(Q_NP * (it.w >> 4)) * 128u;  // bytes between 8-entry groups of B
-            if (n_done > 0) {  // the epilogue has drained the previous item's accumulators
-                if (!wait_or_abort(sm, &sm.acc_empty, (n_done - 1) & 1u)) break;
-                tc_fence_after_sync();
-            }
-            for (int s = 0; s < nst; ++s, ++q) {
-                const int slot = (int)(q % Q_NS);
-                if (!wait_or_abort(sm, &sm.full[slot], (uint32_t)(q / Q_NS) & 1u)) {
-                    ok = false;
-                    break;
-                }
-                fence_proxy_async_smem();
-                tc_fence_after_sync();
-                const uint32_t sA = smem_u32(sm.stage[slot]);
-                const uint32_t sB = sA + Q_A_BYTES;
-                const uint64_t da = umma_desc_nosw(sA, 128u, 1024u, swap);
-                for (int h = 0; h < nmma; ++h) {
-                    const uint64_t db = umma_desc_nosw(sB + (uint32_t)h * (uint32_t)(nn >> 4) * 128u, 128u, stride_k_b, swap);
-                    umma_s8(tmem + (uint32_t)(h * nn), da, db, idesc, s > 0);
-                }
-                umma_commit(&sm.empty[slot]);  // frees the slot once these MMAs have read it
-            }
-            if (!ok) break;
-            if (nst > 0)
-                umma_commit(&sm.acc_full);
-            else
-                mbar_arrive(&sm.acc_full);
-        }
-    }
-    if (sm.abort && p.err && threadIdx.x == 0) atomicExch(p.err, 2);
+    if (warp < Q_PRODUCER_WARPS)
+        run_producer<LAYOUT>(p, sm, stage0, n_items, warp, lane);
+    else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
+        run_epilogue(p, sm, tmem, n_items, warp, lane);
+    else if (lane == 0)
+        run_mma<LAYOUT>(p, sm, stage0, tmem, n_items);
+
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -354,8 +416,11 @@ cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scra
     if (a.n_genes <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(I8Smem));
+        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<Q_LAYOUT_SW128>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(contract_i8_kernel<Q_LAYOUT_INTERLEAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Q_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -382,11 +447,13 @@ cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scra
             p.n_pos = n_pos;
             p.n_chunks = n_chunks;
             p.w_last = w_last;
-            p.swap_strides = a.swap_strides;
             p.err = a.err;
             const int n_items = n_pos * n_chunks;
             const int grid = n_sm < n_items ? n_sm : n_items;
-            contract_i8_kernel<<<grid, Q_THREADS, sizeof(I8Smem), st>>>(p);
+            if (a.layout == Q_LAYOUT_INTERLEAVE)
+                contract_i8_kernel<Q_LAYOUT_INTERLEAVE><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
+            else
+                contract_i8_kernel<Q_LAYOUT_SW128><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             const int nb = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;

@@ -70,6 +70,13 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t stri
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);  // bits 46-47: descriptor version 1 (sm_100)
 }
+// 128-byte-swizzle canonical layout of an MN-major operand: runs of 128 consecutive M/N bytes, 8 consecutive K per
+// 1024-byte atom (K stride 128 bytes, 16-byte pieces XOR-swizzled with K mod 8); "leading byte offset" = stride between
+// 128-byte runs along M/N, "stride byte offset" = stride between groups of 8 K.  Atoms must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t stride_mn_run, uint32_t stride_k_group) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((stride_mn_run >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((stride_k_group >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);  // layout type 2 = SWIZZLE_128B
+}
 // Instruction descriptor of kind::i8: signed 8-bit A and B, both MN-major, 32-bit integer accumulators, M x N tile
 __device__ __forceinline__ uint32_t umma_idesc_s8_mn(int M, int N) {
     return (2u << 4)      // D format: S32

@@ -25,9 +25,10 @@ pytestmark = pytest.mark.gpu
     (4, 64, 40, 96),       # 80 + 16
     (2, 1, 3, 401),        # one-entry lists
 ])
-def test_kernel_exact_on_random_integers(ctx, genes, cells, rows, grid):
+@pytest.mark.parametrize("layout", [0, 1])  # 128-byte-swizzle (production) and interleave operand layouts
+def test_kernel_exact_on_random_integers(ctx, genes, cells, rows, grid, layout):
     pr = P.make_problem(genes, cells, rows, grid, seed=genes + cells)
-    out = P.run(ctx, pr, 0)
+    out = P.run(ctx, pr, layout)
     ok, got, want, clean = P.compare(pr, out)
     assert ok, f"{int(((got != want) & clean).sum())} of {int(clean.sum())} elements differ"
 

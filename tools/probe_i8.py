@@ -1,6 +1,6 @@
 """Probe of the tcgen05 (kind::i8) contraction kernel on random integer operands, checked exactly with numpy.
 
-    python tools/probe_i8.py [--genes 7] [--cells 90] [--rows 300] [--grid 401] [--swap 0|1|both]
+    python tools/probe_i8.py [--genes 7] [--cells 90] [--rows 300] [--grid 401] [--layout 0|1|both]
 
 Prints, per descriptor variant, whether T matches and (if not) where it differs.  Used by tests/test_gpu_i8.py."""
 from __future__ import annotations
@@ -67,7 +67,7 @@ def expected(pr):
     return val, S[:, NV]
 
 
-def run(ctx, pr, swap):
+def run(ctx, pr, layout):
     from scde_b200 import _lib
 
     L = _lib.lib()
@@ -80,7 +80,7 @@ def run(ctx, pr, swap):
     r = L.scde_b200_probe_contract_i8(ctx._h, q.ctypes.data_as(i8p), q.shape[0], pr["n_grid"], w8.ctypes.data_as(i8p),
                                       pr["n_w_rows"], pr["lst_row"].ctypes.data_as(i32p),
                                       pr["lst_cell"].ctypes.data_as(i32p), pr["lst_len"].ctypes.data_as(i32p), G,
-                                      pr["ld"], int(swap), out.ctypes.data_as(f64p))
+                                      pr["ld"], int(layout), out.ctypes.data_as(f64p))
     _lib.check(r)
     return out
 
@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--cells", type=int, default=90)
     ap.add_argument("--rows", type=int, default=300)
     ap.add_argument("--grid", type=int, default=401)
-    ap.add_argument("--swap", default="both")
+    ap.add_argument("--layout", default="both")
     ap.add_argument("--simple", action="store_true", help="planes: only plane 0 non-zero, W = identity-like")
     a = ap.parse_args()
     from scde_b200 import _lib
@@ -142,15 +142,15 @@ def main():
             for p in range(NP):
                 q[:, NP * CW * c + p * w: NP * CW * c + (p + 1) * w] = pr["planes"][:, p, c * CW: c * CW + w]
         pr["q"] = q
-    variants = [0, 1] if a.swap == "both" else [int(a.swap)]
+    variants = [0, 1] if a.layout == "both" else [int(a.layout)]
     good = []
     for sw in variants:
         try:
             out = run(ctx, pr, sw)
         except Exception as e:  # noqa: BLE001
-            print(f"[swap={sw}] error: {e}")
+            print(f"[layout={sw}] error: {e}")
             continue
-        if report(pr, out, f"swap={sw}"):
+        if report(pr, out, f"layout={sw}"):
             good.append(sw)
     print("matching variants:", good)
     return 0 if good else 1

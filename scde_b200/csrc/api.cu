@@ -134,9 +134,10 @@ struct LpTable {
     int64_t n_rows = 0;
     double sentinel = 0;
     DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
-    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc;
+    DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc, scfp;
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
     bool want_q = false, has_q = false;
+    bool f64_rows = true;  // false: the FP64 rows of non-zero counts were not stored (planes only)
     bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
     // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
     // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
@@ -171,10 +172,17 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
         SCDE_CUDA(t.l1.ensure(cl));
         SCDE_CUDA(t.l2.ensure(cl));
         SCDE_CUDA(t.rowc.ensure((size_t)4 * t.n_rows));
+        SCDE_CUDA(t.scfp.ensure((size_t)t.n_cells));
     }
     void *rowc = fast ? (void *)t.rowc.p : nullptr;
     CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
-                  fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr};
+                  fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr, fast ? t.scfp.p : nullptr};
+    // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
+    // counts are then not stored at all), by a separate pass over the FP64 table for the general kernel
+    const bool q_any = t.want_q && t.zero_base && t.ld == KP_TILED;
+    const bool q_fused = q_any && fast && !getenv("SCDE_B200_Q_SEPARATE");
+    if (q_any) SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
+    int8_t *qf = q_fused ? t.q.p : nullptr;
     if (t.zero_base) {
         SCDE_CUDA(t.zero_row.ensure((size_t)t.n_cells));
         SCDE_CUDA(t.based.ensure((size_t)t.n_cells));
@@ -190,20 +198,22 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     if (t.zero_base) {
         SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, rowc, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, rowc, 1, qf,
+                                 st));
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, rowc, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, rowc,
+                                 q_fused ? 0 : 1, qf, st));
         nl += 3;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, rowc, st));
+                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, rowc, 1, nullptr,
+                                 st));
     }
-    t.has_q = false;
-    if (t.want_q && t.zero_base && t.ld == KP_TILED) {
-        SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
+    t.has_q = q_any;
+    t.f64_rows = !(q_fused && t.zero_base);
+    if (q_any && !q_fused) {
         SCDE_CUDA(launch_quantize_rows(t.table.p, t.ld, t.K, t.n_rows, t.q.p, st));
-        t.has_q = true;
         ++nl;
     }
     if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, nl);
@@ -327,6 +337,10 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, scr.T.p, st, &nl));
         if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
         return SCDE_B200_OK;
+    }
+    if (!t.f64_rows) {
+        set_error("internal: the table was built in fixed point only but the FP64 contraction kernel was selected");
+        return SCDE_B200_EINVAL;
     }
     ContractArgs a;
     a.table = t.table.p;

@@ -33,6 +33,7 @@ struct CellPrep {  // per-cell grid vectors, each [n_cells][ld]
     // constant-theta fast path (NULL = use the general saddle-point kernel): drop-out probability and the
     // negative binomial's log p_k = -log1p(mu_k/theta), log q_k = -log1p(theta/mu_k)
     double *cfp, *l1, *l2;
+    double *scfp;  // [n_cells] sum over the grid of the drop-out probability (fast path)
 };
 // models: n_cells x 12 column-major with leading dimension ld_models
 cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, const double *mag, int K,
@@ -50,7 +51,10 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, void *row_const, cudaStream_t st);
+                           const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
+                           cudaStream_t st);
+// write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
+// row's fixed-point planes (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
 cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
                               int64_t n_rows, void *row_const, cudaStream_t st);

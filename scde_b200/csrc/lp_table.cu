@@ -160,7 +160,7 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, int
     auto M = [&](int col) { return models[(size_t)col * ldm + r]; };
     const double corr_a = M(4), corr_b = M(3), conc_a = M(1), conc_b = M(0);
     const double conc_a2 = sqlogit ? M(11) : 0.0;
-    double lmax = -INFINITY;
+    double lmax = -INFINITY, csum = 0.0;
     for (int k = threadIdx.x; k < prep.ld; k += blockDim.x) {
         size_t o = (size_t)c * prep.ld + k;
         if (k >= K) {  // padding: benign values
@@ -192,6 +192,7 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, int
         if (prep.cfp) {  // constant-theta fast path: log p_k, log q_k of the NB parametrisation and the drop-out prob
             const double th0 = M(5), muk = exp(t);
             prep.cfp[o] = cf;
+            csum += cf;
             prep.l1[o] = -log1p(muk / th0);
             prep.l2[o] = -log1p(th0 / muk);
         }
@@ -208,14 +209,23 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, int
             prep.theta[o] = th;
         }
     }
-    __shared__ double red[32];
+    __shared__ double red[32], red2[32];
     lmax = warp_max(lmax);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
+    csum = warp_sum(csum);
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = lmax;
+        red2[threadIdx.x >> 5] = csum;
+    }
     __syncthreads();
     if (threadIdx.x < 32) {
         double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        double u = threadIdx.x < (blockDim.x >> 5) ? red2[threadIdx.x] : 0.0;
         v = warp_max(v);
-        if (threadIdx.x == 0) prep.maxcfp[c] = v;
+        u = warp_sum(u);
+        if (threadIdx.x == 0) {
+            prep.maxcfp[c] = v;
+            if (prep.scfp) prep.scfp[c] = u;
+        }
     }
 }
 
@@ -385,15 +395,52 @@ __global__ void row_const_kernel(const double *__restrict__ models, int ldm, con
     rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
 }
 
+// Fixed-point digits of one table value (contract_i8.cu): value = 2^-Q_FRAC * sum_p 256^p d_p, d_p signed bytes; a value
+// at or below the "log 0" sentinel sets the indicator digit instead.  32-bit arithmetic: the low word's bytes with
+// their carries, then the high byte.
+__device__ __forceinline__ void fixed_point_digits(double v, int (&d)[Q_NP]) {
+    if (!(v > -1.0e290)) {
+#pragma unroll
+        for (int p = 0; p < Q_NV; ++p) d[p] = 0;
+        d[Q_NV] = 1;
+        return;
+    }
+    const long long x = __double2ll_rn(fmin(fmax(v, -1000.0), 1000.0) * (double)(1ll << Q_FRAC));
+    uint32_t u = (uint32_t)x;
+    int hi = (int)(x >> 32);
+#pragma unroll
+    for (int p = 0; p < Q_NV - 1; ++p) {
+        const int dg = (int)(int8_t)(u & 0xFFu);
+        d[p] = dg;
+        u = (u >> 8) + (dg < 0 ? 1u : 0u);
+    }
+    d[Q_NV - 1] = hi + (int)u;
+    d[Q_NV] = 0;
+}
+
+// The sweeps (one warp per row, lanes stride the grid through a per-warp shared-memory row):
+//   1. a_k = log NB_k + log(1 - d_k) and its maximum;  M = max(max_k a_k, max_k log d_k + f)          (:188-192)
+//   2. S = sum_k exp(a_k - M) + exp(f - M) * sum_k d_k.  exp() is only evaluated where a_k - M > -45: the other terms
+//      are below 3e-20 of S >= 1.  The drop-out part of the sum is one multiply (sum_k d_k comes from cell_prep).
+//   3. lp_k = log(exp(a_k - M) + exp(log d_k + f - M)) - log S.  When one term exceeds the other by more than 37.5 nats
+//      the smaller one is below half an ulp of the sum and log(exp(hi)) = hi, so no exp and no log is evaluated; in the
+//      cross-over band, and below -708 where the reference's own exp() underflows gradually, the reference's expression
+//      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
+// Most rows belong to large counts whose NB term is a narrow peak, so sweeps 2 and 3 are a handful of FP64 instructions
+// per element instead of an exp and a log each.
+// Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes (qtable).
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
                     const int32_t *__restrict__ row_x, const double4 *__restrict__ rowc, int64_t n_rows, CellPrep prep,
                     int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
-                    const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
+                    const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
+                    int8_t *__restrict__ qtable, int ldq) {
     __shared__ double s_rows[ROW_WARPS * KP_TILED];
+    __shared__ __align__(16) uint8_t s_q[ROW_WARPS][Q_NP * KP_TILED];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    const int kp = (K + 15) & ~15;
     // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
     // one) and the per-cell grid vectors stay in L1
     const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
@@ -414,11 +461,9 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         const double s = models[(size_t)5 * ldm + c];
         const size_t base = (size_t)c * prep.ld;
         const double *mu = prep.mu + base, *l1 = prep.l1 + base, *l2 = prep.l2 + base;
-        const double *lcfpr = prep.lcfpr + base, *cfp = prep.cfp + base;
+        const double *lcfpr = prep.lcfpr + base, *lcfp = prep.lcfp + base;
         const double4 rc = rowc[row];  // row constants from row_const_kernel
         const double R = rc.x, l1s = rc.y, l2s = rc.z, fp = rc.w;
-        // three sweeps over the grid through a per-warp shared-memory row (partially unrolled: fully unrolling 13
-        // inlined exp/log bodies made the kernel instruction-cache bound, "no instruction" was its top stall)
         double *nb = s_rows + warp * KP_TILED;
         double vmax = -INFINITY;
 #pragma unroll 4
@@ -441,30 +486,53 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         double maxp = vmax;
         const double alt = prep.maxcfp[c] + fp;
         if (maxp < alt) maxp = alt;
-        const double E = exp(fp - maxp);
         double sum = 0;
 #pragma unroll 4
         for (int k = lane; k < K; k += 32) {
-            const double v = exp(nb[k] - maxp) + cfp[k] * E;
-            nb[k] = v;
-            sum += v;
+            const double a = nb[k] - maxp;
+            if (a > -45.0) sum += exp(a);
         }
-        sum = warp_sum(sum);
+        sum = warp_sum(sum) + exp(fp - maxp) * prep.scfp[c];
         const double lsum = log(sum);
         double best = -INFINITY;
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
-#pragma unroll 4
-        for (int k = lane; k < K; k += 32) {
-            double v = log(nb[k]) - lsum;
-            if (besti == 0x7fffffff || v > best) {
-                best = v;
-                besti = k;
+        uint8_t *sq = s_q[warp];
+#pragma unroll 2
+        for (int k = lane; k < kp; k += 32) {
+            double v = 0.0;
+            if (k < K) {
+                const double a = nb[k] - maxp;
+                const double dk = (lcfp[k] + fp) - maxp;
+                const double hi = fmax(a, dk), lo = fmin(a, dk);
+                double L;
+                if (hi < -746.0)
+                    L = -INFINITY;  // both exponentials underflow to exactly 0
+                else if (hi >= -708.0 && hi - lo > 37.5)
+                    L = hi;
+                else
+                    L = log(exp(a) + exp(dk));
+                v = L - lsum;
+                if (besti == 0x7fffffff || v > best) {
+                    best = v;
+                    besti = k;
+                }
+                if (v < sentinel) v = sentinel;
+                if (zr) v -= zr[k];
+                if (write_f64) out[k] = v;
             }
-            if (v < sentinel) v = sentinel;
-            out[k] = zr ? v - zr[k] : v;
+            if (qtable) {
+                int d[Q_NP];
+                fixed_point_digits(v, d);
+                const int ch = k / Q_CW, i = k - ch * Q_CW;
+                const int w = min(Q_CW, kp - ch * Q_CW);
+                uint8_t *dst = sq + ch * (Q_NP * Q_CW) + i;
+#pragma unroll
+                for (int p = 0; p < Q_NP; ++p) dst[p * w] = (uint8_t)d[p];
+            }
         }
-        for (int k = K + lane; k < ld_table; k += 32) out[k] = 0.0;
+        if (write_f64)
+            for (int k = K + lane; k < ld_table; k += 32) out[k] = 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -475,6 +543,12 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
             }
         }
         __syncwarp();
+        if (qtable) {  // the row's planes, 16 bytes per lane and store
+            const uint4 *src = reinterpret_cast<const uint4 *>(sq);
+            uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
+            for (int j = lane; j < (Q_NP * kp) / 16; j += 32) dst[j] = src[j];
+            __syncwarp();
+        }
         if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
     }
 }
@@ -518,19 +592,22 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, void *row_const, cudaStream_t st) {
+                           const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
+                           cudaStream_t st) {
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
     if (n_items <= 0) return cudaSuccess;
     int64_t blocks = (n_items + ROW_WARPS - 1) / ROW_WARPS;
     const int64_t cap = 148 * 64;  // grid-stride beyond this
     if (blocks > cap) blocks = cap;
-    if (prep.cfp && row_const && !local_theta && K <= KP_TILED && ld_table >= K) {
+    if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x,
                                                                         (const double4 *)row_const, n_rows, prep, K,
                                                                         sentinel, table, ld_table, row_mode, which,
-                                                                        zero_row, based);
+                                                                        zero_row, based, write_f64, qtable,
+                                                                        q_row_bytes(K));
         return cudaGetLastError();
     }
+    if (qtable || !write_f64) return cudaErrorInvalidValue;  // the general kernel writes the FP64 table only
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(lp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -44,7 +44,8 @@ constexpr int Q_NS = 10;                         // ring depth
 constexpr int Q_A_BYTES = Q_ES * Q_WB;           // W tile of a stage: 4096
 constexpr int Q_B_BYTES = Q_ES * 512;            // table tile of a stage: 480 bytes per entry, padded to 4 x 128
 constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;  // 20480, a multiple of the 1024-byte swizzle atom
-constexpr int Q_PRODUCER_WARPS = 4, Q_EPILOGUE_WARPS = 4;
+constexpr int Q_PGROUPS = 2;                     // producer warp groups; group g gathers the stages s = g (mod Q_PGROUPS) of an item
+constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS, Q_EPILOGUE_WARPS = 4;
 constexpr int Q_THREADS = (Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS + 1) * 32;  // + the MMA warp
 constexpr int Q_TMEM_COLS = 512;
 constexpr long long Q_WATCHDOG_CYCLES = 4000000000ll;  // a barrier wait longer than ~2 s aborts the kernel (err = 2)
@@ -121,7 +122,11 @@ __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
 // 64-byte global run land 128 bytes apart, i.e. in the same banks).
 template <int LAYOUT>
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
-    int64_t q = 0;
+    // A single warp issues the ~180 instructions of a stage (address arithmetic, ten cp.async, barrier traffic) at well
+    // under one per cycle, so four warps alone ran the gather at half the rate the memory system sustains
+    // (profiles/r01s): Q_PGROUPS groups of four warps take alternate stages.
+    const int grp = warp >> 2, kg = warp & 3;  // k-group of the MMA this warp fills: entries 8 kg .. 8 kg + 7 of a stage
+    int64_t q0 = 0;                            // stages of the items before this one
     const int l7 = lane & 7, l3 = lane >> 3;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const Item it = decode_item(p, item);
@@ -129,11 +134,12 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
         const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
         const int npieces = Q_NP * (it.w >> 4);
         const int8_t *qbase = p.qtable + (int64_t)it.chunk * (Q_NP * Q_CW);
-        const int64_t lbase = gene * p.ld_lst + warp * 8 + l7;
-        // entries of stages 4t + l3 (t = group): registers of groups t, t+1, t+2
+        const int64_t lbase = gene * p.ld_lst + kg * 8 + l7;
+        // this warp's stages are s = grp + Q_PGROUPS * i; lane (l3, l7) holds entry l7 of own-stage 4 t + l3 for the
+        // register groups t, t + 1, t + 2
         int32_t er[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
         auto load_group = [&](int t, int32_t &row, int32_t &cell) {
-            const int s = 4 * t + l3;
+            const int s = grp + Q_PGROUPS * (4 * t + l3);
             row = 0;
             cell = 0;
             if (s < nst) {
@@ -144,28 +150,30 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
         load_group(0, er[0], ec[0]);
         load_group(1, er[1], ec[1]);
         load_group(2, er[2], ec[2]);
-        for (int s = 0; s < nst; ++s, ++q) {
-            if (s > 0 && (s & 3) == 0) {
+        int i = 0;
+        for (int s = grp; s < nst; s += Q_PGROUPS, ++i) {
+            if (i > 0 && (i & 3) == 0) {
                 er[0] = er[1];
                 ec[0] = ec[1];
                 er[1] = er[2];
                 ec[1] = ec[2];
-                load_group((s >> 2) + 2, er[2], ec[2]);
+                load_group((i >> 2) + 2, er[2], ec[2]);
             }
+            const int64_t q = q0 + s;
             const int slot = (int)(q % Q_NS);
             const uint32_t fill = (uint32_t)(q / Q_NS);
             const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
             const uint32_t sB = sA + Q_A_BYTES;
-            const int g4 = (s & 3) << 3;
+            const int g4 = (i & 3) << 3;
             if (LAYOUT == Q_LAYOUT_SW128) {
                 const int32_t row0 = __shfl_sync(0xffffffffu, er[0], g4 | l3), row1 = __shfl_sync(0xffffffffu, er[0], g4 | (l3 + 4));
                 const int32_t cel0 = __shfl_sync(0xffffffffu, ec[0], g4 | l3), cel1 = __shfl_sync(0xffffffffu, ec[0], g4 | (l3 + 4));
                 if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
                 const int8_t *src0 = qbase + (int64_t)row0 * p.ldq + l7 * 16;
                 const int8_t *src1 = qbase + (int64_t)row1 * p.ldq + l7 * 16;
-                // entry kk = l3 (and l3 + 4): line (kk) of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
-                const uint32_t d0 = (uint32_t)warp * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
-                const uint32_t d1 = (uint32_t)warp * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
+                // entry kk = l3 (and l3 + 4): line kk of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
+                const uint32_t d0 = (uint32_t)kg * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
+                const uint32_t d1 = (uint32_t)kg * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
                 for (int run = 0; run * 8 + l7 < npieces; ++run) {
                     cp_async16(sB + (uint32_t)run * 4096u + d0, src0 + run * 128);
                     cp_async16(sB + (uint32_t)run * 4096u + d1, src1 + run * 128);
@@ -177,15 +185,16 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
                 const int32_t cell = __shfl_sync(0xffffffffu, ec[0], g4 | l7);
                 if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
                 const int8_t *src = qbase + (int64_t)row * p.ldq;
-                const uint32_t dB = sB + (uint32_t)warp * (uint32_t)(npieces * 128) + (uint32_t)l7 * 16u;
+                const uint32_t dB = sB + (uint32_t)kg * (uint32_t)(npieces * 128) + (uint32_t)l7 * 16u;
                 for (int j = l3; j < npieces; j += 4) cp_async16(dB + (uint32_t)j * 128u, src + j * 16);
                 const int8_t *wsrc = p.W8 + (int64_t)cell * Q_WB;
-                const uint32_t dA = sA + (uint32_t)warp * 1024u + (uint32_t)l7 * 16u;
+                const uint32_t dA = sA + (uint32_t)kg * 1024u + (uint32_t)l7 * 16u;
                 cp_async16(dA + (uint32_t)l3 * 128u, wsrc + l3 * 16);
                 cp_async16(dA + (uint32_t)(l3 + 4) * 128u, wsrc + (l3 + 4) * 16);
             }
             cp_async_mbar_arrive_noinc(&sm.full[slot]);
         }
+        q0 += nst;
     }
 }
 
@@ -253,7 +262,10 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
         const Item it = decode_item(p, item);
         const int64_t gene = p.order ? p.order[it.pos] : it.pos;
         const bool empty_list = p.lst_len[gene] <= 0;
-        if (!wait_or_abort(sm, &sm.acc_full, n_done & 1u)) return;
+        while (!mbar_try_wait(&sm.acc_full, n_done & 1u)) {  // an item takes tens of microseconds: sleep, do not spin
+            __nanosleep(500);
+            if (sm.abort) return;
+        }
         tc_fence_after_sync();
         double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + it.chunk * Q_CW;
         const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + it.chunk * Q_CW : nullptr;
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Param
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_NS; ++s) {
-            mbar_init(&sm.full[s], Q_PRODUCER_WARPS * 32);  // one cp.async completion arrival per producer thread
+            mbar_init(&sm.full[s], 4 * 32);                 // one cp.async completion arrival per thread of a producer group
             mbar_init(&sm.empty[s], 1);                     // one tcgen05.commit
         }
         mbar_init(&sm.acc_full, 1);

@@ -397,28 +397,27 @@ __global__ void row_const_kernel(const double *__restrict__ models, int ldm, con
 
 // Fixed-point digits of one table value (contract_i8.cu): value = 2^-Q_FRAC * sum_p 256^p d_p, d_p signed bytes; a value
 // at or below the "log 0" sentinel sets the indicator digit instead.  32-bit arithmetic: the low word's bytes with
-// their carries, then the high byte.
-__device__ __forceinline__ void fixed_point_digits(double v, int (&d)[Q_NP]) {
+// their carries, then the high byte.  The digits are OR-ed into byte `e` of word[p] (four grid points per word).
+__device__ __forceinline__ void fixed_point_digits(double v, int e, uint32_t (&word)[Q_NP]) {
+    const int sh = 8 * e;
     if (!(v > -1.0e290)) {
-#pragma unroll
-        for (int p = 0; p < Q_NV; ++p) d[p] = 0;
-        d[Q_NV] = 1;
+        word[Q_NV] |= 1u << sh;
         return;
     }
     const long long x = __double2ll_rn(fmin(fmax(v, -1000.0), 1000.0) * (double)(1ll << Q_FRAC));
     uint32_t u = (uint32_t)x;
-    int hi = (int)(x >> 32);
+    const int hi = (int)(x >> 32);
 #pragma unroll
     for (int p = 0; p < Q_NV - 1; ++p) {
-        const int dg = (int)(int8_t)(u & 0xFFu);
-        d[p] = dg;
-        u = (u >> 8) + (dg < 0 ? 1u : 0u);
+        const uint32_t dg = u & 0xFFu;
+        word[p] |= dg << sh;
+        u = (u >> 8) + (dg >> 7);  // a digit >= 128 stands for digit - 256: carry one into the next
     }
-    d[Q_NV - 1] = hi + (int)u;
-    d[Q_NV] = 0;
+    word[Q_NV - 1] |= ((uint32_t)(hi + (int)u) & 0xFFu) << sh;
 }
 
-// The sweeps (one warp per row, lanes stride the grid through a per-warp shared-memory row):
+// The sweeps (one warp per row; lane l owns the grid points 4 l + 128 j .. + 3, so every access is a 16- or 32-byte
+// vector and the index arithmetic is shared by four points; the row lives in a per-warp shared-memory buffer):
 //   1. a_k = log NB_k + log(1 - d_k) and its maximum;  M = max(max_k a_k, max_k log d_k + f)          (:188-192)
 //   2. S = sum_k exp(a_k - M) + exp(f - M) * sum_k d_k.  exp() is only evaluated where a_k - M > -45: the other terms
 //      are below 3e-20 of S >= 1.  The drop-out part of the sum is one multiply (sum_k d_k comes from cell_prep).
@@ -426,17 +425,15 @@ __device__ __forceinline__ void fixed_point_digits(double v, int (&d)[Q_NP]) {
 //      the smaller one is below half an ulp of the sum and log(exp(hi)) = hi, so no exp and no log is evaluated; in the
 //      cross-over band, and below -708 where the reference's own exp() underflows gradually, the reference's expression
 //      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
-// Most rows belong to large counts whose NB term is a narrow peak, so sweeps 2 and 3 are a handful of FP64 instructions
-// per element instead of an exp and a log each.
 // Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes (qtable).
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 3)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
                     const int32_t *__restrict__ row_x, const double4 *__restrict__ rowc, int64_t n_rows, CellPrep prep,
                     int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
                     int8_t *__restrict__ qtable, int ldq) {
-    __shared__ double s_rows[ROW_WARPS * KP_TILED];
+    __shared__ __align__(16) double s_rows[ROW_WARPS * KP_TILED];
     __shared__ __align__(16) uint8_t s_q[ROW_WARPS][Q_NP * KP_TILED];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
@@ -465,74 +462,112 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         const double4 rc = rowc[row];  // row constants from row_const_kernel
         const double R = rc.x, l1s = rc.y, l2s = rc.z, fp = rc.w;
         double *nb = s_rows + warp * KP_TILED;
+        // ---- sweep 1
         double vmax = -INFINITY;
-#pragma unroll 4
-        for (int k = lane; k < K; k += 32) {
-            const double muv = mu[k];
-            const bool snap = (k < K - 1) ? (x > muv && x < mu[k + 1]) : (x > muv);
-            double v;
+        for (int k0 = 4 * lane; k0 < K; k0 += 128) {
+            double m[5], a1[4], a2[4], lr[4], v[4];
+            *reinterpret_cast<double2 *>(&m[0]) = *reinterpret_cast<const double2 *>(mu + k0);
+            *reinterpret_cast<double2 *>(&m[2]) = *reinterpret_cast<const double2 *>(mu + k0 + 2);
+            m[4] = mu[k0 + 4 < prep.ld ? k0 + 4 : k0 + 3];
+            *reinterpret_cast<double2 *>(&a1[0]) = *reinterpret_cast<const double2 *>(l1 + k0);
+            *reinterpret_cast<double2 *>(&a1[2]) = *reinterpret_cast<const double2 *>(l1 + k0 + 2);
+            *reinterpret_cast<double2 *>(&lr[0]) = *reinterpret_cast<const double2 *>(lcfpr + k0);
+            *reinterpret_cast<double2 *>(&lr[2]) = *reinterpret_cast<const double2 *>(lcfpr + k0 + 2);
             if (x > 0) {
-                const double a1 = snap ? l1s : l1[k];
-                const double a2 = snap ? l2s : l2[k];
-                v = fma(x, a2, fma(s, a1, R));
+                *reinterpret_cast<double2 *>(&a2[0]) = *reinterpret_cast<const double2 *>(l2 + k0);
+                *reinterpret_cast<double2 *>(&a2[2]) = *reinterpret_cast<const double2 *>(l2 + k0 + 2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k0 + e;
+                    const bool snap = (k < K - 1) ? (x > m[e] && x < m[e + 1]) : (x > m[e]);
+                    v[e] = fma(x, snap ? l2s : a2[e], fma(s, snap ? l1s : a1[e], R)) + lr[e];
+                }
             } else {
-                v = s * l1[k];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = s * a1[e] + lr[e];
             }
-            v += lcfpr[k];
-            vmax = fmax(vmax, v);
-            nb[k] = v;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k0 + e < K) vmax = fmax(vmax, v[e]);
+            *reinterpret_cast<double2 *>(nb + k0) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2 *>(nb + k0 + 2) = make_double2(v[2], v[3]);
         }
         vmax = warp_max(vmax);
         double maxp = vmax;
         const double alt = prep.maxcfp[c] + fp;
         if (maxp < alt) maxp = alt;
+        __syncwarp();
+        // ---- sweep 2
         double sum = 0;
-#pragma unroll 4
-        for (int k = lane; k < K; k += 32) {
-            const double a = nb[k] - maxp;
-            if (a > -45.0) sum += exp(a);
+        for (int k0 = 4 * lane; k0 < K; k0 += 128) {
+            double v[4];
+            *reinterpret_cast<double2 *>(&v[0]) = *reinterpret_cast<const double2 *>(nb + k0);
+            *reinterpret_cast<double2 *>(&v[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double a = v[e] - maxp;
+                if (k0 + e < K && a > -45.0) sum += exp(a);
+            }
         }
         sum = warp_sum(sum) + exp(fp - maxp) * prep.scfp[c];
         const double lsum = log(sum);
+        // ---- sweep 3
         double best = -INFINITY;
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
         uint8_t *sq = s_q[warp];
-#pragma unroll 2
-        for (int k = lane; k < kp; k += 32) {
-            double v = 0.0;
-            if (k < K) {
-                const double a = nb[k] - maxp;
-                const double dk = (lcfp[k] + fp) - maxp;
-                const double hi = fmax(a, dk), lo = fmin(a, dk);
-                double L;
-                if (hi < -746.0)
-                    L = -INFINITY;  // both exponentials underflow to exactly 0
-                else if (hi >= -708.0 && hi - lo > 37.5)
-                    L = hi;
-                else
-                    L = log(exp(a) + exp(dk));
-                v = L - lsum;
-                if (besti == 0x7fffffff || v > best) {
-                    best = v;
-                    besti = k;
+        for (int k0 = 4 * lane; k0 < kp; k0 += 128) {
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+            if (k0 < K) {
+                double a[4], dk[4], z[4] = {0.0, 0.0, 0.0, 0.0};
+                *reinterpret_cast<double2 *>(&a[0]) = *reinterpret_cast<const double2 *>(nb + k0);
+                *reinterpret_cast<double2 *>(&a[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
+                *reinterpret_cast<double2 *>(&dk[0]) = *reinterpret_cast<const double2 *>(lcfp + k0);
+                *reinterpret_cast<double2 *>(&dk[2]) = *reinterpret_cast<const double2 *>(lcfp + k0 + 2);
+                if (zr) {
+                    *reinterpret_cast<double2 *>(&z[0]) = *reinterpret_cast<const double2 *>(zr + k0);
+                    *reinterpret_cast<double2 *>(&z[2]) = *reinterpret_cast<const double2 *>(zr + k0 + 2);
                 }
-                if (v < sentinel) v = sentinel;
-                if (zr) v -= zr[k];
-                if (write_f64) out[k] = v;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double ae = a[e] - maxp;
+                    const double de = (dk[e] + fp) - maxp;
+                    const double hi = fmax(ae, de), lo = fmin(ae, de);
+                    double L = hi;
+                    if (hi < -746.0)
+                        L = -INFINITY;  // both exponentials underflow to exactly 0
+                    else if (!(hi >= -708.0 && hi - lo > 37.5))
+                        L = log(exp(ae) + exp(de));  // cross-over or gradual-underflow band: as the reference writes it
+                    double t = L - lsum;
+                    if (k0 + e < K) {
+                        if (besti == 0x7fffffff || t > best) {
+                            best = t;
+                            besti = k0 + e;
+                        }
+                        if (t < sentinel) t = sentinel;
+                        v[e] = t - z[e];
+                    }
+                }
+            }
+            if (write_f64) {
+                *reinterpret_cast<double2 *>(out + k0) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2 *>(out + k0 + 2) = make_double2(v[2], v[3]);
             }
             if (qtable) {
-                int d[Q_NP];
-                fixed_point_digits(v, d);
-                const int ch = k / Q_CW, i = k - ch * Q_CW;
-                const int w = min(Q_CW, kp - ch * Q_CW);
-                uint8_t *dst = sq + ch * (Q_NP * Q_CW) + i;
+                uint32_t word[Q_NP];
 #pragma unroll
-                for (int p = 0; p < Q_NP; ++p) dst[p * w] = (uint8_t)d[p];
+                for (int p = 0; p < Q_NP; ++p) word[p] = 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) fixed_point_digits(v[e], e, word);
+                const int ch = k0 / Q_CW, i = k0 - ch * Q_CW;
+                const int w = min(Q_CW, kp - ch * Q_CW);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(sq + ch * (Q_NP * Q_CW) + i);
+#pragma unroll
+                for (int p = 0; p < Q_NP; ++p) dst[(p * w) >> 2] = word[p];
             }
         }
         if (write_f64)
-            for (int k = K + lane; k < ld_table; k += 32) out[k] = 0.0;
+            for (int k = kp + lane; k < ld_table; k += 32) out[k] = 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -547,8 +582,8 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
             const uint4 *src = reinterpret_cast<const uint4 *>(sq);
             uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
             for (int j = lane; j < (Q_NP * kp) / 16; j += 32) dst[j] = src[j];
-            __syncwarp();
         }
+        __syncwarp();
         if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
     }
 }

@@ -138,6 +138,7 @@ struct LpTable {
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
     bool want_q = false, has_q = false;
     bool f64_rows = true;  // false: the FP64 rows of non-zero counts were not stored (planes only)
+    bool want_modes = true;  // row_mode (argmax of every row) is needed: only for return.individual.posterior.modes
     bool fast_theta = false;  // every corr.theta finite and > 0, no local-theta fit: constant-theta fast path
     // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
     // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
@@ -175,6 +176,7 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
         SCDE_CUDA(t.scfp.ensure((size_t)t.n_cells));
     }
     void *rowc = fast ? (void *)t.rowc.p : nullptr;
+    int32_t *rmode = t.want_modes ? t.row_mode.p : nullptr;
     CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
                   fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr, fast ? t.scfp.p : nullptr};
     // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
@@ -198,16 +200,16 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     if (t.zero_base) {
         SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 1, t.zero_row.p, nullptr, rowc, 1, qf,
+                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 1, t.zero_row.p, nullptr, rowc, 1, qf,
                                  st));
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 2, t.zero_row.p, t.based.p, rowc,
+                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 2, t.zero_row.p, t.based.p, rowc,
                                  q_fused ? 0 : 1, qf, st));
         nl += 3;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, t.row_mode.p, 0, nullptr, nullptr, rowc, 1, nullptr,
+                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 0, nullptr, nullptr, rowc, 1, nullptr,
                                  st));
     }
     t.has_q = q_any;
@@ -607,6 +609,7 @@ static int log_boot_impl(scde_b200_ctx *ctx, const double *models, int32_t n_cel
     t.fast_theta = !local_theta && theta_all_regular(models, n_cells, n_cells);
     t.zero_base = !post_flag && !ensemble && t.ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
     t.want_q = want_i8(ctx) && n_boot > 0;
+    t.want_modes = modes_flag != 0;
     TRY(reset_flags(ctx));
     DBuf<double> d_models, d_mag, d_jp, d_out, d_rs;
     DBuf<int32_t> d_uci, d_boot;
@@ -1202,6 +1205,7 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     const int G = j->G, C = j->C, K = j->K;
     const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
     j->ws->table.want_q = want_i8(ctx);
+    j->ws->table.want_modes = false;
     TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
     TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));

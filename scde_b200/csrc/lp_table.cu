@@ -395,37 +395,78 @@ __global__ void row_const_kernel(const double *__restrict__ models, int ldm, con
     rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
 }
 
-// Fixed-point digits of one table value (contract_i8.cu): value = 2^-Q_FRAC * sum_p 256^p d_p, d_p signed bytes; a value
-// at or below the "log 0" sentinel sets the indicator digit instead.  32-bit arithmetic: the low word's bytes with
-// their carries, then the high byte.  The digits are OR-ed into byte `e` of word[p] (four grid points per word).
-__device__ __forceinline__ void fixed_point_digits(double v, int e, uint32_t (&word)[Q_NP]) {
-    const int sh = 8 * e;
-    if (!(v > -1.0e290)) {
-        word[Q_NV] |= 1u << sh;
-        return;
-    }
-    const long long x = __double2ll_rn(fmin(fmax(v, -1000.0), 1000.0) * (double)(1ll << Q_FRAC));
-    uint32_t u = (uint32_t)x;
-    const int hi = (int)(x >> 32);
+// exp(a) for a in [-50, 0]: round-to-nearest split a = n ln2 + r, |r| <= 0.3466, Taylor polynomial of degree 12
+// (remainder < 3e-16 relative), scaling by an exponent-field add.  Replaces the library exp() in the sweep that only
+// needs the sum of the row (a per-row constant, which the joint posterior does not even see): no special cases, no
+// denormals, 22 instructions.
+__constant__ double c_exp_taylor[13] = {1.0,
+                                        1.0,
+                                        0.5,
+                                        1.66666666666666666667e-01,
+                                        4.16666666666666666667e-02,
+                                        8.33333333333333333333e-03,
+                                        1.38888888888888888889e-03,
+                                        1.98412698412698412698e-04,
+                                        2.48015873015873015873e-05,
+                                        2.75573192239858906526e-06,
+                                        2.75573192239858906526e-07,
+                                        2.50521083854417187751e-08,
+                                        2.08767569878680989792e-09};
+__device__ __forceinline__ double exp_m50_0(double a) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
+    const double t = fma(a, 1.44269504088896340736, MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01, a);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = c_exp_taylor[12];
 #pragma unroll
-    for (int p = 0; p < Q_NV - 1; ++p) {
-        const uint32_t dg = u & 0xFFu;
-        word[p] |= dg << sh;
-        u = (u >> 8) + (dg >> 7);  // a digit >= 128 stands for digit - 256: carry one into the next
-    }
-    word[Q_NV - 1] |= ((uint32_t)(hi + (int)u) & 0xFFu) << sh;
+    for (int i = 11; i >= 0; --i) p = fma(p, r, c_exp_taylor[i]);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
+
+// Fixed-point planes (contract_i8.cu) of four consecutive table values: value = 2^-Q_FRAC * sum_p 256^p d_p with signed
+// bytes d_p, plus the indicator plane for values at or below the "log 0" sentinel.  x = rint(v 2^Q_FRAC) comes from the
+// mantissa of v 2^Q_FRAC + 1.5 2^52; the balanced digits of x are the ordinary bytes of x + 0x8080808080 with the top bit
+// of each flipped (adding 128 to every digit makes them ordinary base-256 digits); byte permutes transpose the four
+// 32-bit words into one word per plane.  |v| <= 752 by construction (a difference of two values in [-752, 0]).
+__device__ __forceinline__ void fixed_point_quad(const double (&v)[4], uint32_t (&word)[Q_NP]) {
+    const double MAGIC = 6755399441055744.0;
+    const long long BIAS = 0x8080808080ll;
+    uint32_t lo[4], hi = 0u, flag = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double y = fma(v[e], (double)(1ll << Q_FRAC), MAGIC);
+        long long x = __double_as_longlong(y) - __double_as_longlong(MAGIC) + BIAS;
+        if (!(v[e] > -1.0e290)) {
+            x = BIAS;
+            flag |= 1u << (8 * e);
+        }
+        lo[e] = (uint32_t)x ^ 0x80808080u;
+        hi |= (((uint32_t)(x >> 32) ^ 0x80u) & 0xFFu) << (8 * e);
+    }
+    const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+    const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+    word[0] = __byte_perm(t0, t1, 0x5410);
+    word[1] = __byte_perm(t0, t1, 0x7632);
+    word[2] = __byte_perm(t2, t3, 0x5410);
+    word[3] = __byte_perm(t2, t3, 0x7632);
+    word[4] = hi;
+    word[5] = flag;
+}
+static_assert(Q_NV == 5 && Q_NP == 6, "fixed_point_quad is written for five value planes and one indicator plane");
 
 // The sweeps (one warp per row; lane l owns the grid points 4 l + 128 j .. + 3, so every access is a 16- or 32-byte
 // vector and the index arithmetic is shared by four points; the row lives in a per-warp shared-memory buffer):
 //   1. a_k = log NB_k + log(1 - d_k) and its maximum;  M = max(max_k a_k, max_k log d_k + f)          (:188-192)
-//   2. S = sum_k exp(a_k - M) + exp(f - M) * sum_k d_k.  exp() is only evaluated where a_k - M > -45: the other terms
-//      are below 3e-20 of S >= 1.  The drop-out part of the sum is one multiply (sum_k d_k comes from cell_prep).
+//   2. S = sum_k exp(a_k - M) + exp(f - M) * sum_k d_k.  Terms with a_k - M <= -45 are below 3e-20 of S >= 1 and are
+//      dropped; the drop-out part of the sum is one multiply (sum_k d_k comes from cell_prep).
 //   3. lp_k = log(exp(a_k - M) + exp(log d_k + f - M)) - log S.  When one term exceeds the other by more than 37.5 nats
 //      the smaller one is below half an ulp of the sum and log(exp(hi)) = hi, so no exp and no log is evaluated; in the
 //      cross-over band, and below -708 where the reference's own exp() underflows gradually, the reference's expression
 //      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
-// Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes (qtable).
+// Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes (qtable); MODES: also row_mode.
+template <bool MODES>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 3)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
                     const int32_t *__restrict__ row_x, const double4 *__restrict__ rowc, int64_t n_rows, CellPrep prep,
@@ -506,7 +547,8 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double a = v[e] - maxp;
-                if (k0 + e < K && a > -45.0) sum += exp(a);
+                const double ex = exp_m50_0(fmax(a, -50.0));
+                sum += (k0 + e < K && a > -45.0) ? ex : 0.0;
             }
         }
         sum = warp_sum(sum) + exp(fp - maxp) * prep.scfp[c];
@@ -519,7 +561,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         for (int k0 = 4 * lane; k0 < kp; k0 += 128) {
             double v[4] = {0.0, 0.0, 0.0, 0.0};
             if (k0 < K) {
-                double a[4], dk[4], z[4] = {0.0, 0.0, 0.0, 0.0};
+                double a[4], dk[4], z[4] = {0.0, 0.0, 0.0, 0.0}, L[4];
                 *reinterpret_cast<double2 *>(&a[0]) = *reinterpret_cast<const double2 *>(nb + k0);
                 *reinterpret_cast<double2 *>(&a[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
                 *reinterpret_cast<double2 *>(&dk[0]) = *reinterpret_cast<const double2 *>(lcfp + k0);
@@ -528,23 +570,33 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                     *reinterpret_cast<double2 *>(&z[0]) = *reinterpret_cast<const double2 *>(zr + k0);
                     *reinterpret_cast<double2 *>(&z[2]) = *reinterpret_cast<const double2 *>(zr + k0 + 2);
                 }
+                bool slow = false;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const double ae = a[e] - maxp;
-                    const double de = (dk[e] + fp) - maxp;
-                    const double hi = fmax(ae, de), lo = fmin(ae, de);
-                    double L = hi;
-                    if (hi < -746.0)
-                        L = -INFINITY;  // both exponentials underflow to exactly 0
-                    else if (!(hi >= -708.0 && hi - lo > 37.5))
-                        L = log(exp(ae) + exp(de));  // cross-over or gradual-underflow band: as the reference writes it
-                    double t = L - lsum;
+                    a[e] -= maxp;
+                    dk[e] = (dk[e] + fp) - maxp;
+                    const double hi = fmax(a[e], dk[e]), lo = fmin(a[e], dk[e]);
+                    const bool dead = hi < -746.0;  // both exponentials underflow to exactly 0
+                    const bool easy = hi >= -708.0 && hi - lo > 37.5;
+                    L[e] = dead ? -INFINITY : hi;
+                    slow = slow || !(dead || easy);
+                }
+                if (slow) {  // cross-over or gradual-underflow band somewhere in this quad: as the reference writes it
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double hi = fmax(a[e], dk[e]), lo = fmin(a[e], dk[e]);
+                        if (!(hi < -746.0) && !(hi >= -708.0 && hi - lo > 37.5)) L[e] = log(exp(a[e]) + exp(dk[e]));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double t = L[e] - lsum;
                     if (k0 + e < K) {
-                        if (besti == 0x7fffffff || t > best) {
+                        if (MODES && (besti == 0x7fffffff || t > best)) {
                             best = t;
                             besti = k0 + e;
                         }
-                        if (t < sentinel) t = sentinel;
+                        if (!(t >= sentinel)) t = sentinel;
                         v[e] = t - z[e];
                     }
                 }
@@ -555,10 +607,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
             }
             if (qtable) {
                 uint32_t word[Q_NP];
-#pragma unroll
-                for (int p = 0; p < Q_NP; ++p) word[p] = 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) fixed_point_digits(v[e], e, word);
+                fixed_point_quad(v, word);
                 const int ch = k0 / Q_CW, i = k0 - ch * Q_CW;
                 const int w = min(Q_CW, kp - ch * Q_CW);
                 uint32_t *dst = reinterpret_cast<uint32_t *>(sq + ch * (Q_NP * Q_CW) + i);
@@ -568,13 +617,15 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         }
         if (write_f64)
             for (int k = kp + lane; k < ld_table; k += 32) out[k] = 0.0;
+        if (MODES) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-            if (ob > best || (ob == best && oi < besti) || (besti == 0x7fffffff && oi != 0x7fffffff)) {
-                best = ob;
-                besti = oi;
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti) || (besti == 0x7fffffff && oi != 0x7fffffff)) {
+                    best = ob;
+                    besti = oi;
+                }
             }
         }
         __syncwarp();
@@ -584,7 +635,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
             for (int j = lane; j < (Q_NP * kp) / 16; j += 32) dst[j] = src[j];
         }
         __syncwarp();
-        if (lane == 0 && row_mode) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
+        if (MODES && lane == 0) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
     }
 }
 
@@ -635,11 +686,14 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, con
     const int64_t cap = 148 * 64;  // grid-stride beyond this
     if (blocks > cap) blocks = cap;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
-        lp_rows_fast_kernel<<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(models, ld_models, n_cells, row_cell_map, row_x,
-                                                                        (const double4 *)row_const, n_rows, prep, K,
-                                                                        sentinel, table, ld_table, row_mode, which,
-                                                                        zero_row, based, write_f64, qtable,
-                                                                        q_row_bytes(K));
+        if (row_mode)
+            lp_rows_fast_kernel<true><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
+                models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
+                ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K));
+        else
+            lp_rows_fast_kernel<false><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
+                models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
+                ld_table, nullptr, which, zero_row, based, write_f64, qtable, q_row_bytes(K));
         return cudaGetLastError();
     }
     if (qtable || !write_f64) return cudaErrorInvalidValue;  // the general kernel writes the FP64 table only

@@ -199,9 +199,10 @@ typedef struct {
 enum {
     SCDE_B200_T_DEDUP = 0,   /* unique-count table indices */
     SCDE_B200_T_LPTABLE,     /* per-cell log-posterior rows */
-    SCDE_B200_T_CONTRACT,    /* bootstrap contraction + softmax + average (all joints) */
+    SCDE_B200_T_CONTRACT,    /* bootstrap contraction (all joints); the FP64 kernels' time includes their soft-max */
     SCDE_B200_T_RATIO,       /* sliding product + summary (all passes) */
-    SCDE_B200_T_OTHER,       /* W build, transposes, memsets */
+    SCDE_B200_T_OTHER,       /* W build, entry lists, zero-count base sums, memsets */
+    SCDE_B200_T_SOFTMAX,     /* soft-max over the grid + average over boots after the tcgen05 contraction kernel */
     SCDE_B200_T_TOTAL,
     SCDE_B200_T_COUNT
 };

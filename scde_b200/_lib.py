@@ -13,8 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCDE_B200_LIB") or os.path.join(_HERE, "libscde_b200.so")
 
-T_DEDUP, T_LPTABLE, T_CONTRACT, T_RATIO, T_OTHER, T_TOTAL, T_COUNT = range(7)
-STAGE_NAMES = ["dedup", "lp_table", "contract", "ratio", "other", "total"]
+T_DEDUP, T_LPTABLE, T_CONTRACT, T_RATIO, T_OTHER, T_SOFTMAX, T_TOTAL, T_COUNT = range(8)
+STAGE_NAMES = ["dedup", "lp_table", "contract", "ratio", "other", "softmax", "total"]
 
 i32p = C.POINTER(C.c_int32)
 f64p = C.POINTER(C.c_double)

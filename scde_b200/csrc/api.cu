@@ -333,11 +333,20 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.ld_jp = ld_jp;
         q.err = ctx->flags.p;
         q.layout = getenv("SCDE_B200_I8_INTERLEAVE") ? 1 : 0;
-        e0 = tm ? tm->begin(st) : -1;
-        int nl = 0;
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
-        SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, scr.T.p, st, &nl));
-        if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, nl);
+        const int max_genes = contract_tiled_max_genes();
+        for (int g0 = 0; g0 < t.n_genes; g0 += max_genes) {
+            const int n_pos = (t.n_genes - g0) < max_genes ? (t.n_genes - g0) : max_genes;
+            for (int ps = 0; ps < passes; ++ps) {
+                e0 = tm ? tm->begin(st) : -1;
+                SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
+                if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
+                const int nb = (n_boot - ps * WP_TILED) < WP_TILED ? (n_boot - ps * WP_TILED) : WP_TILED;
+                e0 = tm ? tm->begin(st) : -1;
+                SCDE_CUDA(launch_softmax_avg(scr.T.p, lists.order + g0, t.K, nb, scale, jp_dev, ld_jp, ps > 0, n_pos, st));
+                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, 1);
+            }
+        }
         return SCDE_B200_OK;
     }
     if (!t.f64_rows) {
@@ -990,7 +999,7 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.ld_jp = 0;
     q.err = ctx->flags.p;
     q.layout = layout;
-    SCDE_CUDA(launch_contract_i8(q, ctx->n_sm, d_t.p, st, nullptr));
+    SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
     SCDE_CUDA(cudaMemcpyAsync(t_out, d_t.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));
     int rerun = 0;

@@ -166,7 +166,10 @@ struct ContractI8Args {
     int layout;        // shared-memory operand layout: 0 = 128-byte swizzle (production), 1 = interleave (cross-check)
 };
 bool contract_i8_supported(int K, int ld_table, int ld_lst);
-cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches);
+// one launch: genes order[g0 .. g0 + n_pos) (n_pos <= contract_tiled_max_genes()), boots [104 pass, 104 pass + 104);
+// raw T[boot, grid] tiles into t_scratch -- follow with launch_softmax_avg
+cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
+                                    cudaStream_t st);
 
 // ---- ratio_summary.cu ----------------------------------------------------------------------------
 struct RatioArgs {

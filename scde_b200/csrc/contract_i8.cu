@@ -424,8 +424,9 @@ bool contract_i8_supported(int K, int ld_table, int ld_lst) {
     return K >= 1 && K <= KP_TILED && ld_table == KP_TILED && (ld_lst % Q_ES) == 0;
 }
 
-cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches) {
-    if (a.n_genes <= 0) return cudaSuccess;
+cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
+                                    cudaStream_t st) {
+    if (n_pos <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<Q_LAYOUT_SW128>,
@@ -438,45 +439,29 @@ cudaError_t launch_contract_i8(const ContractI8Args &a, int n_sm, double *t_scra
     }
     const int kp = round_up(a.K, 16);
     const int n_chunks = (kp + Q_CW - 1) / Q_CW;
-    const int w_last = kp - (n_chunks - 1) * Q_CW;
-    const int passes = (a.n_boot + WP_TILED - 1) / WP_TILED;
-    const int max_genes = contract_tiled_max_genes();
-    for (int g0 = 0; g0 < a.n_genes; g0 += max_genes) {
-        const int n_pos = (a.n_genes - g0) < max_genes ? (a.n_genes - g0) : max_genes;
-        for (int ps = 0; ps < passes; ++ps) {
-            I8Params p;
-            p.qtable = a.qtable;
-            p.ldq = a.ldq;
-            p.lst_row = a.lists.row;
-            p.lst_cell = a.lists.cell;
-            p.lst_len = a.lists.len;
-            p.order = a.lists.order + g0;
-            p.ld_lst = a.lists.ld;
-            p.W8 = a.W8 + (size_t)ps * a.n_w_rows * Q_WB;
-            p.Z = a.Z ? a.Z + (size_t)ps * WP_TILED * KP_TILED : nullptr;
-            p.T = t_scratch;
-            p.sentinel = a.sentinel;
-            p.n_pos = n_pos;
-            p.n_chunks = n_chunks;
-            p.w_last = w_last;
-            p.err = a.err;
-            const int n_items = n_pos * n_chunks;
-            const int grid = n_sm < n_items ? n_sm : n_items;
-            if (a.layout == Q_LAYOUT_INTERLEAVE)
-                contract_i8_kernel<Q_LAYOUT_INTERLEAVE><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
-            else
-                contract_i8_kernel<Q_LAYOUT_SW128><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return e;
-            const int nb = (a.n_boot - ps * WP_TILED) < WP_TILED ? (a.n_boot - ps * WP_TILED) : WP_TILED;
-            if (a.jp) {  // NULL: leave the raw T of the last pass in t_scratch (probe entry)
-                e = launch_softmax_avg(t_scratch, a.lists.order + g0, a.K, nb, a.scale, a.jp, a.ld_jp, ps > 0, n_pos, st);
-                if (e != cudaSuccess) return e;
-            }
-            if (n_launches) *n_launches += a.jp ? 2 : 1;
-        }
-    }
-    return cudaSuccess;
+    I8Params p;
+    p.qtable = a.qtable;
+    p.ldq = a.ldq;
+    p.lst_row = a.lists.row;
+    p.lst_cell = a.lists.cell;
+    p.lst_len = a.lists.len;
+    p.order = a.lists.order ? a.lists.order + g0 : nullptr;
+    p.ld_lst = a.lists.ld;
+    p.W8 = a.W8 + (size_t)pass * a.n_w_rows * Q_WB;
+    p.Z = a.Z ? a.Z + (size_t)pass * WP_TILED * KP_TILED : nullptr;
+    p.T = t_scratch;
+    p.sentinel = a.sentinel;
+    p.n_pos = n_pos;
+    p.n_chunks = n_chunks;
+    p.w_last = kp - (n_chunks - 1) * Q_CW;
+    p.err = a.err;
+    const int n_items = n_pos * n_chunks;
+    const int grid = n_sm < n_items ? n_sm : n_items;
+    if (a.layout == Q_LAYOUT_INTERLEAVE)
+        contract_i8_kernel<Q_LAYOUT_INTERLEAVE><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
+    else
+        contract_i8_kernel<Q_LAYOUT_SW128><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace scde

@@ -14,8 +14,8 @@ indices are all-gathered over NCCL at the end of every step and rank 0 applies t
   value : genes/s with the counts, models, prior and draws already resident in HBM (device work only)
   e2e   : genes/s through the C ABI call with host (pinned) buffers -- H2D of the counts and D2H of results inside
   roofline : contraction kernel (the dominant one).  Default kernel (tcgen05.mma kind::i8 on the fixed-point table):
-             HBM-bound gather -- algorithmic bytes = visited (gene, cell) pairs x (6 planes x 416 B of table + 8 B of list
-             entry), against the measured copy bandwidth of MEASURED_PEAKS.json.  --kernel 1|2 (FP64 kernels): executed
+             HBM-bound gather -- algorithmic bytes = visited (gene, cell) pairs x (5 planes x 401 B of table + 8 B of list
+             entry; the row is stored in 2048 B), against the measured copy bandwidth of MEASURED_PEAKS.json.  --kernel 1|2 (FP64 kernels): executed
              2*K*B flops per visited pair against the FP64 DFMA peak measured live on the same device
   cpu_baseline : oracle port of the reference loop nest, all host cores, bounded gene sample
 """
@@ -338,7 +338,7 @@ def main():
     stage_ms = {k: float(np.mean([s["ms"][k] for s in stats_acc])) for k in stats_acc[-1]["ms"]}
     if args.kernel in (0, 3):
         # tcgen05 fixed-point kernel: a gather.  Per visited pair the kernel has to read the pair's table row once over
-        # all chunk items (6 planes x 416 B) and its list entry (8 B); W rows and the zero-count base are L2-resident
+        # all piece items (5 planes x 401 B; stored as 4 x 512 B) and its list entry (8 B); W rows and the zero-count base are L2-resident
         # and the T tiles it writes are read back by the soft-max kernel from L2, so they are not counted as
         # algorithmic HBM bytes.
         n_kernel = n_c  # launches of contract_i8_kernel (its soft-max launches are timed as their own stage)
@@ -349,7 +349,7 @@ def main():
             peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
         except Exception:
             peak = 6650.0
-        bytes_alg = float(entries) * (6 * 416 + 8)
+        bytes_alg = float(entries) * (5 * K_GRID + 8)
         achieved = bytes_alg / (ms_c * 1e-3) / 1e9
         traffic = None
         try:
@@ -363,10 +363,10 @@ def main():
                 "traffic": traffic, "kernel": "contract_i8_kernel (tcgen05.mma kind::i8)",
                 "launches_per_step": n_kernel, "avg_launch_ms": ms_c / max(1, n_kernel),
                 "bytes_per_launch": bytes_alg / max(1, n_kernel),
-                "bytes_per_visited_pair": 6 * 416 + 8,
+                "bytes_per_visited_pair": 5 * K_GRID + 8, "stored_bytes_per_visited_pair": 2048 + 8,
                 "entries_visited_frac": entries / dense_entries,
                 "peak_source": peak_src,
-                "int8_tops": 6.0 * flops_exec / (ms_c * 1e-3) / 1e12,  # six int8 planes per FP64 multiply-add
+                "int8_tops": 5.0 * flops_exec / (ms_c * 1e-3) / 1e12,  # five int8 planes per FP64 multiply-add
                 "fp64_equivalent_tflops": flops_exec / (ms_c * 1e-3) / 1e12,
                 "fp64_peak_tflops": fp64_peak,
                 "dense_equivalent_tflops": flops_dense / (ms_c * 1e-3) / 1e12,
@@ -400,7 +400,7 @@ def main():
                                f"B={N_BOOT}, K={K_GRID}" + (", batch-corrected" if batch is not None else ""),
                    "genes_total": total_genes, "sharding": "genes, one shard per rank, NCCL all_gather of Z/indices at the end",
                    "l2": "inputs larger than L2 (counts %.1f GB, lp table %.1f GB)" % (
-                       counts.nbytes / 1e9, stats_acc[-1]["table_rows"] * 416 * (6 if args.kernel in (0, 3) else 8) / 1e9)},
+                       counts.nbytes / 1e9, stats_acc[-1]["table_rows"] * (2048 if args.kernel in (0, 3) else 416 * 8) / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "genes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms},

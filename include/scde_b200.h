@@ -242,19 +242,22 @@ SCDE_B200_API int scde_b200_cell_table(scde_b200_ctx *ctx, const double *model_r
  * denominator for the contraction kernel (MEASURED_PEAKS.json has no FP64 entry). */
 SCDE_B200_API int scde_b200_measure_fp64_peak(scde_b200_ctx *ctx, double *tflops);
 /* Contraction kernel of the bootstrap joint posterior: 0 = pick automatically (the tcgen05 fixed-point kernel where it
- * applies: K <= 416 grid points, zero-base table, multiplicities <= 127 -- otherwise FP64); 1 = generic FP64 kernel;
- * 2 = tiled FP64 kernel (mma.sync DMMA, exact to rounding); 3 = tcgen05.mma kind::i8 fixed-point kernel (the table is
- * rounded to 2^-29, sums are exact integers; error if it does not apply). */
+ * applies: K <= 408 grid points, zero-base table, multiplicities <= 127, every (gene, boot) keeps at least one grid point
+ * that no drawn row marks "log 0" -- otherwise FP64); 1 = generic FP64 kernel; 2 = tiled FP64 kernel (mma.sync DMMA, exact
+ * to rounding); 3 = tcgen05.mma kind::i8 fixed-point kernel (the table is rounded to 2^-29, sums are exact integers; error
+ * if it does not apply at all, FP64 rerun if the data leave its range). */
 SCDE_B200_API int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which);
-/* Probe of the tcgen05 contraction kernel alone, on caller-made operands (tests): qtable[n_rows][6 * round_up(n_grid, 16)]
- * int8 in the layout [chunk of 80 grid points][plane 0..5][w], w8[n_w_rows][128] int8, entry lists as (row, W row) with
- * ld_lst a multiple of 32 and entries beyond lst_len[g] up to the next multiple of 32 pointing at an all-zero W row.
- * layout: 0 = 128-byte-swizzle operand layout (production), 1 = interleave layout (cross-check).
- * t_out[n_genes][104][416] = 2^-29 * sum_p 256^p (sum_e plane_p[row_e][k] * w8[cell_e][b]) - 1e300 * (plane-5 sum). */
+/* Probe of the tcgen05 contraction kernel alone, on caller-made operands (tests): qtable[n_rows][512 * ceil(n_grid / 102)]
+ * int8 in the layout [piece of 102 grid points][plane 0..4][102] (+ 2 zero bytes per piece); row_range[n_rows] (may be
+ * NULL) = first | last << 16 grid point of the row that is not "log 0"; w8[n_w_rows][128] int8; entry lists as
+ * (row, W row) with ld_lst a multiple of 32 and entries beyond lst_len[g] up to the next multiple of 32 pointing at an
+ * all-zero W row.
+ * t_out[n_genes][104][416] = 2^-29 * sum_p 256^p (sum_e plane_p[row_e][k] * w8[cell_e][b]), or -1e300 where a drawn row
+ * is "log 0"; *flags_out (may be NULL) = the kernel's status word (4: a (gene, boot) without any admissible grid point). */
 SCDE_B200_API int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
-                                const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row, const int32_t *lst_cell,
-                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t layout,
-                                double *t_out);
+                                const uint32_t *row_range, const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row,
+                                const int32_t *lst_cell, const int32_t *lst_len, int32_t n_genes, int32_t ld_lst,
+                                double *t_out, int32_t *flags_out);
 
 #ifdef __cplusplus
 }

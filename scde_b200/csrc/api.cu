@@ -120,7 +120,8 @@ struct scde_b200_ctx {
     cudaStream_t stream = nullptr;
     int n_sm = 148;
     int contract_kernel = 0;  // 0 auto (tcgen05 int8 where supported), 1 generic, 2 tiled FP64 (DMMA), 3 tcgen05 int8
-    DBuf<int32_t> flags;      // device status word of the int8 path: 1 = a multiplicity > 127, 2 = kernel watchdog
+    DBuf<int32_t> flags;      // device status word of the int8 path: 1 = a multiplicity > 127, 2 = kernel watchdog,
+                              // 4 = sentinel ranges need the FP64 kernel
     DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
     bool ws_busy = false;
 };
@@ -136,6 +137,7 @@ struct LpTable {
     DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
     DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc, scfp;
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
+    DBuf<uint32_t> qrange;  // [n_rows] non-sentinel range of every row (klo | khi << 16)
     bool want_q = false, has_q = false;
     bool f64_rows = true;  // false: the FP64 rows of non-zero counts were not stored (planes only)
     bool want_modes = true;  // row_mode (argmax of every row) is needed: only for return.individual.posterior.modes
@@ -181,10 +183,14 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
                   fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr, fast ? t.scfp.p : nullptr};
     // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
     // counts are then not stored at all), by a separate pass over the FP64 table for the general kernel
-    const bool q_any = t.want_q && t.zero_base && t.ld == KP_TILED;
+    const bool q_any = t.want_q && t.zero_base && t.ld == KP_TILED && t.K <= Q_MAX_K;
     const bool q_fused = q_any && fast && !getenv("SCDE_B200_Q_SEPARATE");
-    if (q_any) SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
+    if (q_any) {
+        SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
+        SCDE_CUDA(t.qrange.ensure((size_t)t.n_rows));
+    }
     int8_t *qf = q_fused ? t.q.p : nullptr;
+    uint32_t *qr = q_fused ? t.qrange.p : nullptr;
     if (t.zero_base) {
         SCDE_CUDA(t.zero_row.ensure((size_t)t.n_cells));
         SCDE_CUDA(t.based.ensure((size_t)t.n_cells));
@@ -201,21 +207,21 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
         SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
                                  local_theta, t.sentinel, t.table.p, t.ld, rmode, 1, t.zero_row.p, nullptr, rowc, 1, qf,
-                                 st));
+                                 qr, st));
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
                                  local_theta, t.sentinel, t.table.p, t.ld, rmode, 2, t.zero_row.p, t.based.p, rowc,
-                                 q_fused ? 0 : 1, qf, st));
+                                 q_fused ? 0 : 1, qf, qr, st));
         nl += 3;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
                                  local_theta, t.sentinel, t.table.p, t.ld, rmode, 0, nullptr, nullptr, rowc, 1, nullptr,
-                                 st));
+                                 nullptr, st));
     }
     t.has_q = q_any;
     t.f64_rows = !(q_fused && t.zero_base);
     if (q_any && !q_fused) {
-        SCDE_CUDA(launch_quantize_rows(t.table.p, t.ld, t.K, t.n_rows, t.q.p, st));
+        SCDE_CUDA(launch_quantize_rows(t.table.p, t.ld, t.K, t.n_rows, t.q.p, t.qrange.p, st));
         ++nl;
     }
     if (tm) tm->end(SCDE_B200_T_LPTABLE, e0, st, nl);
@@ -261,6 +267,7 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 struct JointScratch {
     DBuf<double> W, Z, zpart, T;
     DBuf<int8_t> W8;
+    DBuf<uint32_t> SR;  // sentinel range of every (gene, boot) of one launch of the tcgen05 kernel
     DBuf<int32_t> lst_row, lst_cell, lst_len, order;
     DBuf<unsigned long long> total;  // running sum of list lengths over the joints of one run
 };
@@ -320,6 +327,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         ContractI8Args q{};
         q.qtable = t.q.p;
         q.ldq = q_row_bytes(t.K);
+        q.row_range = t.qrange.p;
         q.lists = lists;
         q.W8 = scr.W8.p;
         q.n_w_rows = n_w_rows;
@@ -332,14 +340,17 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.jp = jp_dev;
         q.ld_jp = ld_jp;
         q.err = ctx->flags.p;
-        q.layout = getenv("SCDE_B200_I8_INTERLEAVE") ? 1 : 0;
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
         const int max_genes = contract_tiled_max_genes();
+        SCDE_CUDA(scr.SR.ensure(contract_i8_range_words(t.n_genes < max_genes ? t.n_genes : max_genes)));
         for (int g0 = 0; g0 < t.n_genes; g0 += max_genes) {
             const int n_pos = (t.n_genes - g0) < max_genes ? (t.n_genes - g0) : max_genes;
             for (int ps = 0; ps < passes; ++ps) {
                 e0 = tm ? tm->begin(st) : -1;
-                SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
+                SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps, scr.SR.p, st));
+                if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
+                e0 = tm ? tm->begin(st) : -1;
+                SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, scr.SR.p, st));
                 if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
                 const int nb = (n_boot - ps * WP_TILED) < WP_TILED ? (n_boot - ps * WP_TILED) : WP_TILED;
                 e0 = tm ? tm->begin(st) : -1;
@@ -390,7 +401,9 @@ int reset_flags(scde_b200_ctx *ctx) {
     SCDE_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int32_t), ctx->stream));
     return SCDE_B200_OK;
 }
-// after the stream has been synchronised: 0 = fine, 1 = rerun on the FP64 kernel (a multiplicity above 127), < 0 error
+// after the stream has been synchronised: 0 = fine, 1 = rerun on the FP64 kernel (a multiplicity above 127, or a
+// (gene, boot) whose drawn rows are "log 0" at every grid point / a row whose "log 0" points are not the two ends of
+// the grid: the FP64 kernel adds the sentinels as the reference does), < 0 error
 int read_flags(scde_b200_ctx *ctx, int *rerun) {
     *rerun = 0;
     if (!ctx->flags.p) return SCDE_B200_OK;
@@ -400,7 +413,7 @@ int read_flags(scde_b200_ctx *ctx, int *rerun) {
         set_error("tcgen05 contraction kernel aborted (pipeline watchdog); use scde_b200_set_contract_kernel(ctx, 2)");
         return SCDE_B200_ECUDA;
     }
-    if (f & 1) *rerun = 1;
+    if (f & (1 | 4)) *rerun = 1;
     return SCDE_B200_OK;
 }
 
@@ -952,9 +965,9 @@ int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, in
 }
 
 int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
-                                const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row, const int32_t *lst_cell,
-                                const int32_t *lst_len, int32_t n_genes, int32_t ld_lst, int32_t layout,
-                                double *t_out) {
+                                const uint32_t *row_range, const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row,
+                                const int32_t *lst_cell, const int32_t *lst_len, int32_t n_genes, int32_t ld_lst,
+                                double *t_out, int32_t *flags_out) {
     CHECK_CTX(ctx);
     if (!qtable || !w8 || !lst_row || !lst_cell || !lst_len || !t_out || n_rows < 1 || n_genes < 1 || n_w_rows < 1 ||
         !contract_i8_supported(n_grid, KP_TILED, ld_lst) || n_genes > contract_tiled_max_genes()) {
@@ -972,20 +985,24 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     cudaStream_t st = ctx->stream;
     DBuf<int8_t> d_q, d_w;
     DBuf<int32_t> d_row, d_cell, d_len;
+    DBuf<uint32_t> d_rr, d_sr;
     DBuf<double> d_t;
     const int ldq = q_row_bytes(n_grid);
     TRY(upload(d_q, qtable, (size_t)n_rows * ldq, st));
+    if (row_range) TRY(upload(d_rr, row_range, (size_t)n_rows, st));
     TRY(upload(d_w, w8, (size_t)n_w_rows * Q_WB, st));
     TRY(upload(d_row, lst_row, (size_t)n_genes * ld_lst, st));
     TRY(upload(d_cell, lst_cell, (size_t)n_genes * ld_lst, st));
     TRY(upload(d_len, lst_len, (size_t)n_genes, st));
     const size_t nt = (size_t)n_genes * WP_TILED * KP_TILED;
     SCDE_CUDA(d_t.ensure(nt));
+    SCDE_CUDA(d_sr.ensure(contract_i8_range_words(n_genes)));
     SCDE_CUDA(cudaMemsetAsync(d_t.p, 0, sizeof(double) * nt, st));
     TRY(reset_flags(ctx));
     ContractI8Args q{};
     q.qtable = d_q.p;
     q.ldq = ldq;
+    q.row_range = row_range ? d_rr.p : nullptr;
     q.lists = GeneLists{d_row.p, d_cell.p, d_len.p, nullptr, ld_lst};
     q.W8 = d_w.p;
     q.n_w_rows = n_w_rows;
@@ -998,12 +1015,17 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.jp = nullptr;
     q.ld_jp = 0;
     q.err = ctx->flags.p;
-    q.layout = layout;
-    SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
+    SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
+    SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, d_sr.p, st));
     SCDE_CUDA(cudaMemcpyAsync(t_out, d_t.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));
-    int rerun = 0;
-    TRY(read_flags(ctx, &rerun));
+    int32_t f = 0;
+    SCDE_CUDA(cudaMemcpy(&f, ctx->flags.p, sizeof(f), cudaMemcpyDeviceToHost));
+    if (flags_out) *flags_out = f;
+    if (f & 2) {
+        set_error("tcgen05 contraction kernel aborted (pipeline watchdog)");
+        return SCDE_B200_ECUDA;
+    }
     return SCDE_B200_OK;
 }
 

@@ -52,9 +52,9 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, con
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
-                           cudaStream_t st);
+                           uint32_t *row_range, cudaStream_t st);
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
-// row's fixed-point planes (contract_i8.cu) -- both only on the constant-theta fast path
+// row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
 cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
                               int64_t n_rows, void *row_const, cudaStream_t st);
@@ -136,22 +136,31 @@ int contract_tiled_max_genes();  // genes per launch of a tiled kernel (bounds t
 
 // ---- contract_i8.cu ------------------------------------------------------------------------------
 // Fixed-point form of the table for the tcgen05 (kind::i8) contraction: value = 2^-Q_FRAC * sum_{p < Q_NV} 256^p d_p with
-// signed 8-bit digits d_p, plus one indicator plane for the "log 0" sentinel.  A row is stored
-// [grid chunk of Q_CW points][plane][w] so the Q_NP planes of one chunk are one contiguous run.
+// signed 8-bit digits d_p.  A row is stored as pieces of Q_PIECE = 512 bytes, one per Q_PW = 102 grid points:
+// [piece][plane][102] (+ 2 zero bytes), so that one piece is exactly the 512 accumulator columns of an SM's tensor memory
+// and a row of the default grid (K = 401) is 2048 bytes.  The reference's "log 0" sentinel (-DBL_MAX/n/1.1) is not a
+// plane: every row carries the range [klo, khi] of its grid points that are NOT the sentinel (they form one interval for
+// every row the error models produce; a row where they do not is marked Q_RANGE_IRREGULAR and sends the call to the FP64
+// kernel), and a grid point of a (gene, boot) is "log 0" exactly when it lies outside the intersection of the ranges
+// of the drawn rows (sentinel_range_kernel).
 constexpr int Q_NV = 5;           // value planes
-constexpr int Q_NP = Q_NV + 1;    // + sentinel indicator plane
 constexpr int Q_FRAC = 29;        // fractional bits (|value| <= 1000 < 2^10 fits 5 digits)
-constexpr int Q_CW = 80;          // grid points per chunk: Q_NP * Q_CW = 480 of the 512 tensor-memory columns
+constexpr int Q_PW = 102;         // grid points per piece: Q_NV * Q_PW = 510 of the 512 tensor-memory columns
+constexpr int Q_PIECE = 512;      // bytes per piece
+constexpr int Q_MAX_K = 4 * Q_PW; // largest grid the kernel takes (T rows are KP_TILED = 416 wide)
 constexpr int Q_WB = 128;         // bytes per int8 W row: 104 boots + zero padding = M of the MMA
-int q_row_bytes(int K);           // Q_NP * round_up(K, 16)
-// planes of every row of an FP64 table (ld_table >= round_up(K, 16), columns K.. zero)
+constexpr uint32_t Q_RANGE_IRREGULAR = 0xFFFFFFFFu;
+inline int q_pieces(int K) { return (K + Q_PW - 1) / Q_PW; }
+inline int q_row_bytes(int K) { return q_pieces(K) * Q_PIECE; }
+// planes and ranges of every row of an FP64 table (ld_table >= K); one warp per row
 cudaError_t launch_quantize_rows(const double *table, int ld_table, int K, int64_t n_rows, int8_t *qtable,
-                                 cudaStream_t st);
+                                 uint32_t *row_range, cudaStream_t st);
 // W8[pass][row][128] = (int8) W[pass][row][0..104); *flag |= 1 if a multiplicity exceeds 127
 cudaError_t launch_w_to_i8(const double *W, int n_w_rows, int n_boot, int8_t *W8, int32_t *flag, cudaStream_t st);
 struct ContractI8Args {
     const int8_t *qtable;
     int ldq;
+    const uint32_t *row_range;  // [rows] klo | khi << 16 (NULL: no row holds a sentinel)
     GeneLists lists;   // ld a multiple of 32, lists padded to a multiple of 32 with zero-W entries
     const int8_t *W8;  // pass-major [ceil(n_boot/104)][n_w_rows][128]
     int n_w_rows;
@@ -162,14 +171,19 @@ struct ContractI8Args {
     int n_genes, K;
     double *jp;
     int ld_jp;
-    int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired
-    int layout;        // shared-memory operand layout: 0 = 128-byte swizzle (production), 1 = interleave (cross-check)
+    int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired, |= 4 if the sentinel ranges need the FP64 kernel
 };
 bool contract_i8_supported(int K, int ld_table, int ld_lst);
+size_t contract_i8_range_words(int n_genes);  // uint32 words of the (gene, boot) sentinel-range scratch
+// sr_scratch[n_pos][128] = sentinel range of every (gene, boot) of genes order[g0 .. g0 + n_pos), boots of `pass`
+// (no-op when a.row_range == NULL)
+cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, int pass, uint32_t *sr_scratch,
+                                   cudaStream_t st);
 // one launch: genes order[g0 .. g0 + n_pos) (n_pos <= contract_tiled_max_genes()), boots [104 pass, 104 pass + 104);
-// raw T[boot, grid] tiles into t_scratch -- follow with launch_softmax_avg
+// raw T[boot, grid] tiles into t_scratch -- follow with launch_softmax_avg.  sr: what launch_sentinel_ranges wrote
+// (required when a.row_range != NULL)
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
-                                    cudaStream_t st);
+                                    const uint32_t *sr, cudaStream_t st);
 
 // ---- ratio_summary.cu ----------------------------------------------------------------------------
 struct RatioArgs {

@@ -6,29 +6,35 @@
 // is bound by the 37 TFLOP/s FP64 rate.  Here the table is held in FIXED POINT instead: in the zero-base form every
 // table value D = lp(x) - lp(0) (or lp(x) itself) lies in [-751, 751] -- log of a normalised double -- or is the
 // reference's "log 0" sentinel (-DBL_MAX/n/1.1, :127,204).  D is rounded to a multiple of 2^-29 and split into five
-// signed radix-256 digits (int8 planes 0..4, value = 2^-29 * sum_p 256^p d_p); a sixth plane holds the sentinel
-// indicator.  W is a small non-negative integer (<= 127 is checked).  Every product and every sum is then EXACT in
-// int32 (|sum| <= 128 * draws), the planes are recombined in int64 and converted to FP64 once per (boot, grid point),
-// so the only error is the table rounding: |T error| <= draws * 2^-30 in the worst case and about
-// sqrt(2 * draws) * 2^-29 / sqrt(12) typically (5e-8 at 5000 cells per group) -- inside the 1e-6 tolerance on
-// log-posteriors, and independent of the summation order, so the result is deterministic by construction.
+// signed radix-256 digits (int8 planes 0..4, value = 2^-29 * sum_p 256^p d_p).  W is a small non-negative integer
+// (<= 127 is checked).  Every product and every sum is then EXACT in int32 (|sum| <= 128 * draws), the planes are
+// recombined in int64 and converted to FP64 once per (boot, grid point), so the only error is the table rounding:
+// |T error| <= draws * 2^-30 in the worst case and about sqrt(2 * draws) * 2^-29 / sqrt(12) typically (5e-8 at 5000
+// cells per group) -- inside the 1e-6 tolerance on log-posteriors, and independent of the summation order, so the
+// result is deterministic by construction.
+//
+// The sentinel is not summed at all.  A grid point of (gene, boot) is "log 0" exactly when some drawn row is "log 0"
+// there; the non-sentinel points of a row form one interval [klo, khi] (common.cuh), so it is enough to intersect the
+// intervals of the drawn rows: sentinel_range_kernel does that per (gene, boot) with packed 16-bit max / min, and the
+// epilogue writes the sentinel outside the intersection.  (gene, boot) pairs with an EMPTY intersection -- where the
+// reference's soft-max would compare multiples of the sentinel -- and irregular rows raise flag 4: the caller reruns on
+// the FP64 kernel, which adds the sentinels as the reference does.
 //
 // Kernel: persistent, one CTA per SM, three warp roles, no CTA-wide barrier in the steady state.
-//   * work item = (gene, grid chunk of up to 80 points).  One item accumulates all six planes of its chunk:
-//     D[boot (128 lanes, 104 real)][plane * w + i] in 6 * 80 = 480 of the SM's 512 tensor-memory columns.
-//   * producers (4 warps): gather the list entries' table pieces (480 contiguous bytes per entry: the table is stored
-//     [row][chunk][plane][w]) and W rows (128 bytes) with 16-byte cp.async straight into the UMMA "interleave" (no
-//     swizzle) canonical layout for MN-major operands -- lane (kk = lane & 7, piece) writes 16 bytes of entry kk to
-//     [k-group][piece][kk][16 B], so one warp instruction fills 512 contiguous bytes of shared memory (no bank
-//     conflicts) from eight 64-byte runs of global memory.  Completion is signalled by cp.async.mbarrier.arrive; a
-//     10-stage ring of 32 entries (19 KB per stage) keeps ~190 KB in flight per SM.
-//   * MMA (1 thread): per stage two tcgen05.mma (M = 128 boots, N = 240 = three planes, K = 32 entries), then
-//     tcgen05.commit onto the stage's "empty" barrier; after the last stage a commit onto the accumulator barrier.
-//   * epilogue (4 warps, one per 32-lane quarter of tensor memory): tcgen05.ld the six planes of 8 grid points at a
-//     time, recombine in int64, add the zero-count base Z[b, k] (FP64), store T[b, k]; softmax_avg_kernel
-//     (boot_contract.cu) finishes the gene.  Producers keep prefetching the next item's stages meanwhile.
-// Roofline: HBM/L2 gather bandwidth (608 bytes per visited (gene, cell) pair and chunk); the tensor pipe needs
-// 2 x 120 cycles per 32 entries, about a quarter of the time the gather takes.
+//   * work item = (gene, piece): one 512-byte piece of the gene's table rows = 102 grid points x 5 planes.  The item
+//     accumulates D[boot (128 lanes, 104 real)][plane * 102 + i] in all 512 tensor-memory columns of the SM.
+//   * producers (Q_PGROUPS x 4 warps): gather the list entries' pieces (512 contiguous, 512-byte-aligned bytes per
+//     entry) and W rows (128 bytes) with 16-byte cp.async straight into the canonical 128-byte-swizzle layout of an
+//     MN-major operand; completion is signalled by cp.async.mbarrier.arrive; a 10-stage ring of 32 entries (20 KB per
+//     stage) keeps up to 200 KB in flight per SM.  The loop is branch-free per stage: constant offsets, slot / phase
+//     counters instead of divisions, list entries fetched 8-16 of the group's stages ahead.
+//   * MMA (1 thread): per stage two tcgen05.mma (M = 128 boots, N = 256, K = 32 entries), then tcgen05.commit onto the
+//     stage's "empty" barrier; after the last stage a commit onto the accumulator barrier.
+//   * epilogue (4 warps, one per 32-lane quarter of tensor memory): tcgen05.ld the five planes of 8 grid points at a
+//     time, recombine in int64, add the zero-count base Z[b, k] (FP64), apply the sentinel range, store T[b, k];
+//     softmax_avg_kernel (boot_contract.cu) finishes the gene.  Producers keep prefetching the next item meanwhile.
+// Roofline: HBM gather bandwidth (512 bytes per visited (gene, cell) pair and piece; tools/gather_bench.cu measures
+// 6.8 TB/s for this access pattern with 128 KB in flight per SM); the tensor pipe needs 2 x 128 cycles per 32 entries.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include <cfloat>
@@ -42,14 +48,18 @@ using namespace ptx;
 constexpr int Q_ES = 32;                         // list entries per stage = K of one tcgen05.mma.kind::i8
 constexpr int Q_NS = 10;                         // ring depth
 constexpr int Q_A_BYTES = Q_ES * Q_WB;           // W tile of a stage: 4096
-constexpr int Q_B_BYTES = Q_ES * 512;            // table tile of a stage: 480 bytes per entry, padded to 4 x 128
+constexpr int Q_B_BYTES = Q_ES * Q_PIECE;        // table tile of a stage: 16384
 constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;  // 20480, a multiple of the 1024-byte swizzle atom
-constexpr int Q_PGROUPS = 2;                     // producer warp groups; group g gathers the stages s = g (mod Q_PGROUPS) of an item
+#ifndef SCDE_Q_PGROUPS
+#define SCDE_Q_PGROUPS 2
+#endif
+constexpr int Q_PGROUPS = SCDE_Q_PGROUPS;        // producer warp groups; group g gathers the stages s = g (mod Q_PGROUPS) of an item
 constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS, Q_EPILOGUE_WARPS = 4;
 constexpr int Q_THREADS = (Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS + 1) * 32;  // + the MMA warp
 constexpr int Q_TMEM_COLS = 512;
 constexpr long long Q_WATCHDOG_CYCLES = 4000000000ll;  // a barrier wait longer than ~2 s aborts the kernel (err = 2)
-constexpr int Q_LAYOUT_SW128 = 0, Q_LAYOUT_INTERLEAVE = 1;
+static_assert(Q_NV * Q_PW <= Q_TMEM_COLS && Q_NV * Q_PW <= Q_PIECE, "a piece is one pass of tensor memory");
+static_assert((Q_PW & 1) == 0, "the epilogue reads pairs of columns");
 
 struct I8Smem {
     uint64_t full[Q_NS];
@@ -61,18 +71,18 @@ struct I8Smem {
 constexpr size_t Q_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)Q_NS * Q_STAGE_BYTES + sizeof(I8Smem);
 
 struct I8Params {
-    const int8_t *qtable;  // [rows][ldq]: row = [chunk][plane][w_chunk]
+    const int8_t *qtable;  // [rows][ldq]: row = [piece][plane][102] (+ 2)
     int64_t ldq;
     const int32_t *lst_row, *lst_cell, *lst_len, *order;
     int64_t ld_lst;
-    const int8_t *W8;  // this pass: [n_w_rows][128]
-    const double *Z;   // this pass: [104][416] or NULL
-    double *T;         // [n_pos][104][416]
-    double sentinel;   // added once per drawn "log 0" entry, as the FP64 path does
-    int n_pos;         // genes in this launch: positions [0, n_pos) of `order`
-    int n_chunks;      // grid chunks per gene; all but the last are Q_CW wide
-    int w_last;        // width of the last chunk (multiple of 16, <= Q_CW)
-    int32_t *err;      // device flag: 2 = watchdog abort
+    const int8_t *W8;    // this pass: [n_w_rows][128]
+    const double *Z;     // this pass: [104][416] or NULL
+    const uint32_t *SR;  // [n_pos][128] klo | khi << 16 of (gene position, boot), or NULL
+    double *T;           // [n_pos][104][416]
+    double sentinel;     // written where a drawn row is "log 0"
+    int n_pos;           // genes in this launch: positions [0, n_pos) of `order`
+    int n_pieces;        // pieces per gene
+    int32_t *err;        // device flag: 2 = watchdog abort
 };
 
 __device__ __forceinline__ bool wait_or_abort(I8Smem &sm, uint64_t *bar, uint32_t parity) {
@@ -88,161 +98,162 @@ __device__ __forceinline__ bool wait_or_abort(I8Smem &sm, uint64_t *bar, uint32_
     return true;
 }
 
+// item -> (gene position, piece); the pieces of one gene go to neighbouring CTAs of the same round, so the W rows and
+// list entries they share are L2 hits for three of the four
 struct Item {
-    int pos, chunk, w;
+    int pos, piece;
 };
 __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
-    // all full-width chunks first (genes heaviest first), the narrow last chunks at the end: they even out the tail
-    const int nfull = p.n_chunks - 1, n_first = p.n_pos * nfull;
     Item it;
-    if (item < n_first) {
-        it.pos = item / nfull;
-        it.chunk = item - it.pos * nfull;
-        it.w = Q_CW;
-    } else {
-        it.pos = item - n_first;
-        it.chunk = nfull;
-        it.w = p.w_last;
-    }
+    it.pos = item / p.n_pieces;
+    it.piece = item - it.pos * p.n_pieces;
     return it;
+}
+__device__ __forceinline__ int64_t item_gene(const I8Params &p, int item) {
+    const int pos = item / p.n_pieces;
+    return p.order ? p.order[pos] : pos;
 }
 
 // ---- producers ------------------------------------------------------------------------------------------------------
-// Warp w gathers entries 8w .. 8w+7 (one k-group of the MMA) of every stage.  List entries are read one coalesced load
-// per four stages and three groups ahead (a load issued at stage 4t is first used at stage 4t + 8), so the gather never
-// waits on the list: with a one-stage look-ahead the kernel ran at the latency of that dependent load (long-scoreboard
-// stalls were 66 % of the producers' cycles, profiles/r01p).
+// Warp (grp, kg) gathers entries 8 kg .. 8 kg + 7 (one k-group of the MMA) of the stages s = grp (mod Q_PGROUPS) of
+// every item.  Canonical 128-byte-swizzle layout of an MN-major operand: the bytes of one entry are split into runs of
+// 128 (8 pieces of 16 bytes); run r of entry kk of k-group kg sits at [r][kg][kk][128 B] and its piece j at
+// 16 * (j ^ kk).  Lane (l3 = lane >> 3, l7 = lane & 7) copies piece l7 of every run of entries l3 and l3 + 4: a warp
+// instruction moves four 128-byte runs of global memory into four 128-byte lines of shared memory -- coalesced on both
+// sides, no bank conflicts.
 //
-// SW128 layout (canonical 128-byte-swizzle layout of an MN-major operand): the bytes of one entry are split into runs of
-// 128 (8 pieces of 16 bytes), a run of entry kk sits at [run][k-group][kk][128 B] and its piece j at 16 * (j ^ kk).
-// Lane (r = lane >> 3, j = lane & 7) copies piece j of entries r and r + 4: a warp instruction moves four 128-byte runs of
-// global memory into four 128-byte lines of shared memory -- coalesced on both sides, no bank conflicts.
-// INTERLEAVE layout (no swizzle): piece j of entry kk at [k-group][j][kk][16 B]; lane (kk = lane & 7, q = lane >> 3) copies
-// pieces q, q + 4, ...  Verified first; kept as a cross-check (its shared-memory side serialises: the four pieces of one
-// 64-byte global run land 128 bytes apart, i.e. in the same banks).
-template <int LAYOUT>
+// List entries: lane (l3, l7) holds entries l3 and l3 + 4 of the warp's own-stage 8 t + l7 -- one load instruction
+// fetches the entries of eight own-stages, issued one block (8 own-stages = 8 Q_PGROUPS stages) before its first use, the
+// first two blocks at the start of the item; the identity of the NEXT item (gene, list length) is loaded one item
+// ahead.  An earlier version with a shorter look-ahead spent 17 % of the producers' cycles waiting on these loads and
+// 55 % issuing ~180 dependent instructions per stage (profiles/r01v); this loop issues about 45.
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void cp_async16_at(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst_smem), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
-    // A single warp issues the ~180 instructions of a stage (address arithmetic, ten cp.async, barrier traffic) at well
-    // under one per cycle, so four warps alone ran the gather at half the rate the memory system sustains
-    // (profiles/r01s): Q_PGROUPS groups of four warps take alternate stages.
-    const int grp = warp >> 2, kg = warp & 3;  // k-group of the MMA this warp fills: entries 8 kg .. 8 kg + 7 of a stage
-    int64_t q0 = 0;                            // stages of the items before this one
+    const int grp = warp >> 2, kg = warp & 3;
     const int l7 = lane & 7, l3 = lane >> 3;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // entry kk = l3 (and l3 + 4): line kk of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
+    const uint32_t d0 = (uint32_t)kg * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
+    const uint32_t d1 = (uint32_t)kg * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
+    const int8_t *wbase = p.W8 + l7 * 16;
+    int slot_b = 0;        // ring slot of the first stage of the current item
+    uint32_t fill_b = 0;   // how often that slot has been filled before
+    int item = blockIdx.x;
+    int64_t gene_n = 0;
+    int len_n = 0;
+    if (item < n_items) {
+        gene_n = item_gene(p, item);
+        len_n = p.lst_len[gene_n];
+    }
+    for (; item < n_items; item += gridDim.x) {
         const Item it = decode_item(p, item);
-        const int64_t gene = p.order ? p.order[it.pos] : it.pos;
-        const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
-        const int npieces = Q_NP * (it.w >> 4);
-        const int8_t *qbase = p.qtable + (int64_t)it.chunk * (Q_NP * Q_CW);
-        const int64_t lbase = gene * p.ld_lst + kg * 8 + l7;
-        // this warp's stages are s = grp + Q_PGROUPS * i; lane (l3, l7) holds entry l7 of own-stage 4 t + l3 for the
-        // register groups t, t + 1, t + 2
-        int32_t er[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
-        auto load_group = [&](int t, int32_t &row, int32_t &cell) {
-            const int s = grp + Q_PGROUPS * (4 * t + l3);
-            row = 0;
-            cell = 0;
+        const int64_t gene = gene_n;
+        const int nst = (len_n + Q_ES - 1) / Q_ES;
+        if (item + (int)gridDim.x < n_items) {
+            gene_n = item_gene(p, item + gridDim.x);
+            len_n = p.lst_len[gene_n];
+        }
+        const int8_t *qbase = p.qtable + (int64_t)it.piece * Q_PIECE + l7 * 16;
+        const int32_t *lrow = p.lst_row + gene * p.ld_lst + kg * 8 + l3;
+        const int32_t *lcell = p.lst_cell + gene * p.ld_lst + kg * 8 + l3;
+        int32_t r0a = 0, r1a = 0, c0a = 0, c1a = 0, r0b = 0, r1b = 0, c0b = 0, c1b = 0;
+        auto load_block = [&](int t, int32_t &r0, int32_t &r1, int32_t &c0, int32_t &c1) {
+            const int s = grp + Q_PGROUPS * (8 * t + l7);
+            r0 = r1 = c0 = c1 = 0;
             if (s < nst) {
-                row = p.lst_row[lbase + (int64_t)s * Q_ES];
-                cell = p.lst_cell[lbase + (int64_t)s * Q_ES];
+                r0 = __ldg(lrow + s * Q_ES);
+                r1 = __ldg(lrow + s * Q_ES + 4);
+                c0 = __ldg(lcell + s * Q_ES);
+                c1 = __ldg(lcell + s * Q_ES + 4);
             }
         };
-        load_group(0, er[0], ec[0]);
-        load_group(1, er[1], ec[1]);
-        load_group(2, er[2], ec[2]);
-        int i = 0;
-        for (int s = grp; s < nst; s += Q_PGROUPS, ++i) {
-            if (i > 0 && (i & 3) == 0) {
-                er[0] = er[1];
-                ec[0] = ec[1];
-                er[1] = er[2];
-                ec[1] = ec[2];
-                load_group((i >> 2) + 2, er[2], ec[2]);
-            }
-            const int64_t q = q0 + s;
-            const int slot = (int)(q % Q_NS);
-            const uint32_t fill = (uint32_t)(q / Q_NS);
-            const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
-            const uint32_t sB = sA + Q_A_BYTES;
-            const int g4 = (i & 3) << 3;
-            if (LAYOUT == Q_LAYOUT_SW128) {
-                const int32_t row0 = __shfl_sync(0xffffffffu, er[0], g4 | l3), row1 = __shfl_sync(0xffffffffu, er[0], g4 | (l3 + 4));
-                const int32_t cel0 = __shfl_sync(0xffffffffu, ec[0], g4 | l3), cel1 = __shfl_sync(0xffffffffu, ec[0], g4 | (l3 + 4));
-                if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
-                const int8_t *src0 = qbase + (int64_t)row0 * p.ldq + l7 * 16;
-                const int8_t *src1 = qbase + (int64_t)row1 * p.ldq + l7 * 16;
-                // entry kk = l3 (and l3 + 4): line kk of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
-                const uint32_t d0 = (uint32_t)kg * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
-                const uint32_t d1 = (uint32_t)kg * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
-                for (int run = 0; run * 8 + l7 < npieces; ++run) {
-                    cp_async16(sB + (uint32_t)run * 4096u + d0, src0 + run * 128);
-                    cp_async16(sB + (uint32_t)run * 4096u + d1, src1 + run * 128);
-                }
-                cp_async16(sA + d0, p.W8 + (int64_t)cel0 * Q_WB + l7 * 16);
-                cp_async16(sA + d1, p.W8 + (int64_t)cel1 * Q_WB + l7 * 16);
-            } else {
-                const int32_t row = __shfl_sync(0xffffffffu, er[0], g4 | l7);
-                const int32_t cell = __shfl_sync(0xffffffffu, ec[0], g4 | l7);
-                if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
-                const int8_t *src = qbase + (int64_t)row * p.ldq;
-                const uint32_t dB = sB + (uint32_t)kg * (uint32_t)(npieces * 128) + (uint32_t)l7 * 16u;
-                for (int j = l3; j < npieces; j += 4) cp_async16(dB + (uint32_t)j * 128u, src + j * 16);
-                const int8_t *wsrc = p.W8 + (int64_t)cell * Q_WB;
-                const uint32_t dA = sA + (uint32_t)kg * 1024u + (uint32_t)l7 * 16u;
-                cp_async16(dA + (uint32_t)l3 * 128u, wsrc + l3 * 16);
-                cp_async16(dA + (uint32_t)(l3 + 4) * 128u, wsrc + (l3 + 4) * 16);
-            }
-            cp_async_mbar_arrive_noinc(&sm.full[slot]);
+        load_block(0, r0a, r1a, c0a, c1a);
+        load_block(1, r0b, r1b, c0b, c1b);
+        int slot = slot_b + grp;
+        uint32_t fill = fill_b;
+        if (slot >= Q_NS) {
+            slot -= Q_NS;
+            ++fill;
         }
-        q0 += nst;
+        for (int t = 0; grp + Q_PGROUPS * 8 * t < nst; ++t) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s = grp + Q_PGROUPS * (8 * t + u);
+                if (s < nst) {  // warp-uniform
+                    const int from = (lane & 24) | u;
+                    const int32_t row0 = __shfl_sync(0xffffffffu, r0a, from), row1 = __shfl_sync(0xffffffffu, r1a, from);
+                    const int32_t cel0 = __shfl_sync(0xffffffffu, c0a, from), cel1 = __shfl_sync(0xffffffffu, c1a, from);
+                    const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
+                    const uint32_t sB0 = sA + Q_A_BYTES + d0, sB1 = sA + Q_A_BYTES + d1;
+                    const int8_t *src0 = qbase + (int64_t)row0 * p.ldq;
+                    const int8_t *src1 = qbase + (int64_t)row1 * p.ldq;
+                    const int8_t *w0 = wbase + (int64_t)cel0 * Q_WB;
+                    const int8_t *w1 = wbase + (int64_t)cel1 * Q_WB;
+                    if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
+                    cp_async16_at<0, 0>(sB0, src0);
+                    cp_async16_at<0, 0>(sB1, src1);
+                    cp_async16_at<4096, 128>(sB0, src0);
+                    cp_async16_at<4096, 128>(sB1, src1);
+                    cp_async16_at<8192, 256>(sB0, src0);
+                    cp_async16_at<8192, 256>(sB1, src1);
+                    cp_async16_at<12288, 384>(sB0, src0);
+                    cp_async16_at<12288, 384>(sB1, src1);
+                    cp_async16_at<0, 0>(sA + d0, w0);
+                    cp_async16_at<0, 0>(sA + d1, w1);
+                    cp_async_mbar_arrive_noinc(&sm.full[slot]);
+                    slot += Q_PGROUPS;
+                    if (slot >= Q_NS) {
+                        slot -= Q_NS;
+                        ++fill;
+                    }
+                }
+            }
+            r0a = r0b;
+            r1a = r1b;
+            c0a = c0b;
+            c1a = c1b;
+            load_block(t + 2, r0b, r1b, c0b, c1b);
+        }
+        slot_b += nst % Q_NS;
+        fill_b += (uint32_t)(nst / Q_NS);
+        if (slot_b >= Q_NS) {
+            slot_b -= Q_NS;
+            ++fill_b;
+        }
     }
 }
 
 // ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
-template <int LAYOUT>
 __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t stage0, uint32_t tmem, int n_items) {
-    int64_t q = 0;
-    uint32_t n_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-        const Item it = decode_item(p, item);
-        const int64_t gene = p.order ? p.order[it.pos] : it.pos;
-        const int nst = (p.lst_len[gene] + Q_ES - 1) / Q_ES;
-        const int ntot = Q_NP * it.w;  // accumulator columns of this item (480 for a full chunk)
-        // N <= 256 per instruction.  SW128: the second MMA has to start on a 128-byte run of the entry -> 256 + 224;
-        // INTERLEAVE: any multiple of 16 -> two halves
-        int n1, n2;
-        if (LAYOUT == Q_LAYOUT_SW128) {
-            n1 = ntot > 256 ? 256 : ntot;
-            n2 = ntot - n1;
-        } else {
-            n1 = ntot > 256 ? ntot / 2 : ntot;
-            n2 = ntot - n1;
-        }
-        const uint32_t idesc1 = umma_idesc_s8_mn(128, n1), idesc2 = umma_idesc_s8_mn(128, n2 > 0 ? n2 : 16);
-        const uint32_t stride_k_b = (uint32_t)(Q_NP * (it.w >> 4)) * 128u;  // INTERLEAVE: bytes between 8-entry groups of B
+    const uint32_t idesc = umma_idesc_s8_mn(128, 256);
+    int slot = 0;
+    uint32_t fill = 0, n_done = 0;
+    int item = blockIdx.x;
+    int len_n = item < n_items ? p.lst_len[item_gene(p, item)] : 0;
+    for (; item < n_items; item += gridDim.x, ++n_done) {
+        const int nst = (len_n + Q_ES - 1) / Q_ES;
+        if (item + (int)gridDim.x < n_items) len_n = p.lst_len[item_gene(p, item + gridDim.x)];
         if (n_done > 0) {  // the epilogue has drained the previous item's accumulators
             if (!wait_or_abort(sm, &sm.acc_empty, (n_done - 1) & 1u)) return;
             tc_fence_after_sync();
         }
-        for (int s = 0; s < nst; ++s, ++q) {
-            const int slot = (int)(q % Q_NS);
-            if (!wait_or_abort(sm, &sm.full[slot], (uint32_t)(q / Q_NS) & 1u)) return;
+        for (int s = 0; s < nst; ++s) {
+            if (!wait_or_abort(sm, &sm.full[slot], fill & 1u)) return;
             fence_proxy_async_smem();
             tc_fence_after_sync();
             const uint32_t sA = stage0 + (uint32_t)slot * Q_STAGE_BYTES;
             const uint32_t sB = sA + Q_A_BYTES;
-            if (LAYOUT == Q_LAYOUT_SW128) {
-                const uint64_t da = umma_desc_sw128(sA, 4096u, 1024u);
-                umma_s8(tmem, da, umma_desc_sw128(sB, 4096u, 1024u), idesc1, s > 0);
-                if (n2 > 0) umma_s8(tmem + 256u, da, umma_desc_sw128(sB + 2u * 4096u, 4096u, 1024u), idesc2, s > 0);
-            } else {
-                const uint64_t da = umma_desc_nosw(sA, 128u, 1024u, false);
-                umma_s8(tmem, da, umma_desc_nosw(sB, 128u, stride_k_b, false), idesc1, s > 0);
-                if (n2 > 0)
-                    umma_s8(tmem + (uint32_t)n1, da, umma_desc_nosw(sB + (uint32_t)(n1 >> 4) * 128u, 128u, stride_k_b, false),
-                            idesc2, s > 0);
-            }
+            const uint64_t da = umma_desc_sw128(sA, 4096u, 1024u);
+            umma_s8(tmem, da, umma_desc_sw128(sB, 4096u, 1024u), idesc, s > 0);                      // runs 0, 1
+            umma_s8(tmem + 256u, da, umma_desc_sw128(sB + 2u * 4096u, 4096u, 1024u), idesc, s > 0);  // runs 2, 3
             umma_commit(&sm.empty[slot]);  // frees the slot once these MMAs have read it
+            if (++slot == Q_NS) {
+                slot = 0;
+                ++fill;
+            }
         }
         if (nst > 0)
             umma_commit(&sm.acc_full);
@@ -262,24 +273,30 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
         const Item it = decode_item(p, item);
         const int64_t gene = p.order ? p.order[it.pos] : it.pos;
         const bool empty_list = p.lst_len[gene] <= 0;
+        const uint32_t sr = p.SR ? p.SR[(int64_t)it.pos * Q_WB + b] : 0xFFFF0000u;
+        const int klo = (int)(sr & 0xFFFFu), khi = (int)(sr >> 16);
         while (!mbar_try_wait(&sm.acc_full, n_done & 1u)) {  // an item takes tens of microseconds: sleep, do not spin
             __nanosleep(500);
             if (sm.abort) return;
         }
         tc_fence_after_sync();
-        double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + it.chunk * Q_CW;
-        const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + it.chunk * Q_CW : nullptr;
-        for (int i0 = 0; i0 < it.w; i0 += 8) {
-            uint32_t r[Q_NP][8];
+        const int kbase = it.piece * Q_PW;
+        double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + kbase;
+        const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + kbase : nullptr;
+        for (int i0 = 0; i0 < Q_PW; i0 += 8) {
+            const int n = Q_PW - i0 < 8 ? Q_PW - i0 : 8;  // 8, or 6 in the last round
+            uint32_t r[Q_NV][8];
+#pragma unroll
+            for (int pl = 0; pl < Q_NV; ++pl)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[pl][j] = 0u;
             if (!empty_list) {
 #pragma unroll
-                for (int pl = 0; pl < Q_NP; ++pl) tmem_ld_32x32b_x8(tlane + (uint32_t)(pl * it.w + i0), r[pl]);
+                for (int pl = 0; pl < Q_NV; ++pl)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2)
+                        if (j < n) tmem_ld_32x32b_x2(tlane + (uint32_t)(pl * Q_PW + i0 + j), r[pl][j], r[pl][j + 1]);
                 tmem_wait_ld();
-            } else {
-#pragma unroll
-                for (int pl = 0; pl < Q_NP; ++pl)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r[pl][j] = 0u;
             }
             if (b < WP_TILED) {
                 double out[8];
@@ -289,14 +306,14 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
 #pragma unroll
                     for (int pl = Q_NV - 1; pl >= 0; --pl) s = s * 256 + (long long)(int32_t)r[pl][j];
                     double t = (double)s * scale;
-                    if (Zrow) t += Zrow[i0 + j];
-                    const int32_t ns = (int32_t)r[Q_NV][j];  // draws that hit a "log 0" entry at this grid point
-                    if (ns != 0) t = fma((double)ns, p.sentinel, t);
+                    if (Zrow && j < n) t += Zrow[i0 + j];
+                    const int k = kbase + i0 + j;
+                    if (k < klo || k > khi) t = p.sentinel;  // some drawn row is "log 0" at this grid point
                     out[j] = t;
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j += 2)
-                    *reinterpret_cast<double2 *>(Trow + i0 + j) = make_double2(out[j], out[j + 1]);
+                    if (j < n) *reinterpret_cast<double2 *>(Trow + i0 + j) = make_double2(out[j], out[j + 1]);
             }
         }
         tc_fence_before_sync();
@@ -304,7 +321,6 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
     }
 }
 
-template <int LAYOUT>
 __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // stage buffers on a 1024-byte boundary (the swizzle pattern is a function of the shared-memory address bits)
@@ -327,14 +343,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Param
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = sm.tmem_base;
-    const int n_items = p.n_pos * p.n_chunks;
+    const int n_items = p.n_pos * p.n_pieces;
 
     if (warp < Q_PRODUCER_WARPS)
-        run_producer<LAYOUT>(p, sm, stage0, n_items, warp, lane);
+        run_producer(p, sm, stage0, n_items, warp, lane);
     else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
         run_epilogue(p, sm, tmem, n_items, warp, lane);
     else if (lane == 0)
-        run_mma<LAYOUT>(p, sm, stage0, tmem, n_items);
+        run_mma(p, sm, stage0, tmem, n_items);
 
     tc_fence_before_sync();
     __syncthreads();
@@ -344,38 +360,113 @@ __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Param
 }
 
 // ------------------------------------------------------------------------------------------------
-// fixed-point planes of the table: one thread per four consecutive grid points of a row
-__global__ void quantize_rows_kernel(const double *__restrict__ table, int ld_table, int kp, int64_t n_rows,
-                                     int8_t *__restrict__ qtable, int64_t ldq) {
-    const int tpr = kp >> 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_rows * tpr) return;
-    const int64_t row = idx / tpr;
-    const int k = (int)(idx - row * tpr) * 4;
-    const double *src = table + row * ld_table + k;
-    const int c = k / Q_CW, i = k - c * Q_CW;
-    const int w = min(Q_CW, kp - c * Q_CW);
-    uint32_t word[Q_NP];
-#pragma unroll
-    for (int pl = 0; pl < Q_NP; ++pl) word[pl] = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double v = (k + j < ld_table) ? src[j] : 0.0;
-        if (!(v > -1.0e290)) {  // the "log 0" sentinel (or a difference to it)
-            word[Q_NV] |= 1u << (8 * j);
-        } else {
-            long long x = __double2ll_rn(fmin(fmax(v, -1000.0), 1000.0) * (double)(1ll << Q_FRAC));
-#pragma unroll
-            for (int pl = 0; pl < Q_NV; ++pl) {
-                const int d = (int)(int8_t)(x & 0xFF);
-                word[pl] |= (uint32_t)(d & 0xFF) << (8 * j);
-                x = (x - d) >> 8;
+// Sentinel range of every (gene, boot): [max klo, min khi] over the list entries the boot drew.  One warp per gene, lane l
+// owns boots 4 l .. 4 l + 3 (one 32-bit word of the entry's W row); klo / khi are kept as packed 16-bit pairs and
+// combined with __vmaxu2 / __vminu2 under a mask made of the non-zero multiplicities.  Entries whose row has no sentinel
+// (the common case) are skipped after one uniform load.  flag |= 4 when a drawn row is irregular or an intersection is
+// empty.
+__global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__restrict__ lst_row, const int32_t *__restrict__ lst_cell,
+                                                             const int32_t *__restrict__ lst_len, const int32_t *__restrict__ order,
+                                                             int64_t ld_lst, const uint32_t *__restrict__ row_range,
+                                                             const int8_t *__restrict__ W8, int n_pos, int K, int n_boot,
+                                                             uint32_t *__restrict__ SR, int32_t *__restrict__ flag) {
+    const int pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pos >= n_pos) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t gene = order ? order[pos] : pos;
+    const int len = lst_len[gene];
+    const int32_t *lr = lst_row + gene * ld_lst, *lc = lst_cell + gene * ld_lst;
+    const uint32_t full = (uint32_t)(K - 1) << 16;
+    uint32_t lo01 = 0u, lo23 = 0u, hi01 = 0xFFFFFFFFu, hi23 = 0xFFFFFFFFu;
+    bool irregular = false;
+    for (int e0 = 0; e0 < len; e0 += 32) {
+        const int e = e0 + lane;
+        uint32_t rr = full;
+        int32_t cell = 0;
+        if (e < len) {
+            rr = row_range[lr[e]];
+            cell = lc[e];
+        }
+        unsigned need = __ballot_sync(0xffffffffu, rr != full);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t r = __shfl_sync(0xffffffffu, rr, src);
+            const int32_t c = __shfl_sync(0xffffffffu, cell, src);
+            if (r == Q_RANGE_IRREGULAR) {
+                irregular = true;
+                continue;
             }
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(W8 + (int64_t)c * Q_WB + 4 * lane);
+            const uint32_t m = __vcmpne4(w, 0u);                        // 0xFF per boot that drew this cell
+            const uint32_t m01 = __byte_perm(m, 0u, 0x1100), m23 = __byte_perm(m, 0u, 0x3322);
+            const uint32_t klo2 = (r & 0xFFFFu) * 0x10001u, khi2 = (r >> 16) * 0x10001u;
+            lo01 = __vmaxu2(lo01, klo2 & m01);
+            lo23 = __vmaxu2(lo23, klo2 & m23);
+            hi01 = __vminu2(hi01, khi2 | ~m01);
+            hi23 = __vminu2(hi23, khi2 | ~m23);
         }
     }
-    int8_t *dst = qtable + row * ldq + (int64_t)c * (Q_NP * Q_CW) + i;
+    uint32_t out[4];
+    bool bad = irregular;
 #pragma unroll
-    for (int pl = 0; pl < Q_NP; ++pl) *reinterpret_cast<uint32_t *>(dst + pl * w) = word[pl];
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = ((j < 2 ? lo01 : lo23) >> (16 * (j & 1))) & 0xFFFFu;
+        uint32_t hi = ((j < 2 ? hi01 : hi23) >> (16 * (j & 1))) & 0xFFFFu;
+        if (hi > (uint32_t)(K - 1)) hi = (uint32_t)(K - 1);
+        if (4 * lane + j < n_boot && lo > hi) bad = true;
+        // points beyond khi: only real grid points matter, padding columns are never read by the soft-max
+        out[j] = lo | (hi == (uint32_t)(K - 1) ? 0xFFFF0000u : hi << 16);
+    }
+    *reinterpret_cast<uint4 *>(SR + (int64_t)pos * Q_WB + 4 * lane) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-point planes and non-sentinel range of every row of an FP64 table (the general row kernel writes FP64 only; the
+// constant-theta fast kernel emits both itself, lp_table.cu): one warp per row
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const double *__restrict__ table, int ld_table, int K, int64_t n_rows,
+                                                            int8_t *__restrict__ qtable, int64_t ldq,
+                                                            uint32_t *__restrict__ row_range) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const double *src = table + row * ld_table;
+    int8_t *dst = qtable + row * ldq;
+    for (int64_t j = lane; j < ldq / 4; j += 32) reinterpret_cast<uint32_t *>(dst)[j] = 0u;
+    __syncwarp();
+    int n_ok = 0, kmin = 0x7fffffff, kmax = -1;
+    for (int k = lane; k < K; k += 32) {
+        const double v = src[k];
+        if (!(v > -1.0e290)) continue;  // the "log 0" sentinel (or a difference to it): digits stay zero
+        ++n_ok;
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+        long long x = __double2ll_rn(fmin(fmax(v, -1000.0), 1000.0) * (double)(1ll << Q_FRAC));
+        const int pc = k / Q_PW, i = k - pc * Q_PW;
+#pragma unroll
+        for (int pl = 0; pl < Q_NV; ++pl) {
+            const int d = (int)(int8_t)(x & 0xFF);
+            dst[pc * Q_PIECE + pl * Q_PW + i] = (int8_t)d;
+            x = (x - d) >> 8;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) {
+        uint32_t rr;
+        if (n_ok == 0)
+            rr = Q_RANGE_IRREGULAR;  // a row of sentinels only: let the FP64 kernel deal with it
+        else if (kmax - kmin + 1 != n_ok)
+            rr = Q_RANGE_IRREGULAR;
+        else
+            rr = (uint32_t)kmin | ((uint32_t)kmax << 16);
+        row_range[row] = rr;
+    }
 }
 
 // W (FP64 multiplicities, pass-major [pass][n_w_rows][108]) -> int8 rows of 128 bytes; flag |= 1 when a count > 127
@@ -400,15 +491,12 @@ __global__ void w_to_i8_kernel(const double *__restrict__ W, int64_t n_rows_tota
 
 }  // namespace
 
-int q_row_bytes(int K) { return Q_NP * round_up(K, 16); }
-
 cudaError_t launch_quantize_rows(const double *table, int ld_table, int K, int64_t n_rows, int8_t *qtable,
-                                 cudaStream_t st) {
+                                 uint32_t *row_range, cudaStream_t st) {
     if (n_rows <= 0) return cudaSuccess;
-    const int kp = round_up(K, 16);
-    if (kp > ld_table) return cudaErrorInvalidValue;
-    const int64_t n = n_rows * (kp >> 2);
-    quantize_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, ld_table, kp, n_rows, qtable, q_row_bytes(K));
+    if (K > ld_table || K > Q_MAX_K) return cudaErrorInvalidValue;
+    quantize_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(table, ld_table, K, n_rows, qtable, q_row_bytes(K),
+                                                                        row_range);
     return cudaGetLastError();
 }
 
@@ -421,24 +509,12 @@ cudaError_t launch_w_to_i8(const double *W, int n_w_rows, int n_boot, int8_t *W8
 }
 
 bool contract_i8_supported(int K, int ld_table, int ld_lst) {
-    return K >= 1 && K <= KP_TILED && ld_table == KP_TILED && (ld_lst % Q_ES) == 0;
+    return K >= 1 && K <= Q_MAX_K && ld_table == KP_TILED && (ld_lst % Q_ES) == 0;
 }
 
-cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
-                                    cudaStream_t st) {
-    if (n_pos <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<Q_LAYOUT_SW128>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(contract_i8_kernel<Q_LAYOUT_INTERLEAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)Q_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const int kp = round_up(a.K, 16);
-    const int n_chunks = (kp + Q_CW - 1) / Q_CW;
+size_t contract_i8_range_words(int n_genes) { return (size_t)(n_genes > 0 ? n_genes : 1) * Q_WB; }
+
+static I8Params make_params(const ContractI8Args &a, int g0, int n_pos, int pass, double *t_scratch) {
     I8Params p;
     p.qtable = a.qtable;
     p.ldq = a.ldq;
@@ -449,18 +525,41 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
     p.ld_lst = a.lists.ld;
     p.W8 = a.W8 + (size_t)pass * a.n_w_rows * Q_WB;
     p.Z = a.Z ? a.Z + (size_t)pass * WP_TILED * KP_TILED : nullptr;
+    p.SR = nullptr;
     p.T = t_scratch;
     p.sentinel = a.sentinel;
     p.n_pos = n_pos;
-    p.n_chunks = n_chunks;
-    p.w_last = kp - (n_chunks - 1) * Q_CW;
+    p.n_pieces = q_pieces(a.K);
     p.err = a.err;
-    const int n_items = n_pos * n_chunks;
+    return p;
+}
+
+cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, int pass, uint32_t *sr_scratch,
+                                   cudaStream_t st) {
+    if (n_pos <= 0 || !a.row_range) return cudaSuccess;
+    if (!sr_scratch) return cudaErrorInvalidValue;
+    const I8Params p = make_params(a, g0, n_pos, pass, nullptr);
+    const int nb = (a.n_boot - pass * WP_TILED) < WP_TILED ? (a.n_boot - pass * WP_TILED) : WP_TILED;
+    sentinel_range_kernel<<<(unsigned)((n_pos + 7) / 8), 256, 0, st>>>(p.lst_row, p.lst_cell, p.lst_len, p.order, p.ld_lst,
+                                                                       a.row_range, p.W8, n_pos, a.K, nb, sr_scratch, a.err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
+                                    const uint32_t *sr, cudaStream_t st) {
+    if (n_pos <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (a.row_range && !sr) return cudaErrorInvalidValue;
+    I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
+    p.SR = a.row_range ? sr : nullptr;
+    const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
-    if (a.layout == Q_LAYOUT_INTERLEAVE)
-        contract_i8_kernel<Q_LAYOUT_INTERLEAVE><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
-    else
-        contract_i8_kernel<Q_LAYOUT_SW128><<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
+    contract_i8_kernel<<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
 }
 

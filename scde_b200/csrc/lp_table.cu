@@ -426,21 +426,22 @@ __device__ __forceinline__ double exp_m50_0(double a) {
 }
 
 // Fixed-point planes (contract_i8.cu) of four consecutive table values: value = 2^-Q_FRAC * sum_p 256^p d_p with signed
-// bytes d_p, plus the indicator plane for values at or below the "log 0" sentinel.  x = rint(v 2^Q_FRAC) comes from the
-// mantissa of v 2^Q_FRAC + 1.5 2^52; the balanced digits of x are the ordinary bytes of x + 0x8080808080 with the top bit
-// of each flipped (adding 128 to every digit makes them ordinary base-256 digits); byte permutes transpose the four
+// bytes d_p; values at or below the "log 0" sentinel get zero digits and a bit in `sent`.  x = rint(v 2^Q_FRAC) comes
+// from the mantissa of v 2^Q_FRAC + 1.5 2^52; the balanced digits of x are the ordinary bytes of x + 0x8080808080 with the
+// top bit of each flipped (adding 128 to every digit makes them ordinary base-256 digits); byte permutes transpose the four
 // 32-bit words into one word per plane.  |v| <= 752 by construction (a difference of two values in [-752, 0]).
-__device__ __forceinline__ void fixed_point_quad(const double (&v)[4], uint32_t (&word)[Q_NP]) {
+__device__ __forceinline__ void fixed_point_quad(const double (&v)[4], uint32_t (&word)[Q_NV], uint32_t &sent) {
     const double MAGIC = 6755399441055744.0;
     const long long BIAS = 0x8080808080ll;
-    uint32_t lo[4], hi = 0u, flag = 0u;
+    uint32_t lo[4], hi = 0u;
+    sent = 0u;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const double y = fma(v[e], (double)(1ll << Q_FRAC), MAGIC);
         long long x = __double_as_longlong(y) - __double_as_longlong(MAGIC) + BIAS;
         if (!(v[e] > -1.0e290)) {
             x = BIAS;
-            flag |= 1u << (8 * e);
+            sent |= 1u << e;
         }
         lo[e] = (uint32_t)x ^ 0x80808080u;
         hi |= (((uint32_t)(x >> 32) ^ 0x80u) & 0xFFu) << (8 * e);
@@ -452,9 +453,13 @@ __device__ __forceinline__ void fixed_point_quad(const double (&v)[4], uint32_t 
     word[2] = __byte_perm(t2, t3, 0x5410);
     word[3] = __byte_perm(t2, t3, 0x7632);
     word[4] = hi;
-    word[5] = flag;
 }
-static_assert(Q_NV == 5 && Q_NP == 6, "fixed_point_quad is written for five value planes and one indicator plane");
+static_assert(Q_NV == 5, "fixed_point_quad is written for five value planes");
+// byte offset of grid point k (even) in the row's fixed-point form [piece][plane][Q_PW]: plane 0 of its piece
+__device__ __forceinline__ int q_offset(int k) {
+    const int pc = (k >= Q_PW) + (k >= 2 * Q_PW) + (k >= 3 * Q_PW);
+    return pc * Q_PIECE + (k - pc * Q_PW);
+}
 
 // The sweeps (one warp per row; lane l owns the grid points 4 l + 128 j .. + 3, so every access is a 16- or 32-byte
 // vector and the index arithmetic is shared by four points; the row lives in a per-warp shared-memory buffer):
@@ -465,7 +470,8 @@ static_assert(Q_NV == 5 && Q_NP == 6, "fixed_point_quad is written for five valu
 //      the smaller one is below half an ulp of the sum and log(exp(hi)) = hi, so no exp and no log is evaluated; in the
 //      cross-over band, and below -708 where the reference's own exp() underflows gradually, the reference's expression
 //      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
-// Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes (qtable); MODES: also row_mode.
+// Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes and non-sentinel range (qtable,
+// row_range); MODES: also row_mode.
 template <bool MODES>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 3)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
@@ -473,10 +479,14 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                     int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
-                    int8_t *__restrict__ qtable, int ldq) {
+                    int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
     __shared__ __align__(16) double s_rows[ROW_WARPS * KP_TILED];
-    __shared__ __align__(16) uint8_t s_q[ROW_WARPS][Q_NP * KP_TILED];
+    __shared__ __align__(16) uint8_t s_q[ROW_WARPS][4 * Q_PIECE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (qtable) {  // the two spare bytes of every piece, and the pieces beyond the grid, stay zero
+        for (int j = lane; j < (4 * Q_PIECE) / 4; j += 32) reinterpret_cast<uint32_t *>(s_q[warp])[j] = 0u;
+        __syncwarp();
+    }
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
     const int kp = (K + 15) & ~15;
     // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
@@ -558,6 +568,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
         uint8_t *sq = s_q[warp];
+        int n_ok = 0, kmin = 0x7fffffff, kmax = -1;  // the row's grid points that are not "log 0"
         for (int k0 = 4 * lane; k0 < kp; k0 += 128) {
             double v[4] = {0.0, 0.0, 0.0, 0.0};
             if (k0 < K) {
@@ -605,14 +616,24 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
                 *reinterpret_cast<double2 *>(out + k0) = make_double2(v[0], v[1]);
                 *reinterpret_cast<double2 *>(out + k0 + 2) = make_double2(v[2], v[3]);
             }
-            if (qtable) {
-                uint32_t word[Q_NP];
-                fixed_point_quad(v, word);
-                const int ch = k0 / Q_CW, i = k0 - ch * Q_CW;
-                const int w = min(Q_CW, kp - ch * Q_CW);
-                uint32_t *dst = reinterpret_cast<uint32_t *>(sq + ch * (Q_NP * Q_CW) + i);
+            if (qtable && k0 < Q_MAX_K) {
+                uint32_t word[Q_NV], sent;
+                fixed_point_quad(v, word, sent);
 #pragma unroll
-                for (int p = 0; p < Q_NP; ++p) dst[(p * w) >> 2] = word[p];
+                for (int e = 0; e < 4; ++e)
+                    if (k0 + e < K && !((sent >> e) & 1u)) {
+                        ++n_ok;
+                        kmin = min(kmin, k0 + e);
+                        kmax = max(kmax, k0 + e);
+                    }
+                // pairs (k0, k0 + 1) and (k0 + 2, k0 + 3) never straddle a piece (Q_PW is even): 16-bit stores
+                uint16_t *dst0 = reinterpret_cast<uint16_t *>(sq + q_offset(k0));
+                uint16_t *dst1 = reinterpret_cast<uint16_t *>(sq + q_offset(k0 + 2));
+#pragma unroll
+                for (int p = 0; p < Q_NV; ++p) {
+                    dst0[(p * Q_PW) >> 1] = (uint16_t)(word[p] & 0xFFFFu);
+                    dst1[(p * Q_PW) >> 1] = (uint16_t)(word[p] >> 16);
+                }
             }
         }
         if (write_f64)
@@ -632,7 +653,16 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         if (qtable) {  // the row's planes, 16 bytes per lane and store
             const uint4 *src = reinterpret_cast<const uint4 *>(sq);
             uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
-            for (int j = lane; j < (Q_NP * kp) / 16; j += 32) dst[j] = src[j];
+            for (int j = lane; j < ldq / 16; j += 32) dst[j] = src[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
+                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            if (lane == 0)
+                row_range[row] = (n_ok > 0 && kmax - kmin + 1 == n_ok) ? ((uint32_t)kmin | ((uint32_t)kmax << 16))
+                                                                        : Q_RANGE_IRREGULAR;
         }
         __syncwarp();
         if (MODES && lane == 0) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
@@ -679,21 +709,22 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, con
                            const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
-                           cudaStream_t st) {
+                           uint32_t *row_range, cudaStream_t st) {
     const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
     if (n_items <= 0) return cudaSuccess;
     int64_t blocks = (n_items + ROW_WARPS - 1) / ROW_WARPS;
     const int64_t cap = 148 * 64;  // grid-stride beyond this
     if (blocks > cap) blocks = cap;
+    if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         if (row_mode)
             lp_rows_fast_kernel<true><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
                 models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
-                ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K));
+                ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
         else
             lp_rows_fast_kernel<false><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
                 models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
-                ld_table, nullptr, which, zero_row, based, write_f64, qtable, q_row_bytes(K));
+                ld_table, nullptr, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
         return cudaGetLastError();
     }
     if (qtable || !write_f64) return cudaErrorInvalidValue;  // the general kernel writes the FP64 table only

@@ -16,35 +16,51 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("genes,cells,rows,grid", [
-    (7, 90, 300, 401),     # the default grid: five 80-point chunks + one 16-point chunk
+    (7, 90, 300, 401),     # the default grid: four 512-byte pieces (102 + 102 + 102 + 95 grid points)
     (3, 700, 900, 401),    # lists of 22 stages: the 10-slot ring wraps twice within an item
-    (400, 40, 64, 401),    # 2400 items on 148 CTAs: many items per CTA, accumulator hand-over every item
-    (5, 33, 50, 201),      # chunks 80 + 80 + 48 (two MMAs of N = 144 in the last one)
-    (5, 33, 50, 80),       # a single full chunk
-    (5, 33, 50, 16),       # a single narrow chunk (one MMA of N = 96)
-    (4, 64, 40, 96),       # 80 + 16
+    (400, 40, 64, 401),    # 1600 items on 148 CTAs: many items per CTA, accumulator hand-over every item
+    (5, 33, 50, 201),      # two pieces
+    (5, 33, 50, 102),      # exactly one piece
+    (5, 33, 50, 16),       # a single, mostly empty piece
+    (4, 64, 40, 408),      # the largest grid the kernel takes
     (2, 1, 3, 401),        # one-entry lists
 ])
-@pytest.mark.parametrize("layout", [0, 1])  # 128-byte-swizzle (production) and interleave operand layouts
-def test_kernel_exact_on_random_integers(ctx, genes, cells, rows, grid, layout):
+def test_kernel_exact_on_random_integers(ctx, genes, cells, rows, grid):
     pr = P.make_problem(genes, cells, rows, grid, seed=genes + cells)
-    out = P.run(ctx, pr, layout)
+    out = P.run(ctx, pr)
     ok, got, want, clean = P.compare(pr, out)
-    assert ok, f"{int(((got != want) & clean).sum())} of {int(clean.sum())} elements differ"
+    assert ok, (f"{int(((got != want) & clean).sum())} of {int(clean.sum())} elements differ, "
+                f"{int((got[~clean] != P.SENTINEL).sum())} sentinel points wrong, flags {pr['flags']}")
+
+
+def test_kernel_without_ranges(ctx):
+    """row_range = NULL: no row holds a sentinel, no range kernel runs"""
+    pr = P.make_problem(6, 70, 100, 401, seed=9, sentinel_frac=0.0)
+    out = P.run(ctx, pr, with_ranges=False)
+    ok, got, want, clean = P.compare(pr, out, with_ranges=False)
+    assert ok
 
 
 def test_kernel_extreme_digits(ctx):
     """all digits at -128 / 127 and multiplicities at 127: the int32 accumulators hold |sum| <= 128 * 127 * entries"""
     pr = P.make_problem(3, 200, 16, 401, seed=5, max_w=127, sentinel_frac=0.0, full_lists=True)
-    pr["planes"][:, :P.NV, :] = np.where(np.random.default_rng(1).random(pr["planes"][:, :P.NV, :].shape) < 0.5, -128, 127)
-    kp = pr["kp"]
-    q = np.zeros_like(pr["q"])
-    for c in range((kp + P.CW - 1) // P.CW):
-        w = min(P.CW, kp - c * P.CW)
-        for p in range(P.NP):
-            q[:, P.NP * P.CW * c + p * w: P.NP * P.CW * c + (p + 1) * w] = pr["planes"][:, p, c * P.CW: c * P.CW + w]
-    pr["q"] = q
-    out = P.run(ctx, pr, 0)
+    pr["planes"][:] = np.where(np.random.default_rng(1).random(pr["planes"].shape) < 0.5, -128, 127)
+    pr["q"] = P.pack_rows(pr["planes"], 401)
+    out = P.run(ctx, pr)
+    ok, got, want, clean = P.compare(pr, out)
+    assert ok
+
+
+def test_kernel_flags_empty_sentinel_intersection(ctx):
+    """two rows whose admissible grid ranges do not overlap, both drawn by every boot: flag 4 (the caller reruns in FP64)"""
+    pr = P.make_problem(2, 4, 4, 401, seed=1, max_w=1, sentinel_frac=0.0, full_lists=True)
+    pr["w8"][:4, :P.WP] = 1
+    pr["lo"][:] = [0, 300, 0, 0]
+    pr["hi"][:] = [100, 400, 400, 400]
+    pr["row_range"] = (pr["lo"] | (pr["hi"] << 16)).astype(np.uint32)
+    pr["lst_row"][:, :4] = [0, 1, 2, 3]
+    out = P.run(ctx, pr)
+    assert pr["flags"] & 4
     ok, got, want, clean = P.compare(pr, out)
     assert ok
 
@@ -79,9 +95,9 @@ def test_fixed_point_path_vs_fp64_kernel(ctx, G, Cn):
     assert np.all(np.abs(za - zb) <= np.where(za < -6.0, 2e-4, 1e-6 * np.maximum(1.0, np.abs(za)) + 1e-9))
 
 
-def test_large_counts_sentinel_plane(ctx):
+def test_large_counts_sentinel_ranges(ctx):
     """counts in the tens of thousands put the reference's "log 0" clamp (-DBL_MAX/n/1.1) on the low end of the grid: the
-    indicator plane has to reproduce the FP64 path's hard exclusion of those grid points"""
+    per-row ranges have to reproduce the FP64 path's hard exclusion of those grid points"""
     w = synth.make_workload(3, n_genes=80, n_cells=30, seed=3)
     counts = np.array(w.counts, copy=True)
     rng = np.random.default_rng(0)

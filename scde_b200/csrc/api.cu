@@ -312,7 +312,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     if (zb)
         SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
                                   scr.Z.p, scr.zpart.p, st));
-    const bool i8 = zb && t.has_q && want_i8(ctx) && contract_i8_supported(t.K, t.ld, ld_lst);
+    const bool i8 = zb && t.has_q && want_i8(ctx) && contract_i8_supported(t.K, t.ld, ld_lst, D);
     if (ctx->contract_kernel == 3 && !i8) {
         set_error("tcgen05 int8 contraction forced but unsupported here (K=%d, zero-base form %d)", t.K, (int)zb);
         return SCDE_B200_EINVAL;
@@ -970,7 +970,7 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
                                 double *t_out, int32_t *flags_out) {
     CHECK_CTX(ctx);
     if (!qtable || !w8 || !lst_row || !lst_cell || !lst_len || !t_out || n_rows < 1 || n_genes < 1 || n_w_rows < 1 ||
-        !contract_i8_supported(n_grid, KP_TILED, ld_lst) || n_genes > contract_tiled_max_genes()) {
+        !contract_i8_supported(n_grid, KP_TILED, ld_lst, 1) || n_genes > contract_tiled_max_genes()) {
         set_error("probe_contract_i8: bad arguments");
         return SCDE_B200_EINVAL;
     }

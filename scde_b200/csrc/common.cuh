@@ -173,7 +173,8 @@ struct ContractI8Args {
     int ld_jp;
     int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired, |= 4 if the sentinel ranges need the FP64 kernel
 };
-bool contract_i8_supported(int K, int ld_table, int ld_lst);
+// n_draws: draws per randomization (the plane sums are combined pairwise in 32 bits: 257 * 128 * draws < 2^31)
+bool contract_i8_supported(int K, int ld_table, int ld_lst, int n_draws);
 size_t contract_i8_range_words(int n_genes);  // uint32 words of the (gene, boot) sentinel-range scratch
 // sr_scratch[n_pos][128] = sentinel range of every (gene, boot) of genes order[g0 .. g0 + n_pos), boots of `pass`
 // (no-op when a.row_range == NULL)

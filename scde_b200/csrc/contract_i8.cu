@@ -39,6 +39,7 @@
 #include "ptx_sm100.cuh"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace scde {
 namespace {
@@ -50,12 +51,13 @@ constexpr int Q_NS = 10;                         // ring depth
 constexpr int Q_A_BYTES = Q_ES * Q_WB;           // W tile of a stage: 4096
 constexpr int Q_B_BYTES = Q_ES * Q_PIECE;        // table tile of a stage: 16384
 constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;  // 20480, a multiple of the 1024-byte swizzle atom
-#ifndef SCDE_Q_PGROUPS
-#define SCDE_Q_PGROUPS 2
-#endif
-constexpr int Q_PGROUPS = SCDE_Q_PGROUPS;        // producer warp groups; group g gathers the stages s = g (mod Q_PGROUPS) of an item
-constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS, Q_EPILOGUE_WARPS = 4;
-constexpr int Q_THREADS = (Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS + 1) * 32;  // + the MMA warp
+// PG producer warp groups (template parameter of the kernel); group g gathers the stages s = g (mod PG) of an item.
+// Eight epilogue warps: a warp may only read the tensor-memory lanes 32 (warp id mod 4) .. + 31, so two warps share each
+// quarter and split its columns.  (With four warps the epilogue of an item took longer than the ring can cover, and the
+// tensor memory is not free for the next item before it ends.)
+constexpr int Q_EPILOGUE_WARPS = 8;
+constexpr int q_threads(int pg) { return (4 * pg + Q_EPILOGUE_WARPS + 1) * 32; }  // + the MMA warp
+constexpr int Q_EPI_ROUNDS = (Q_PW + 7) / 8;  // rounds of 8 grid points per piece
 constexpr int Q_TMEM_COLS = 512;
 constexpr long long Q_WATCHDOG_CYCLES = 4000000000ll;  // a barrier wait longer than ~2 s aborts the kernel (err = 2)
 static_assert(Q_NV * Q_PW <= Q_TMEM_COLS && Q_NV * Q_PW <= Q_PIECE, "a piece is one pass of tensor memory");
@@ -132,6 +134,7 @@ __device__ __forceinline__ void cp_async16_at(uint32_t dst_smem, const void *src
     asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst_smem), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
 }
 
+template <int Q_PGROUPS>
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
     const int grp = warp >> 2, kg = warp & 3;
     const int l7 = lane & 7, l3 = lane >> 3;
@@ -262,12 +265,17 @@ __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t 
     }
 }
 
-// ---- epilogue: warp (4 + qd) owns tensor-memory lanes 32 qd .. 32 qd + 31 ----------------------------------------------
-__device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t tmem, int n_items, int warp, int lane) {
-    const int qd = warp & 3;
+// ---- epilogue: warps e = 0..7; warp e reads tensor-memory lanes 32 (e & 3) .. + 31 and the rounds of half e >> 2 --------
+// Recombination of the five plane sums: |sum_p| <= 128 * draws < 2^23 (draws <= 65535 is checked by the launcher), so
+// a = s0 + 256 s1 and b = s2 + 256 s3 fit 32 bits and the value is a + 2^16 b + 2^32 s4 in 64 bits; its two 32-bit
+// halves become doubles by the 2^52 mantissa trick (exact), and the 2^-29 scaling rides on the FMA that adds the
+// zero-count base.
+__device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t tmem, int n_items, int ewarp, int lane) {
+    const int qd = ewarp & 3, half = ewarp >> 2;
     const int b = qd * 32 + lane;  // boot of this thread
     const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
     const double scale = 1.0 / (double)(1ll << Q_FRAC);
+    const int r_begin = half ? (Q_EPI_ROUNDS + 1) / 2 : 0, r_end = half ? Q_EPI_ROUNDS : (Q_EPI_ROUNDS + 1) / 2;
     uint32_t n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const Item it = decode_item(p, item);
@@ -283,7 +291,8 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
         const int kbase = it.piece * Q_PW;
         double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + kbase;
         const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + kbase : nullptr;
-        for (int i0 = 0; i0 < Q_PW; i0 += 8) {
+        for (int rd = r_begin; rd < r_end; ++rd) {
+            const int i0 = rd * 8;
             const int n = Q_PW - i0 < 8 ? Q_PW - i0 : 8;  // 8, or 6 in the last round
             uint32_t r[Q_NV][8];
 #pragma unroll
@@ -302,11 +311,14 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
                 double out[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    long long s = 0;
-#pragma unroll
-                    for (int pl = Q_NV - 1; pl >= 0; --pl) s = s * 256 + (long long)(int32_t)r[pl][j];
-                    double t = (double)s * scale;
-                    if (Zrow && j < n) t += Zrow[i0 + j];
+                    const int32_t a = (int32_t)r[0][j] + ((int32_t)r[1][j] << 8);
+                    const int32_t c = (int32_t)r[2][j] + ((int32_t)r[3][j] << 8);
+                    const long long s = (long long)a + ((long long)c << 16) + ((long long)(int32_t)r[4][j] << 32);
+                    const double lo_d = __hiloint2double(0x43300000, (int)(uint32_t)s) - 4503599627370496.0;
+                    const double hi_d = __hiloint2double(0x43300000, (int)((uint32_t)(s >> 32) ^ 0x80000000u)) -
+                                        (4503599627370496.0 + 2147483648.0);
+                    const double v = fma(hi_d, 4294967296.0, lo_d);
+                    double t = (Zrow && j < n) ? fma(v, scale, Zrow[i0 + j]) : v * scale;
                     const int k = kbase + i0 + j;
                     if (k < klo || k > khi) t = p.sentinel;  // some drawn row is "log 0" at this grid point
                     out[j] = t;
@@ -321,7 +333,9 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
     }
 }
 
-__global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Params p) {
+template <int Q_PGROUPS>
+__global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(const I8Params p) {
+    constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // stage buffers on a 1024-byte boundary (the swizzle pattern is a function of the shared-memory address bits)
     const uint32_t raw = smem_u32(smem_raw);
@@ -346,9 +360,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) contract_i8_kernel(const I8Param
     const int n_items = p.n_pos * p.n_pieces;
 
     if (warp < Q_PRODUCER_WARPS)
-        run_producer(p, sm, stage0, n_items, warp, lane);
+        run_producer<Q_PGROUPS>(p, sm, stage0, n_items, warp, lane);
     else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
-        run_epilogue(p, sm, tmem, n_items, warp, lane);
+        run_epilogue(p, sm, tmem, n_items, warp - Q_PRODUCER_WARPS, lane);
     else if (lane == 0)
         run_mma(p, sm, stage0, tmem, n_items);
 
@@ -508,8 +522,8 @@ cudaError_t launch_w_to_i8(const double *W, int n_w_rows, int n_boot, int8_t *W8
     return cudaGetLastError();
 }
 
-bool contract_i8_supported(int K, int ld_table, int ld_lst) {
-    return K >= 1 && K <= Q_MAX_K && ld_table == KP_TILED && (ld_lst % Q_ES) == 0;
+bool contract_i8_supported(int K, int ld_table, int ld_lst, int n_draws) {
+    return K >= 1 && K <= Q_MAX_K && ld_table == KP_TILED && (ld_lst % Q_ES) == 0 && n_draws <= 65000;
 }
 
 size_t contract_i8_range_words(int n_genes) { return (size_t)(n_genes > 0 ? n_genes : 1) * Q_WB; }
@@ -548,18 +562,24 @@ cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, i
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
                                     const uint32_t *sr, cudaStream_t st) {
     if (n_pos <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+    static int pgroups = 0;
+    if (!pgroups) {
+        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        e = cudaFuncSetAttribute(contract_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        const char *env = getenv("SCDE_B200_PGROUPS");  // experiment switch: producer warp groups (2 or 3)
+        pgroups = (env && env[0] == '3') ? 3 : 2;
     }
     if (a.row_range && !sr) return cudaErrorInvalidValue;
     I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     p.SR = a.row_range ? sr : nullptr;
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
-    contract_i8_kernel<<<grid, Q_THREADS, Q_SMEM_BYTES, st>>>(p);
+    if (pgroups == 3)
+        contract_i8_kernel<3><<<grid, q_threads(3), Q_SMEM_BYTES, st>>>(p);
+    else
+        contract_i8_kernel<2><<<grid, q_threads(2), Q_SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -311,6 +311,88 @@ def quick_distribution_summary(pmat1, pmat2, prior, expectation=0.0, skip_prior_
 
 
 # ------------------------------------------------------------------------------------------------
+def _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes, n_batch_levels, zero_index,
+               zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range):
+    """scde_b200_diff_args for the C ABI; returns (args, the host arrays it points into, processed genes, K, has_batch)."""
+    keep_alive = []
+
+    def keep(a):
+        keep_alive.append(a)
+        return a
+
+    counts = keep(i32(counts))
+    G_all, Cn = counts.shape
+    K = len(prior_x)
+    a = _lib.DiffArgs()
+    a.n_genes, a.n_cells, a.n_grid = G_all, Cn, K
+    a.counts = p_i32(counts)
+    a.models = p_f64(keep(f64(mm)))
+    a.prior_x = p_f64(keep(f64(prior_x)))
+    a.prior_y = p_f64(keep(f64(prior_y)))
+    a.group = p_i32(keep(i32(group_codes)))
+    has_batch = batch_codes is not None and n_batch_levels > 1
+    a.batch = p_i32(keep(i32(batch_codes))) if batch_codes is not None else None
+    a.n_batch_levels = int(n_batch_levels)
+    a.n_boot, a.seed = int(n_boot), int(seed)
+    for i in range(4):
+        a.boot_idx[i] = p_i32(keep(i32(boot_idx[i], order="C"))) if boot_idx[i] is not None else None
+    zi = keep(i32(zero_index if zero_index is not None else [K]))
+    a.zero_index, a.n_zero = p_i32(zi), len(zi)
+    zia = keep(i32(zero_index_adjusted if zero_index_adjusted is not None else [2 * K - 1] * len(zi)))
+    a.zero_index_adjusted = p_i32(zia)
+    a.local_theta, a.square_logit_conc = int(local_theta), int(sqlogit)
+    a.gene_begin, a.gene_end = int(gene_range[0]), int(gene_range[1])
+    G = (gene_range[1] - gene_range[0]) if tuple(gene_range) != (0, 0) else G_all
+    return a, keep_alive, G, K, has_batch
+
+
+def _diff_out(G, K, has_batch, want_posteriors, joint_posteriors):
+    """scde_b200_diff_out pointing into freshly allocated host arrays; returns (out, dict of those arrays)."""
+    o = _lib.DiffOut()
+    res = {"idx": np.empty((G, 3), np.int32, order="F"), "z": np.empty(G)}
+    o.idx, o.z = p_i32(res["idx"]), p_f64(res["z"])
+    if has_batch:
+        for k in ("batch", "adjusted"):
+            res[k + "_idx"] = np.empty((G, 3), np.int32, order="F")
+            res[k + "_z"] = np.empty(G)
+        o.batch_idx, o.batch_z = p_i32(res["batch_idx"]), p_f64(res["batch_z"])
+        o.adjusted_idx, o.adjusted_z = p_i32(res["adjusted_idx"]), p_f64(res["adjusted_z"])
+    if want_posteriors:
+        res["difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
+        o.difference_posterior = p_f64(res["difference_posterior"])
+        if has_batch:
+            res["batch_difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
+            res["adjusted_difference_posterior"] = np.empty((G, 4 * K - 3), order="F")
+            o.batch_difference_posterior = p_f64(res["batch_difference_posterior"])
+            o.adjusted_difference_posterior = p_f64(res["adjusted_difference_posterior"])
+    if joint_posteriors or want_posteriors:
+        res["joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
+        for i in range(2):
+            o.joint_posteriors[i] = p_f64(res["joint_posteriors"][i])
+        if has_batch:
+            res["batch_joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
+            for i in range(2):
+                o.batch_joint_posteriors[i] = p_f64(res["batch_joint_posteriors"][i])
+    return o, res
+
+
+def expression_difference_call(ctx: _lib.Context, counts: np.ndarray, mm: np.ndarray, prior_x, prior_y, group_codes,
+                               n_boot: int, seed: int = 1, batch_codes=None, n_batch_levels: int = 0, zero_index=None,
+                               zero_index_adjusted=None, local_theta: int = 0, sqlogit: int = 0, boot_idx=(None,) * 4,
+                               gene_range=(0, 0), want_posteriors: bool = False, joint_posteriors: bool = False):
+    """The one-shot C-ABI call (scde_b200_expression_difference): host buffers in, host buffers out.  The count matrix is
+    uploaded in cell chunks while the table rows of the chunks already on the device are being built."""
+    a, keep_alive, G, K, has_batch = _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes,
+                                                n_batch_levels, zero_index, zero_index_adjusted, local_theta, sqlogit,
+                                                boot_idx, gene_range)
+    o, res = _diff_out(G, K, has_batch, want_posteriors, joint_posteriors)
+    st = _lib.Stats()
+    check(lib().scde_b200_expression_difference(ctx.handle, C.byref(a), C.byref(o), C.byref(st)))
+    del keep_alive
+    res["stats"] = st.as_dict()
+    return res
+
+
 class DifferenceJob:
     """Device-resident scde.expression.difference: upload once, run, download (C ABI split form)."""
 
@@ -319,72 +401,20 @@ class DifferenceJob:
                  zero_index_adjusted=None, local_theta: int = 0, sqlogit: int = 0, boot_idx=(None,) * 4,
                  gene_range=(0, 0), want_posteriors: bool = False):
         self.ctx = ctx
-        self._keep = []  # host arrays must outlive the upload call
-
-        def keep(a):
-            self._keep.append(a)
-            return a
-
-        counts = keep(i32(counts))
-        G_all, Cn = counts.shape
-        K = len(prior_x)
-        a = _lib.DiffArgs()
-        a.n_genes, a.n_cells, a.n_grid = G_all, Cn, K
-        a.counts = p_i32(counts)
-        a.models = p_f64(keep(f64(mm)))
-        a.prior_x = p_f64(keep(f64(prior_x)))
-        a.prior_y = p_f64(keep(f64(prior_y)))
-        a.group = p_i32(keep(i32(group_codes)))
-        self.has_batch = batch_codes is not None and n_batch_levels > 1
-        a.batch = p_i32(keep(i32(batch_codes))) if batch_codes is not None else None
-        a.n_batch_levels = int(n_batch_levels)
-        a.n_boot, a.seed = int(n_boot), int(seed)
-        for i in range(4):
-            a.boot_idx[i] = p_i32(keep(i32(boot_idx[i], order="C"))) if boot_idx[i] is not None else None
-        zi = keep(i32(zero_index if zero_index is not None else [K]))
-        a.zero_index, a.n_zero = p_i32(zi), len(zi)
-        zia = keep(i32(zero_index_adjusted if zero_index_adjusted is not None else [2 * K - 1] * len(zi)))
-        a.zero_index_adjusted = p_i32(zia)
-        a.local_theta, a.square_logit_conc = int(local_theta), int(sqlogit)
-        a.gene_begin, a.gene_end = int(gene_range[0]), int(gene_range[1])
-        self.G = (gene_range[1] - gene_range[0]) if gene_range != (0, 0) else G_all
-        self.K = K
+        a, keep_alive, self.G, self.K, self.has_batch = _diff_args(
+            counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes, n_batch_levels, zero_index,
+            zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range)
         self.want_posteriors = bool(want_posteriors)
         self._job = C.c_void_p()
         check(lib().scde_b200_diff_upload(ctx.handle, C.byref(a), int(want_posteriors), C.byref(self._job)))
-        self._keep.clear()
+        del keep_alive  # the host arrays only had to outlive the upload call
 
     def run(self):
         """Queue all device work on the context stream (asynchronous)."""
         check(lib().scde_b200_diff_run(self.ctx.handle, self._job))
 
     def download(self, joint_posteriors: bool = False):
-        G, K = self.G, self.K
-        o = _lib.DiffOut()
-        res = {"idx": np.empty((G, 3), np.int32, order="F"), "z": np.empty(G)}
-        o.idx, o.z = p_i32(res["idx"]), p_f64(res["z"])
-        if self.has_batch:
-            for k in ("batch", "adjusted"):
-                res[k + "_idx"] = np.empty((G, 3), np.int32, order="F")
-                res[k + "_z"] = np.empty(G)
-            o.batch_idx, o.batch_z = p_i32(res["batch_idx"]), p_f64(res["batch_z"])
-            o.adjusted_idx, o.adjusted_z = p_i32(res["adjusted_idx"]), p_f64(res["adjusted_z"])
-        if self.want_posteriors:
-            res["difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
-            o.difference_posterior = p_f64(res["difference_posterior"])
-            if self.has_batch:
-                res["batch_difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
-                res["adjusted_difference_posterior"] = np.empty((G, 4 * K - 3), order="F")
-                o.batch_difference_posterior = p_f64(res["batch_difference_posterior"])
-                o.adjusted_difference_posterior = p_f64(res["adjusted_difference_posterior"])
-        if joint_posteriors or self.want_posteriors:
-            res["joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
-            for i in range(2):
-                o.joint_posteriors[i] = p_f64(res["joint_posteriors"][i])
-            if self.has_batch:
-                res["batch_joint_posteriors"] = [np.empty((G, K), order="F") for _ in range(2)]
-                for i in range(2):
-                    o.batch_joint_posteriors[i] = p_f64(res["batch_joint_posteriors"][i])
+        o, res = _diff_out(self.G, self.K, self.has_batch, self.want_posteriors, joint_posteriors)
         st = _lib.Stats()
         check(lib().scde_b200_diff_download(self.ctx.handle, self._job, C.byref(o), C.byref(st)))
         res["stats"] = st.as_dict()
@@ -447,17 +477,13 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
     adiffv = r_as_character_numeric(r_seq_length(diffv[0] - diffv[-1], diffv[-1] - diffv[0], 2 * len(diffv) - 1))
     zia = _zero_index(adiffv, expectation)
     ctx = context or _lib.default_context()
-    job = DifferenceJob(ctx, cm, mm, x, np.asarray(prior["y"], dtype=np.float64), gcodes, n_randomizations, seed,
-                        batch_codes=bcodes if correct_batch else None, n_batch_levels=len(blev) if correct_batch else 0,
-                        zero_index=zi, zero_index_adjusted=zia, local_theta=lt, sqlogit=sq, boot_idx=boot_idx,
-                        want_posteriors=return_posteriors)
-    try:
-        if verbose:
-            sys.stdout.write("calculating difference posterior\n")
-        job.run()
-        res = job.download()
-    finally:
-        job.close()
+    if verbose:
+        sys.stdout.write("calculating difference posterior\n")
+    res = expression_difference_call(ctx, cm, mm, x, np.asarray(prior["y"], dtype=np.float64), gcodes, n_randomizations, seed,
+                                     batch_codes=bcodes if correct_batch else None,
+                                     n_batch_levels=len(blev) if correct_batch else 0, zero_index=zi,
+                                     zero_index_adjusted=zia, local_theta=lt, sqlogit=sq, boot_idx=boot_idx,
+                                     want_posteriors=return_posteriors)
     if verbose:
         sys.stdout.write("summarizing differences\n")
     bdiffp_rep = _summary_frame(res["idx"], res["z"], diffv, genes)

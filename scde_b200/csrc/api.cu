@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 namespace scde {
@@ -124,6 +125,8 @@ struct scde_b200_ctx {
                               // 4 = sentinel ranges need the FP64 kernel
     DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
     bool ws_busy = false;
+    cudaStream_t copy_stream = nullptr;     // H2D of the count matrix in cell chunks, overlapped with the table build
+    std::vector<cudaEvent_t> copy_events;   // one per chunk (+ 1: "the compute stream has released the counts buffer")
 };
 
 namespace {
@@ -147,6 +150,12 @@ struct LpTable {
     bool zero_base = false;
 };
 
+#define TRY(x)                          \
+    do {                                \
+        int _r = (x);                   \
+        if (_r != SCDE_B200_OK) return _r; \
+    } while (0)
+
 #define CHECK_CTX(ctx)                                                  \
     do {                                                                \
         if (!(ctx)) {                                                   \
@@ -156,9 +165,29 @@ struct LpTable {
         SCDE_CUDA(cudaSetDevice((ctx)->device));                        \
     } while (0)
 
-// rows of the table from the per-cell model rows; t.row_off / t.row_x / t.n_rows must be set
-int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_models, const double *mag_dev,
-               int local_theta, int sqlogit, StageTimer *tm) {
+// What fill_table decides once per table and the row-level launches need: which kernels, which outputs.
+struct TablePlan {
+    bool fast = false;     // constant-theta fast row kernel
+    bool q_any = false;    // the table also exists in fixed point (tcgen05 contraction)
+    bool q_fused = false;  // ... emitted by the row kernel itself; the FP64 rows of non-zero counts are then not stored
+    CellPrep prep{};
+    void *rowc = nullptr;
+    int32_t *rmode = nullptr;
+    int8_t *qf = nullptr;
+    uint32_t *qr = nullptr;
+};
+
+TablePlan plan_table(const LpTable &t, int local_theta) {
+    TablePlan pl;
+    pl.fast = t.fast_theta && !local_theta && t.K <= KP_TILED;
+    pl.q_any = t.want_q && t.zero_base && t.ld == KP_TILED && t.K <= Q_MAX_K;
+    pl.q_fused = pl.q_any && pl.fast && !getenv("SCDE_B200_Q_SEPARATE");
+    return pl;
+}
+
+// per-cell buffers (independent of the number of table rows) + the per-cell grid vectors
+int prepare_cells(scde_b200_ctx *ctx, LpTable &t, TablePlan &pl, const double *models_dev, int ld_models,
+                  const double *mag_dev, int local_theta, int sqlogit) {
     cudaStream_t st = ctx->stream;
     const size_t cl = (size_t)t.n_cells * t.ld;
     SCDE_CUDA(t.mu.ensure(cl));
@@ -166,61 +195,84 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     SCDE_CUDA(t.lcfpr.ensure(cl));
     if (local_theta) SCDE_CUDA(t.theta.ensure(cl));
     SCDE_CUDA(t.maxcfp.ensure(t.n_cells));
-    SCDE_CUDA(t.table.ensure((size_t)t.n_rows * t.ld));
-    SCDE_CUDA(t.row_mode.ensure((size_t)t.n_rows));
-    SCDE_CUDA(t.row_cell.ensure((size_t)t.n_rows));
-    const bool fast = t.fast_theta && !local_theta && t.K <= KP_TILED;
-    if (fast) {
+    if (pl.fast) {
         SCDE_CUDA(t.cfp.ensure(cl));
         SCDE_CUDA(t.l1.ensure(cl));
         SCDE_CUDA(t.l2.ensure(cl));
-        SCDE_CUDA(t.rowc.ensure((size_t)4 * t.n_rows));
         SCDE_CUDA(t.scfp.ensure((size_t)t.n_cells));
     }
-    void *rowc = fast ? (void *)t.rowc.p : nullptr;
-    int32_t *rmode = t.want_modes ? t.row_mode.p : nullptr;
-    CellPrep prep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
-                  fast ? t.cfp.p : nullptr, fast ? t.l1.p : nullptr, fast ? t.l2.p : nullptr, fast ? t.scfp.p : nullptr};
-    // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
-    // counts are then not stored at all), by a separate pass over the FP64 table for the general kernel
-    const bool q_any = t.want_q && t.zero_base && t.ld == KP_TILED && t.K <= Q_MAX_K;
-    const bool q_fused = q_any && fast && !getenv("SCDE_B200_Q_SEPARATE");
-    if (q_any) {
-        SCDE_CUDA(t.q.ensure((size_t)t.n_rows * q_row_bytes(t.K)));
-        SCDE_CUDA(t.qrange.ensure((size_t)t.n_rows));
-    }
-    int8_t *qf = q_fused ? t.q.p : nullptr;
-    uint32_t *qr = q_fused ? t.qrange.p : nullptr;
     if (t.zero_base) {
         SCDE_CUDA(t.zero_row.ensure((size_t)t.n_cells));
         SCDE_CUDA(t.based.ensure((size_t)t.n_cells));
     }
-    int e0 = tm ? tm->begin(st) : -1;
-    int nl = 3;
-    SCDE_CUDA(launch_cell_prep(models_dev, ld_models, t.n_cells, mag_dev, t.K, local_theta, sqlogit, prep, st));
-    SCDE_CUDA(launch_row_cell(t.row_off.p, t.n_cells, t.row_cell.p, st));
-    if (fast) {
-        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_cell.p, t.row_x.p, t.n_rows, rowc, st));
-        ++nl;
+    pl.prep = CellPrep{t.mu.p, t.lcfp.p, t.lcfpr.p, local_theta ? t.theta.p : nullptr, t.maxcfp.p, t.ld,
+                       pl.fast ? t.cfp.p : nullptr, pl.fast ? t.l1.p : nullptr, pl.fast ? t.l2.p : nullptr,
+                       pl.fast ? t.scfp.p : nullptr};
+    SCDE_CUDA(launch_cell_prep(models_dev, ld_models, t.n_cells, mag_dev, t.K, local_theta, sqlogit, pl.prep, st));
+    return SCDE_B200_OK;
+}
+
+// per-row buffers for `rows` table rows
+int reserve_rows(LpTable &t, TablePlan &pl, size_t rows) {
+    SCDE_CUDA(t.table.ensure(rows * t.ld));
+    SCDE_CUDA(t.row_mode.ensure(rows));
+    SCDE_CUDA(t.row_cell.ensure(rows));
+    if (pl.fast) SCDE_CUDA(t.rowc.ensure(4 * rows));
+    if (pl.q_any) {
+        SCDE_CUDA(t.q.ensure(rows * q_row_bytes(t.K)));
+        SCDE_CUDA(t.qrange.ensure(rows));
+    }
+    pl.rowc = pl.fast ? (void *)t.rowc.p : nullptr;
+    pl.rmode = t.want_modes ? t.row_mode.p : nullptr;
+    pl.qf = pl.q_fused ? t.q.p : nullptr;
+    pl.qr = pl.q_fused ? t.qrange.p : nullptr;
+    return SCDE_B200_OK;
+}
+
+// the row-level kernels for the cells of `cr` (their rows are read from t.row_off on the device); returns the number of
+// launches through *nl
+int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl, CellRange cr, const double *models_dev,
+                      int ld_models, int local_theta, int *nl) {
+    cudaStream_t st = ctx->stream;
+    const int n = cr.c1 - cr.c0;
+    SCDE_CUDA(launch_row_cell(t.row_off.p, cr, t.row_cell.p, st));
+    ++*nl;
+    if (pl.fast) {
+        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_off.p, cr, t.row_cell.p, t.row_x.p, pl.rowc, st));
+        ++*nl;
     }
     if (t.zero_base) {
-        SCDE_CUDA(launch_zero_rows(t.row_off.p, t.row_x.p, t.n_cells, t.zero_row.p, st));
-        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 1, t.zero_row.p, nullptr, rowc, 1, qf,
-                                 qr, st));
-        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p, t.n_cells, t.based.p, st));
-        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 2, t.zero_row.p, t.based.p, rowc,
-                                 q_fused ? 0 : 1, qf, qr, st));
-        nl += 3;
+        SCDE_CUDA(launch_zero_rows(t.row_off.p + cr.c0, t.row_x.p, n, t.zero_row.p + cr.c0, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, 1, pl.qf, pl.qr, st));
+        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc,
+                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st));
+        *nl += 4;
     } else {
-        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, t.n_cells, t.row_off.p, t.row_cell.p, t.row_x.p, t.n_rows, prep, t.K,
-                                 local_theta, t.sentinel, t.table.p, t.ld, rmode, 0, nullptr, nullptr, rowc, 1, nullptr,
-                                 nullptr, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 0, nullptr, nullptr, pl.rowc, 1, nullptr, nullptr, st));
+        ++*nl;
     }
-    t.has_q = q_any;
-    t.f64_rows = !(q_fused && t.zero_base);
-    if (q_any && !q_fused) {
+    return SCDE_B200_OK;
+}
+
+// rows of the table from the per-cell model rows; t.row_off / t.row_x / t.n_rows must be set
+int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_models, const double *mag_dev,
+               int local_theta, int sqlogit, StageTimer *tm) {
+    cudaStream_t st = ctx->stream;
+    TablePlan pl = plan_table(t, local_theta);
+    TRY(reserve_rows(t, pl, (size_t)t.n_rows));
+    int e0 = tm ? tm->begin(st) : -1;
+    int nl = 1;
+    TRY(prepare_cells(ctx, t, pl, models_dev, ld_models, mag_dev, local_theta, sqlogit));
+    // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
+    // counts are then not stored at all), by a separate pass over the FP64 table for the general kernel
+    TRY(launch_table_rows(ctx, t, pl, CellRange{0, t.n_cells, (int64_t)t.n_rows}, models_dev, ld_models, local_theta, &nl));
+    t.has_q = pl.q_any;
+    t.f64_rows = !(pl.q_fused && t.zero_base);
+    if (pl.q_any && !pl.q_fused) {
         SCDE_CUDA(launch_quantize_rows(t.table.p, t.ld, t.K, t.n_rows, t.q.p, t.qrange.p, st));
         ++nl;
     }
@@ -244,7 +296,7 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
     int e0 = tm ? tm->begin(st) : -1;
     SCDE_CUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
     SCDE_CUDA(launch_dedup_count(counts_dev, ldc, g0, G, C, t.n_unique.p, t.err.p, st));
-    SCDE_CUDA(launch_exclusive_scan(t.n_unique.p, t.row_off.p, C, st));
+    SCDE_CUDA(launch_exclusive_scan(t.n_unique.p, t.row_off.p, C, nullptr, st));
     int32_t total = 0, err = 0;
     SCDE_CUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -259,7 +311,8 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
     }
     t.n_rows = total;
     SCDE_CUDA(t.row_x.ensure((size_t)total));
-    SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p, st));
+    SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p,
+                                (int64_t)total, st));
     if (tm) tm->end(SCDE_B200_T_DEDUP, e0, st, 3);
     return SCDE_B200_OK;
 }
@@ -439,11 +492,6 @@ int upload(DBuf<T> &d, const T *h, size_t n, cudaStream_t st) {
     if (n) SCDE_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
     return SCDE_B200_OK;
 }
-#define TRY(x)                          \
-    do {                                \
-        int _r = (x);                   \
-        if (_r != SCDE_B200_OK) return _r; \
-    } while (0)
 
 int validate_index(const int32_t *v, size_t n, int lo, int hi, const char *what) {
     for (size_t i = 0; i < n; ++i)
@@ -505,6 +553,12 @@ int scde_b200_create(int device, scde_b200_ctx **out) {
 void scde_b200_destroy(scde_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx->ws;
     delete ctx;
@@ -1054,8 +1108,11 @@ struct scde_b200_diff_job {
 
 extern "C" {
 
-int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int32_t want_posteriors,
-                          scde_b200_diff_job **out) {
+}  // extern "C"
+
+// defer_counts: the count matrix is not copied here (the one-shot call overlaps its upload with the table build)
+static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int32_t want_posteriors,
+                            scde_b200_diff_job **out, bool defer_counts) {
     CHECK_CTX(ctx);
     if (!a || !out) return SCDE_B200_EINVAL;
     *out = nullptr;
@@ -1123,9 +1180,20 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
     j->n_levels = has_batch ? a->n_batch_levels : 0;
     j->n_zero = a->n_zero;
     // counts shard: rows [g0, g1) of every column
+    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;
+    const auto tu0 = std::chrono::steady_clock::now();
     JCUDA(j->ws->counts.ensure((size_t)G * C));
-    JCUDA(cudaMemcpy2DAsync(j->ws->counts.p, sizeof(int32_t) * G, a->counts + g0, sizeof(int32_t) * (size_t)a->n_genes,
-                            sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
+    const auto tu1 = std::chrono::steady_clock::now();
+    if (!defer_counts)
+        JCUDA(cudaMemcpy2DAsync(j->ws->counts.p, sizeof(int32_t) * G, a->counts + g0, sizeof(int32_t) * (size_t)a->n_genes,
+                                sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
+    if (trace && !defer_counts) {
+        JCUDA(cudaStreamSynchronize(st));
+        const auto tu2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scde_b200] upload: counts buffer %.2f ms, counts H2D (%.1f MB) %.2f ms\n",
+                std::chrono::duration<double, std::milli>(tu1 - tu0).count(), sizeof(int32_t) * (double)G * C / 1e6,
+                std::chrono::duration<double, std::milli>(tu2 - tu1).count());
+    }
     JTRY(upload(j->models, a->models, (size_t)C * 12, st));
     JTRY(upload(j->prior_y, a->prior_y, (size_t)K, st));
     std::vector<double> mag(K);
@@ -1224,7 +1292,136 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
 #undef JCUDA
 }
 
-int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
+// Chunked front of the one-shot call: the count matrix goes up in N_CHUNKS cell ranges on the copy stream, and every
+// range is deduplicated and its table rows are built on the compute stream as soon as it has landed, so the 1.2 GB H2D of
+// config 4 (22 ms at PCIe rate) hides behind the row kernels.  Row offsets are chunk-local scans carried forward on the
+// device; the row-level kernels read their bounds there (CellRange), so nothing waits for the host except one 4-byte read
+// after the first chunk: its row count sizes the buffers (x 1.25).  If the estimate turns out too small the kernels stop
+// at the capacity and *done stays false: the caller rebuilds index and table the classic way from the resident counts.
+static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host,
+                         bool *done) {
+    *done = false;
+    LpTable &t = j->ws->table;
+    const int G = j->G, C = j->C;
+    cudaStream_t st = ctx->stream;
+    StageTimer &tm = j->timer;
+    t.n_cells = C;
+    t.n_genes = G;
+    t.ld_ridx = C;
+    TablePlan pl = plan_table(t, j->local_theta);
+    constexpr int N_CHUNKS = 8;
+    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * N_CHUNKS && !getenv("SCDE_B200_NO_PIPELINE");
+    if (!pipelined) {
+        SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p, sizeof(int32_t) * G, counts_host, sizeof(int32_t) * (size_t)ld_host,
+                                    sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
+        return SCDE_B200_OK;
+    }
+    if (!ctx->copy_stream) SCDE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->copy_events.size() < N_CHUNKS + 1) {
+        cudaEvent_t e;
+        SCDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    SCDE_CUDA(t.n_unique.ensure(C));
+    SCDE_CUDA(t.row_off.ensure((size_t)C + 1));
+    SCDE_CUDA(t.err.ensure(1));
+    SCDE_CUDA(t.ridx.ensure((size_t)G * C));
+    // the copy stream may overwrite the counts buffer only after earlier work on the compute stream is done with it
+    SCDE_CUDA(cudaEventRecord(ctx->copy_events[N_CHUNKS], st));
+    SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_CHUNKS], 0));
+    const int chunk = round_up((C + N_CHUNKS - 1) / N_CHUNKS, 32);
+    int n_ch = 0;
+    for (int c0 = 0; c0 < C; c0 += chunk, ++n_ch) {
+        const int n = (C - c0) < chunk ? (C - c0) : chunk;
+        SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p + (size_t)c0 * G, sizeof(int32_t) * G, counts_host + (size_t)c0 * ld_host,
+                                    sizeof(int32_t) * (size_t)ld_host, sizeof(int32_t) * G, n, cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+        SCDE_CUDA(cudaEventRecord(ctx->copy_events[n_ch], ctx->copy_stream));
+    }
+    auto drain = [&](int r) {  // never return while the copy engine may still read the caller's buffer
+        cudaStreamSynchronize(ctx->copy_stream);
+        return r;
+    };
+#define FTRY(x)                                   \
+    do {                                          \
+        int _r = (x);                             \
+        if (_r != SCDE_B200_OK) return drain(_r); \
+    } while (0)
+#define FCUDA(x)                                                                    \
+    do {                                                                            \
+        cudaError_t _e = (x);                                                       \
+        if (_e != cudaSuccess) return drain(cuda_fail(_e, #x, __FILE__, __LINE__));  \
+    } while (0)
+    FCUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
+    int e0 = tm.begin(st);
+    FTRY(prepare_cells(ctx, t, pl, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit));
+    tm.end(SCDE_B200_T_LPTABLE, e0, st, 1);
+    int64_t cap = 0;
+    int i = 0;
+    for (int c0 = 0; c0 < C; c0 += chunk, ++i) {
+        const int n = (C - c0) < chunk ? (C - c0) : chunk;
+        const int32_t *cnt = j->ws->counts.p + (size_t)c0 * G;
+        FCUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
+        e0 = tm.begin(st);
+        FCUDA(launch_dedup_count(cnt, G, 0, G, n, t.n_unique.p + c0, t.err.p, st));
+        FCUDA(launch_exclusive_scan(t.n_unique.p + c0, t.row_off.p + c0, n, i ? t.row_off.p + c0 : nullptr, st));
+        if (i == 0) {
+            int32_t rows0 = 0;
+            FCUDA(cudaMemcpyAsync(&rows0, t.row_off.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            FCUDA(cudaStreamSynchronize(st));
+            cap = (int64_t)((double)rows0 * C / n * 1.25) + 4096;
+            const int64_t have = (int64_t)(t.q.cap / (size_t)q_row_bytes(t.K));  // a workspace from an earlier call
+            if (have > cap) cap = have;
+            if (cap > 0x7fffffff) cap = 0x7fffffff;
+            FTRY(reserve_rows(t, pl, (size_t)cap));
+            FCUDA(t.row_x.ensure((size_t)cap));
+        }
+        FCUDA(launch_dedup_emit(cnt, G, 0, G, n, t.row_off.p + c0, t.row_x.p, t.ridx.p + c0, t.ld_ridx, t.err.p, cap, st));
+        tm.end(SCDE_B200_T_DEDUP, e0, st, 3);
+        e0 = tm.begin(st);
+        int nl = 0;
+        FTRY(launch_table_rows(ctx, t, pl, CellRange{c0, c0 + n, cap}, j->models.p, C, j->local_theta, &nl));
+        tm.end(SCDE_B200_T_LPTABLE, e0, st, nl);
+    }
+    int32_t total = 0, err = 0;
+    FCUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FCUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FCUDA(cudaStreamSynchronize(st));
+    FCUDA(cudaStreamSynchronize(ctx->copy_stream));
+#undef FTRY
+#undef FCUDA
+    if (err & 1) {
+        set_error("negative count in the count matrix");
+        return SCDE_B200_EINVAL;
+    }
+    if (err & 2) {
+        set_error("a cell has >= 32768 distinct count values among the processed genes (hash capacity)");
+        return SCDE_B200_ELIMIT;
+    }
+    if (total < 0 || (int64_t)total > cap) return SCDE_B200_OK;  // more rows than estimated: classic rebuild
+    t.n_rows = total;
+    t.has_q = true;
+    t.f64_rows = false;
+    *done = true;
+    return SCDE_B200_OK;
+}
+
+static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host);
+
+extern "C" {
+
+int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int32_t want_posteriors,
+                          scde_b200_diff_job **out) {
+    return diff_upload_impl(ctx, a, want_posteriors, out, false);
+}
+
+int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) { return diff_run_impl(ctx, j, nullptr, 0); }
+
+}  // extern "C"
+
+// counts_host != NULL: the count matrix has not been uploaded yet (one-shot call); rows of the shard start at
+// counts_host[0], columns are ld_host apart
+static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host) {
     CHECK_CTX(ctx);
     if (!j) return SCDE_B200_EINVAL;
     cudaStream_t st = ctx->stream;
@@ -1239,8 +1436,12 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     j->ws->table.want_modes = false;
     TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
-    TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
-    TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
+    bool front_done = false;
+    if (counts_host) TRY(front_chunked(ctx, j, counts_host, ld_host, &front_done));
+    if (!front_done) {
+        TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
+        TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
+    }
     // group joints: cells of one factor level, draws are local indices (R/functions.R:372-374)
     for (int i = 0; i < 2; ++i)
         TRY(run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
@@ -1303,6 +1504,8 @@ int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) {
     j->ran = true;
     return SCDE_B200_OK;
 }
+
+extern "C" {
 
 static int download_matrix(scde_b200_ctx *ctx, scde_b200_diff_job *j, const double *src, int ld_src, int cols, double *dst) {
     cudaStream_t st = ctx->stream;
@@ -1393,12 +1596,24 @@ int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_arg
     CHECK_CTX(ctx);
     if (!args || !out) return SCDE_B200_EINVAL;
     const int want_post = out->difference_posterior || out->adjusted_difference_posterior;
+    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;  // host wall-clock of the three phases on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
     scde_b200_diff_job *job = nullptr;
-    int r = scde_b200_diff_upload(ctx, args, want_post, &job);
+    int r = diff_upload_impl(ctx, args, want_post, &job, true);
     if (r != SCDE_B200_OK) return r;
-    r = scde_b200_diff_run(ctx, job);
+    const auto t1 = now();
+    r = diff_run_impl(ctx, job, args->counts + args->gene_begin, args->n_genes);
+    const auto t2 = now();
     if (r == SCDE_B200_OK) r = scde_b200_diff_download(ctx, job, out, stats);
+    const auto t3 = now();
     scde_b200_diff_free(ctx, job);
+    if (trace)
+        fprintf(stderr, "[scde_b200] expression_difference: upload %.2f ms, run (queued) %.2f ms, download (incl. wait) %.2f ms, free %.2f ms\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
     return r;
 }
 

@@ -21,6 +21,7 @@
 //   * softmax_avg_kernel then does the log-sum-exp over the grid with warp shuffles and the average over boots.
 // contract_generic_kernel handles any K / any B (used for K > 416 and as an on-device cross-check).
 #include "common.cuh"
+#include "fastmath.cuh"
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -448,48 +449,59 @@ __global__ void __launch_bounds__(T_THREADS, 1) contract_mma_kernel(const TiledP
 
 // ------------------------------------------------------------------------------------------------
 // softmax_avg_kernel: jp[gene, k] (+)= sum_b exp(T[b, k] - max_k T[b, :]) / (sum_k exp(...) * scale)
-// (src/jpmatLogBoot.cpp:264-269).  One CTA per gene.  Phase A: one warp per boot row -- log-sum-exp pieces by warp
-// shuffles, exponentials written back over T (the 346 KB tile is L2-resident).  Phase B: one thread per grid point adds
-// the boots in ascending order, as the reference does.
+// (src/jpmatLogBoot.cpp:264-269).  One CTA per gene, one warp per boot row at a time: the row is read once into
+// registers (13 grid points per lane), its log-sum-exp pieces come from warp shuffles, and the normalised exponentials are
+// added to per-lane accumulators -- T is read exactly once and never written.  exp() is fastmath.cuh's exp_nonpos
+// (3e-13 relative; the soft-max weights feed a 1e-6 contract).  The eight warps' partial sums (boots
+// b = w mod 8, ascending) are added in warp order through shared memory, so the result is deterministic.
 constexpr int SM_THREADS = 256;
 __global__ void __launch_bounds__(SM_THREADS)
-softmax_avg_kernel(double *__restrict__ T, const int32_t *__restrict__ order, int K, int n_boot_pass, double scale,
+softmax_avg_kernel(const double *__restrict__ T, const int32_t *__restrict__ order, int K, int n_boot_pass, double scale,
                    double *__restrict__ jp, int64_t ld_jp, int accumulate) {
-    __shared__ double s_inv[T_WP];
+    constexpr int NW = SM_THREADS / 32, NJ = KP_TILED / 32;
+    __shared__ double s_acc[NW][KP_TILED];
     const int pos = blockIdx.x;
     const int64_t gene = order ? order[pos] : pos;
-    double *Tg = T + (int64_t)pos * (T_WP * KP_TILED);
+    const double *Tg = T + (int64_t)pos * (T_WP * KP_TILED);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = warp; b < n_boot_pass; b += SM_THREADS / 32) {
-        double *row = Tg + (int64_t)b * KP_TILED;
-        double v[KP_TILED / 32];
+    double acc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.0;
+    for (int b = warp; b < n_boot_pass; b += NW) {
+        const double *row = Tg + (int64_t)b * KP_TILED;
+        double v[NJ];
         double m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < KP_TILED / 32; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int k = lane + 32 * j;
-            v[j] = k < K ? row[k] : -INFINITY;
+            v[j] = k < K ? __ldcs(row + k) : -INFINITY;
             m = fmax(m, v[j]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         double sum = 0.0;
 #pragma unroll
-        for (int j = 0; j < KP_TILED / 32; ++j) {
-            const int k = lane + 32 * j;
-            if (k < K) {
-                const double e = exp(v[j] - m);
-                row[k] = e;
-                sum += e;
-            }
+        for (int j = 0; j < NJ; ++j) {
+            // a joint posterior is sharply peaked: most 32-point stretches of the grid lie more than 746 nats below the
+            // row maximum, where exp() is exactly 0 -- skip them warp-wide
+            const double d = v[j] - m;
+            v[j] = 0.0;
+            if (__any_sync(0xffffffffu, d > -746.0)) v[j] = (lane + 32 * j < K) ? exp_nonpos(d) : 0.0;
+            sum += v[j];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) s_inv[b] = 1.0 / (sum * scale);
+        const double inv = 1.0 / (sum * scale);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = fma(v[j], inv, acc[j]);
     }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s_acc[warp][lane + 32 * j] = acc[j];
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += SM_THREADS) {
         double r = 0.0;
-        for (int b = 0; b < n_boot_pass; ++b) r += Tg[(int64_t)b * KP_TILED + k] * s_inv[b];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) r += s_acc[w][k];
         double *out = jp + gene * ld_jp + k;
         *out = accumulate ? *out + r : r;
     }

@@ -38,8 +38,15 @@ struct CellPrep {  // per-cell grid vectors, each [n_cells][ld]
 // models: n_cells x 12 column-major with leading dimension ld_models
 cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, const double *mag, int K,
                              int local_theta, int sqlogit, CellPrep prep, cudaStream_t st);
+// A range of cells processed by one launch of the row-level kernels: cells [c0, c1) of row_off (device), i.e. table rows
+// [row_off[c0], min(row_off[c1], row_cap)) -- the bounds are read on the device, so a launch can be queued before the
+// host knows them (the chunked front of scde_b200_expression_difference).
+struct CellRange {
+    int c0, c1;
+    int64_t row_cap;
+};
 // row_cell[r] = cell of table row r (from row_off)
-cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_cell, cudaStream_t st);
+cudaError_t launch_row_cell(const int32_t *row_off, CellRange cr, int32_t *row_cell, cudaStream_t st);
 // zero_row[c] = the row of cell c whose count is 0, or -1
 cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st);
 // based[c] = 1 when cell c has a zero-count row and that row holds no "log 0" sentinel (it can be subtracted)
@@ -48,16 +55,16 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 // One warp per table row.  Writes table[r*ld_table + k] (k >= K zero-filled up to ld_table) and row_mode[r] (first
 // argmax, before the clamp).  which: 0 = every row, plain values; 1 = only the zero-count rows (plain values);
 // 2 = every row except the zero-count ones, stored as the difference to the cell's zero-count row when based[cell].
-cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
-                           const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, const int32_t *row_off,
+                           const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
                            uint32_t *row_range, cudaStream_t st);
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
-cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
-                              int64_t n_rows, void *row_const, cudaStream_t st);
+cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_off, CellRange cr,
+                              const int32_t *row_cell, const int32_t *row_x, void *row_const, cudaStream_t st);
 
 // ---- dedup.cu ------------------------------------------------------------------------------------
 // counts: column-major with leading dimension ld_counts; genes [g0, g0+G) of n_cells columns.
@@ -66,10 +73,11 @@ cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t
 // 2 = more distinct values than the hash capacity.
 cudaError_t launch_dedup_count(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
                                int32_t *n_unique, int32_t *err_flag, cudaStream_t st);
-cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, cudaStream_t st);  // out[n] = total
+// out[i] = base + sum of in[0..i), out[n] = base + total; base = *base_dev (device) or 0 when NULL
+cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, const int32_t *base_dev, cudaStream_t st);
 cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
                               const int32_t *row_off, int32_t *row_x, int32_t *ridx, int ld_ridx,
-                              int32_t *err_flag, cudaStream_t st);
+                              int32_t *err_flag, int64_t row_cap /* rows row_x can hold */, cudaStream_t st);
 // (ucl, uci)-given form: ridx[g*ld_ridx + c] = ucl_off[c] + uci[g + G*c]
 cudaError_t launch_uci_to_ridx(const int32_t *uci, int G, int n_cells, const int32_t *ucl_off, int32_t *ridx,
                                int ld_ridx, cudaStream_t st);

@@ -92,7 +92,7 @@ dedup_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int 
 __global__ void __launch_bounds__(DEDUP_THREADS)
 dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells, int log2cap_max,
                   const int32_t *__restrict__ row_off, int32_t *__restrict__ row_x, int32_t *__restrict__ ridx,
-                  int ld_ridx, int32_t *err_flag) {
+                  int ld_ridx, int32_t *err_flag, int64_t row_cap) {
     extern __shared__ uint32_t s_tab[];
     __shared__ int s_count;
     const int c = blockIdx.x;
@@ -105,7 +105,8 @@ dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G
     const int U = s_count;
     bitonic_sort(s_tab, 1u << log2cap);
     const int base = row_off[c];
-    for (int i = threadIdx.x; i < U; i += blockDim.x) row_x[base + i] = (int32_t)s_tab[i];
+    for (int i = threadIdx.x; i < U; i += blockDim.x)
+        if ((int64_t)base + i < row_cap) row_x[base + i] = (int32_t)s_tab[i];  // beyond the capacity: api.cu falls back
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         int32_t xi = col[g];
         uint32_t x = xi < 0 ? 0u : (uint32_t)xi;
@@ -118,11 +119,12 @@ dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G
     }
 }
 
-__global__ void exclusive_scan_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
-    // single CTA, 1024 threads, chunked Hillis-Steele over n elements; out[n] = total
+__global__ void exclusive_scan_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n,
+                                      const int32_t *__restrict__ base_ptr) {
+    // single CTA, 1024 threads, chunked Hillis-Steele over n elements; out[n] = base + total
     __shared__ int32_t s[1024];
     __shared__ int32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = base_ptr ? *base_ptr : 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
         int i = base + threadIdx.x;
@@ -180,21 +182,21 @@ cudaError_t launch_dedup_count(const int32_t *counts, int64_t ld_counts, int g0,
     return cudaGetLastError();
 }
 
-cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, cudaStream_t st) {
-    exclusive_scan_kernel<<<1, 1024, 0, st>>>(in, out, n);
+cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, const int32_t *base, cudaStream_t st) {
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(in, out, n, base);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
                               const int32_t *row_off, int32_t *row_x, int32_t *ridx, int ld_ridx,
-                              int32_t *err_flag, cudaStream_t st) {
+                              int32_t *err_flag, int64_t row_cap, cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
     int l = pick_log2cap(G);
     size_t smem = sizeof(uint32_t) << l;
     cudaError_t e = cudaFuncSetAttribute(dedup_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dedup_emit_kernel<<<n_cells, DEDUP_THREADS, smem, st>>>(counts, ld_counts, g0, G, n_cells, l, row_off, row_x, ridx,
-                                                            ld_ridx, err_flag);
+                                                            ld_ridx, err_flag, row_cap);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,38 @@
+// fastmath.cuh -- exp() for non-positive arguments, used where only a normalising sum or a soft-max weight is needed.
+#pragma once
+
+namespace scde {
+
+// exp(a) for a <= 0 (any magnitude): round-to-nearest split a = n ln2 + r, |r| <= 0.3466, Taylor polynomial of degree 10
+// (remainder < 3e-13 relative), scaling by an exponent-field add.  Below -700 the scaling is done in two steps so the
+// result is a correctly scaled denormal (the last bit of a denormal may differ from libm's); below -745.2 it is exactly 0.
+// No special cases for +-Inf / NaN: -Inf gives 0, NaN gives garbage -- callers pass finite or -Inf arguments only.
+// About 22 instructions instead of the ~45 of the library routine.
+// FULL_RANGE = false: the caller guarantees a >= -700 (no clamp, no two-step scaling).
+template <bool FULL_RANGE = true>
+__device__ __forceinline__ double exp_nonpos(double a) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
+    if (FULL_RANGE) a = fmax(a, -746.0);
+    const bool tiny = FULL_RANGE && a < -700.0;
+    const double t = fma(a, 1.44269504088896340736, MAGIC);
+    int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01, a);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 2.75573192239858906526e-07;  // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    n += tiny ? 64 : 0;
+    const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return tiny ? res * 5.42101086242752217004e-20 /* 2^-64 */ : res;
+}
+
+}  // namespace scde

@@ -14,6 +14,7 @@
 // k-independent pieces of the saddle-point formula (three stirlerr terms, two logs) are hoisted per row when
 // theta is constant.  FP64 throughout.
 #include "common.cuh"
+#include "fastmath.cuh"
 #include <cfloat>
 #include <cmath>
 
@@ -261,26 +262,31 @@ __global__ void based_flags_kernel(const double *__restrict__ table, int ld_tabl
     if (lane == 0) based[c] = ok ? 1 : 0;
 }
 
-__global__ void row_cell_kernel(const int32_t *__restrict__ row_off, int n_cells, int32_t *__restrict__ row_cell) {
-    const int c = blockIdx.x;
-    if (c >= n_cells) return;
-    for (int r = row_off[c] + threadIdx.x; r < row_off[c + 1]; r += blockDim.x) row_cell[r] = c;
+__global__ void row_cell_kernel(const int32_t *__restrict__ row_off, CellRange cr, int32_t *__restrict__ row_cell) {
+    const int c = cr.c0 + blockIdx.x;
+    if (c >= cr.c1) return;
+    const int64_t end = min((int64_t)row_off[c + 1], cr.row_cap);
+    for (int64_t r = row_off[c] + threadIdx.x; r < end; r += blockDim.x) row_cell[r] = c;
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
-               const int32_t *__restrict__ row_x, int64_t n_rows, CellPrep prep, int K, int local_theta, double sentinel,
+lp_rows_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
+               const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x, CellPrep prep, int K, int local_theta,
+               double sentinel,
                double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based) {
     extern __shared__ double s_buf[];  // ROW_WARPS x K
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *nb = s_buf + (size_t)warp * K;
-    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    // items: the cells [c0, c1) (which == 1) or their table rows (bounds read here, on the device)
+    const int64_t item0 = which == 1 ? (int64_t)cr.c0 : (int64_t)row_off[cr.c0];
+    const int64_t item1 = which == 1 ? (int64_t)cr.c1 : min((int64_t)row_off[cr.c1], cr.row_cap);
+    const int64_t n_items = item1 > item0 ? item1 - item0 : 0;
     // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
     // one) and the per-cell grid vectors stay in L1
     const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const int64_t item_end = min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
-    for (int64_t item = (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
+    const int64_t item_end = item0 + min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
+    for (int64_t item = item0 + (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
         int64_t row = item;
         int c;
         if (which == 1) {
@@ -375,10 +381,8 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, int n_cells, const in
 
 // Row constants, one THREAD per row (the warp-per-row kernel below would execute this scalar code once per warp, i.e.
 // 32 times more instruction issues): R(x, s), the "snap" pair log p / log q at mu~ = x, and the Poisson term.
-__global__ void row_const_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_cell,
-                                 const int32_t *__restrict__ row_x, int64_t n_rows, double4 *__restrict__ rowc) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
+__device__ __forceinline__ void row_const_one(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_cell,
+                                              const int32_t *__restrict__ row_x, double4 *__restrict__ rowc, int64_t row) {
     const int c = row_cell[row];
     const double x = (double)row_x[row];
     const double s = models[(size_t)5 * ldm + c];
@@ -394,35 +398,13 @@ __global__ void row_const_kernel(const double *__restrict__ models, int ldm, con
     }
     rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
 }
-
-// exp(a) for a in [-50, 0]: round-to-nearest split a = n ln2 + r, |r| <= 0.3466, Taylor polynomial of degree 12
-// (remainder < 3e-16 relative), scaling by an exponent-field add.  Replaces the library exp() in the sweep that only
-// needs the sum of the row (a per-row constant, which the joint posterior does not even see): no special cases, no
-// denormals, 22 instructions.
-__constant__ double c_exp_taylor[13] = {1.0,
-                                        1.0,
-                                        0.5,
-                                        1.66666666666666666667e-01,
-                                        4.16666666666666666667e-02,
-                                        8.33333333333333333333e-03,
-                                        1.38888888888888888889e-03,
-                                        1.98412698412698412698e-04,
-                                        2.48015873015873015873e-05,
-                                        2.75573192239858906526e-06,
-                                        2.75573192239858906526e-07,
-                                        2.50521083854417187751e-08,
-                                        2.08767569878680989792e-09};
-__device__ __forceinline__ double exp_m50_0(double a) {
-    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + MAGIC) is rint(t)
-    const double t = fma(a, 1.44269504088896340736, MAGIC);
-    const int n = __double2loint(t);
-    const double nf = t - MAGIC;
-    double r = fma(nf, -6.93147180369123816490e-01, a);
-    r = fma(nf, -1.90821492927058770002e-10, r);
-    double p = c_exp_taylor[12];
-#pragma unroll
-    for (int i = 11; i >= 0; --i) p = fma(p, r, c_exp_taylor[i]);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+__global__ void row_const_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_off,
+                                 CellRange cr, const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
+                                 double4 *__restrict__ rowc) {
+    const int64_t row_end = min((int64_t)row_off[cr.c1], cr.row_cap);
+    for (int64_t row = (int64_t)row_off[cr.c0] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end;
+         row += (int64_t)gridDim.x * blockDim.x)
+        row_const_one(models, ldm, row_cell, row_x, rowc, row);
 }
 
 // Fixed-point planes (contract_i8.cu) of four consecutive table values: value = 2^-Q_FRAC * sum_p 256^p d_p with signed
@@ -474,9 +456,9 @@ __device__ __forceinline__ int q_offset(int k) {
 // row_range); MODES: also row_mode.
 template <bool MODES>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 3)
-lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, const int32_t *__restrict__ row_cell,
-                    const int32_t *__restrict__ row_x, const double4 *__restrict__ rowc, int64_t n_rows, CellPrep prep,
-                    int K, double sentinel,
+lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
+                    const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
+                    const double4 *__restrict__ rowc, CellPrep prep, int K, double sentinel,
                     double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
                     int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
@@ -487,13 +469,16 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
         for (int j = lane; j < (4 * Q_PIECE) / 4; j += 32) reinterpret_cast<uint32_t *>(s_q[warp])[j] = 0u;
         __syncwarp();
     }
-    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
+    // items: the cells [c0, c1) (which == 1) or their table rows (bounds read here, on the device)
+    const int64_t item0 = which == 1 ? (int64_t)cr.c0 : (int64_t)row_off[cr.c0];
+    const int64_t item1 = which == 1 ? (int64_t)cr.c1 : min((int64_t)row_off[cr.c1], cr.row_cap);
+    const int64_t n_items = item1 > item0 ? item1 - item0 : 0;
     const int kp = (K + 15) & ~15;
     // each CTA walks one contiguous run of rows, so consecutive rows of a warp belong to the same cell (or the next
     // one) and the per-cell grid vectors stay in L1
     const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const int64_t item_end = min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
-    for (int64_t item = (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
+    const int64_t item_end = item0 + min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
+    for (int64_t item = item0 + (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
         int64_t row = item;
         int c;
         if (which == 1) {
@@ -557,7 +542,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, int n_cells, con
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double a = v[e] - maxp;
-                const double ex = exp_m50_0(fmax(a, -50.0));
+                const double ex = exp_nonpos<false>(fmax(a, -50.0));
                 sum += (k0 + e < K && a > -45.0) ? ex : 0.0;
             }
         }
@@ -678,17 +663,17 @@ cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_cell(const int32_t *row_off, int n_cells, int32_t *row_cell, cudaStream_t st) {
-    if (n_cells <= 0) return cudaSuccess;
-    row_cell_kernel<<<n_cells, 128, 0, st>>>(row_off, n_cells, row_cell);
+cudaError_t launch_row_cell(const int32_t *row_off, CellRange cr, int32_t *row_cell, cudaStream_t st) {
+    if (cr.c1 <= cr.c0) return cudaSuccess;
+    row_cell_kernel<<<cr.c1 - cr.c0, 128, 0, st>>>(row_off, cr, row_cell);
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_cell, const int32_t *row_x,
-                              int64_t n_rows, void *row_const, cudaStream_t st) {
-    if (n_rows <= 0) return cudaSuccess;
-    row_const_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(models, ld_models, row_cell, row_x, n_rows,
-                                                                       (double4 *)row_const);
+cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_off, CellRange cr,
+                              const int32_t *row_cell, const int32_t *row_x, void *row_const, cudaStream_t st) {
+    if (cr.c1 <= cr.c0) return cudaSuccess;
+    const int blocks = min(148 * 16, 4 * (cr.c1 - cr.c0) + 1);  // grid-stride: the row count is only known on the device
+    row_const_kernel<<<blocks, 256, 0, st>>>(models, ld_models, row_off, cr, row_cell, row_x, (double4 *)row_const);
     return cudaGetLastError();
 }
 
@@ -705,25 +690,25 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
     return cudaGetLastError();
 }
 
-cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, const int32_t *row_off,
-                           const int32_t *row_cell_map, const int32_t *row_x, int64_t n_rows, CellPrep prep, int K,
+cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, const int32_t *row_off,
+                           const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
                            uint32_t *row_range, cudaStream_t st) {
-    const int64_t n_items = which == 1 ? (int64_t)n_cells : n_rows;
-    if (n_items <= 0) return cudaSuccess;
-    int64_t blocks = (n_items + ROW_WARPS - 1) / ROW_WARPS;
-    const int64_t cap = 148 * 64;  // grid-stride beyond this
+    if (cr.c1 <= cr.c0) return cudaSuccess;
+    // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
+    int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
+    const int64_t cap = 148 * 64;
     if (blocks > cap) blocks = cap;
     if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         if (row_mode)
             lp_rows_fast_kernel<true><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
-                models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
+                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, prep, K, sentinel, table,
                 ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
         else
             lp_rows_fast_kernel<false><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
-                models, ld_models, n_cells, row_cell_map, row_x, (const double4 *)row_const, n_rows, prep, K, sentinel, table,
+                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, prep, K, sentinel, table,
                 ld_table, nullptr, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
         return cudaGetLastError();
     }
@@ -733,9 +718,9 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, int n_cells, con
         cudaError_t e = cudaFuncSetAttribute(lp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, n_cells, row_cell_map, row_x, n_rows,
-                                                                  prep, K, local_theta, sentinel, table, ld_table,
-                                                                  row_mode, which, zero_row, based);
+    lp_rows_kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x, prep, K,
+                                                                  local_theta, sentinel, table, ld_table, row_mode, which,
+                                                                  zero_row, based);
     return cudaGetLastError();
 }
 

@@ -459,3 +459,48 @@ def test_single_randomization_and_single_cell_groups(ctx):
     got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=1, context=ctx)
     _z_close(got["Z"].to_numpy(), want["results"][:, 4])
     np.testing.assert_allclose(got[["lb", "mle", "ub"]].to_numpy(), want["results"][:, :3], rtol=1e-12, atol=1e-300)
+
+
+def _call_and_job(ctx, w, counts, **kw):
+    """the one-shot C-ABI call (chunked upload overlapped with the table build) and the upload / run / download job"""
+    mm, lt, sq = api.pack_models(w.models)
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    codes = np.asarray(w.groups.codes, dtype=np.int32)
+    zi = api._zero_index(api.fold_change_grid(x), 0.0)
+    one = api.expression_difference_call(ctx, counts, mm, x, y, codes, 100, 1, zero_index=zi, local_theta=lt, sqlogit=sq,
+                                         joint_posteriors=True, **kw)
+    job = api.DifferenceJob(ctx, counts, mm, x, y, codes, 100, 1, zero_index=zi, local_theta=lt, sqlogit=sq, **kw)
+    try:
+        job.run()
+        two = job.download(joint_posteriors=True)
+    finally:
+        job.close()
+    return one, two
+
+
+def test_one_shot_call_pipelined_front_equals_job(ctx):
+    """640 cells go up in seven chunks of 96; every chunk is deduplicated and its rows are built while the next ones are
+    still in flight.  Row numbering, table and results must be those of the resident-counts path, bit for bit."""
+    w = synth.make_workload(3, n_genes=150, n_cells=640, seed=21)
+    one, two = _call_and_job(ctx, w, np.asarray(w.counts, dtype=np.int32, order="F"))
+    assert one["stats"]["table_rows"] == two["stats"]["table_rows"]
+    assert np.array_equal(one["idx"], two["idx"])
+    assert np.array_equal(one["z"], two["z"])
+    for i in range(2):
+        assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])
+
+
+def test_one_shot_call_gene_shard_and_row_estimate_fallback(ctx):
+    """a gene shard of a wider matrix (strided upload), with the first chunk of cells all-zero: the row estimate made from
+    that chunk is far too small, the kernels stop at the capacity and the library rebuilds index and table from the
+    resident counts -- same results as the job path"""
+    w = synth.make_workload(3, n_genes=200, n_cells=640, seed=22)
+    counts = np.array(w.counts, dtype=np.int32, order="F")
+    counts[:, :96] = 0
+    counts[:, 96:] += np.arange(200, dtype=np.int32)[:, None] * 37  # hundreds of distinct counts per cell
+    one, two = _call_and_job(ctx, w, counts, gene_range=(40, 190))
+    assert one["stats"]["table_rows"] == two["stats"]["table_rows"] > 5000
+    assert np.array_equal(one["idx"], two["idx"])
+    assert np.array_equal(one["z"], two["z"])
+    for i in range(2):
+        assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])

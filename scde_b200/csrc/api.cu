@@ -137,7 +137,7 @@ struct LpTable {
     int n_cells = 0, n_genes = 0, K = 0, ld = 0, ld_ridx = 0;
     int64_t n_rows = 0;
     double sentinel = 0;
-    DBuf<int32_t> row_off, row_x, row_mode, row_cell, ridx, n_unique, err, zero_row, based;
+    DBuf<int32_t> row_off, row_x, row_mode, row_cell, row_snap, ridx, n_unique, err, zero_row, based;
     DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc, scfp;
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
     DBuf<uint32_t> qrange;  // [n_rows] non-sentinel range of every row (klo | khi << 16)
@@ -217,7 +217,10 @@ int reserve_rows(LpTable &t, TablePlan &pl, size_t rows) {
     SCDE_CUDA(t.table.ensure(rows * t.ld));
     SCDE_CUDA(t.row_mode.ensure(rows));
     SCDE_CUDA(t.row_cell.ensure(rows));
-    if (pl.fast) SCDE_CUDA(t.rowc.ensure(4 * rows));
+    if (pl.fast) {
+        SCDE_CUDA(t.rowc.ensure(4 * rows));
+        SCDE_CUDA(t.row_snap.ensure(rows));
+    }
     if (pl.q_any) {
         SCDE_CUDA(t.q.ensure(rows * q_row_bytes(t.K)));
         SCDE_CUDA(t.qrange.ensure(rows));
@@ -238,21 +241,24 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
     SCDE_CUDA(launch_row_cell(t.row_off.p, cr, t.row_cell.p, st));
     ++*nl;
     if (pl.fast) {
-        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_off.p, cr, t.row_cell.p, t.row_x.p, pl.rowc, st));
+        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_off.p, cr, t.row_cell.p, t.row_x.p, pl.rowc, t.row_snap.p,
+                                    pl.prep, t.K, st));
         ++*nl;
     }
     if (t.zero_base) {
         SCDE_CUDA(launch_zero_rows(t.row_off.p + cr.c0, t.row_x.p, n, t.zero_row.p + cr.c0, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
-                                 t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, 1, pl.qf, pl.qr, st));
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, t.row_snap.p, 1, pl.qf, pl.qr,
+                                 st));
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
-                                 t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
                                  pl.q_fused ? 0 : 1, pl.qf, pl.qr, st));
         *nl += 4;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
-                                 t.sentinel, t.table.p, t.ld, pl.rmode, 0, nullptr, nullptr, pl.rowc, 1, nullptr, nullptr, st));
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 0, nullptr, nullptr, pl.rowc, t.row_snap.p, 1, nullptr, nullptr,
+                                 st));
         ++*nl;
     }
     return SCDE_B200_OK;

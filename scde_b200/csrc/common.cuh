@@ -58,13 +58,15 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
-                           uint32_t *row_range, cudaStream_t st);
+                           const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st);
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
+// ... and row_snap[r] = grid point where the reference's snap rule replaces mu_k by the count, or -1 (needs prep.mu)
 cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_off, CellRange cr,
-                              const int32_t *row_cell, const int32_t *row_x, void *row_const, cudaStream_t st);
+                              const int32_t *row_cell, const int32_t *row_x, void *row_const, int32_t *row_snap,
+                              CellPrep prep, int K, cudaStream_t st);
 
 // ---- dedup.cu ------------------------------------------------------------------------------------
 // counts: column-major with leading dimension ld_counts; genes [g0, g0+G) of n_cells columns.

@@ -17,6 +17,7 @@
 #include "fastmath.cuh"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace scde {
 namespace {
@@ -382,7 +383,9 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, CellRange cr, const i
 // Row constants, one THREAD per row (the warp-per-row kernel below would execute this scalar code once per warp, i.e.
 // 32 times more instruction issues): R(x, s), the "snap" pair log p / log q at mu~ = x, and the Poisson term.
 __device__ __forceinline__ void row_const_one(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_cell,
-                                              const int32_t *__restrict__ row_x, double4 *__restrict__ rowc, int64_t row) {
+                                              const int32_t *__restrict__ row_x, double4 *__restrict__ rowc,
+                                              int32_t *__restrict__ row_snap, const double *__restrict__ mu_all, int ld_mu, int K,
+                                              int64_t row) {
     const int c = row_cell[row];
     const double x = (double)row_x[row];
     const double s = models[(size_t)5 * ldm + c];
@@ -397,14 +400,30 @@ __device__ __forceinline__ void row_const_one(const double *__restrict__ models,
         l2s = -log1p(s / x);
     }
     rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
+    // The snap rule (:173,182) replaces mu_k by x at the one grid point with mu_k < x < mu_{k+1} (or x > mu_{K-1} at the
+    // last one).  mu_k = exp(corr.a m_k + corr.b) is non-decreasing along the grid (corr.a > 0), so that point is the last k
+    // with mu_k < x: a binary search per row instead of two compares per table element.
+    int ks = -1;
+    if (x > 0) {
+        const double *mu = mu_all + (size_t)c * ld_mu;
+        int lo = -1, hi = K;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (mu[mid] < x) lo = mid; else hi = mid;
+        }
+        if (lo == K - 1) ks = K - 1;
+        else if (lo >= 0 && x < mu[lo + 1]) ks = lo;
+    }
+    row_snap[row] = ks;
 }
 __global__ void row_const_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_off,
                                  CellRange cr, const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
-                                 double4 *__restrict__ rowc) {
+                                 double4 *__restrict__ rowc, int32_t *__restrict__ row_snap, const double *__restrict__ mu_all,
+                                 int ld_mu, int K) {
     const int64_t row_end = min((int64_t)row_off[cr.c1], cr.row_cap);
     for (int64_t row = (int64_t)row_off[cr.c0] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end;
          row += (int64_t)gridDim.x * blockDim.x)
-        row_const_one(models, ldm, row_cell, row_x, rowc, row);
+        row_const_one(models, ldm, row_cell, row_x, rowc, row_snap, mu_all, ld_mu, K, row);
 }
 
 // Fixed-point planes (contract_i8.cu) of four consecutive table values: value = 2^-Q_FRAC * sum_p 256^p d_p with signed
@@ -454,19 +473,27 @@ __device__ __forceinline__ int q_offset(int k) {
 //      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
 // Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes and non-sentinel range (qtable,
 // row_range); MODES: also row_mode.
-template <bool MODES>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 3)
+// LW lanes per row (32: one row per warp; 16: two rows per warp, side by side in the two half-warps -- 101 quads of a
+// 401-point grid then occupy 7 x 16 = 112 lane slots instead of 4 x 32 = 128, every warp shuffle of the reductions serves
+// two rows, and twice as many independent rows are in flight per warp).
+template <bool MODES, int LW>
+__global__ void __launch_bounds__(ROW_WARPS * 32, LW == 32 ? 3 : 2)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                     const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
-                    const double4 *__restrict__ rowc, CellPrep prep, int K, double sentinel,
-                    double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
+                    const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
+                    double sentinel, double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
                     const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
                     int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
-    __shared__ __align__(16) double s_rows[ROW_WARPS * KP_TILED];
-    __shared__ __align__(16) uint8_t s_q[ROW_WARPS][4 * Q_PIECE];
+    constexpr int RPW = 32 / LW;  // rows per warp
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double *s_rows = reinterpret_cast<double *>(s_dyn);                                  // [ROW_WARPS * RPW][KP_TILED]
+    uint8_t *s_q = s_dyn + sizeof(double) * ROW_WARPS * RPW * KP_TILED;                  // [ROW_WARPS * RPW][4 * Q_PIECE]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = lane / LW, l = lane % LW;
+    double *nb = s_rows + (warp * RPW + h) * KP_TILED;
+    uint8_t *sq = s_q + (warp * RPW + h) * (4 * Q_PIECE);
     if (qtable) {  // the two spare bytes of every piece, and the pieces beyond the grid, stay zero
-        for (int j = lane; j < (4 * Q_PIECE) / 4; j += 32) reinterpret_cast<uint32_t *>(s_q[warp])[j] = 0u;
+        for (int j = l; j < (4 * Q_PIECE) / 4; j += LW) reinterpret_cast<uint32_t *>(sq)[j] = 0u;
         __syncwarp();
     }
     // items: the cells [c0, c1) (which == 1) or their table rows (bounds read here, on the device)
@@ -478,33 +505,39 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
     // one) and the per-cell grid vectors stay in L1
     const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
     const int64_t item_end = item0 + min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
-    for (int64_t item = item0 + (int64_t)blockIdx.x * per_cta + warp; item < item_end; item += ROW_WARPS) {
+    for (int64_t first = item0 + (int64_t)blockIdx.x * per_cta + warp * RPW; first < item_end; first += ROW_WARPS * RPW) {
+        // every lane runs the whole body (the reductions are full-warp shuffles); a half without a row of its own
+        // recomputes a neighbour's and stores nothing
+        int64_t item = first + h;
+        bool valid = item < item_end;
+        if (!valid) item = item_end - 1;
         int64_t row = item;
         int c;
         if (which == 1) {
             c = (int)item;
             row = zero_row[c];
-            if (row < 0) continue;
+            if (row < 0) {
+                valid = false;
+                row = row_off[c];
+            }
         } else {
             c = row_cell[row];
-            if (which == 2 && zero_row[c] == row) continue;
+            if (which == 2 && zero_row[c] == row) valid = false;
         }
         const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
         const double x = (double)row_x[row];
         const double s = models[(size_t)5 * ldm + c];
         const size_t base = (size_t)c * prep.ld;
-        const double *mu = prep.mu + base, *l1 = prep.l1 + base, *l2 = prep.l2 + base;
+        const double *l1 = prep.l1 + base, *l2 = prep.l2 + base;
         const double *lcfpr = prep.lcfpr + base, *lcfp = prep.lcfp + base;
         const double4 rc = rowc[row];  // row constants from row_const_kernel
         const double R = rc.x, l1s = rc.y, l2s = rc.z, fp = rc.w;
-        double *nb = s_rows + warp * KP_TILED;
+        const int ks = row_snap[row];  // the grid point where mu~ snaps to x (:173,182), or -1
+        const double snapv = fma(x, l2s, fma(s, l1s, R));
         // ---- sweep 1
         double vmax = -INFINITY;
-        for (int k0 = 4 * lane; k0 < K; k0 += 128) {
-            double m[5], a1[4], a2[4], lr[4], v[4];
-            *reinterpret_cast<double2 *>(&m[0]) = *reinterpret_cast<const double2 *>(mu + k0);
-            *reinterpret_cast<double2 *>(&m[2]) = *reinterpret_cast<const double2 *>(mu + k0 + 2);
-            m[4] = mu[k0 + 4 < prep.ld ? k0 + 4 : k0 + 3];
+        for (int k0 = 4 * l; k0 < K; k0 += 4 * LW) {
+            double a1[4], a2[4], lr[4], v[4];
             *reinterpret_cast<double2 *>(&a1[0]) = *reinterpret_cast<const double2 *>(l1 + k0);
             *reinterpret_cast<double2 *>(&a1[2]) = *reinterpret_cast<const double2 *>(l1 + k0 + 2);
             *reinterpret_cast<double2 *>(&lr[0]) = *reinterpret_cast<const double2 *>(lcfpr + k0);
@@ -513,11 +546,10 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                 *reinterpret_cast<double2 *>(&a2[0]) = *reinterpret_cast<const double2 *>(l2 + k0);
                 *reinterpret_cast<double2 *>(&a2[2]) = *reinterpret_cast<const double2 *>(l2 + k0 + 2);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + e;
-                    const bool snap = (k < K - 1) ? (x > m[e] && x < m[e + 1]) : (x > m[e]);
-                    v[e] = fma(x, snap ? l2s : a2[e], fma(s, snap ? l1s : a1[e], R)) + lr[e];
-                }
+                for (int e = 0; e < 4; ++e) v[e] = fma(x, a2[e], fma(s, a1[e], R)) + lr[e];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k0 + e == ks) v[e] = snapv + lr[e];
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v[e] = s * a1[e] + lr[e];
@@ -528,14 +560,15 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
             *reinterpret_cast<double2 *>(nb + k0) = make_double2(v[0], v[1]);
             *reinterpret_cast<double2 *>(nb + k0 + 2) = make_double2(v[2], v[3]);
         }
-        vmax = warp_max(vmax);
+#pragma unroll
+        for (int o = LW / 2; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         double maxp = vmax;
         const double alt = prep.maxcfp[c] + fp;
         if (maxp < alt) maxp = alt;
         __syncwarp();
         // ---- sweep 2
         double sum = 0;
-        for (int k0 = 4 * lane; k0 < K; k0 += 128) {
+        for (int k0 = 4 * l; k0 < K; k0 += 4 * LW) {
             double v[4];
             *reinterpret_cast<double2 *>(&v[0]) = *reinterpret_cast<const double2 *>(nb + k0);
             *reinterpret_cast<double2 *>(&v[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
@@ -546,15 +579,16 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                 sum += (k0 + e < K && a > -45.0) ? ex : 0.0;
             }
         }
-        sum = warp_sum(sum) + exp(fp - maxp) * prep.scfp[c];
+#pragma unroll
+        for (int o = LW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sum += exp(fp - maxp) * prep.scfp[c];
         const double lsum = log(sum);
         // ---- sweep 3
         double best = -INFINITY;
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
-        uint8_t *sq = s_q[warp];
         int n_ok = 0, kmin = 0x7fffffff, kmax = -1;  // the row's grid points that are not "log 0"
-        for (int k0 = 4 * lane; k0 < kp; k0 += 128) {
+        for (int k0 = 4 * l; k0 < kp; k0 += 4 * LW) {
             double v[4] = {0.0, 0.0, 0.0, 0.0};
             if (k0 < K) {
                 double a[4], dk[4], z[4] = {0.0, 0.0, 0.0, 0.0}, L[4];
@@ -597,7 +631,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                     }
                 }
             }
-            if (write_f64) {
+            if (write_f64 && valid) {
                 *reinterpret_cast<double2 *>(out + k0) = make_double2(v[0], v[1]);
                 *reinterpret_cast<double2 *>(out + k0 + 2) = make_double2(v[2], v[3]);
             }
@@ -621,11 +655,11 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                 }
             }
         }
-        if (write_f64)
-            for (int k = kp + lane; k < ld_table; k += 32) out[k] = 0.0;
+        if (write_f64 && valid)
+            for (int k = kp + l; k < ld_table; k += LW) out[k] = 0.0;
         if (MODES) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = LW / 2; o > 0; o >>= 1) {
                 double ob = __shfl_xor_sync(0xffffffffu, best, o);
                 int oi = __shfl_xor_sync(0xffffffffu, besti, o);
                 if (ob > best || (ob == best && oi < besti) || (besti == 0x7fffffff && oi != 0x7fffffff)) {
@@ -638,19 +672,20 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         if (qtable) {  // the row's planes, 16 bytes per lane and store
             const uint4 *src = reinterpret_cast<const uint4 *>(sq);
             uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
-            for (int j = lane; j < ldq / 16; j += 32) dst[j] = src[j];
+            if (valid)
+                for (int j = l; j < ldq / 16; j += LW) dst[j] = src[j];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = LW / 2; o > 0; o >>= 1) {
                 n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
                 kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
                 kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
             }
-            if (lane == 0)
+            if (l == 0 && valid)
                 row_range[row] = (n_ok > 0 && kmax - kmin + 1 == n_ok) ? ((uint32_t)kmin | ((uint32_t)kmax << 16))
                                                                         : Q_RANGE_IRREGULAR;
         }
         __syncwarp();
-        if (MODES && lane == 0) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
+        if (MODES && l == 0 && valid) row_mode[row] = (besti == 0x7fffffff) ? 0 : besti;
     }
 }
 
@@ -670,10 +705,12 @@ cudaError_t launch_row_cell(const int32_t *row_off, CellRange cr, int32_t *row_c
 }
 
 cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t *row_off, CellRange cr,
-                              const int32_t *row_cell, const int32_t *row_x, void *row_const, cudaStream_t st) {
+                              const int32_t *row_cell, const int32_t *row_x, void *row_const, int32_t *row_snap,
+                              CellPrep prep, int K, cudaStream_t st) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     const int blocks = min(148 * 16, 4 * (cr.c1 - cr.c0) + 1);  // grid-stride: the row count is only known on the device
-    row_const_kernel<<<blocks, 256, 0, st>>>(models, ld_models, row_off, cr, row_cell, row_x, (double4 *)row_const);
+    row_const_kernel<<<blocks, 256, 0, st>>>(models, ld_models, row_off, cr, row_cell, row_x, (double4 *)row_const, row_snap,
+                                             prep.mu, prep.ld, K);
     return cudaGetLastError();
 }
 
@@ -693,8 +730,8 @@ cudaError_t launch_based_flags(const double *table, int ld_table, int K, double 
 cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, const int32_t *row_off,
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
-                           const int32_t *zero_row, const int32_t *based, void *row_const, int write_f64, int8_t *qtable,
-                           uint32_t *row_range, cudaStream_t st) {
+                           const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
@@ -702,15 +739,24 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
     if (blocks > cap) blocks = cap;
     if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
-        if (row_mode)
-            lp_rows_fast_kernel<true><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
-                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, prep, K, sentinel, table,
-                ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
-        else
-            lp_rows_fast_kernel<false><<<(unsigned)blocks, ROW_WARPS * 32, 0, st>>>(
-                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, prep, K, sentinel, table,
-                ld_table, nullptr, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
-        return cudaGetLastError();
+        if (!row_snap) return cudaErrorInvalidValue;
+        static int lanes_per_row = 0;
+        if (!lanes_per_row) {
+            const char *env = getenv("SCDE_B200_LP_LANES");  // experiment switch: 32 = one row per warp
+            lanes_per_row = (env && env[0] == '3') ? 32 : 16;
+        }
+        auto launch = [&](auto kernel, int rpw) -> cudaError_t {
+            const size_t smem = (size_t)ROW_WARPS * rpw * (sizeof(double) * KP_TILED + 4 * Q_PIECE);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(
+                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, row_snap, prep, K, sentinel,
+                table, ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
+            return cudaGetLastError();
+        };
+        if (lanes_per_row == 32)
+            return row_mode ? launch(lp_rows_fast_kernel<true, 32>, 1) : launch(lp_rows_fast_kernel<false, 32>, 1);
+        return row_mode ? launch(lp_rows_fast_kernel<true, 16>, 2) : launch(lp_rows_fast_kernel<false, 16>, 2);
     }
     if (qtable || !write_f64) return cudaErrorInvalidValue;  // the general kernel writes the FP64 table only
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);

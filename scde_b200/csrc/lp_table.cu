@@ -505,34 +505,57 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
     // one) and the per-cell grid vectors stay in L1
     const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
     const int64_t item_end = item0 + min(n_items, (int64_t)(blockIdx.x + 1) * per_cta);
-    for (int64_t first = item0 + (int64_t)blockIdx.x * per_cta + warp * RPW; first < item_end; first += ROW_WARPS * RPW) {
+    // Row headers (row id, cell, count, row constants, snap point) are fetched one iteration ahead: they are dependent
+    // global loads (row -> cell -> per-cell values) and were a quarter of the kernel's stall samples when fetched at the
+    // top of the row's own iteration (profiles/r01w).
+    struct Header {
+        int64_t row;
+        int c, ks;
+        bool valid;
+        double x;
+        double4 rc;
+    };
+    auto load_header = [&](int64_t first) {
         // every lane runs the whole body (the reductions are full-warp shuffles); a half without a row of its own
         // recomputes a neighbour's and stores nothing
+        Header hd;
         int64_t item = first + h;
-        bool valid = item < item_end;
-        if (!valid) item = item_end - 1;
-        int64_t row = item;
-        int c;
+        hd.valid = item < item_end;
+        if (!hd.valid) item = item_end - 1;
+        hd.row = item;
         if (which == 1) {
-            c = (int)item;
-            row = zero_row[c];
-            if (row < 0) {
-                valid = false;
-                row = row_off[c];
+            hd.c = (int)item;
+            hd.row = zero_row[hd.c];
+            if (hd.row < 0) {
+                hd.valid = false;
+                hd.row = row_off[hd.c];
             }
         } else {
-            c = row_cell[row];
-            if (which == 2 && zero_row[c] == row) valid = false;
+            hd.c = row_cell[hd.row];
         }
+        hd.x = (double)row_x[hd.row];
+        hd.rc = rowc[hd.row];
+        hd.ks = row_snap[hd.row];
+        return hd;
+    };
+    const int64_t first0 = item0 + (int64_t)blockIdx.x * per_cta + warp * RPW;
+    Header nxt{};
+    if (first0 < item_end) nxt = load_header(first0);
+    for (int64_t first = first0; first < item_end; first += ROW_WARPS * RPW) {
+        const Header cur = nxt;
+        if (first + ROW_WARPS * RPW < item_end) nxt = load_header(first + ROW_WARPS * RPW);
+        const int64_t row = cur.row;
+        const int c = cur.c;
+        bool valid = cur.valid;
+        if (which == 2 && zero_row[c] == row) valid = false;
         const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
-        const double x = (double)row_x[row];
+        const double x = cur.x;
         const double s = models[(size_t)5 * ldm + c];
         const size_t base = (size_t)c * prep.ld;
         const double *l1 = prep.l1 + base, *l2 = prep.l2 + base;
         const double *lcfpr = prep.lcfpr + base, *lcfp = prep.lcfp + base;
-        const double4 rc = rowc[row];  // row constants from row_const_kernel
-        const double R = rc.x, l1s = rc.y, l2s = rc.z, fp = rc.w;
-        const int ks = row_snap[row];  // the grid point where mu~ snaps to x (:173,182), or -1
+        const double R = cur.rc.x, l1s = cur.rc.y, l2s = cur.rc.z, fp = cur.rc.w;  // row constants from row_const_kernel
+        const int ks = cur.ks;  // the grid point where mu~ snaps to x (:173,182), or -1
         const double snapv = fma(x, l2s, fma(s, l1s, R));
         // ---- sweep 1
         double vmax = -INFINITY;
@@ -557,6 +580,9 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (k0 + e < K) vmax = fmax(vmax, v[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k0 + e >= K) v[e] = -INFINITY;  // padding of the last quad (sweep 2 sums the whole quad)
             *reinterpret_cast<double2 *>(nb + k0) = make_double2(v[0], v[1]);
             *reinterpret_cast<double2 *>(nb + k0 + 2) = make_double2(v[2], v[3]);
         }
@@ -574,9 +600,9 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
             *reinterpret_cast<double2 *>(&v[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const double a = v[e] - maxp;
-                const double ex = exp_nonpos<false>(fmax(a, -50.0));
-                sum += (k0 + e < K && a > -45.0) ? ex : 0.0;
+                // terms more than 50 nats below the maximum enter as exp(-50) = 2e-22 (401 of them are below an ulp of
+                // S >= 1); the padding of the row buffer beyond K holds -Inf and enters the same way
+                sum += exp_nonpos<false>(fmax(v[e] - maxp, -50.0));
             }
         }
 #pragma unroll
@@ -587,8 +613,9 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         double best = -INFINITY;
         int besti = 0x7fffffff;
         double *out = table + (size_t)row * ld_table;
-        int n_ok = 0, kmin = 0x7fffffff, kmax = -1;  // the row's grid points that are not "log 0"
-        for (int k0 = 4 * l; k0 < kp; k0 += 4 * LW) {
+        uint32_t okmask = 0u;  // bit 4 j + e: grid point 4 l + 4 LW j + e is not "log 0" (j-th quad of this lane)
+        int jq = 0;
+        for (int k0 = 4 * l; k0 < kp; k0 += 4 * LW, ++jq) {
             double v[4] = {0.0, 0.0, 0.0, 0.0};
             if (k0 < K) {
                 double a[4], dk[4], z[4] = {0.0, 0.0, 0.0, 0.0}, L[4];
@@ -605,29 +632,35 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                 for (int e = 0; e < 4; ++e) {
                     a[e] -= maxp;
                     dk[e] = (dk[e] + fp) - maxp;
-                    const double hi = fmax(a[e], dk[e]), lo = fmin(a[e], dk[e]);
-                    const bool dead = hi < -746.0;  // both exponentials underflow to exactly 0
-                    const bool easy = hi >= -708.0 && hi - lo > 37.5;
-                    L[e] = dead ? -INFINITY : hi;
+                    const double d = a[e] - dk[e];
+                    const double hi = d > 0.0 ? a[e] : dk[e];
+                    const bool dead = hi < -746.0;  // both exponentials underflow to exactly 0: "log 0"
+                    const bool easy = hi >= -708.0 && fabs(d) > 37.5;
+                    L[e] = dead ? sentinel : hi - lsum;  // finite and far above the sentinel unless dead
                     slow = slow || !(dead || easy);
                 }
                 if (slow) {  // cross-over or gradual-underflow band somewhere in this quad: as the reference writes it
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const double hi = fmax(a[e], dk[e]), lo = fmin(a[e], dk[e]);
-                        if (!(hi < -746.0) && !(hi >= -708.0 && hi - lo > 37.5)) L[e] = log(exp(a[e]) + exp(dk[e]));
+                        const double d = a[e] - dk[e];
+                        const double hi = d > 0.0 ? a[e] : dk[e];
+                        if (!(hi < -746.0) && !(hi >= -708.0 && fabs(d) > 37.5)) {
+                            const double t = log(exp(a[e]) + exp(dk[e])) - lsum;
+                            L[e] = t >= sentinel ? t : sentinel;
+                        }
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    double t = L[e] - lsum;
                     if (k0 + e < K) {
-                        if (MODES && (besti == 0x7fffffff || t > best)) {
-                            best = t;
-                            besti = k0 + e;
+                        if (MODES) {  // argmax of the row before the clamp (:198-202): "log 0" counts as -Inf
+                            const double t = L[e] > sentinel ? L[e] : -INFINITY;
+                            if (besti == 0x7fffffff || t > best) {
+                                best = t;
+                                besti = k0 + e;
+                            }
                         }
-                        if (!(t >= sentinel)) t = sentinel;
-                        v[e] = t - z[e];
+                        v[e] = L[e] - z[e];
                     }
                 }
             }
@@ -638,13 +671,8 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
             if (qtable && k0 < Q_MAX_K) {
                 uint32_t word[Q_NV], sent;
                 fixed_point_quad(v, word, sent);
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (k0 + e < K && !((sent >> e) & 1u)) {
-                        ++n_ok;
-                        kmin = min(kmin, k0 + e);
-                        kmax = max(kmax, k0 + e);
-                    }
+                const int nk = K - k0;  // real grid points in this quad
+                okmask |= (~sent & (nk >= 4 ? 0xFu : nk > 0 ? (1u << nk) - 1u : 0u)) << (4 * jq);
                 // pairs (k0, k0 + 1) and (k0 + 2, k0 + 3) never straddle a piece (Q_PW is even): 16-bit stores
                 uint16_t *dst0 = reinterpret_cast<uint16_t *>(sq + q_offset(k0));
                 uint16_t *dst1 = reinterpret_cast<uint16_t *>(sq + q_offset(k0 + 2));
@@ -674,6 +702,13 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
             uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
             if (valid)
                 for (int j = l; j < ldq / 16; j += LW) dst[j] = src[j];
+            // count, first and last of the grid points that are not "log 0" (bit b of a lane <-> k = 4 l + 4 LW (b >> 2) + (b & 3))
+            int n_ok = __popc(okmask), kmin = 0x7fffffff, kmax = -1;
+            if (okmask) {
+                const int b0 = __ffs(okmask) - 1, b1 = 31 - __clz(okmask);
+                kmin = 4 * l + 4 * LW * (b0 >> 2) + (b0 & 3);
+                kmax = 4 * l + 4 * LW * (b1 >> 2) + (b1 & 3);
+            }
 #pragma unroll
             for (int o = LW / 2; o > 0; o >>= 1) {
                 n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);

@@ -402,23 +402,34 @@ __global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__re
             cell = lc[e];
         }
         unsigned need = __ballot_sync(0xffffffffu, rr != full);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const uint32_t r = __shfl_sync(0xffffffffu, rr, src);
-            const int32_t c = __shfl_sync(0xffffffffu, cell, src);
-            if (r == Q_RANGE_IRREGULAR) {
-                irregular = true;
-                continue;
+        while (need) {  // four entries per round: their W words are loaded before any is used (the loop is latency-bound)
+            uint32_t r[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                r[u] = full;
+                w[u] = 0u;
+                if (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    r[u] = __shfl_sync(0xffffffffu, rr, src);
+                    const int32_t c = __shfl_sync(0xffffffffu, cell, src);
+                    w[u] = __ldg(reinterpret_cast<const uint32_t *>(W8 + (int64_t)c * Q_WB + 4 * lane));
+                }
             }
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(W8 + (int64_t)c * Q_WB + 4 * lane);
-            const uint32_t m = __vcmpne4(w, 0u);                        // 0xFF per boot that drew this cell
-            const uint32_t m01 = __byte_perm(m, 0u, 0x1100), m23 = __byte_perm(m, 0u, 0x3322);
-            const uint32_t klo2 = (r & 0xFFFFu) * 0x10001u, khi2 = (r >> 16) * 0x10001u;
-            lo01 = __vmaxu2(lo01, klo2 & m01);
-            lo23 = __vmaxu2(lo23, klo2 & m23);
-            hi01 = __vminu2(hi01, khi2 | ~m01);
-            hi23 = __vminu2(hi23, khi2 | ~m23);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (r[u] == Q_RANGE_IRREGULAR) {
+                    irregular = true;
+                    continue;
+                }
+                const uint32_t m = __vcmpne4(w[u], 0u);  // 0xFF per boot that drew this cell
+                const uint32_t m01 = __byte_perm(m, 0u, 0x1100), m23 = __byte_perm(m, 0u, 0x3322);
+                const uint32_t klo2 = (r[u] & 0xFFFFu) * 0x10001u, khi2 = (r[u] >> 16) * 0x10001u;
+                lo01 = __vmaxu2(lo01, klo2 & m01);
+                lo23 = __vmaxu2(lo23, klo2 & m23);
+                hi01 = __vminu2(hi01, khi2 | ~m01);
+                hi23 = __vminu2(hi23, khi2 | ~m23);
+            }
         }
     }
     uint32_t out[4];

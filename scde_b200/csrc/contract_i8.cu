@@ -393,14 +393,23 @@ __global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__re
     const uint32_t full = (uint32_t)(K - 1) << 16;
     uint32_t lo01 = 0u, lo23 = 0u, hi01 = 0xFFFFFFFFu, hi23 = 0xFFFFFFFFu;
     bool irregular = false;
-    for (int e0 = 0; e0 < len; e0 += 32) {
+    // the (row -> range) lookups of the next 32 entries are in flight while the current ones are combined
+    auto fetch = [&](int e0, uint32_t &rr, int32_t &cell) {
         const int e = e0 + lane;
-        uint32_t rr = full;
-        int32_t cell = 0;
+        rr = full;
+        cell = 0;
         if (e < len) {
-            rr = row_range[lr[e]];
+            rr = __ldg(row_range + lr[e]);
             cell = lc[e];
         }
+    };
+    uint32_t rr_n = full;
+    int32_t cell_n = 0;
+    if (len > 0) fetch(0, rr_n, cell_n);
+    for (int e0 = 0; e0 < len; e0 += 32) {
+        const uint32_t rr = rr_n;
+        const int32_t cell = cell_n;
+        if (e0 + 32 < len) fetch(e0 + 32, rr_n, cell_n);
         unsigned need = __ballot_sync(0xffffffffu, rr != full);
         while (need) {  // four entries per round: their W words are loaded before any is used (the loop is latency-bound)
             uint32_t r[4], w[4];

@@ -476,7 +476,11 @@ __device__ __forceinline__ int q_offset(int k) {
 // LW lanes per row (32: one row per warp; 16: two rows per warp, side by side in the two half-warps -- 101 quads of a
 // 401-point grid then occupy 7 x 16 = 112 lane slots instead of 4 x 32 = 128, every warp shuffle of the reductions serves
 // two rows, and twice as many independent rows are in flight per warp).
-template <bool MODES, int LW>
+// NORM = false: the row is stored without its normalising constant log S (sweep 2 is skipped).  A constant added to a
+// whole table row adds a constant to T[b, :] of every (gene, boot) that draws the row, which the soft-max over the grid
+// removes: the joint posterior cannot see it.  Only the fixed-point rows of the fused path are stored this way; FP64
+// rows (zero-count rows, the `post` / cell-table outputs) are always normalised.
+template <bool MODES, int LW, bool NORM>
 __global__ void __launch_bounds__(ROW_WARPS * 32, LW == 32 ? 3 : 2)
 lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                     const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
@@ -593,22 +597,25 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         if (maxp < alt) maxp = alt;
         __syncwarp();
         // ---- sweep 2
-        double sum = 0;
-        for (int k0 = 4 * l; k0 < K; k0 += 4 * LW) {
-            double v[4];
-            *reinterpret_cast<double2 *>(&v[0]) = *reinterpret_cast<const double2 *>(nb + k0);
-            *reinterpret_cast<double2 *>(&v[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
+        double lsum = 0.0;
+        if (NORM) {
+            double sum = 0;
+            for (int k0 = 4 * l; k0 < K; k0 += 4 * LW) {
+                double v[4];
+                *reinterpret_cast<double2 *>(&v[0]) = *reinterpret_cast<const double2 *>(nb + k0);
+                *reinterpret_cast<double2 *>(&v[2]) = *reinterpret_cast<const double2 *>(nb + k0 + 2);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                // terms more than 50 nats below the maximum enter as exp(-50) = 2e-22 (401 of them are below an ulp of
-                // S >= 1); the padding of the row buffer beyond K holds -Inf and enters the same way
-                sum += exp_nonpos<false>(fmax(v[e] - maxp, -50.0));
+                for (int e = 0; e < 4; ++e) {
+                    // terms more than 50 nats below the maximum enter as exp(-50) = 2e-22 (401 of them are below an ulp
+                    // of S >= 1); the padding of the row buffer beyond K holds -Inf and enters the same way
+                    sum += exp_nonpos<false>(fmax(v[e] - maxp, -50.0));
+                }
             }
-        }
 #pragma unroll
-        for (int o = LW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sum += exp(fp - maxp) * prep.scfp[c];
-        const double lsum = log(sum);
+            for (int o = LW / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sum += exp(fp - maxp) * prep.scfp[c];
+            lsum = log(sum);
+        }
         // ---- sweep 3
         double best = -INFINITY;
         int besti = 0x7fffffff;
@@ -789,9 +796,12 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                 table, ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
             return cudaGetLastError();
         };
+        const bool norm = write_f64 != 0;  // rows that exist in fixed point only need no normalising constant
         if (lanes_per_row == 32)
-            return row_mode ? launch(lp_rows_fast_kernel<true, 32>, 1) : launch(lp_rows_fast_kernel<false, 32>, 1);
-        return row_mode ? launch(lp_rows_fast_kernel<true, 16>, 2) : launch(lp_rows_fast_kernel<false, 16>, 2);
+            return row_mode ? launch(lp_rows_fast_kernel<true, 32, true>, 1) : launch(lp_rows_fast_kernel<false, 32, true>, 1);
+        if (row_mode)
+            return norm ? launch(lp_rows_fast_kernel<true, 16, true>, 2) : launch(lp_rows_fast_kernel<true, 16, false>, 2);
+        return norm ? launch(lp_rows_fast_kernel<false, 16, true>, 2) : launch(lp_rows_fast_kernel<false, 16, false>, 2);
     }
     if (qtable || !write_f64) return cudaErrorInvalidValue;  // the general kernel writes the FP64 table only
     size_t smem = (size_t)ROW_WARPS * K * sizeof(double);

@@ -141,6 +141,7 @@ struct LpTable {
     DBuf<double> table, mu, lcfp, lcfpr, theta, maxcfp, cfp, l1, l2, rowc, scfp;
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
     DBuf<uint32_t> qrange;  // [n_rows] non-sentinel range of every row (klo | khi << 16)
+    DBuf<uint32_t> dedup_bits;  // per-cell bitmaps between the two dedup passes
     bool want_q = false, has_q = false;
     bool f64_rows = true;  // false: the FP64 rows of non-zero counts were not stored (planes only)
     bool want_modes = true;  // row_mode (argmax of every row) is needed: only for return.individual.posterior.modes
@@ -301,7 +302,8 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
     SCDE_CUDA(t.ridx.ensure((size_t)G * C));
     int e0 = tm ? tm->begin(st) : -1;
     SCDE_CUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
-    SCDE_CUDA(launch_dedup_count(counts_dev, ldc, g0, G, C, t.n_unique.p, t.err.p, st));
+    SCDE_CUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
+    SCDE_CUDA(launch_dedup_count(counts_dev, ldc, g0, G, C, t.n_unique.p, t.err.p, t.dedup_bits.p, st));
     SCDE_CUDA(launch_exclusive_scan(t.n_unique.p, t.row_off.p, C, nullptr, st));
     int32_t total = 0, err = 0;
     SCDE_CUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -318,8 +320,8 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
     t.n_rows = total;
     SCDE_CUDA(t.row_x.ensure((size_t)total));
     SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p,
-                                (int64_t)total, st));
-    if (tm) tm->end(SCDE_B200_T_DEDUP, e0, st, 3);
+                                (int64_t)total, t.dedup_bits.p, st));
+    if (tm) tm->end(SCDE_B200_T_DEDUP, e0, st, 5);
     return SCDE_B200_OK;
 }
 
@@ -1332,6 +1334,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
     SCDE_CUDA(t.row_off.ensure((size_t)C + 1));
     SCDE_CUDA(t.err.ensure(1));
     SCDE_CUDA(t.ridx.ensure((size_t)G * C));
+    SCDE_CUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
     // the copy stream may overwrite the counts buffer only after earlier work on the compute stream is done with it
     SCDE_CUDA(cudaEventRecord(ctx->copy_events[N_CHUNKS], st));
     SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_CHUNKS], 0));
@@ -1369,7 +1372,8 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
         const int32_t *cnt = j->ws->counts.p + (size_t)c0 * G;
         FCUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
         e0 = tm.begin(st);
-        FCUDA(launch_dedup_count(cnt, G, 0, G, n, t.n_unique.p + c0, t.err.p, st));
+        uint32_t *bits = t.dedup_bits.p + dedup_scratch_words(c0) * (c0 > 0);
+        FCUDA(launch_dedup_count(cnt, G, 0, G, n, t.n_unique.p + c0, t.err.p, bits, st));
         FCUDA(launch_exclusive_scan(t.n_unique.p + c0, t.row_off.p + c0, n, i ? t.row_off.p + c0 : nullptr, st));
         if (i == 0) {
             int32_t rows0 = 0;
@@ -1382,8 +1386,9 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
             FTRY(reserve_rows(t, pl, (size_t)cap));
             FCUDA(t.row_x.ensure((size_t)cap));
         }
-        FCUDA(launch_dedup_emit(cnt, G, 0, G, n, t.row_off.p + c0, t.row_x.p, t.ridx.p + c0, t.ld_ridx, t.err.p, cap, st));
-        tm.end(SCDE_B200_T_DEDUP, e0, st, 3);
+        FCUDA(launch_dedup_emit(cnt, G, 0, G, n, t.row_off.p + c0, t.row_x.p, t.ridx.p + c0, t.ld_ridx, t.err.p, cap, bits,
+                                st));
+        tm.end(SCDE_B200_T_DEDUP, e0, st, 5);
         e0 = tm.begin(st);
         int nl = 0;
         FTRY(launch_table_rows(ctx, t, pl, CellRange{c0, c0 + n, cap}, j->models.p, C, j->local_theta, &nl));

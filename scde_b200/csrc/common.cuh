@@ -73,13 +73,16 @@ cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t
 // Pass 1: n_unique[c].  Pass 2 (after an exclusive scan into row_off): row_x[row_off[c] + i] = i-th smallest
 // distinct count of cell c; ridx[g*ld_ridx + c] = row id of counts[g0+g, c].  err_flag: 1 = negative count,
 // 2 = more distinct values than the hash capacity.
+// scratch: dedup_scratch_words(n_cells) uint32 words, written by the count pass and read by the emit pass of the same cells
+size_t dedup_scratch_words(int n_cells);
 cudaError_t launch_dedup_count(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
-                               int32_t *n_unique, int32_t *err_flag, cudaStream_t st);
+                               int32_t *n_unique, int32_t *err_flag, uint32_t *scratch, cudaStream_t st);
 // out[i] = base + sum of in[0..i), out[n] = base + total; base = *base_dev (device) or 0 when NULL
 cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, const int32_t *base_dev, cudaStream_t st);
 cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
                               const int32_t *row_off, int32_t *row_x, int32_t *ridx, int ld_ridx,
-                              int32_t *err_flag, int64_t row_cap /* rows row_x can hold */, cudaStream_t st);
+                              int32_t *err_flag, int64_t row_cap /* rows row_x can hold */, const uint32_t *scratch,
+                              cudaStream_t st);
 // (ucl, uci)-given form: ridx[g*ld_ridx + c] = ucl_off[c] + uci[g + G*c]
 cudaError_t launch_uci_to_ridx(const int32_t *uci, int G, int n_cells, const int32_t *ucl_off, int32_t *ridx,
                                int ld_ridx, cudaStream_t st);

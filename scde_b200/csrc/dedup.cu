@@ -1,14 +1,20 @@
 // dedup.cu -- the unique-count table indices (what scde.posteriors builds with unique()/match(),
 // R/functions.R:631-632), on the device.
 //
-// One CTA per cell (one column of the count matrix).  The column's distinct values are collected in a shared
-// memory open-addressing hash set, the set is sorted in place (bitonic, unsigned order so empty slots
-// 0xFFFFFFFF sink to the end) and every gene's count is mapped to its rank by binary search.  Row ids are
-// ascending in the count value within a cell -- a different order from R's first-appearance `unique()`, which
-// is unobservable: rows are only ever addressed through the index matrix built here.
+// Row ids are ascending in the count value within a cell -- a different order from R's first-appearance `unique()`,
+// which is unobservable: rows are only ever addressed through the index matrix built here.
 //
-// HBM traffic: the count column is read twice per pass (coalesced), the index matrix is written once
-// gene-major (ridx[g][c]) so the contraction kernel reads one contiguous run per gene.
+// Bitmap kernels (the common case: every count of the cell is below 65536).  One CTA per eight neighbouring cells.  Pass 1
+// marks the cells' counts in eight 8 KB shared-memory bitmaps (a plain read before the atomicOr: after the first few
+// genes almost every bit is already set), counts the bits and saves the bitmaps (80 MB for 10 000 cells).  Pass 2 reloads
+// them, turns them into ranks (prefix population counts per word), writes the distinct values in ascending order and maps
+// every gene's count to its row with two shared-memory reads and a popc; the eight cells' row ids of a gene are stored
+// as one 32-byte sector of the gene-major index matrix ridx[g][c] (a CTA per cell would write 4 bytes per sector).
+// HBM traffic: the counts are read once per pass, the index matrix is written once.
+//
+// Hash kernels (cells with a count >= 65536, flagged by pass 1): one CTA per cell; the column's distinct values are
+// collected in a shared-memory open-addressing hash set, the set is sorted in place (bitonic, unsigned order so empty
+// slots 0xFFFFFFFF sink to the end) and every gene's count is mapped to its rank by binary search.
 #include "common.cuh"
 
 namespace scde {
@@ -16,6 +22,10 @@ namespace {
 
 constexpr int DEDUP_THREADS = 1024;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr int BM_WORDS = 2048;            // bitmap of the counts 0 .. 65535
+constexpr int BM_STRIDE = BM_WORDS + 8;   // words per cell in the global bitmap scratch; word BM_WORDS = "has a count >= 65536"
+constexpr int BM_CPB = 8;                 // cells per CTA = one 32-byte sector of ridx per gene
+constexpr int BM_THREADS = 512;
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t x, int log2cap) { return (x * 2654435761u) >> (32 - log2cap); }
 
@@ -80,10 +90,11 @@ __device__ void bitonic_sort(uint32_t *s, uint32_t n) {  // n a power of two; as
 
 __global__ void __launch_bounds__(DEDUP_THREADS)
 dedup_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells, int log2cap,
-                   int32_t *__restrict__ n_unique, int32_t *err_flag) {
+                   int32_t *__restrict__ n_unique, int32_t *err_flag, const uint32_t *__restrict__ bits) {
     extern __shared__ uint32_t s_tab[];
     __shared__ int s_count;
     const int c = blockIdx.x;
+    if (bits && !bits[(size_t)c * BM_STRIDE + BM_WORDS]) return;  // the bitmap kernel has done this cell
     const int32_t *col = counts + (size_t)c * ldc + g0;
     build_set(col, G, s_tab, log2cap, err_flag, &s_count);
     if (threadIdx.x == 0) n_unique[c] = s_count;
@@ -92,10 +103,11 @@ dedup_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int 
 __global__ void __launch_bounds__(DEDUP_THREADS)
 dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells, int log2cap_max,
                   const int32_t *__restrict__ row_off, int32_t *__restrict__ row_x, int32_t *__restrict__ ridx,
-                  int ld_ridx, int32_t *err_flag, int64_t row_cap) {
+                  int ld_ridx, int32_t *err_flag, int64_t row_cap, const uint32_t *__restrict__ bits) {
     extern __shared__ uint32_t s_tab[];
     __shared__ int s_count;
     const int c = blockIdx.x;
+    if (bits && !bits[(size_t)c * BM_STRIDE + BM_WORDS]) return;  // the bitmap kernel has done this cell
     const int32_t *col = counts + (size_t)c * ldc + g0;
     // the count pass told us how many distinct values this cell has: size the set (and the sort) for that, not for G
     const int n_distinct = row_off[c + 1] - row_off[c];
@@ -116,6 +128,131 @@ dedup_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G
             if (s_tab[mid] < x) lo = mid + 1; else hi = mid;
         }
         ridx[(size_t)g * ld_ridx + c] = base + lo;
+    }
+}
+
+// ---- bitmap kernels --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BM_THREADS)
+dedup_bitmap_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells,
+                          uint32_t *__restrict__ bits, int32_t *__restrict__ n_unique, int32_t *err_flag) {
+    extern __shared__ uint32_t s_bm[];  // [BM_CPB][BM_WORDS]
+    __shared__ int s_big[BM_CPB], s_cnt[BM_CPB];
+    const int c0 = blockIdx.x * BM_CPB;
+    const int nc = min(BM_CPB, n_cells - c0);
+    for (int i = threadIdx.x; i < BM_CPB * BM_WORDS; i += BM_THREADS) s_bm[i] = (i % BM_WORDS) == 0 ? 1u : 0u;  // count 0
+    if (threadIdx.x < BM_CPB) s_big[threadIdx.x] = s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += BM_THREADS) {
+        int32_t x[BM_CPB];
+#pragma unroll
+        for (int j = 0; j < BM_CPB; ++j) x[j] = j < nc ? counts[(size_t)(c0 + j) * ldc + g0 + g] : 0;
+#pragma unroll
+        for (int j = 0; j < BM_CPB; ++j) {
+            if (x[j] < 0) {
+                atomicOr(err_flag, 1);
+            } else if (x[j] >= 32 * BM_WORDS) {
+                s_big[j] = 1;
+            } else {
+                uint32_t *w = s_bm + j * BM_WORDS + (x[j] >> 5);
+                const uint32_t b = 1u << (x[j] & 31);
+                if (!(*w & b)) atomicOr(w, b);
+            }
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < nc; j += BM_THREADS / 32) {  // one warp per cell: population count, bitmap to global memory
+        int n = 0;
+        uint32_t *dst = bits + (size_t)(c0 + j) * BM_STRIDE;
+        for (int w = lane; w < BM_WORDS; w += 32) {
+            const uint32_t v = s_bm[j * BM_WORDS + w];
+            n += __popc(v);
+            dst[w] = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) {
+            dst[BM_WORDS] = (uint32_t)s_big[j];
+            n_unique[c0 + j] = s_big[j] ? 0 : n;  // flagged cells are counted by the hash kernel
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BM_THREADS)
+dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells,
+                         const uint32_t *__restrict__ bits, const int32_t *__restrict__ row_off,
+                         int32_t *__restrict__ row_x, int32_t *__restrict__ ridx, int ld_ridx, int64_t row_cap) {
+    extern __shared__ uint32_t s_bm[];                                               // [BM_CPB][BM_WORDS]
+    uint16_t *s_pre = reinterpret_cast<uint16_t *>(s_bm + BM_CPB * BM_WORDS);        // [BM_CPB][BM_WORDS] ranks of the words
+    __shared__ int s_part[BM_CPB][BM_THREADS / BM_CPB];
+    __shared__ int s_base[BM_CPB], s_big[BM_CPB];
+    const int c0 = blockIdx.x * BM_CPB;
+    const int nc = min(BM_CPB, n_cells - c0);
+    for (int i = threadIdx.x; i < BM_CPB * BM_WORDS; i += BM_THREADS) {
+        const int j = i / BM_WORDS;
+        s_bm[i] = j < nc ? bits[(size_t)(c0 + j) * BM_STRIDE + (i % BM_WORDS)] : 0u;
+    }
+    if (threadIdx.x < BM_CPB) {
+        const int j = threadIdx.x;
+        s_big[j] = j < nc ? (int)bits[(size_t)(c0 + j) * BM_STRIDE + BM_WORDS] : 1;
+        s_base[j] = j < nc ? row_off[c0 + j] : 0;
+    }
+    __syncthreads();
+    // ranks: thread t owns WPT consecutive words of cell t / TPC
+    constexpr int TPC = BM_THREADS / BM_CPB, WPT = BM_WORDS / TPC;
+    const int cj = threadIdx.x / TPC, ct = threadIdx.x % TPC;
+    const uint32_t *mine = s_bm + cj * BM_WORDS + ct * WPT;
+    int local = 0;
+#pragma unroll 4
+    for (int w = 0; w < WPT; ++w) local += __popc(mine[w]);
+    s_part[cj][ct] = local;
+    __syncthreads();
+    if (ct == 0) {  // exclusive scan over the cell's TPC partial sums
+        int run = 0;
+        for (int t = 0; t < TPC; ++t) {
+            const int v = s_part[cj][t];
+            s_part[cj][t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    {
+        int run = s_part[cj][ct];
+        const bool emit = cj < nc && !s_big[cj];
+        const int64_t base = s_base[cj];
+        for (int w = 0; w < WPT; ++w) {
+            uint32_t v = mine[w];
+            s_pre[cj * BM_WORDS + ct * WPT + w] = (uint16_t)run;
+            while (v) {  // the distinct values in ascending order
+                const int b = __ffs(v) - 1;
+                v &= v - 1;
+                if (emit && base + run < row_cap) row_x[base + run] = 32 * (ct * WPT + w) + b;
+                ++run;
+            }
+        }
+    }
+    __syncthreads();
+    const bool all8 = nc == BM_CPB && (ld_ridx % 4) == 0 && (reinterpret_cast<uintptr_t>(ridx + c0) % 16) == 0 && !s_big[0] &&
+                      !s_big[1] && !s_big[2] && !s_big[3] && !s_big[4] && !s_big[5] && !s_big[6] && !s_big[7];
+    for (int g = threadIdx.x; g < G; g += BM_THREADS) {
+        int32_t x[BM_CPB], r[BM_CPB];
+#pragma unroll
+        for (int j = 0; j < BM_CPB; ++j) x[j] = j < nc ? counts[(size_t)(c0 + j) * ldc + g0 + g] : 0;
+#pragma unroll
+        for (int j = 0; j < BM_CPB; ++j) {
+            const uint32_t xv = x[j] < 0 ? 0u : (uint32_t)x[j];
+            const uint32_t w = min(xv >> 5, (uint32_t)(BM_WORDS - 1));
+            r[j] = s_base[j] + (int)s_pre[j * BM_WORDS + w] + __popc(s_bm[j * BM_WORDS + w] & ((1u << (xv & 31)) - 1u));
+        }
+        int32_t *dst = ridx + (size_t)g * ld_ridx + c0;
+        if (all8) {
+            reinterpret_cast<int4 *>(dst)[0] = make_int4(r[0], r[1], r[2], r[3]);
+            reinterpret_cast<int4 *>(dst)[1] = make_int4(r[4], r[5], r[6], r[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BM_CPB; ++j)
+                if (j < nc && !s_big[j]) dst[j] = r[j];
+        }
     }
 }
 
@@ -171,14 +308,24 @@ int pick_log2cap(int G) {
 
 }  // namespace
 
+size_t dedup_scratch_words(int n_cells) { return (size_t)(n_cells > 0 ? n_cells : 1) * BM_STRIDE; }
+
 cudaError_t launch_dedup_count(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
-                               int32_t *n_unique, int32_t *err_flag, cudaStream_t st) {
+                               int32_t *n_unique, int32_t *err_flag, uint32_t *scratch, cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
+    const size_t bsmem = sizeof(uint32_t) * BM_CPB * BM_WORDS;
+    cudaError_t e = cudaFuncSetAttribute(dedup_bitmap_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+    if (e != cudaSuccess) return e;
+    dedup_bitmap_count_kernel<<<(n_cells + BM_CPB - 1) / BM_CPB, BM_THREADS, bsmem, st>>>(counts, ld_counts, g0, G, n_cells,
+                                                                                          scratch, n_unique, err_flag);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // cells with a count >= 65536 (flagged in the scratch): hash kernel, every other CTA leaves at once
     int l = pick_log2cap(G);
     size_t smem = sizeof(uint32_t) << l;
-    cudaError_t e = cudaFuncSetAttribute(dedup_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(dedup_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dedup_count_kernel<<<n_cells, DEDUP_THREADS, smem, st>>>(counts, ld_counts, g0, G, n_cells, l, n_unique, err_flag);
+    dedup_count_kernel<<<n_cells, DEDUP_THREADS, smem, st>>>(counts, ld_counts, g0, G, n_cells, l, n_unique, err_flag, scratch);
     return cudaGetLastError();
 }
 
@@ -189,14 +336,21 @@ cudaError_t launch_exclusive_scan(const int32_t *in, int32_t *out, int n, const 
 
 cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, int G, int n_cells,
                               const int32_t *row_off, int32_t *row_x, int32_t *ridx, int ld_ridx,
-                              int32_t *err_flag, int64_t row_cap, cudaStream_t st) {
+                              int32_t *err_flag, int64_t row_cap, const uint32_t *scratch, cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
+    const size_t bsmem = (sizeof(uint32_t) + sizeof(uint16_t)) * BM_CPB * BM_WORDS;
+    cudaError_t e = cudaFuncSetAttribute(dedup_bitmap_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+    if (e != cudaSuccess) return e;
+    dedup_bitmap_emit_kernel<<<(n_cells + BM_CPB - 1) / BM_CPB, BM_THREADS, bsmem, st>>>(
+        counts, ld_counts, g0, G, n_cells, scratch, row_off, row_x, ridx, ld_ridx, row_cap);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     int l = pick_log2cap(G);
     size_t smem = sizeof(uint32_t) << l;
-    cudaError_t e = cudaFuncSetAttribute(dedup_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(dedup_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dedup_emit_kernel<<<n_cells, DEDUP_THREADS, smem, st>>>(counts, ld_counts, g0, G, n_cells, l, row_off, row_x, ridx,
-                                                            ld_ridx, err_flag, row_cap);
+                                                            ld_ridx, err_flag, row_cap, scratch);
     return cudaGetLastError();
 }
 

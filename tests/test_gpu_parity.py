@@ -504,3 +504,36 @@ def test_one_shot_call_gene_shard_and_row_estimate_fallback(ctx):
     assert np.array_equal(one["z"], two["z"])
     for i in range(2):
         assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])
+
+
+def test_dedup_bitmap_and_hash_cells_mixed(ctx):
+    """cells whose counts all lie below 65536 are indexed by the bitmap kernels (eight cells per CTA), cells with a larger
+    count by the hash kernels; both kinds side by side, a ragged last group of cells, against the oracle"""
+    w = synth.make_workload(3, n_genes=120, n_cells=21, seed=31)
+    counts = np.array(w.counts, dtype=np.int32, order="F")
+    rng = np.random.default_rng(5)
+    counts[:30, 3] = rng.integers(65536, 400000, size=30)   # cell 3 and cell 17 leave the bitmap range
+    counts[5, 17] = 65536
+    counts[:, 9] = 0                                         # a cell with the single distinct count 0
+    counts[7, 20] = 65535                                    # the last value the bitmap holds
+    mm, lt, sq = api.pack_models(w.models)
+    mag = api.marginals_from_prior(w.prior)
+    flat, off, uci = O.unique_counts(counts)
+    bi = O.boot_indices(1, counts.shape[1], 100)
+    want = O.log_boot_posterior(mm, flat, off, uci, mag, 100, boot_idx=bi)["jp"]
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    codes = np.zeros(counts.shape[1], dtype=np.int32)
+    codes[11:] = 1
+    zi = api._zero_index(api.fold_change_grid(x), 0.0)
+    # the fused call builds the index on the device from the raw counts (scde_posteriors takes the caller's ucl / uci)
+    res = api.expression_difference_call(ctx, counts, mm, x, y, codes, 100, 1, zero_index=zi, local_theta=lt, sqlogit=sq,
+                                         joint_posteriors=True)
+    assert res["stats"]["table_rows"] == len(flat)
+    for lev in (0, 1):
+        ii = np.nonzero(codes == lev)[0]
+        fl, of, uc = O.unique_counts(counts[:, ii])
+        wj = O.log_boot_posterior(np.asfortranarray(mm[ii]), fl, of, uc, mag, 100,
+                                  boot_idx=O.boot_indices(1, len(ii), 100))["jp"]
+        ok, worst = _logp_close(res["joint_posteriors"][lev], wj)
+        assert ok, worst
+    assert want.shape == (120, len(mag))

@@ -48,7 +48,8 @@ struct CellRange {
 // row_cell[r] = cell of table row r (from row_off)
 cudaError_t launch_row_cell(const int32_t *row_off, CellRange cr, int32_t *row_cell, cudaStream_t st);
 // zero_row[c] = the row of cell c whose count is 0, or -1
-cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st);
+cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, int64_t row_cap,
+                             cudaStream_t st);
 // based[c] = 1 when cell c has a zero-count row and that row holds no "log 0" sentinel (it can be subtracted)
 cudaError_t launch_based_flags(const double *table, int ld_table, int K, double sentinel, const int32_t *zero_row,
                                int n_cells, int32_t *based, cudaStream_t st);

@@ -235,14 +235,16 @@ __global__ void cell_prep_kernel(const double *__restrict__ models, int ldm, int
 constexpr int ROW_WARPS = 8;
 
 __global__ void zero_rows_kernel(const int32_t *__restrict__ row_off, const int32_t *__restrict__ row_x, int n_cells,
-                                 int32_t *__restrict__ zero_row) {
+                                 int32_t *__restrict__ zero_row, int64_t row_cap) {
     const int c = blockIdx.x;
     if (c >= n_cells) return;
     __shared__ int found;
     if (threadIdx.x == 0) found = -1;
     __syncthreads();
-    for (int r = row_off[c] + threadIdx.x; r < row_off[c + 1]; r += blockDim.x)
-        if (row_x[r] == 0) found = r;  // a cell's distinct counts contain 0 at most once
+    // rows at or beyond the capacity do not exist (the chunked front's row estimate was too small: api.cu rebuilds)
+    const int64_t end = min((int64_t)row_off[c + 1], row_cap);
+    for (int64_t r = row_off[c] + threadIdx.x; r < end; r += blockDim.x)
+        if (row_x[r] == 0) found = (int)r;  // a cell's distinct counts contain 0 at most once
     __syncthreads();
     if (threadIdx.x == 0) zero_row[c] = found;
 }
@@ -530,9 +532,9 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         if (which == 1) {
             hd.c = (int)item;
             hd.row = zero_row[hd.c];
-            if (hd.row < 0) {
+            if (hd.row < 0) {  // no zero-count row (or it lies beyond the capacity): any existing row will do, nothing is stored
                 hd.valid = false;
-                hd.row = row_off[hd.c];
+                hd.row = min((int64_t)row_off[hd.c], cr.row_cap - 1);
             }
         } else {
             hd.c = row_cell[hd.row];
@@ -756,9 +758,10 @@ cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, cudaStream_t st) {
+cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n_cells, int32_t *zero_row, int64_t row_cap,
+                             cudaStream_t st) {
     if (n_cells <= 0) return cudaSuccess;
-    zero_rows_kernel<<<n_cells, 128, 0, st>>>(row_off, row_x, n_cells, zero_row);
+    zero_rows_kernel<<<n_cells, 128, 0, st>>>(row_off, row_x, n_cells, zero_row, row_cap);
     return cudaGetLastError();
 }
 

@@ -1112,7 +1112,37 @@ struct scde_b200_diff_job {
     StageTimer timer;
     int64_t contract_cells = 0;
     bool ran = false;
+    int copy_chunks = 0, copy_chunk_cells = 0;  // chunked H2D of the counts in flight on the context's copy stream
 };
+
+constexpr int N_COUNT_CHUNKS = 8;
+
+// Queue the H2D of the shard's count matrix on the copy stream in N_COUNT_CHUNKS cell ranges, one event per range, so
+// the 22 ms of PCIe time at config 4 run under the front kernels.
+int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host) {
+    const int G = j->G, C = j->C;
+    if (!ctx->copy_stream) SCDE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->copy_events.size() < N_COUNT_CHUNKS + 1) {
+        cudaEvent_t e;
+        SCDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    // the copy stream may overwrite the counts buffer only after earlier work on the compute stream is done with it
+    SCDE_CUDA(cudaEventRecord(ctx->copy_events[N_COUNT_CHUNKS], ctx->stream));
+    SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_COUNT_CHUNKS], 0));
+    const int chunk = round_up((C + N_COUNT_CHUNKS - 1) / N_COUNT_CHUNKS, 32);
+    int n_ch = 0;
+    for (int c0 = 0; c0 < C; c0 += chunk, ++n_ch) {
+        const int n = (C - c0) < chunk ? (C - c0) : chunk;
+        SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p + (size_t)c0 * G, sizeof(int32_t) * G, counts_host + (size_t)c0 * ld_host,
+                                    sizeof(int32_t) * (size_t)ld_host, sizeof(int32_t) * G, n, cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+        SCDE_CUDA(cudaEventRecord(ctx->copy_events[n_ch], ctx->copy_stream));
+    }
+    j->copy_chunks = n_ch;
+    j->copy_chunk_cells = chunk;
+    return SCDE_B200_OK;
+}
 
 extern "C" {
 
@@ -1163,6 +1193,7 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
     j->owner = ctx;
     ctx->ws_busy = true;
     auto fail = [&](int r) {
+        if (j->copy_chunks) cudaStreamSynchronize(ctx->copy_stream);  // the copy engine reads the caller's buffer
         ctx->ws_busy = false;
         delete j;
         return r;
@@ -1294,6 +1325,8 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
     j->ws->table.zero_base = ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
     j->ws->table.want_q = want_i8(ctx);
     JCUDA(cudaStreamSynchronize(st));
+    // last: the small uploads above share the one H2D copy engine with these 1.2 GB and would queue behind them
+    if (defer_counts) JTRY(start_count_copies(ctx, j, a->counts + g0, a->n_genes));
     *out = j;
     return SCDE_B200_OK;
 #undef JTRY
@@ -1306,8 +1339,7 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
 // device; the row-level kernels read their bounds there (CellRange), so nothing waits for the host except one 4-byte read
 // after the first chunk: its row count sizes the buffers (x 1.25).  If the estimate turns out too small the kernels stop
 // at the capacity and *done stays false: the caller rebuilds index and table the classic way from the resident counts.
-static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host,
-                         bool *done) {
+static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) {
     *done = false;
     LpTable &t = j->ws->table;
     const int G = j->G, C = j->C;
@@ -1317,36 +1349,18 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
     t.n_genes = G;
     t.ld_ridx = C;
     TablePlan pl = plan_table(t, j->local_theta);
-    constexpr int N_CHUNKS = 8;
-    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * N_CHUNKS && !getenv("SCDE_B200_NO_PIPELINE");
+    // the copies are already in flight (start_count_copies); every path below waits for them on the compute stream
+    const int chunk = j->copy_chunk_cells;
+    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * N_COUNT_CHUNKS && !getenv("SCDE_B200_NO_PIPELINE");
     if (!pipelined) {
-        SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p, sizeof(int32_t) * G, counts_host, sizeof(int32_t) * (size_t)ld_host,
-                                    sizeof(int32_t) * G, C, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < j->copy_chunks; ++i) SCDE_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
         return SCDE_B200_OK;
-    }
-    if (!ctx->copy_stream) SCDE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while ((int)ctx->copy_events.size() < N_CHUNKS + 1) {
-        cudaEvent_t e;
-        SCDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->copy_events.push_back(e);
     }
     SCDE_CUDA(t.n_unique.ensure(C));
     SCDE_CUDA(t.row_off.ensure((size_t)C + 1));
     SCDE_CUDA(t.err.ensure(1));
     SCDE_CUDA(t.ridx.ensure((size_t)G * C));
     SCDE_CUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
-    // the copy stream may overwrite the counts buffer only after earlier work on the compute stream is done with it
-    SCDE_CUDA(cudaEventRecord(ctx->copy_events[N_CHUNKS], st));
-    SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_CHUNKS], 0));
-    const int chunk = round_up((C + N_CHUNKS - 1) / N_CHUNKS, 32);
-    int n_ch = 0;
-    for (int c0 = 0; c0 < C; c0 += chunk, ++n_ch) {
-        const int n = (C - c0) < chunk ? (C - c0) : chunk;
-        SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p + (size_t)c0 * G, sizeof(int32_t) * G, counts_host + (size_t)c0 * ld_host,
-                                    sizeof(int32_t) * (size_t)ld_host, sizeof(int32_t) * G, n, cudaMemcpyHostToDevice,
-                                    ctx->copy_stream));
-        SCDE_CUDA(cudaEventRecord(ctx->copy_events[n_ch], ctx->copy_stream));
-    }
     auto drain = [&](int r) {  // never return while the copy engine may still read the caller's buffer
         cudaStreamSynchronize(ctx->copy_stream);
         return r;
@@ -1417,7 +1431,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
     return SCDE_B200_OK;
 }
 
-static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host);
+static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked_counts);
 
 extern "C" {
 
@@ -1426,13 +1440,12 @@ int scde_b200_diff_upload(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int3
     return diff_upload_impl(ctx, a, want_posteriors, out, false);
 }
 
-int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) { return diff_run_impl(ctx, j, nullptr, 0); }
+int scde_b200_diff_run(scde_b200_ctx *ctx, scde_b200_diff_job *j) { return diff_run_impl(ctx, j, false); }
 
 }  // extern "C"
 
-// counts_host != NULL: the count matrix has not been uploaded yet (one-shot call); rows of the shard start at
-// counts_host[0], columns are ld_host apart
-static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host) {
+// chunked_counts: the count matrix is arriving in cell chunks on the copy stream (one-shot call)
+static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked_counts) {
     CHECK_CTX(ctx);
     if (!j) return SCDE_B200_EINVAL;
     cudaStream_t st = ctx->stream;
@@ -1448,7 +1461,7 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_
     TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
     bool front_done = false;
-    if (counts_host) TRY(front_chunked(ctx, j, counts_host, ld_host, &front_done));
+    if (chunked_counts) TRY(front_chunked(ctx, j, &front_done));
     if (!front_done) {
         TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
         TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
@@ -1617,7 +1630,8 @@ int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_arg
     int r = diff_upload_impl(ctx, args, want_post, &job, true);
     if (r != SCDE_B200_OK) return r;
     const auto t1 = now();
-    r = diff_run_impl(ctx, job, args->counts + args->gene_begin, args->n_genes);
+    r = diff_run_impl(ctx, job, true);
+    if (r != SCDE_B200_OK && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     const auto t2 = now();
     if (r == SCDE_B200_OK) r = scde_b200_diff_download(ctx, job, out, stats);
     const auto t3 = now();

@@ -475,6 +475,14 @@ __device__ __forceinline__ int q_offset(int k) {
 //      is evaluated as written (denormal rounding included); below -746 both exponentials are exactly 0 -> "log 0".
 // Outputs: the FP64 table row (table, when write_f64) and / or its fixed-point planes and non-sentinel range (qtable,
 // row_range); MODES: also row_mode.
+// The reference's own expression for one table element, log(exp(nb - M) + exp(log d + f - M)) - log S with the clamp
+// (:193-195,204): only evaluated in the cross-over and gradual-underflow bands.  Out of line, so that libm's exp / log
+// (and their register demands) stay out of the row kernel's hot loop.
+__device__ __noinline__ double lp_slow_element(double a, double dk, double lsum, double sentinel) {
+    const double t = log(exp(a) + exp(dk)) - lsum;
+    return t >= sentinel ? t : sentinel;
+}
+
 // LW lanes per row (32: one row per warp; 16: two rows per warp, side by side in the two half-warps -- 101 quads of a
 // 401-point grid then occupy 7 x 16 = 112 lane slots instead of 4 x 32 = 128, every warp shuffle of the reductions serves
 // two rows, and twice as many independent rows are in flight per warp).
@@ -653,10 +661,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                     for (int e = 0; e < 4; ++e) {
                         const double d = a[e] - dk[e];
                         const double hi = d > 0.0 ? a[e] : dk[e];
-                        if (!(hi < -746.0) && !(hi >= -708.0 && fabs(d) > 37.5)) {
-                            const double t = log(exp(a[e]) + exp(dk[e])) - lsum;
-                            L[e] = t >= sentinel ? t : sentinel;
-                        }
+                        if (!(hi < -746.0) && !(hi >= -708.0 && fabs(d) > 37.5)) L[e] = lp_slow_element(a[e], dk[e], lsum, sentinel);
                     }
                 }
 #pragma unroll

@@ -318,6 +318,7 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
                     const double hi_d = __hiloint2double(0x43300000, (int)((uint32_t)(s >> 32) ^ 0x80000000u)) -
                                         (4503599627370496.0 + 2147483648.0);
                     const double v = fma(hi_d, 4294967296.0, lo_d);
+                    // (fetching the base one round ahead measured 3 % slower: the loads then compete with tcgen05.ld)
                     double t = (Zrow && j < n) ? fma(v, scale, Zrow[i0 + j]) : v * scale;
                     const int k = kbase + i0 + j;
                     if (k < klo || k > khi) t = p.sentinel;  // some drawn row is "log 0" at this grid point
@@ -582,24 +583,21 @@ cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, i
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
                                     const uint32_t *sr, cudaStream_t st) {
     if (n_pos <= 0) return cudaSuccess;
-    static int pgroups = 0;
-    if (!pgroups) {
-        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+    // two producer groups: a third one (12 producer warps) measured 1 % slower -- the producers already wait on free
+    // ring slots most of the time (profiles/r01w)
+    constexpr int PG = 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(contract_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        const char *env = getenv("SCDE_B200_PGROUPS");  // experiment switch: producer warp groups (2 or 3)
-        pgroups = (env && env[0] == '3') ? 3 : 2;
+        attr_set = true;
     }
     if (a.row_range && !sr) return cudaErrorInvalidValue;
     I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     p.SR = a.row_range ? sr : nullptr;
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
-    if (pgroups == 3)
-        contract_i8_kernel<3><<<grid, q_threads(3), Q_SMEM_BYTES, st>>>(p);
-    else
-        contract_i8_kernel<2><<<grid, q_threads(2), Q_SMEM_BYTES, st>>>(p);
+    contract_i8_kernel<PG><<<grid, q_threads(PG), Q_SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -790,11 +790,6 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
     if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         if (!row_snap) return cudaErrorInvalidValue;
-        static int lanes_per_row = 0;
-        if (!lanes_per_row) {
-            const char *env = getenv("SCDE_B200_LP_LANES");  // experiment switch: 32 = one row per warp
-            lanes_per_row = (env && env[0] == '3') ? 32 : 16;
-        }
         auto launch = [&](auto kernel, int rpw) -> cudaError_t {
             const size_t smem = (size_t)ROW_WARPS * rpw * (sizeof(double) * KP_TILED + 4 * Q_PIECE);
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -805,8 +800,6 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
             return cudaGetLastError();
         };
         const bool norm = write_f64 != 0;  // rows that exist in fixed point only need no normalising constant
-        if (lanes_per_row == 32)
-            return row_mode ? launch(lp_rows_fast_kernel<true, 32, true>, 1) : launch(lp_rows_fast_kernel<false, 32, true>, 1);
         if (row_mode)
             return norm ? launch(lp_rows_fast_kernel<true, 16, true>, 2) : launch(lp_rows_fast_kernel<true, 16, false>, 2);
         return norm ? launch(lp_rows_fast_kernel<false, 16, true>, 2) : launch(lp_rows_fast_kernel<false, 16, false>, 2);

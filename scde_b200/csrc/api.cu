@@ -125,6 +125,7 @@ struct scde_b200_ctx {
                               // 4 = sentinel ranges need the FP64 kernel
     DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
     bool ws_busy = false;
+    DBuf<unsigned long long> epi_dbg;       // SCDE_B200_EPI_TIMING: cycle counters of the tcgen05 kernel's epilogue
     cudaStream_t copy_stream = nullptr;     // H2D of the count matrix in cell chunks, overlapped with the table build
     std::vector<cudaEvent_t> copy_events;   // one per chunk (+ 1: "the compute stream has released the counts buffer")
 };
@@ -326,7 +327,7 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 }
 
 struct JointScratch {
-    DBuf<double> W, Z, zpart, T;
+    DBuf<double> W, Z, zpart, T, spart;
     DBuf<int8_t> W8;
     DBuf<uint32_t> SR;  // sentinel range of every (gene, boot) of one launch of the tcgen05 kernel
     DBuf<int32_t> lst_row, lst_cell, lst_len, order;
@@ -401,9 +402,16 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.jp = jp_dev;
         q.ld_jp = ld_jp;
         q.err = ctx->flags.p;
+        q.dbg = nullptr;
+        if (getenv("SCDE_B200_EPI_TIMING")) {
+            SCDE_CUDA(ctx->epi_dbg.ensure(3));
+            SCDE_CUDA(cudaMemsetAsync(ctx->epi_dbg.p, 0, 3 * sizeof(unsigned long long), st));
+            q.dbg = ctx->epi_dbg.p;
+        }
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
         const int max_genes = contract_tiled_max_genes();
         SCDE_CUDA(scr.SR.ensure(contract_i8_range_words(t.n_genes < max_genes ? t.n_genes : max_genes)));
+        SCDE_CUDA(scr.spart.ensure(softmax_i8_scratch_doubles(t.n_genes < max_genes ? t.n_genes : max_genes)));
         for (int g0 = 0; g0 < t.n_genes; g0 += max_genes) {
             const int n_pos = (t.n_genes - g0) < max_genes ? (t.n_genes - g0) : max_genes;
             for (int ps = 0; ps < passes; ++ps) {
@@ -411,13 +419,20 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
                 SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps, scr.SR.p, st));
                 if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
-                SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, scr.SR.p, st));
+                SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
                 if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
-                const int nb = (n_boot - ps * WP_TILED) < WP_TILED ? (n_boot - ps * WP_TILED) : WP_TILED;
                 e0 = tm ? tm->begin(st) : -1;
-                SCDE_CUDA(launch_softmax_avg(scr.T.p, lists.order + g0, t.K, nb, scale, jp_dev, ld_jp, ps > 0, n_pos, st));
-                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, 1);
+                SCDE_CUDA(launch_softmax_i8(q, g0, n_pos, ps, scr.T.p, scr.SR.p, scr.spart.p, ctx->n_sm, st));
+                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, 2);
             }
+        }
+        if (q.dbg) {
+            unsigned long long h[3];
+            SCDE_CUDA(cudaMemcpyAsync(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+            SCDE_CUDA(cudaStreamSynchronize(st));
+            fprintf(stderr, "[scde_b200] tcgen05 epilogue: %llu items, %.0f cycles from accumulators ready to tensor memory released, "
+                    "MMA thread waited %.0f cycles per item for the release\n", h[1], h[1] ? (double)h[0] / h[1] : 0.0,
+                    h[1] ? (double)h[2] / h[1] : 0.0);
         }
         return SCDE_B200_OK;
     }
@@ -1078,7 +1093,8 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.ld_jp = 0;
     q.err = ctx->flags.p;
     SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
-    SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, d_sr.p, st));
+    SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
+    SCDE_CUDA(launch_finalize_t(q, n_genes, d_t.p, d_sr.p, st));
     SCDE_CUDA(cudaMemcpyAsync(t_out, d_t.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));
     int32_t f = 0;

@@ -186,6 +186,7 @@ struct ContractI8Args {
     double *jp;
     int ld_jp;
     int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired, |= 4 if the sentinel ranges need the FP64 kernel
+    unsigned long long *dbg;  // optional [3] cycle counters of the epilogue (see contract_i8.cu), or NULL
 };
 // n_draws: draws per randomization (the plane sums are combined pairwise in 32 bits: 257 * 128 * draws < 2^31)
 bool contract_i8_supported(int K, int ld_table, int ld_lst, int n_draws);
@@ -195,10 +196,17 @@ size_t contract_i8_range_words(int n_genes);  // uint32 words of the (gene, boot
 cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, int pass, uint32_t *sr_scratch,
                                    cudaStream_t st);
 // one launch: genes order[g0 .. g0 + n_pos) (n_pos <= contract_tiled_max_genes()), boots [104 pass, 104 pass + 104);
-// raw T[boot, grid] tiles into t_scratch -- follow with launch_softmax_avg.  sr: what launch_sentinel_ranges wrote
-// (required when a.row_range != NULL)
+// writes 2^29 * T[boot, grid] as exact 64-bit integers (without the zero-count base, without sentinels) into t_scratch
+// ([n_pos][104][416], contract_tiled_scratch_doubles()) -- follow with launch_softmax_i8
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
-                                    const uint32_t *sr, cudaStream_t st);
+                                    cudaStream_t st);
+// the rest of the gene: a.jp[gene][k] (+)= sum_b softmax_k(2^-29 T + Z)[k] / a.scale with the sentinel ranges `sr` (what
+// launch_sentinel_ranges wrote; required when a.row_range != NULL); part_scratch: softmax_i8_scratch_doubles(n_pos)
+size_t softmax_i8_scratch_doubles(int n_pos);
+cudaError_t launch_softmax_i8(const ContractI8Args &a, int g0, int n_pos, int pass, const double *t_scratch, const uint32_t *sr,
+                              double *part_scratch, int n_sm, cudaStream_t st);
+// tests: turns the integer tiles in t_scratch into FP64 T (a.sentinel outside the ranges, no zero-count base), in place
+cudaError_t launch_finalize_t(const ContractI8Args &a, int n_pos, double *t_scratch, const uint32_t *sr, cudaStream_t st);
 
 // ---- ratio_summary.cu ----------------------------------------------------------------------------
 struct RatioArgs {

@@ -31,12 +31,14 @@
 //   * MMA (1 thread): per stage two tcgen05.mma (M = 128 boots, N = 256, K = 32 entries), then tcgen05.commit onto the
 //     stage's "empty" barrier; after the last stage a commit onto the accumulator barrier.
 //   * epilogue (4 warps, one per 32-lane quarter of tensor memory): tcgen05.ld the five planes of 8 grid points at a
-//     time, recombine in int64, add the zero-count base Z[b, k] (FP64), apply the sentinel range, store T[b, k];
-//     softmax_avg_kernel (boot_contract.cu) finishes the gene.  Producers keep prefetching the next item meanwhile.
+//     time, recombine into one 64-bit integer per (boot, grid point) and store it; softmax_i8_kernel finishes the gene
+//     (conversion, zero-count base Z[b, k], sentinel ranges, soft-max, average).  Producers keep prefetching the next
+//     item meanwhile.
 // Roofline: HBM gather bandwidth (512 bytes per visited (gene, cell) pair and piece; tools/gather_bench.cu measures
 // 6.8 TB/s for this access pattern with 128 KB in flight per SM); the tensor pipe needs 2 x 128 cycles per 32 entries.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "fastmath.cuh"
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -70,7 +72,8 @@ struct I8Smem {
     uint32_t tmem_base;
     volatile int abort;
 };
-constexpr size_t Q_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)Q_NS * Q_STAGE_BYTES + sizeof(I8Smem);
+constexpr int Q_XBUF_BYTES = Q_EPILOGUE_WARPS * 2048;  // per epilogue warp: one [32 boots][8 grid points] tile of 64-bit sums
+constexpr size_t Q_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)Q_NS * Q_STAGE_BYTES + Q_XBUF_BYTES + sizeof(I8Smem);
 
 struct I8Params {
     const int8_t *qtable;  // [rows][ldq]: row = [piece][plane][102] (+ 2)
@@ -78,13 +81,13 @@ struct I8Params {
     const int32_t *lst_row, *lst_cell, *lst_len, *order;
     int64_t ld_lst;
     const int8_t *W8;    // this pass: [n_w_rows][128]
-    const double *Z;     // this pass: [104][416] or NULL
-    const uint32_t *SR;  // [n_pos][128] klo | khi << 16 of (gene position, boot), or NULL
-    double *T;           // [n_pos][104][416]
-    double sentinel;     // written where a drawn row is "log 0"
+    long long *T;        // [n_pos][104][416]: 2^29 * T[boot, grid] as exact integers (without Z, without sentinels)
+    int n_boot;          // real boots of this pass: rows beyond are not stored
     int n_pos;           // genes in this launch: positions [0, n_pos) of `order`
     int n_pieces;        // pieces per gene
     int32_t *err;        // device flag: 2 = watchdog abort
+    unsigned long long *dbg;  // optional diagnostics: [0] += cycles between "accumulators ready" and "tensor memory released",
+                              // [1] += items, [2] += cycles the MMA thread waited for the release (epilogue warp 0 / MMA thread)
 };
 
 __device__ __forceinline__ bool wait_or_abort(I8Smem &sm, uint64_t *bar, uint32_t parity) {
@@ -133,7 +136,6 @@ template <int DOFF, int SOFF>
 __device__ __forceinline__ void cp_async16_at(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst_smem), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
 }
-
 template <int Q_PGROUPS>
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
     const int grp = warp >> 2, kg = warp & 3;
@@ -240,8 +242,10 @@ __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t 
         const int nst = (len_n + Q_ES - 1) / Q_ES;
         if (item + (int)gridDim.x < n_items) len_n = p.lst_len[item_gene(p, item + gridDim.x)];
         if (n_done > 0) {  // the epilogue has drained the previous item's accumulators
+            const long long t0 = p.dbg ? clock64() : 0;
             if (!wait_or_abort(sm, &sm.acc_empty, (n_done - 1) & 1u)) return;
             tc_fence_after_sync();
+            if (p.dbg) atomicAdd(p.dbg + 2, (unsigned long long)(clock64() - t0));
         }
         for (int s = 0; s < nst; ++s) {
             if (!wait_or_abort(sm, &sm.full[slot], fill & 1u)) return;
@@ -266,31 +270,36 @@ __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t 
 }
 
 // ---- epilogue: warps e = 0..7; warp e reads tensor-memory lanes 32 (e & 3) .. + 31 and the rounds of half e >> 2 --------
-// Recombination of the five plane sums: |sum_p| <= 128 * draws < 2^23 (draws <= 65535 is checked by the launcher), so
-// a = s0 + 256 s1 and b = s2 + 256 s3 fit 32 bits and the value is a + 2^16 b + 2^32 s4 in 64 bits; its two 32-bit
-// halves become doubles by the 2^52 mantissa trick (exact), and the 2^-29 scaling rides on the FMA that adds the
-// zero-count base.
-__device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t tmem, int n_items, int ewarp, int lane) {
+// The tensor memory is not free for the next item's MMAs before the epilogue ends (all 512 columns belong to one item), so
+// the epilogue does the minimum: tcgen05.ld 8 grid points x 5 planes, recombine the plane sums into ONE 64-bit integer
+// per (boot, grid point) and store it with streaming stores -- no loads, no floating point.  |sum_p| <= 128 * draws < 2^23
+// (draws <= 65000 is checked by the launcher), so a = s0 + 256 s1 and b = s2 + 256 s3 fit 32 bits and the value is
+// a + 2^16 b + 2^32 s4.  Conversion to FP64, the zero-count base Z and the sentinel ranges are applied by
+// softmax_i8_kernel when it reads T.  (An epilogue that did all of that took 16 800 cycles per item -- 8.9 us, of which
+// the ring hides 3 -- and cost a quarter of the kernel: SCDE_B200_EPI_TIMING, profiles/r01x.)
+__device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t xbuf, uint32_t tmem, int n_items, int ewarp,
+                                             int lane) {
     const int qd = ewarp & 3, half = ewarp >> 2;
-    const int b = qd * 32 + lane;  // boot of this thread
     const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
-    const double scale = 1.0 / (double)(1ll << Q_FRAC);
+    // A thread holds 8 grid points of ONE boot (64 bytes of a T row; rows are 3328 bytes apart): stored directly, a warp
+    // store touches 32 lines.  The round's [32 boots][8 points] tile is turned through shared memory instead, so that a
+    // store instruction writes the complete 64-byte runs of 8 boots (8 lines, every sector full).  Tile layout: 16-byte
+    // chunk j of boot l at unit (l + 8 j) mod 32 of row j -- conflict-free both ways.
+    const uint32_t xw = xbuf + (uint32_t)ewarp * 2048u;
+    const int rb = lane >> 2, rc = lane & 3;  // read side: boot rb + 8 i of the warp, chunk rc
     const int r_begin = half ? (Q_EPI_ROUNDS + 1) / 2 : 0, r_end = half ? Q_EPI_ROUNDS : (Q_EPI_ROUNDS + 1) / 2;
     uint32_t n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const Item it = decode_item(p, item);
         const int64_t gene = p.order ? p.order[it.pos] : it.pos;
         const bool empty_list = p.lst_len[gene] <= 0;
-        const uint32_t sr = p.SR ? p.SR[(int64_t)it.pos * Q_WB + b] : 0xFFFF0000u;
-        const int klo = (int)(sr & 0xFFFFu), khi = (int)(sr >> 16);
         while (!mbar_try_wait(&sm.acc_full, n_done & 1u)) {  // an item takes tens of microseconds: sleep, do not spin
-            __nanosleep(500);
+            __nanosleep(200);
             if (sm.abort) return;
         }
         tc_fence_after_sync();
-        const int kbase = it.piece * Q_PW;
-        double *Trow = p.T + ((int64_t)it.pos * WP_TILED + b) * KP_TILED + kbase;
-        const double *Zrow = p.Z ? p.Z + (int64_t)b * KP_TILED + kbase : nullptr;
+        const long long t_ready = p.dbg ? clock64() : 0;
+        long long *Tbase = p.T + ((int64_t)it.pos * WP_TILED + qd * 32) * KP_TILED + it.piece * Q_PW;
         for (int rd = r_begin; rd < r_end; ++rd) {
             const int i0 = rd * 8;
             const int n = Q_PW - i0 < 8 ? Q_PW - i0 : 8;  // 8, or 6 in the last round
@@ -300,37 +309,45 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
 #pragma unroll
                 for (int j = 0; j < 8; ++j) r[pl][j] = 0u;
             if (!empty_list) {
+                // eight columns per load (the columns past a plane's 102 points belong to the next plane or are the
+                // piece's two spare columns: read, not used)
 #pragma unroll
-                for (int pl = 0; pl < Q_NV; ++pl)
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2)
-                        if (j < n) tmem_ld_32x32b_x2(tlane + (uint32_t)(pl * Q_PW + i0 + j), r[pl][j], r[pl][j + 1]);
+                for (int pl = 0; pl < Q_NV; ++pl) tmem_ld_32x32b_x8(tlane + (uint32_t)(pl * Q_PW + i0), r[pl]);
                 tmem_wait_ld();
             }
-            if (b < WP_TILED) {
-                double out[8];
+            long long out[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int32_t a = (int32_t)r[0][j] + ((int32_t)r[1][j] << 8);
-                    const int32_t c = (int32_t)r[2][j] + ((int32_t)r[3][j] << 8);
-                    const long long s = (long long)a + ((long long)c << 16) + ((long long)(int32_t)r[4][j] << 32);
-                    const double lo_d = __hiloint2double(0x43300000, (int)(uint32_t)s) - 4503599627370496.0;
-                    const double hi_d = __hiloint2double(0x43300000, (int)((uint32_t)(s >> 32) ^ 0x80000000u)) -
-                                        (4503599627370496.0 + 2147483648.0);
-                    const double v = fma(hi_d, 4294967296.0, lo_d);
-                    // (fetching the base one round ahead measured 3 % slower: the loads then compete with tcgen05.ld)
-                    double t = (Zrow && j < n) ? fma(v, scale, Zrow[i0 + j]) : v * scale;
-                    const int k = kbase + i0 + j;
-                    if (k < klo || k > khi) t = p.sentinel;  // some drawn row is "log 0" at this grid point
-                    out[j] = t;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j += 2)
-                    if (j < n) *reinterpret_cast<double2 *>(Trow + i0 + j) = make_double2(out[j], out[j + 1]);
+            for (int j = 0; j < 8; ++j) {
+                const int32_t a = (int32_t)r[0][j] + ((int32_t)r[1][j] << 8);
+                const int32_t c = (int32_t)r[2][j] + ((int32_t)r[3][j] << 8);
+                out[j] = (long long)a + ((long long)c << 16) + ((long long)(int32_t)r[4][j] << 32);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(xw + 512u * j + (uint32_t)(((lane + 8 * j) & 31) << 4)),
+                             "l"(out[2 * j]), "l"(out[2 * j + 1])
+                             : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int bw = rb + 8 * i;  // boot within the warp's 32
+                long long v0, v1;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1)
+                             : "r"(xw + 512u * rc + (uint32_t)(((bw + 8 * rc) & 31) << 4)) : "memory");
+                // streaming stores: T is read back once, by the soft-max kernel, long after it has left the L2 -- it
+                // should not push table rows out (an evict-first hint on the table loads, on the other hand, cost
+                // 4 %: the rows of small counts are shared by thousands of genes and live in the L2)
+                if (qd * 32 + bw < p.n_boot && 2 * rc < n)
+                    __stcs(reinterpret_cast<longlong2 *>(Tbase + (int64_t)bw * KP_TILED + i0 + 2 * rc), make_longlong2(v0, v1));
+            }
+            __syncwarp();
         }
         tc_fence_before_sync();
         mbar_arrive(&sm.acc_empty);
+        if (p.dbg && ewarp == 0 && lane == 0) {
+            atomicAdd(p.dbg, (unsigned long long)(clock64() - t_ready));
+            atomicAdd(p.dbg + 1, 1ull);
+        }
     }
 }
 
@@ -341,7 +358,8 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     // stage buffers on a 1024-byte boundary (the swizzle pattern is a function of the shared-memory address bits)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t stage0 = (raw + 1023u) & ~1023u;
-    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw + (stage0 - raw) + (size_t)Q_NS * Q_STAGE_BYTES);
+    const uint32_t xbuf = stage0 + (uint32_t)Q_NS * Q_STAGE_BYTES;
+    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw + (stage0 - raw) + (size_t)Q_NS * Q_STAGE_BYTES + Q_XBUF_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_NS; ++s) {
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     if (warp < Q_PRODUCER_WARPS)
         run_producer<Q_PGROUPS>(p, sm, stage0, n_items, warp, lane);
     else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
-        run_epilogue(p, sm, tmem, n_items, warp - Q_PRODUCER_WARPS, lane);
+        run_epilogue(p, sm, xbuf, tmem, n_items, warp - Q_PRODUCER_WARPS, lane);
     else if (lane == 0)
         run_mma(p, sm, stage0, tmem, n_items);
 
@@ -455,6 +473,112 @@ __global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__re
     }
     *reinterpret_cast<uint4 *>(SR + (int64_t)pos * Q_WB + 4 * lane) = make_uint4(out[0], out[1], out[2], out[3]);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax_i8_kernel + softmax_i8_reduce_kernel: jp[gene, k] (+)= sum_b softmax_k(T[b, :])[k] / scale from the integer T tiles
+// of contract_i8_kernel (src/jpmatLogBoot.cpp:264-269).  T[b, k] = 2^-29 * integer + Z[b, k], "log 0" (excluded from the
+// soft-max) outside the (gene, boot) sentinel range.
+// A CTA owns one group of 13 boots -- one boot per warp, so the warp keeps its row of the zero-count base Z in registers
+// for all the genes it walks (read from every gene's CTA, Z cost as much L2 traffic as T costs HBM traffic).  Per gene a
+// warp reads its T row once (13 grid points per lane), takes the log-sum-exp pieces by shuffles (exp_nonpos, skipped
+// warp-wide where a 32-point stretch lies > 746 nats below the row maximum: a joint posterior is sharply peaked), and the
+// 13 normalised rows are added in ascending boot order through shared memory.  The eight groups' partial sums are added
+// in group order by the reduce kernel: the result is deterministic.
+constexpr int SP_GROUPS = 8, SP_ROWS = WP_TILED / SP_GROUPS;
+static_assert(SP_GROUPS * SP_ROWS == WP_TILED && SP_ROWS * 32 == KP_TILED, "13 warps x 32 lanes = the 416 grid slots");
+__global__ void __launch_bounds__(SP_ROWS * 32)
+softmax_i8_kernel(const long long *__restrict__ T, const double *__restrict__ Z, const uint32_t *__restrict__ SR, int K,
+                  int n_boot_pass, double scale, double *__restrict__ part, int n_pos) {
+    constexpr int NJ = KP_TILED / 32;
+    __shared__ double s_acc[SP_ROWS][KP_TILED];
+    const int group = blockIdx.x % SP_GROUPS, batch = blockIdx.x / SP_GROUPS, n_batch = gridDim.x / SP_GROUPS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = group * SP_ROWS + warp;
+    const bool active = b < n_boot_pass;
+    double zr[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) zr[j] = (Z && active) ? Z[(int64_t)b * KP_TILED + lane + 32 * j] : 0.0;
+    const double q = 1.0 / (double)(1ll << Q_FRAC);
+    // the next gene's row is pulled into the L2 while the current one is processed (26 lines of 128 bytes, one per lane):
+    // a CTA is otherwise bound by one HBM latency per gene
+    auto prefetch_row = [&](int pos) {
+        if (active && lane < (KP_TILED * 8) / 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(T + ((int64_t)pos * WP_TILED + b) * KP_TILED + lane * 16));
+    };
+    for (int pos = batch; pos < n_pos; pos += n_batch) {
+        double v[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) v[j] = 0.0;
+        if (pos + n_batch < n_pos) prefetch_row(pos + n_batch);
+        if (active) {
+            const long long *row = T + ((int64_t)pos * WP_TILED + b) * KP_TILED;
+            const uint32_t sr = SR ? SR[(int64_t)pos * Q_WB + b] : 0xFFFF0000u;
+            const int klo = (int)(sr & 0xFFFFu), khi = (int)(sr >> 16);
+            double m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int k = lane + 32 * j;
+                // some drawn row is "log 0" outside [klo, khi]: the reference's T is a multiple of the sentinel there
+                v[j] = (k < K && k >= klo && k <= khi) ? fma((double)__ldcs(row + k), q, zr[j]) : -INFINITY;
+                m = fmax(m, v[j]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const double d = v[j] - m;
+                v[j] = 0.0;
+                if (__any_sync(0xffffffffu, d > -746.0)) v[j] = d > -INFINITY ? exp_nonpos(d) : 0.0;
+                sum += v[j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const double inv = 1.0 / (sum * scale);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) v[j] *= inv;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s_acc[warp][lane + 32 * j] = v[j];
+        __syncthreads();
+        {
+            const int k = threadIdx.x;  // 416 threads = 416 grid slots
+            double r = 0.0;
+#pragma unroll
+            for (int w = 0; w < SP_ROWS; ++w) r += s_acc[w][k];
+            part[((int64_t)group * n_pos + pos) * KP_TILED + k] = r;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void softmax_i8_reduce_kernel(const double *__restrict__ part, const int32_t *__restrict__ order, int K, int n_pos,
+                                         double *__restrict__ jp, int64_t ld_jp, int accumulate) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_pos * KP_TILED) return;
+    const int pos = (int)(idx / KP_TILED), k = (int)(idx - (int64_t)pos * KP_TILED);
+    if (k >= K) return;
+    double r = 0.0;
+#pragma unroll
+    for (int g = 0; g < SP_GROUPS; ++g) r += part[((int64_t)g * n_pos + pos) * KP_TILED + k];
+    const int64_t gene = order ? order[pos] : pos;
+    double *out = jp + gene * ld_jp + k;
+    *out = accumulate ? *out + r : r;
+}
+
+// the integer T tiles as the FP64 values the reference would hold (tests: scde_b200_probe_contract_i8), in place
+__global__ void finalize_t_kernel(long long *__restrict__ T, const uint32_t *__restrict__ SR, double sentinel, int64_t n) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int k = (int)(idx % KP_TILED);
+    const int64_t row = idx / KP_TILED;
+    const int b = (int)(row % WP_TILED);
+    const int64_t pos = row / WP_TILED;
+    const uint32_t sr = SR ? SR[pos * Q_WB + b] : 0xFFFF0000u;
+    double t = (double)T[idx] * (1.0 / (double)(1ll << Q_FRAC));
+    if (k < (int)(sr & 0xFFFFu) || k > (int)(sr >> 16)) t = sentinel;
+    reinterpret_cast<double *>(T)[idx] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -559,13 +683,12 @@ static I8Params make_params(const ContractI8Args &a, int g0, int n_pos, int pass
     p.order = a.lists.order ? a.lists.order + g0 : nullptr;
     p.ld_lst = a.lists.ld;
     p.W8 = a.W8 + (size_t)pass * a.n_w_rows * Q_WB;
-    p.Z = a.Z ? a.Z + (size_t)pass * WP_TILED * KP_TILED : nullptr;
-    p.SR = nullptr;
-    p.T = t_scratch;
-    p.sentinel = a.sentinel;
+    p.T = reinterpret_cast<long long *>(t_scratch);
+    p.n_boot = (a.n_boot - pass * WP_TILED) < WP_TILED ? (a.n_boot - pass * WP_TILED) : WP_TILED;
     p.n_pos = n_pos;
     p.n_pieces = q_pieces(a.K);
     p.err = a.err;
+    p.dbg = a.dbg;
     return p;
 }
 
@@ -581,7 +704,7 @@ cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, i
 }
 
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
-                                    const uint32_t *sr, cudaStream_t st) {
+                                    cudaStream_t st) {
     if (n_pos <= 0) return cudaSuccess;
     // two producer groups: a third one (12 producer warps) measured 1 % slower -- the producers already wait on free
     // ring slots most of the time (profiles/r01w)
@@ -592,12 +715,40 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (a.row_range && !sr) return cudaErrorInvalidValue;
-    I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
-    p.SR = a.row_range ? sr : nullptr;
+    const I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
     contract_i8_kernel<PG><<<grid, q_threads(PG), Q_SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
+}
+
+size_t softmax_i8_scratch_doubles(int n_pos) { return (size_t)SP_GROUPS * (n_pos > 0 ? n_pos : 1) * KP_TILED; }
+
+cudaError_t launch_softmax_i8(const ContractI8Args &a, int g0, int n_pos, int pass, const double *t_scratch, const uint32_t *sr,
+                              double *part_scratch, int n_sm, cudaStream_t st) {
+    if (n_pos <= 0) return cudaSuccess;
+    if (a.row_range && !sr) return cudaErrorInvalidValue;
+    const int nb = (a.n_boot - pass * WP_TILED) < WP_TILED ? (a.n_boot - pass * WP_TILED) : WP_TILED;
+    const double *Z = a.Z ? a.Z + (size_t)pass * WP_TILED * KP_TILED : nullptr;
+    int batches = n_sm * 4 / SP_GROUPS;  // four CTAs of 416 threads per SM
+    if (batches > n_pos) batches = n_pos;
+    if (batches < 1) batches = 1;
+    softmax_i8_kernel<<<batches * SP_GROUPS, SP_ROWS * 32, 0, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
+                                                                    a.row_range ? sr : nullptr, a.K, nb, a.scale, part_scratch,
+                                                                    n_pos);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int64_t n = (int64_t)n_pos * KP_TILED;
+    softmax_i8_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part_scratch, a.lists.order ? a.lists.order + g0 : nullptr,
+                                                                          a.K, n_pos, a.jp, a.ld_jp, pass > 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_t(const ContractI8Args &a, int n_pos, double *t_scratch, const uint32_t *sr, cudaStream_t st) {
+    if (n_pos <= 0) return cudaSuccess;
+    const int64_t n = (int64_t)n_pos * WP_TILED * KP_TILED;
+    finalize_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long *>(t_scratch),
+                                                                   a.row_range ? sr : nullptr, a.sentinel, n);
     return cudaGetLastError();
 }
 

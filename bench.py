@@ -13,7 +13,8 @@ indices are all-gathered over NCCL at the end of every step and rank 0 applies t
 
   value : genes/s with the counts, models, prior and draws already resident in HBM (device work only)
   e2e   : genes/s through the C ABI call with host (pinned) buffers -- H2D of the counts and D2H of results inside
-  roofline : contraction kernel (the dominant one).  Default kernel (tcgen05.mma kind::i8 on the fixed-point table):
+  roofline : contraction kernel (the dominant one).  Default kernel (tcgen05.mma kind::i8 on the fixed-point table; its
+             soft-max kernel is timed as its own stage):
              HBM-bound gather -- algorithmic bytes = visited (gene, cell) pairs x (5 planes x 401 B of table + 8 B of list
              entry; the row is stored in 2048 B), against the measured copy bandwidth of MEASURED_PEAKS.json.  --kernel 1|2 (FP64 kernels): executed
              2*K*B flops per visited pair against the FP64 DFMA peak measured live on the same device
@@ -364,6 +365,11 @@ def main():
                 "launches_per_step": n_kernel, "avg_launch_ms": ms_c / max(1, n_kernel),
                 "bytes_per_launch": bytes_alg / max(1, n_kernel),
                 "bytes_per_visited_pair": 5 * K_GRID + 8, "stored_bytes_per_visited_pair": 2048 + 8,
+                "dram_gbs": (traffic / (ms_c / max(1, n_kernel) * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (ms_c / max(1, n_kernel) * 1e-3) / 1e9 / peak) if traffic else None,
+                "note": "achieved = algorithmic bytes (every visited pair's row once) / launch time; rows of small counts are shared "
+                        "by thousands of genes and hit the 126 MB L2, so the DRAM traffic of the launch (`traffic`, ncu) is "
+                        "smaller than the algorithmic bytes and `frac` can exceed the DRAM fraction `dram_frac`",
                 "entries_visited_frac": entries / dense_entries,
                 "peak_source": peak_src,
                 "int8_tops": 5.0 * flops_exec / (ms_c * 1e-3) / 1e12,  # five int8 planes per FP64 multiply-add

@@ -1129,7 +1129,64 @@ struct scde_b200_diff_job {
     int64_t contract_cells = 0;
     bool ran = false;
     int copy_chunks = 0, copy_chunk_cells = 0;  // chunked H2D of the counts in flight on the context's copy stream
+    std::vector<int32_t> ids[2];                 // cells of the two groups
+    std::vector<int32_t> gen[4];                 // generated draws, alive until their uploads have completed
+    const scde_b200_diff_args *deferred_args = nullptr;  // one-shot call: the draws are still to be generated and uploaded
 };
+
+// Bootstrap draws of the group joints (local indices) and, with a batch factor, of the composition-sampled joints (global
+// cell ids): the caller's, or generated from the seed (src/jpmatLogBoot.cpp:221,254-257 / :467-481).  The uploads are
+// queued on the context stream; the host vectors live in the job.
+int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_args *a) {
+    cudaStream_t st = ctx->stream;
+    const int C = j->C;
+    const int32_t *src[4] = {nullptr, nullptr, nullptr, nullptr};
+    // host work first (the uploads below may wait for the kernels already queued on the stream)
+    for (int i = 0; i < 2; ++i) {
+        const int n = j->n_group[i];
+        src[i] = a->boot_idx[i];
+        if (!src[i]) {
+            j->gen[i] = gen_boot(a->seed, n, a->n_boot);
+            src[i] = j->gen[i].data();
+        }
+        TRY(validate_index(src[i], (size_t)a->n_boot * n, 0, n, "boot_idx"));
+        j->D[i] = n;
+    }
+    if (j->has_batch) {
+        const int L = a->n_batch_levels;
+        std::vector<int32_t> off(L + 1, 0), cells;
+        for (int c = 0; c < C; ++c) {
+            if (a->batch[c] < 0 || a->batch[c] >= L) {
+                set_error("batch[%d] = %d outside [0, %d)", c, a->batch[c], L);
+                return SCDE_B200_EINVAL;
+            }
+            off[a->batch[c] + 1]++;
+        }
+        for (int l = 0; l < L; ++l) off[l + 1] += off[l];
+        cells.resize(C);
+        {
+            std::vector<int32_t> pos(off.begin(), off.end() - 1);
+            for (int c = 0; c < C; ++c) cells[pos[a->batch[c]]++] = c;  // tapply(0:(n-1), batch, I): ascending
+        }
+        for (int i = 0; i < 2; ++i) {
+            std::vector<int32_t> comp(L, 0);  // table(batch[ii])
+            for (int c : j->ids[i]) comp[a->batch[c]]++;
+            const int D = j->n_group[i];
+            src[2 + i] = a->boot_idx[2 + i];
+            if (!src[2 + i]) {
+                j->gen[2 + i].resize((size_t)a->n_boot * D);
+                TRY(scde_b200_batch_boot_indices(a->seed, L, off.data(), cells.data(), comp.data(), a->n_boot,
+                                                 j->gen[2 + i].data()));
+                src[2 + i] = j->gen[2 + i].data();
+            }
+            TRY(validate_index(src[2 + i], (size_t)a->n_boot * D, 0, C, "batch boot_idx"));
+            j->D[2 + i] = D;
+        }
+    }
+    for (int i = 0; i < (j->has_batch ? 4 : 2); ++i) TRY(upload(j->boot[i], src[i], (size_t)a->n_boot * j->D[i], st));
+    SCDE_CUDA(cudaStreamSynchronize(st));  // the caller's (or the job's) host arrays have been read
+    return SCDE_B200_OK;
+}
 
 constexpr int N_COUNT_CHUNKS = 8;
 
@@ -1262,53 +1319,14 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
         j->n_group[i] = (int)ids[i].size();
         JTRY(upload(j->cell_ids[i], ids[i].data(), ids[i].size(), st));
     }
-    // draws
-    for (int i = 0; i < 2; ++i) {
-        const int n = j->n_group[i];
-        std::vector<int32_t> gen;
-        const int32_t *bi = a->boot_idx[i];
-        if (!bi) {
-            gen = gen_boot(a->seed, n, a->n_boot);
-            bi = gen.data();
-        }
-        JTRY(validate_index(bi, (size_t)a->n_boot * n, 0, n, "boot_idx"));
-        JTRY(upload(j->boot[i], bi, (size_t)a->n_boot * n, st));
-        j->D[i] = n;
-        JCUDA(cudaStreamSynchronize(st));  // `gen` goes out of scope
-    }
-    if (has_batch) {
-        const int L = a->n_batch_levels;
-        std::vector<int32_t> off(L + 1, 0), cells;
-        for (int c = 0; c < C; ++c) {
-            if (a->batch[c] < 0 || a->batch[c] >= L) {
-                set_error("batch[%d] = %d outside [0, %d)", c, a->batch[c], L);
-                return fail(SCDE_B200_EINVAL);
-            }
-            off[a->batch[c] + 1]++;
-        }
-        for (int l = 0; l < L; ++l) off[l + 1] += off[l];
-        cells.resize(C);
-        {
-            std::vector<int32_t> pos(off.begin(), off.end() - 1);
-            for (int c = 0; c < C; ++c) cells[pos[a->batch[c]]++] = c;  // tapply(0:(n-1), batch, I): ascending
-        }
-        for (int i = 0; i < 2; ++i) {
-            std::vector<int32_t> comp(L, 0);  // table(batch[ii])
-            for (int c : ids[i]) comp[a->batch[c]]++;
-            const int D = j->n_group[i];
-            std::vector<int32_t> gen;
-            const int32_t *bi = a->boot_idx[2 + i];
-            if (!bi) {
-                gen.resize((size_t)a->n_boot * D);
-                JTRY(scde_b200_batch_boot_indices(a->seed, L, off.data(), cells.data(), comp.data(), a->n_boot, gen.data()));
-                bi = gen.data();
-            }
-            JTRY(validate_index(bi, (size_t)a->n_boot * D, 0, C, "batch boot_idx"));
-            JTRY(upload(j->boot[2 + i], bi, (size_t)a->n_boot * D, st));
-            j->D[2 + i] = D;
-            JCUDA(cudaStreamSynchronize(st));
-        }
-    }
+    // draws: generated (host RNG, 1.3 ms per group at config 4) and uploaded now, or -- one-shot call -- while the front
+    // kernels run (upload_draws is then called by diff_run_impl)
+    j->ids[0] = ids[0];
+    j->ids[1] = ids[1];
+    if (defer_counts)
+        j->deferred_args = a;
+    else
+        JTRY(upload_draws(ctx, j, a));
     {
         std::vector<int32_t> zi(a->n_zero == 1 ? 1 : G);
         for (size_t i = 0; i < zi.size(); ++i) zi[i] = a->zero_index[a->n_zero == 1 ? 0 : g0 + i];
@@ -1424,6 +1442,11 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
         FTRY(launch_table_rows(ctx, t, pl, CellRange{c0, c0 + n, cap}, j->models.p, C, j->local_theta, &nl));
         tm.end(SCDE_B200_T_LPTABLE, e0, st, nl);
     }
+    if (j->deferred_args) {  // the bootstrap draws: host RNG work while the kernels queued above run
+        const scde_b200_diff_args *da = j->deferred_args;
+        j->deferred_args = nullptr;
+        FTRY(upload_draws(ctx, j, da));
+    }
     int32_t total = 0, err = 0;
     FCUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FCUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1478,6 +1501,11 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
     int t_all = tm.begin(st);
     bool front_done = false;
     if (chunked_counts) TRY(front_chunked(ctx, j, &front_done));
+    if (j->deferred_args) {  // not done by the chunked front (small problem or fallback)
+        const scde_b200_diff_args *da = j->deferred_args;
+        j->deferred_args = nullptr;
+        TRY(upload_draws(ctx, j, da));
+    }
     if (!front_done) {
         TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
         TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));

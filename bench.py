@@ -223,16 +223,16 @@ def main():
 
     def gather_and_correct(res):
         """the one exchange of the path: per-shard Z and grid indices -> all ranks; BH over all genes on rank 0"""
-        z = torch.from_numpy(res["z"]).to(device, non_blocking=True)
-        idx = torch.from_numpy(np.ascontiguousarray(res["idx"])).to(device, non_blocking=True)
         if world > 1:
+            z = torch.from_numpy(res["z"]).to(device, non_blocking=True)
+            idx = torch.from_numpy(np.ascontiguousarray(res["idx"])).to(device, non_blocking=True)
             zs = [torch.empty_like(z) for _ in range(world)]
             ids = [torch.empty_like(idx) for _ in range(world)]
             dist.all_gather(zs, z)
             dist.all_gather(ids, idx)
             z_all = torch.cat(zs).cpu().numpy()
         else:
-            z_all = z.cpu().numpy()
+            z_all = res["z"]  # one rank: the shard's results are already the whole job's, on the host
         if rank == 0:
             cz = np.empty_like(z_all)
             _lib.check(_lib.lib().scde_b200_bh_cz(_lib.p_f64(z_all), len(z_all), _lib.p_f64(cz)))

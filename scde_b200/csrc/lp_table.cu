@@ -738,6 +738,278 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
     }
 }
 
+// ---- fixed-point rows of the fused path, cell state in registers -----------------------------------
+// The rows the tcgen05 contraction reads (non-zero counts of a constant-theta model, stored in fixed point only, as the
+// difference to the cell's zero-count row and without a normalising constant) are 99.9 % of the table.  For them a
+// table element is   hi_k - Z_k,   hi_k = max(a_k, E_k + f) - M,   a_k = R + A_k + x L_k
+// with the per-cell grid vectors A = theta log p + log(1 - d), L = log q, E = log d, Z = lp(0) and the row constants R, f,
+// M -- everything a row adds is three scalars.  One warp walks a contiguous run of rows (consecutive rows belong to the
+// same cell) and keeps A, L, E, Z of its 13 grid points per lane in registers, so the two sweeps of a row (maximum, then
+// values) read nothing from memory: the kernel that loads the vectors per element (lp_rows_fast_kernel) spends 14 vector
+// loads / stores per four elements and ~105 instructions per element, this one ~30.
+//   Lane l owns the quads 4 (l + 32 j) .. + 3 for j < 3 (grid points 0..383) and the single point 384 + l: 13 points per
+// lane, 416 per warp, so a 401-point grid uses 96 % of the lane slots (quads alone: 4 rounds for 101 quads = 79 %).
+//   Row headers (count, row constants, snap point and its value) are loaded 32 rows at a time, one row per lane, one
+// batch ahead, and broadcast by shuffles.
+// Fixed point: y = v 2^29 + (1.5 2^52 + 0x8080808080) holds the biased digits of rint(v 2^29) in the low 40 bits of its
+// mantissa (|v| <= 753, so 0 <= rint(v 2^29) + 0x8080808080 < 2^40); flipping the top bit of every byte gives the signed
+// radix-256 digits.
+constexpr int QR_WARPS = 4;
+constexpr int QR_MAIN = 3;  // quads per lane
+
+__device__ __forceinline__ double warp_max_redux(double v) {
+    // order-preserving map double -> (hi, lo) unsigned, maximum by two 32-bit redux.sync
+    const long long b = __double_as_longlong(v);
+    uint32_t hi = (uint32_t)((unsigned long long)b >> 32), lo = (uint32_t)b;
+    const uint32_t neg = (uint32_t)((int32_t)hi >> 31);  // all ones for negative values
+    hi ^= neg | 0x80000000u;
+    lo ^= neg;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const uint32_t back = (mh & 0x80000000u) ? 0x80000000u : 0xffffffffu;  // was non-negative : was negative
+    const uint32_t rh = mh ^ back, rl = ml ^ ((mh & 0x80000000u) ? 0u : 0xffffffffu);
+    return __longlong_as_double((long long)(((unsigned long long)rh << 32) | rl));
+}
+
+__global__ void __launch_bounds__(QR_WARPS * 32, 3)
+lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
+                 const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
+                 const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
+                 double sentinel, const double *__restrict__ table, int ld_table, const int32_t *__restrict__ zero_row,
+                 const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][4 * Q_PIECE]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *sq = s_dyn + warp * (4 * Q_PIECE);
+    for (int j = lane; j < (4 * Q_PIECE) / 16; j += 32) reinterpret_cast<uint4 *>(sq)[j] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const int64_t row0 = (int64_t)row_off[cr.c0];
+    const int64_t row1 = min((int64_t)row_off[cr.c1], cr.row_cap);
+    const int64_t n_rows = row1 > row0 ? row1 - row0 : 0;
+    const int64_t n_warps = (int64_t)gridDim.x * QR_WARPS, gw = (int64_t)blockIdx.x * QR_WARPS + warp;
+    const int64_t per_warp = (n_rows + n_warps - 1) / n_warps;
+    const int64_t r_begin = row0 + min(n_rows, gw * per_warp), r_end = row0 + min(n_rows, (gw + 1) * per_warp);
+    if (r_begin >= r_end) return;
+
+    // this lane's grid points and where their digits go in the staged row
+    const int kt = 4 * 32 * QR_MAIN + lane;  // the single point
+    uint32_t vmask = 0u;  // bit 4 j + e: main point (j, e) exists; bit 12: the single point exists
+#pragma unroll
+    for (int j = 0; j < QR_MAIN; ++j) {
+        const int k0 = 4 * (lane + 32 * j);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (k0 + e < K) vmask |= 1u << (4 * j + e);
+    }
+    if (kt < K) vmask |= 1u << (4 * QR_MAIN);
+    const int offt = q_offset(min(kt, Q_MAX_K - 1));
+
+    // cell state
+    double A[4 * QR_MAIN + 1], L[4 * QR_MAIN + 1], E[4 * QR_MAIN + 1], Z[4 * QR_MAIN + 1];
+    int cur_c = -1;
+    int64_t cur_zero = -1;
+    double theta = 0.0, maxcfp = 0.0;
+    const double DEAD_FILL = -1.0e300;  // points beyond the grid: far below every threshold, never the maximum
+
+    struct Header {
+        int c, xi, ks;
+        double R, fp, asnap;
+    };
+    auto load_header = [&](int64_t base) {
+        Header h;
+        int64_t row = base + lane;
+        if (row >= r_end) row = r_end - 1;
+        h.c = row_cell[row];
+        h.xi = row_x[row];
+        h.ks = row_snap[row];
+        const double4 rc = rowc[row];
+        h.R = rc.x;
+        h.fp = rc.w;
+        h.asnap = -INFINITY;
+        if (h.ks >= 0) {
+            const double s = models[(size_t)5 * ldm + h.c];
+            h.asnap = fma((double)h.xi, rc.z, fma(s, rc.y, rc.x)) + prep.lcfpr[(size_t)h.c * prep.ld + h.ks];
+        }
+        return h;
+    };
+
+    const double SCALE = (double)(1ll << Q_FRAC);
+    const double MAGICB = 6755399441055744.0 + 551911719040.0;  // 1.5 2^52 + 0x8080808080
+    Header nxt = load_header(r_begin);
+    for (int64_t base = r_begin; base < r_end; base += 32) {
+        const Header cur = nxt;
+        if (base + 32 < r_end) nxt = load_header(base + 32);
+        const int nb = (int)min((int64_t)32, r_end - base);
+        for (int i = 0; i < nb; ++i) {
+            const int64_t row = base + i;
+            const int c = __shfl_sync(0xffffffffu, cur.c, i);
+            if (c != cur_c) {  // next cell: reload the grid vectors of this lane's points
+                cur_c = c;
+                theta = models[(size_t)5 * ldm + c];
+                maxcfp = prep.maxcfp[c];
+                const int zr = zero_row[c];
+                cur_zero = zr;
+                const bool bs = zr >= 0 && based[c] != 0;
+                const size_t pb = (size_t)c * prep.ld;
+                const double *zrow = table + (size_t)(zr >= 0 ? zr : 0) * ld_table;
+#pragma unroll
+                for (int p = 0; p < 4 * QR_MAIN + 1; ++p) {
+                    const int k = p < 4 * QR_MAIN ? 4 * (lane + 32 * (p >> 2)) + (p & 3) : kt;
+                    if (k < K) {
+                        A[p] = fma(theta, prep.l1[pb + k], prep.lcfpr[pb + k]);
+                        L[p] = prep.l2[pb + k];
+                        E[p] = prep.lcfp[pb + k];
+                        Z[p] = bs ? zrow[k] : 0.0;
+                    } else {
+                        A[p] = DEAD_FILL;
+                        L[p] = 0.0;
+                        E[p] = DEAD_FILL;
+                        Z[p] = 0.0;
+                    }
+                }
+            }
+            if (row == cur_zero) continue;  // the zero-count row is an FP64 row (lp_rows_fast_kernel, which == 1)
+            const double x = (double)__shfl_sync(0xffffffffu, cur.xi, i);
+            const int ks = __shfl_sync(0xffffffffu, cur.ks, i);
+            const double R = __shfl_sync(0xffffffffu, cur.R, i);
+            const double fp = __shfl_sync(0xffffffffu, cur.fp, i);
+            const double asnap = __shfl_sync(0xffffffffu, cur.asnap, i);
+            // ---- sweep 1: the row maximum.  The snapped value (mu~ = x maximises the NB term) replaces a_ks and is not
+            // below it, so max(regular values, snapped value) is the maximum of the row as the reference builds it.
+            double vmax = asnap;
+#pragma unroll
+            for (int p = 0; p < 4 * QR_MAIN + 1; ++p) {
+                const double a = fma(x, L[p], R) + A[p];
+                vmax = a > vmax ? a : vmax;
+            }
+            vmax = warp_max_redux(vmax);
+            const double alt = maxcfp + fp;
+            const double maxp = vmax > alt ? vmax : alt;
+            const double Rm = R - maxp, fm = fp - maxp, asn = asnap - maxp;
+            // ---- sweep 2: values, digits.  hi = max(a, e) (both relative to the row maximum, so hi <= 0 up to rounding).
+            // The classes of lp_rows_fast_kernel's sweep 3 are decided on the high words of hi and of d = a - e, on the safe
+            // side: "dead" (hi < -746: log 0) only when the high word alone proves it, "easy" (hi >= -708 and
+            // |d| > 37.5: the value is hi) likewise; everything else -- the cross-over and gradual-underflow bands, and
+            // the 1e-10-wide margins of the high-word tests -- evaluates the reference's expression as written.
+            uint32_t okmask = 0u;
+            const int qs = ks >> 2;  // (-1 -> -1: no quad)
+            const int js = qs >> 5, es = ks & 3;
+            const bool snap_lane = lane == (qs & 31);
+            constexpr uint32_t H_DEAD = 0xC0875000u, H_LOW = 0xC0862000u, H_BAND = 0x4042C000u;  // -746, -708, 37.5
+            auto element = [&](double a, double e, double &hi, bool &alive) -> bool {  // true: needs the slow path
+                const double d = a - e;
+                const uint32_t hd = (uint32_t)__double2hiint(d);
+                hi = (int32_t)hd >= 0 ? a : e;  // d >= 0 (for d == -0 the two are equal)
+                const uint32_t hh = (uint32_t)__double2hiint(hi);
+                const bool dead = hh > H_DEAD;
+                const bool easy = hh < H_LOW && (hd & 0x7fffffffu) > H_BAND;
+                alive = !dead;
+                return !(dead || easy);
+            };
+#pragma unroll
+            for (int j = 0; j < QR_MAIN; ++j) {
+                double a[4], e[4], hi[4];
+                bool alive[4], slow = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a[q] = fma(x, L[4 * j + q], Rm) + A[4 * j + q];
+                    e[q] = E[4 * j + q] + fm;
+                }
+                if (js == j) {  // warp-uniform: the snap point lies in this round
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = (snap_lane && es == q) ? asn : a[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) slow = element(a[q], e[q], hi[q], alive[q]) || slow;
+                if (slow) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        double h2;
+                        bool a2;
+                        if (element(a[q], e[q], h2, a2)) {
+                            hi[q] = lp_slow_element(a[q], e[q], 0.0, sentinel);
+                            alive[q] = hi[q] > sentinel;
+                        }
+                    }
+                }
+                uint32_t lo[4], hw[4], nib = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long yb = __double_as_longlong(fma(hi[q] - Z[4 * j + q], SCALE, MAGICB));
+                    lo[q] = (uint32_t)yb;
+                    hw[q] = (uint32_t)((unsigned long long)yb >> 32);
+                    nib |= alive[q] ? (1u << q) : 0u;
+                }
+                okmask |= nib << (4 * j);
+                // byte q of every plane word belongs to element q: 0xFF where it is alive (dead elements store zero digits)
+                const uint32_t am = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+                const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+                uint32_t word[Q_NV];
+                word[0] = (__byte_perm(t0, t1, 0x5410) ^ 0x80808080u) & am;
+                word[1] = (__byte_perm(t0, t1, 0x7632) ^ 0x80808080u) & am;
+                word[2] = (__byte_perm(t2, t3, 0x5410) ^ 0x80808080u) & am;
+                word[3] = (__byte_perm(t2, t3, 0x7632) ^ 0x80808080u) & am;
+                word[4] = (__byte_perm(__byte_perm(hw[0], hw[1], 0x0040), __byte_perm(hw[2], hw[3], 0x0040), 0x5410) ^ 0x80808080u) & am;
+                const int k0 = 4 * (lane + 32 * j);
+                uint16_t *dst0 = reinterpret_cast<uint16_t *>(sq + q_offset(min(k0, Q_MAX_K - 2)));
+                uint16_t *dst1 = reinterpret_cast<uint16_t *>(sq + q_offset(min(k0 + 2, Q_MAX_K - 2)));
+                if (k0 < K) {
+#pragma unroll
+                    for (int p = 0; p < Q_NV; ++p) dst0[(p * Q_PW) >> 1] = (uint16_t)(word[p] & 0xFFFFu);
+                }
+                if (k0 + 2 < K) {
+#pragma unroll
+                    for (int p = 0; p < Q_NV; ++p) dst1[(p * Q_PW) >> 1] = (uint16_t)(word[p] >> 16);
+                }
+            }
+            {  // the single point
+                constexpr int P = 4 * QR_MAIN;
+                double a = fma(x, L[P], Rm) + A[P];
+                const double e = E[P] + fm;
+                a = ks == kt ? asn : a;
+                double hi;
+                bool alive;
+                if (element(a, e, hi, alive)) {
+                    hi = lp_slow_element(a, e, 0.0, sentinel);
+                    alive = hi > sentinel;
+                }
+                const long long yb = __double_as_longlong(fma(hi - Z[P], SCALE, MAGICB));
+                const uint32_t am = alive ? 0xFFFFFFFFu : 0u;
+                const uint32_t lo = ((uint32_t)yb ^ 0x80808080u) & am, h8 = ((uint32_t)((unsigned long long)yb >> 32) ^ 0x80u) & 0xFFu & am;
+                okmask |= alive ? (1u << P) : 0u;
+                if (kt < K) {
+                    sq[offt] = (uint8_t)lo;
+                    sq[offt + Q_PW] = (uint8_t)(lo >> 8);
+                    sq[offt + 2 * Q_PW] = (uint8_t)(lo >> 16);
+                    sq[offt + 3 * Q_PW] = (uint8_t)(lo >> 24);
+                    sq[offt + 4 * Q_PW] = (uint8_t)h8;
+                }
+            }
+            okmask &= vmask;
+            __syncwarp();
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(sq);
+                uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
+                for (int j = lane; j < ldq / 16; j += 32) dst[j] = src[j];
+            }
+            // count, first and last of the grid points that are not "log 0"; a lane's points ascend with the bit number
+            int kmin = 0x7fffffff, kmax = -1;
+            if (okmask) {
+                const int b0 = __ffs(okmask) - 1, b1 = 31 - __clz(okmask);
+                kmin = b0 < 4 * QR_MAIN ? 4 * (lane + 32 * (b0 >> 2)) + (b0 & 3) : kt;
+                kmax = b1 < 4 * QR_MAIN ? 4 * (lane + 32 * (b1 >> 2)) + (b1 & 3) : kt;
+            }
+            const int n_ok = __reduce_add_sync(0xffffffffu, __popc(okmask));
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            if (lane == 0)
+                row_range[row] = (n_ok > 0 && kmax - kmin + 1 == n_ok) ? ((uint32_t)kmin | ((uint32_t)kmax << 16))
+                                                                        : Q_RANGE_IRREGULAR;
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_cell_prep(const double *models, int ld_models, int n_cells, const double *mag, int K,
@@ -790,7 +1062,15 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
     if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         if (!row_snap) return cudaErrorInvalidValue;
-        auto launch = [&](auto kernel, int rpw) -> cudaError_t {
+        if (which == 2 && qtable && !write_f64 && !row_mode && zero_row && based && prep.ld >= K && !getenv("SCDE_B200_LP_OLD")) {
+            // fixed-point rows only: the register-resident kernel; one contiguous run of rows per warp
+            const size_t smem = (size_t)QR_WARPS * 4 * Q_PIECE;
+            lp_rows_q_kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(
+                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, row_snap, prep, K, sentinel,
+                table, ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
+            return cudaGetLastError();
+        }
+        auto launch =[&](auto kernel, int rpw) -> cudaError_t {
             const size_t smem = (size_t)ROW_WARPS * rpw * (sizeof(double) * KP_TILED + 4 * Q_PIECE);
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

@@ -130,3 +130,27 @@ def test_multiplicity_above_127_falls_back_to_fp64(ctx):
         finally:
             ctx.set_contract_kernel(0)
     assert np.array_equal(res[0], res[2])
+
+
+@pytest.mark.parametrize("length_out", [400, 200, 407])
+def test_register_resident_row_kernel_equals_per_element_kernel(ctx, monkeypatch, length_out):
+    """lp_rows_q_kernel (cell vectors in registers, 13 grid points per lane) against lp_rows_fast_kernel (the same rows
+    built with per-element loads; SCDE_B200_LP_OLD=1): the fixed-point tables may differ by one unit of 2^-29 where a
+    value sits on a rounding boundary (the row sum is associated differently), so the joint posteriors agree to 1e-7;
+    counts up to 60000 exercise the snap point on every part of the grid, the sentinel ranges and the slow band; grids
+    of 201 and 408 points exercise the lanes without a point of their own and the largest grid of the fixed-point form."""
+    w = synth.make_workload(3, n_genes=120, n_cells=40, seed=11)
+    prior = synth.make_prior(120, length_out=length_out)
+    counts = np.array(w.counts, copy=True)
+    rng = np.random.default_rng(5)
+    counts[:30] = rng.integers(0, 60000, size=counts[:30].shape)
+    counts[30:50] = rng.integers(0, 40, size=counts[30:50].shape)
+    res = {}
+    for old in ("1", None):
+        if old:
+            monkeypatch.setenv("SCDE_B200_LP_OLD", old)
+        else:
+            monkeypatch.delenv("SCDE_B200_LP_OLD", raising=False)
+        res[old] = api.scde_posteriors(w.models, counts, prior, n_randomizations=50, context=ctx).to_numpy()
+    assert _err(res[None], res["1"]) < 1e-7
+    assert np.array_equal(res[None] == 0.0, res["1"] == 0.0)

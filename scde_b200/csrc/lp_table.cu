@@ -15,6 +15,7 @@
 // theta is constant.  FP64 throughout.
 #include "common.cuh"
 #include "fastmath.cuh"
+#include "ptx_sm100.cuh"
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -386,8 +387,8 @@ lp_rows_kernel(const double *__restrict__ models, int ldm, CellRange cr, const i
 // 32 times more instruction issues): R(x, s), the "snap" pair log p / log q at mu~ = x, and the Poisson term.
 __device__ __forceinline__ void row_const_one(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_cell,
                                               const int32_t *__restrict__ row_x, double4 *__restrict__ rowc,
-                                              int32_t *__restrict__ row_snap, const double *__restrict__ mu_all, int ld_mu, int K,
-                                              int64_t row) {
+                                              int32_t *__restrict__ row_snap, const double *__restrict__ mu_all,
+                                              const double *__restrict__ lcfpr_all, int ld_mu, int K, int64_t row) {
     const int c = row_cell[row];
     const double x = (double)row_x[row];
     const double s = models[(size_t)5 * ldm + c];
@@ -401,7 +402,6 @@ __device__ __forceinline__ void row_const_one(const double *__restrict__ models,
         l1s = -log1p(x / s);  // "snap": mu~ = x
         l2s = -log1p(s / x);
     }
-    rowc[row] = make_double4(R, l1s, l2s, d_dpois_log(x, lambda));
     // The snap rule (:173,182) replaces mu_k by x at the one grid point with mu_k < x < mu_{k+1} (or x > mu_{K-1} at the
     // last one).  mu_k = exp(corr.a m_k + corr.b) is non-decreasing along the grid (corr.a > 0), so that point is the last k
     // with mu_k < x: a binary search per row instead of two compares per table element.
@@ -417,15 +417,18 @@ __device__ __forceinline__ void row_const_one(const double *__restrict__ models,
         else if (lo >= 0 && x < mu[lo + 1]) ks = lo;
     }
     row_snap[row] = ks;
+    // (R, NB term at the snap point, the same + log(1 - d) at the snap grid point, Poisson term)
+    const double snapv = fma(x, l2s, fma(s, l1s, R));
+    rowc[row] = make_double4(R, snapv, ks >= 0 ? snapv + lcfpr_all[(size_t)c * ld_mu + ks] : -INFINITY, d_dpois_log(x, lambda));
 }
 __global__ void row_const_kernel(const double *__restrict__ models, int ldm, const int32_t *__restrict__ row_off,
                                  CellRange cr, const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                                  double4 *__restrict__ rowc, int32_t *__restrict__ row_snap, const double *__restrict__ mu_all,
-                                 int ld_mu, int K) {
+                                 const double *__restrict__ lcfpr_all, int ld_mu, int K) {
     const int64_t row_end = min((int64_t)row_off[cr.c1], cr.row_cap);
     for (int64_t row = (int64_t)row_off[cr.c0] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end;
          row += (int64_t)gridDim.x * blockDim.x)
-        row_const_one(models, ldm, row_cell, row_x, rowc, row_snap, mu_all, ld_mu, K, row);
+        row_const_one(models, ldm, row_cell, row_x, rowc, row_snap, mu_all, lcfpr_all, ld_mu, K, row);
 }
 
 // Fixed-point planes (contract_i8.cu) of four consecutive table values: value = 2^-Q_FRAC * sum_p 256^p d_p with signed
@@ -568,9 +571,8 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         const size_t base = (size_t)c * prep.ld;
         const double *l1 = prep.l1 + base, *l2 = prep.l2 + base;
         const double *lcfpr = prep.lcfpr + base, *lcfp = prep.lcfp + base;
-        const double R = cur.rc.x, l1s = cur.rc.y, l2s = cur.rc.z, fp = cur.rc.w;  // row constants from row_const_kernel
+        const double R = cur.rc.x, snapv = cur.rc.y, fp = cur.rc.w;  // row constants from row_const_kernel
         const int ks = cur.ks;  // the grid point where mu~ snaps to x (:173,182), or -1
-        const double snapv = fma(x, l2s, fma(s, l1s, R));
         // ---- sweep 1
         double vmax = -INFINITY;
         for (int k0 = 4 * l; k0 < K; k0 += 4 * LW) {
@@ -754,6 +756,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
 // Fixed point: y = v 2^29 + (1.5 2^52 + 0x8080808080) holds the biased digits of rint(v 2^29) in the low 40 bits of its
 // mantissa (|v| <= 753, so 0 <= rint(v 2^29) + 0x8080808080 < 2^40); flipping the top bit of every byte gives the signed
 // radix-256 digits.
+using namespace ptx;
 constexpr int QR_WARPS = 4;
 constexpr int QR_MAIN = 3;  // quads per lane
 
@@ -771,15 +774,31 @@ __device__ __forceinline__ double warp_max_redux(double v) {
     return __longlong_as_double((long long)(((unsigned long long)rh << 32) | rl));
 }
 
-__global__ void __launch_bounds__(QR_WARPS * 32, 3)
+// row headers of one batch of 32 rows, staged by cp.async (two batches per warp)
+struct QrHeaders {
+    double4 rc[32];  // (R, -, value at the snap point, Poisson term)
+    int32_t c[32], x[32], ks[32], pad[32];
+};
+// E = log d and Z = lp(0) of the lane's points are read once per element: they live in shared memory, [2 j + half][lane]
+// as 16-byte pairs (every lane reads back what it wrote; consecutive lanes are consecutive: no bank conflicts), the
+// single point in [2 QR_MAIN][lane].x
+struct QrCell {
+    double2 E[2 * QR_MAIN + 1][32], Z[2 * QR_MAIN + 1][32];
+};
+constexpr int QR_SMEM_WARP = 4 * Q_PIECE + 2 * (int)sizeof(QrHeaders) + (int)sizeof(QrCell);
+
+template <bool FULL, int MINB>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
+__global__ void __launch_bounds__(QR_WARPS * 32, MINB)
 lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                  const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
                  double sentinel, const double *__restrict__ table, int ld_table, const int32_t *__restrict__ zero_row,
                  const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][4 * Q_PIECE]
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][QR_SMEM_WARP]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *sq = s_dyn + warp * (4 * Q_PIECE);
+    uint8_t *sq = s_dyn + warp * QR_SMEM_WARP;
+    QrHeaders *hdr = reinterpret_cast<QrHeaders *>(sq + 4 * Q_PIECE);
+    QrCell *cell = reinterpret_cast<QrCell *>(sq + 4 * Q_PIECE + 2 * sizeof(QrHeaders));
     for (int j = lane; j < (4 * Q_PIECE) / 16; j += 32) reinterpret_cast<uint4 *>(sq)[j] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
     const int64_t row0 = (int64_t)row_off[cr.c0];
@@ -790,89 +809,101 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
     const int64_t r_begin = row0 + min(n_rows, gw * per_warp), r_end = row0 + min(n_rows, (gw + 1) * per_warp);
     if (r_begin >= r_end) return;
 
-    // this lane's grid points and where their digits go in the staged row
+    // this lane's grid points and where their digits go in the staged row (shared-memory byte addresses)
     const int kt = 4 * 32 * QR_MAIN + lane;  // the single point
+    const uint32_t sq_addr = smem_u32(sq);
+    uint32_t off[QR_MAIN][2];
     uint32_t vmask = 0u;  // bit 4 j + e: main point (j, e) exists; bit 12: the single point exists
 #pragma unroll
     for (int j = 0; j < QR_MAIN; ++j) {
         const int k0 = 4 * (lane + 32 * j);
+        off[j][0] = sq_addr + q_offset(min(k0, Q_MAX_K - 2));
+        off[j][1] = sq_addr + q_offset(min(k0 + 2, Q_MAX_K - 2));
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (k0 + e < K) vmask |= 1u << (4 * j + e);
     }
     if (kt < K) vmask |= 1u << (4 * QR_MAIN);
-    const int offt = q_offset(min(kt, Q_MAX_K - 1));
+    uint32_t offt = sq_addr + q_offset(min(kt, Q_MAX_K - 1));
+#pragma unroll
+    for (int j = 0; j < QR_MAIN; ++j) asm volatile("" : "+r"(off[j][0]), "+r"(off[j][1]));  // keep them in registers
+    asm volatile("" : "+r"(offt));
 
     // cell state
-    double A[4 * QR_MAIN + 1], L[4 * QR_MAIN + 1], E[4 * QR_MAIN + 1], Z[4 * QR_MAIN + 1];
+    double A[4 * QR_MAIN + 1], L[4 * QR_MAIN + 1];
+    const bool tail_ok = kt < K;
     int cur_c = -1;
     int64_t cur_zero = -1;
-    double theta = 0.0, maxcfp = 0.0;
+    double maxcfp = 0.0;
     const double DEAD_FILL = -1.0e300;  // points beyond the grid: far below every threshold, never the maximum
 
-    struct Header {
-        int c, xi, ks;
-        double R, fp, asnap;
-    };
-    auto load_header = [&](int64_t base) {
-        Header h;
+    auto fetch_headers = [&](int64_t base, int slot) {  // one row per lane
         int64_t row = base + lane;
         if (row >= r_end) row = r_end - 1;
-        h.c = row_cell[row];
-        h.xi = row_x[row];
-        h.ks = row_snap[row];
-        const double4 rc = rowc[row];
-        h.R = rc.x;
-        h.fp = rc.w;
-        h.asnap = -INFINITY;
-        if (h.ks >= 0) {
-            const double s = models[(size_t)5 * ldm + h.c];
-            h.asnap = fma((double)h.xi, rc.z, fma(s, rc.y, rc.x)) + prep.lcfpr[(size_t)h.c * prep.ld + h.ks];
-        }
-        return h;
+        QrHeaders *h = hdr + slot;
+        cp_async16(smem_u32(&h->rc[lane]), &rowc[row]);
+        cp_async16(smem_u32(&h->rc[lane]) + 16, reinterpret_cast<const char *>(&rowc[row]) + 16);
+        cp_async4(smem_u32(&h->c[lane]), &row_cell[row]);
+        cp_async4(smem_u32(&h->x[lane]), &row_x[row]);
+        cp_async4(smem_u32(&h->ks[lane]), &row_snap[row]);
+        cp_async_commit();
     };
 
     const double SCALE = (double)(1ll << Q_FRAC);
     const double MAGICB = 6755399441055744.0 + 551911719040.0;  // 1.5 2^52 + 0x8080808080
-    Header nxt = load_header(r_begin);
-    for (int64_t base = r_begin; base < r_end; base += 32) {
-        const Header cur = nxt;
-        if (base + 32 < r_end) nxt = load_header(base + 32);
+    constexpr uint32_t H_DEAD = 0xC0875000u, H_LOW = 0xC0862000u, H_BAND = 0x4042C000u;  // high words of -746, -708, 37.5
+    fetch_headers(r_begin, 0);
+    int slot = 0;
+    for (int64_t base = r_begin; base < r_end; base += 32, slot ^= 1) {
+        if (base + 32 < r_end) {
+            fetch_headers(base + 32, slot ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const QrHeaders *h = hdr + slot;
         const int nb = (int)min((int64_t)32, r_end - base);
         for (int i = 0; i < nb; ++i) {
             const int64_t row = base + i;
-            const int c = __shfl_sync(0xffffffffu, cur.c, i);
+            const int c = h->c[i];
             if (c != cur_c) {  // next cell: reload the grid vectors of this lane's points
                 cur_c = c;
-                theta = models[(size_t)5 * ldm + c];
+                const double theta = models[(size_t)5 * ldm + c];
                 maxcfp = prep.maxcfp[c];
                 const int zr = zero_row[c];
                 cur_zero = zr;
                 const bool bs = zr >= 0 && based[c] != 0;
                 const size_t pb = (size_t)c * prep.ld;
                 const double *zrow = table + (size_t)(zr >= 0 ? zr : 0) * ld_table;
+                double Ev[4 * QR_MAIN + 2], Zv[4 * QR_MAIN + 2];
+                Ev[4 * QR_MAIN + 1] = Zv[4 * QR_MAIN + 1] = 0.0;
 #pragma unroll
                 for (int p = 0; p < 4 * QR_MAIN + 1; ++p) {
                     const int k = p < 4 * QR_MAIN ? 4 * (lane + 32 * (p >> 2)) + (p & 3) : kt;
                     if (k < K) {
                         A[p] = fma(theta, prep.l1[pb + k], prep.lcfpr[pb + k]);
                         L[p] = prep.l2[pb + k];
-                        E[p] = prep.lcfp[pb + k];
-                        Z[p] = bs ? zrow[k] : 0.0;
+                        Ev[p] = prep.lcfp[pb + k];
+                        Zv[p] = bs ? zrow[k] : 0.0;
                     } else {
                         A[p] = DEAD_FILL;
                         L[p] = 0.0;
-                        E[p] = DEAD_FILL;
-                        Z[p] = 0.0;
+                        Ev[p] = DEAD_FILL;
+                        Zv[p] = 0.0;
                     }
+                }
+#pragma unroll
+                for (int t = 0; t < 2 * QR_MAIN + 1; ++t) {
+                    cell->E[t][lane] = make_double2(Ev[2 * t], Ev[2 * t + 1]);
+                    cell->Z[t][lane] = make_double2(Zv[2 * t], Zv[2 * t + 1]);
                 }
             }
             if (row == cur_zero) continue;  // the zero-count row is an FP64 row (lp_rows_fast_kernel, which == 1)
-            const double x = (double)__shfl_sync(0xffffffffu, cur.xi, i);
-            const int ks = __shfl_sync(0xffffffffu, cur.ks, i);
-            const double R = __shfl_sync(0xffffffffu, cur.R, i);
-            const double fp = __shfl_sync(0xffffffffu, cur.fp, i);
-            const double asnap = __shfl_sync(0xffffffffu, cur.asnap, i);
+            const double x = (double)h->x[i];
+            const int ks = h->ks[i];
+            const double4 rc = h->rc[i];
+            const double R = rc.x, asnap = rc.z, fp = rc.w;
             // ---- sweep 1: the row maximum.  The snapped value (mu~ = x maximises the NB term) replaces a_ks and is not
             // below it, so max(regular values, snapped value) is the maximum of the row as the reference builds it.
             double vmax = asnap;
@@ -894,54 +925,64 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
             const int qs = ks >> 2;  // (-1 -> -1: no quad)
             const int js = qs >> 5, es = ks & 3;
             const bool snap_lane = lane == (qs & 31);
-            constexpr uint32_t H_DEAD = 0xC0875000u, H_LOW = 0xC0862000u, H_BAND = 0x4042C000u;  // -746, -708, 37.5
-            auto element = [&](double a, double e, double &hi, bool &alive) -> bool {  // true: needs the slow path
-                const double d = a - e;
-                const uint32_t hd = (uint32_t)__double2hiint(d);
-                hi = (int32_t)hd >= 0 ? a : e;  // d >= 0 (for d == -0 the two are equal)
-                const uint32_t hh = (uint32_t)__double2hiint(hi);
-                const bool dead = hh > H_DEAD;
-                const bool easy = hh < H_LOW && (hd & 0x7fffffffu) > H_BAND;
-                alive = !dead;
-                return !(dead || easy);
-            };
 #pragma unroll
             for (int j = 0; j < QR_MAIN; ++j) {
-                double a[4], e[4], hi[4];
-                bool alive[4], slow = false;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    a[q] = fma(x, L[4 * j + q], Rm) + A[4 * j + q];
-                    e[q] = E[4 * j + q] + fm;
+                double a[4], e[4], hi[4], z[4];
+                {
+                    const double2 e0 = cell->E[2 * j][lane], e1 = cell->E[2 * j + 1][lane];
+                    const double2 z0 = cell->Z[2 * j][lane], z1 = cell->Z[2 * j + 1][lane];
+                    e[0] = e0.x + fm, e[1] = e0.y + fm, e[2] = e1.x + fm, e[3] = e1.y + fm;
+                    z[0] = z0.x, z[1] = z0.y, z[2] = z1.x, z[3] = z1.y;
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = fma(x, L[4 * j + q], Rm) + A[4 * j + q];
                 if (js == j) {  // warp-uniform: the snap point lies in this round
 #pragma unroll
                     for (int q = 0; q < 4; ++q) a[q] = (snap_lane && es == q) ? asn : a[q];
                 }
+                // alive bits per element; the slow band is looked for per quad first (all four "easy": nothing to do),
+                // per element only inside the branch
+                uint32_t alive = 0u, hh_max = 0u, band_min = 0xffffffffu;
+                double d[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) slow = element(a[q], e[q], hi[q], alive[q]) || slow;
-                if (slow) {
+                for (int q = 0; q < 4; ++q) {
+                    d[q] = a[q] - e[q];
+                    const uint32_t hd = (uint32_t)__double2hiint(d[q]);
+                    hi[q] = (int32_t)hd >= 0 ? a[q] : e[q];  // a >= e (for a - e == -0 the two are equal)
+                    const uint32_t hh = (uint32_t)__double2hiint(hi[q]);
+                    alive |= hh <= H_DEAD ? (1u << q) : 0u;
+                    hh_max = max(hh_max, hh);
+                    band_min = min(band_min, hd & 0x7fffffffu);
+                }
+                if (alive != 0u && !(hh_max < H_LOW && band_min > H_BAND)) {
+                    if (hh_max < H_LOW) {
+                        // cross-over band only, no exponential underflows: log(exp(a) + exp(e)) = hi + log1p(exp(-|d|)) to
+                        // 1e-13 (for the quad's elements outside the band the correction is below their last bit)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        double h2;
-                        bool a2;
-                        if (element(a[q], e[q], h2, a2)) {
-                            hi[q] = lp_slow_element(a[q], e[q], 0.0, sentinel);
-                            alive[q] = hi[q] > sentinel;
+                        for (int q = 0; q < 4; ++q)
+                            hi[q] += log1p_unit(exp_nonpos<false>(fmax(-fabs(d[q]), -50.0)));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t hh = (uint32_t)__double2hiint(hi[q]);
+                            const uint32_t hd = (uint32_t)__double2hiint(d[q]);
+                            if (hh <= H_DEAD && !(hh < H_LOW && (hd & 0x7fffffffu) > H_BAND)) {
+                                hi[q] = lp_slow_element(a[q], e[q], 0.0, sentinel);
+                                if (!(hi[q] > sentinel)) alive &= ~(1u << q);
+                            }
                         }
                     }
                 }
-                uint32_t lo[4], hw[4], nib = 0u;
+                okmask |= alive << (4 * j);
+                uint32_t lo[4], hw[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const long long yb = __double_as_longlong(fma(hi[q] - Z[4 * j + q], SCALE, MAGICB));
+                    const long long yb = __double_as_longlong(fma(hi[q] - z[q], SCALE, MAGICB));
                     lo[q] = (uint32_t)yb;
                     hw[q] = (uint32_t)((unsigned long long)yb >> 32);
-                    nib |= alive[q] ? (1u << q) : 0u;
                 }
-                okmask |= nib << (4 * j);
                 // byte q of every plane word belongs to element q: 0xFF where it is alive (dead elements store zero digits)
-                const uint32_t am = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t am = ((alive * 0x00204081u) & 0x01010101u) * 0xFFu;
                 const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
                 const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
                 uint32_t word[Q_NV];
@@ -951,54 +992,61 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                 word[3] = (__byte_perm(t2, t3, 0x7632) ^ 0x80808080u) & am;
                 word[4] = (__byte_perm(__byte_perm(hw[0], hw[1], 0x0040), __byte_perm(hw[2], hw[3], 0x0040), 0x5410) ^ 0x80808080u) & am;
                 const int k0 = 4 * (lane + 32 * j);
-                uint16_t *dst0 = reinterpret_cast<uint16_t *>(sq + q_offset(min(k0, Q_MAX_K - 2)));
-                uint16_t *dst1 = reinterpret_cast<uint16_t *>(sq + q_offset(min(k0 + 2, Q_MAX_K - 2)));
-                if (k0 < K) {
+                if (FULL || k0 < K) {
 #pragma unroll
-                    for (int p = 0; p < Q_NV; ++p) dst0[(p * Q_PW) >> 1] = (uint16_t)(word[p] & 0xFFFFu);
+                    for (int p = 0; p < Q_NV; ++p) st_shared_u16(off[j][0] + p * Q_PW, word[p]);
                 }
-                if (k0 + 2 < K) {
+                if (FULL || k0 + 2 < K) {
 #pragma unroll
-                    for (int p = 0; p < Q_NV; ++p) dst1[(p * Q_PW) >> 1] = (uint16_t)(word[p] >> 16);
+                    for (int p = 0; p < Q_NV; ++p) st_shared_u16(off[j][1] + p * Q_PW, word[p] >> 16);
                 }
             }
             {  // the single point
                 constexpr int P = 4 * QR_MAIN;
                 double a = fma(x, L[P], Rm) + A[P];
-                const double e = E[P] + fm;
+                const double e = cell->E[2 * QR_MAIN][lane].x + fm;
                 a = ks == kt ? asn : a;
-                double hi;
-                bool alive;
-                if (element(a, e, hi, alive)) {
+                const uint32_t hd = (uint32_t)__double2hiint(a - e);
+                double hi = (int32_t)hd >= 0 ? a : e;
+                const uint32_t hh = (uint32_t)__double2hiint(hi);
+                bool live = hh <= H_DEAD;
+                if (live && !(hh < H_LOW && (hd & 0x7fffffffu) > H_BAND)) {
                     hi = lp_slow_element(a, e, 0.0, sentinel);
-                    alive = hi > sentinel;
+                    live = hi > sentinel;
                 }
-                const long long yb = __double_as_longlong(fma(hi - Z[P], SCALE, MAGICB));
-                const uint32_t am = alive ? 0xFFFFFFFFu : 0u;
-                const uint32_t lo = ((uint32_t)yb ^ 0x80808080u) & am, h8 = ((uint32_t)((unsigned long long)yb >> 32) ^ 0x80u) & 0xFFu & am;
-                okmask |= alive ? (1u << P) : 0u;
-                if (kt < K) {
-                    sq[offt] = (uint8_t)lo;
-                    sq[offt + Q_PW] = (uint8_t)(lo >> 8);
-                    sq[offt + 2 * Q_PW] = (uint8_t)(lo >> 16);
-                    sq[offt + 3 * Q_PW] = (uint8_t)(lo >> 24);
-                    sq[offt + 4 * Q_PW] = (uint8_t)h8;
+                const long long yb = __double_as_longlong(fma(hi - cell->Z[2 * QR_MAIN][lane].x, SCALE, MAGICB));
+                const uint32_t am = live ? 0xFFFFFFFFu : 0u;
+                const uint32_t lo = ((uint32_t)yb ^ 0x80808080u) & am, h8 = ((uint32_t)((unsigned long long)yb >> 32) ^ 0x80u) & am;
+                okmask |= live ? (1u << P) : 0u;
+                if (tail_ok) {
+                    st_shared_u8(offt, lo);
+                    st_shared_u8(offt + Q_PW, lo >> 8);
+                    st_shared_u8(offt + 2 * Q_PW, lo >> 16);
+                    st_shared_u8(offt + 3 * Q_PW, lo >> 24);
+                    st_shared_u8(offt + 4 * Q_PW, h8);
                 }
             }
             okmask &= vmask;
             __syncwarp();
             {
-                const uint4 *src = reinterpret_cast<const uint4 *>(sq);
-                uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq);
-                for (int j = lane; j < ldq / 16; j += 32) dst[j] = src[j];
+                const uint4 *src = reinterpret_cast<const uint4 *>(sq) + lane;
+                uint4 *dst = reinterpret_cast<uint4 *>(qtable + (size_t)row * ldq) + lane;
+                if (FULL) {  // four pieces: 2048 bytes
+                    const uint4 v0 = src[0], v1 = src[32], v2 = src[64], v3 = src[96];
+                    dst[0] = v0, dst[32] = v1, dst[64] = v2, dst[96] = v3;
+                } else {
+                    for (int j = 0; j < ldq / 16 - lane; j += 32) dst[j] = src[j];
+                }
             }
-            // count, first and last of the grid points that are not "log 0"; a lane's points ascend with the bit number
-            int kmin = 0x7fffffff, kmax = -1;
-            if (okmask) {
-                const int b0 = __ffs(okmask) - 1, b1 = 31 - __clz(okmask);
-                kmin = b0 < 4 * QR_MAIN ? 4 * (lane + 32 * (b0 >> 2)) + (b0 & 3) : kt;
-                kmax = b1 < 4 * QR_MAIN ? 4 * (lane + 32 * (b1 >> 2)) + (b1 & 3) : kt;
-            }
+            // count, first and last of the grid points that are not "log 0"; a lane's points ascend with the bit number:
+            // bit b < 12 is grid point 4 lane + 128 (b >> 2) + (b & 3) = (4 lane - 96 (b >> 2)) + 32 b... written as
+            // lane4 + 32 (b & 12) + (b & 3); bit 12 is 384 + lane
+            const int lane4 = 4 * lane;
+            const int b0 = __ffs(okmask) - 1, b1 = 31 - __clz(okmask);
+            int kmin = b0 < 4 * QR_MAIN ? lane4 + 32 * (b0 & 12) + (b0 & 3) : kt;
+            int kmax = b1 < 4 * QR_MAIN ? lane4 + 32 * (b1 & 12) + (b1 & 3) : kt;
+            kmin = okmask ? kmin : 0x7fffffff;
+            kmax = okmask ? kmax : -1;
             const int n_ok = __reduce_add_sync(0xffffffffu, __popc(okmask));
             kmin = __reduce_min_sync(0xffffffffu, kmin);
             kmax = __reduce_max_sync(0xffffffffu, kmax);
@@ -1007,6 +1055,7 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                                                                         : Q_RANGE_IRREGULAR;
             __syncwarp();
         }
+        __syncwarp();  // the headers of this slot are overwritten by the next iteration's fetch
     }
 }
 
@@ -1031,7 +1080,7 @@ cudaError_t launch_row_consts(const double *models, int ld_models, const int32_t
     if (cr.c1 <= cr.c0) return cudaSuccess;
     const int blocks = min(148 * 16, 4 * (cr.c1 - cr.c0) + 1);  // grid-stride: the row count is only known on the device
     row_const_kernel<<<blocks, 256, 0, st>>>(models, ld_models, row_off, cr, row_cell, row_x, (double4 *)row_const, row_snap,
-                                             prep.mu, prep.ld, K);
+                                             prep.mu, prep.lcfpr, prep.ld, K);
     return cudaGetLastError();
 }
 
@@ -1064,11 +1113,18 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
         if (!row_snap) return cudaErrorInvalidValue;
         if (which == 2 && qtable && !write_f64 && !row_mode && zero_row && based && prep.ld >= K && !getenv("SCDE_B200_LP_OLD")) {
             // fixed-point rows only: the register-resident kernel; one contiguous run of rows per warp
-            const size_t smem = (size_t)QR_WARPS * 4 * Q_PIECE;
-            lp_rows_q_kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(
-                models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, row_snap, prep, K, sentinel,
-                table, ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
-            return cudaGetLastError();
+            const size_t smem = (size_t)QR_WARPS * QR_SMEM_WARP;
+            const int minb = getenv("SCDE_B200_LP_MINB") ? atoi(getenv("SCDE_B200_LP_MINB")) : 3;
+            auto launch_q = [&](auto kernel) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                kernel<<<148 * minb, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
+                                                             (const double4 *)row_const, row_snap, prep, K, sentinel, table,
+                                                             ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
+                return cudaGetLastError();
+            };
+            if (K < 4 * 32 * QR_MAIN) return launch_q(lp_rows_q_kernel<false, 3>);
+            return minb == 4 ? launch_q(lp_rows_q_kernel<true, 4>) : launch_q(lp_rows_q_kernel<true, 3>);
         }
         auto launch =[&](auto kernel, int rpw) -> cudaError_t {
             const size_t smem = (size_t)ROW_WARPS * rpw * (sizeof(double) * KP_TILED + 4 * Q_PIECE);

@@ -32,6 +32,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+// 4-byte copies (through L1) and group completion, for small staged headers (lp_table.cu)
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v & 0xFFu) : "memory");
+}
 // the barrier receives one arrival once every cp.async this thread has issued so far has landed; .noinc: the arrival is
 // part of the barrier's expected count (initialise the barrier with the number of threads that call this per phase)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {

@@ -305,6 +305,8 @@ def main():
             o.adjusted_idx, o.adjusted_z = _lib.p_i32(out["adjusted_idx"]), _lib.p_f64(out["adjusted_z"])
         st = _lib.Stats()
         _lib.check(_lib.lib().scde_b200_expression_difference(ctx.handle, Cc.byref(a), Cc.byref(o), Cc.byref(st)))
+        if os.environ.get("SCDE_B200_TRACE"):
+            sys.stderr.write(f"[bench] one-shot call stage ms: {st.as_dict()['ms']}\n")
         return gather_and_correct(out)
 
     e2e_step()

@@ -1188,12 +1188,18 @@ int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff
     return SCDE_B200_OK;
 }
 
-constexpr int N_COUNT_CHUNKS = 8;
+constexpr int N_COUNT_CHUNKS_DEFAULT = 8;
+static int n_count_chunks() {
+    const char *e = getenv("SCDE_B200_CHUNKS");
+    const int n = e ? atoi(e) : N_COUNT_CHUNKS_DEFAULT;
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
+}
 
 // Queue the H2D of the shard's count matrix on the copy stream in N_COUNT_CHUNKS cell ranges, one event per range, so
 // the 22 ms of PCIe time at config 4 run under the front kernels.
 int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host) {
     const int G = j->G, C = j->C;
+    const int N_COUNT_CHUNKS = n_count_chunks();
     if (!ctx->copy_stream) SCDE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->copy_events.size() < N_COUNT_CHUNKS + 1) {
         cudaEvent_t e;
@@ -1385,7 +1391,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
     TablePlan pl = plan_table(t, j->local_theta);
     // the copies are already in flight (start_count_copies); every path below waits for them on the compute stream
     const int chunk = j->copy_chunk_cells;
-    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * N_COUNT_CHUNKS && !getenv("SCDE_B200_NO_PIPELINE");
+    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * j->copy_chunks && !getenv("SCDE_B200_NO_PIPELINE");
     if (!pipelined) {
         for (int i = 0; i < j->copy_chunks; ++i) SCDE_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
         return SCDE_B200_OK;
@@ -1409,6 +1415,10 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
         cudaError_t _e = (x);                                                       \
         if (_e != cudaSuccess) return drain(cuda_fail(_e, #x, __FILE__, __LINE__));  \
     } while (0)
+    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;
+    const auto tf0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count(); };
+    double tr_first = 0, tr_queued = 0, tr_draws = 0, tr_front = 0, tr_copy = 0;
     FCUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
     int e0 = tm.begin(st);
     FTRY(prepare_cells(ctx, t, pl, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit));
@@ -1427,6 +1437,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
             int32_t rows0 = 0;
             FCUDA(cudaMemcpyAsync(&rows0, t.row_off.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             FCUDA(cudaStreamSynchronize(st));
+            tr_first = since();
             cap = (int64_t)((double)rows0 * C / n * 1.25) + 4096;
             const int64_t have = (int64_t)(t.q.cap / (size_t)q_row_bytes(t.K));  // a workspace from an earlier call
             if (have > cap) cap = have;
@@ -1442,16 +1453,26 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
         FTRY(launch_table_rows(ctx, t, pl, CellRange{c0, c0 + n, cap}, j->models.p, C, j->local_theta, &nl));
         tm.end(SCDE_B200_T_LPTABLE, e0, st, nl);
     }
+    tr_queued = since();
+    if (trace) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        tr_copy = since();
+    }
     if (j->deferred_args) {  // the bootstrap draws: host RNG work while the kernels queued above run
         const scde_b200_diff_args *da = j->deferred_args;
         j->deferred_args = nullptr;
         FTRY(upload_draws(ctx, j, da));
     }
+    tr_draws = since();
     int32_t total = 0, err = 0;
     FCUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FCUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FCUDA(cudaStreamSynchronize(st));
     FCUDA(cudaStreamSynchronize(ctx->copy_stream));
+    tr_front = since();
+    if (trace)
+        fprintf(stderr, "[scde_b200] front: first chunk counted %.2f ms, all chunks queued %.2f, copies done %.2f, draws uploaded (incl. wait) %.2f, front done %.2f\n",
+                tr_first, tr_queued, tr_copy, tr_draws, tr_front);
 #undef FTRY
 #undef FCUDA
     if (err & 1) {

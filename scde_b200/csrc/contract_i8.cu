@@ -553,6 +553,89 @@ softmax_i8_kernel(const long long *__restrict__ T, const double *__restrict__ Z,
     }
 }
 
+// softmax_i8_warp_kernel: the same result with a warp per gene instead of a warp per boot.  A CTA still owns one group
+// of 13 boots, whose Z rows it keeps in shared memory (43 KB); each of its warps walks genes on its own and, for a gene,
+// the 13 boots in ascending order: T row (the next boot's row is already in flight), soft-max pieces by shuffles, and the
+// normalised row is added to 13 accumulators per lane -- the same additions in the same order as the shared-memory
+// column sums of softmax_i8_kernel, without the two CTA barriers per gene, the 13 x 416 shared-memory stores and loads,
+// and with the skipped stretches (a joint posterior is sharply peaked) skipped in the accumulation too.
+constexpr int SW_WARPS = 8;
+__global__ void __launch_bounds__(SW_WARPS * 32, 2)
+softmax_i8_warp_kernel(const long long *__restrict__ T, const double *__restrict__ Z, const uint32_t *__restrict__ SR, int K,
+                       int n_boot_pass, double scale, double *__restrict__ part, int n_pos) {
+    constexpr int NJ = KP_TILED / 32;
+    extern __shared__ double s_z[];  // [SP_ROWS][KP_TILED]
+    const int group = blockIdx.x % SP_GROUPS, batch = blockIdx.x / SP_GROUPS, n_batch = gridDim.x / SP_GROUPS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = group * SP_ROWS;
+    const int nb = min(SP_ROWS, n_boot_pass - b0);  // boots of this group (<= 0: none)
+    for (int i = threadIdx.x; i < SP_ROWS * KP_TILED; i += SW_WARPS * 32)
+        s_z[i] = (Z && i / KP_TILED < nb) ? Z[(int64_t)b0 * KP_TILED + i] : 0.0;
+    __syncthreads();
+    const double q = 1.0 / (double)(1ll << Q_FRAC);
+    for (int pos = batch * SW_WARPS + warp; pos < n_pos; pos += n_batch * SW_WARPS) {
+        double acc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = 0.0;
+        const long long *rows = T + ((int64_t)pos * WP_TILED + b0) * KP_TILED + lane;
+        // the group's 13 range words, one per lane
+        const uint32_t sr_l = (SR && lane < SP_ROWS) ? SR[(int64_t)pos * Q_WB + b0 + lane] : 0xFFFF0000u;
+        long long nxt[NJ];
+        if (nb > 0) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) nxt[j] = __ldcs(rows + 32 * j);
+        }
+        for (int bi = 0; bi < nb; ++bi) {
+            long long cur[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
+            if (bi + 1 < nb) {
+                const long long *r2 = rows + (int64_t)(bi + 1) * KP_TILED;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) nxt[j] = __ldcs(r2 + 32 * j);
+            }
+            const uint32_t sr = __shfl_sync(0xffffffffu, sr_l, bi);
+            const int klo = (int)(sr & 0xFFFFu), span = min((int)(sr >> 16), K - 1) - klo;  // admissible: klo .. klo + span
+            const double *zr = s_z + bi * KP_TILED + lane;
+            double v[NJ], m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int k = lane + 32 * j;
+                // some drawn row is "log 0" outside the range: the reference's T is a multiple of the sentinel there
+                const double t = fma((double)cur[j], q, zr[32 * j]);
+                v[j] = (unsigned)(k - klo) <= (unsigned)span && span >= 0 ? t : -INFINITY;
+                m = v[j] > m ? v[j] : m;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double mo = __shfl_xor_sync(0xffffffffu, m, o);
+                m = mo > m ? mo : m;
+            }
+            double sum = 0.0;
+            uint32_t amask = 0u;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const double d = v[j] - m;
+                v[j] = 0.0;
+                if (__any_sync(0xffffffffu, d > -746.0)) {
+                    v[j] = d > -INFINITY ? exp_nonpos(d) : 0.0;
+                    amask |= 1u << j;
+                }
+                sum += v[j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const double inv = 1.0 / (sum * scale);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                if (amask & (1u << j)) acc[j] = __dadd_rn(acc[j], __dmul_rn(v[j], inv));
+        }
+        double *dst = part + ((int64_t)group * n_pos + pos) * KP_TILED + lane;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dst[32 * j] = acc[j];
+    }
+}
+
 __global__ void softmax_i8_reduce_kernel(const double *__restrict__ part, const int32_t *__restrict__ order, int K, int n_pos,
                                          double *__restrict__ jp, int64_t ld_jp, int accumulate) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,10 +816,23 @@ cudaError_t launch_softmax_i8(const ContractI8Args &a, int g0, int n_pos, int pa
     int batches = n_sm * 4 / SP_GROUPS;  // four CTAs of 416 threads per SM
     if (batches > n_pos) batches = n_pos;
     if (batches < 1) batches = 1;
-    softmax_i8_kernel<<<batches * SP_GROUPS, SP_ROWS * 32, 0, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
-                                                                    a.row_range ? sr : nullptr, a.K, nb, a.scale, part_scratch,
-                                                                    n_pos);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (getenv("SCDE_B200_SOFTMAX_OLD")) {
+        softmax_i8_kernel<<<batches * SP_GROUPS, SP_ROWS * 32, 0, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
+                                                                        a.row_range ? sr : nullptr, a.K, nb, a.scale,
+                                                                        part_scratch, n_pos);
+    } else {
+        const size_t smem = sizeof(double) * SP_ROWS * KP_TILED;
+        e = cudaFuncSetAttribute(softmax_i8_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int wb = n_sm * 2 / SP_GROUPS;  // two CTAs of eight warps per SM
+        if (wb * SW_WARPS > n_pos) wb = (n_pos + SW_WARPS - 1) / SW_WARPS;
+        if (wb < 1) wb = 1;
+        softmax_i8_warp_kernel<<<wb * SP_GROUPS, SW_WARPS * 32, smem, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
+                                                                            a.row_range ? sr : nullptr, a.K, nb, a.scale,
+                                                                            part_scratch, n_pos);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t n = (int64_t)n_pos * KP_TILED;
     softmax_i8_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part_scratch, a.lists.order ? a.lists.order + g0 : nullptr,

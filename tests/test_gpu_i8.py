@@ -154,3 +154,19 @@ def test_register_resident_row_kernel_equals_per_element_kernel(ctx, monkeypatch
         res[old] = api.scde_posteriors(w.models, counts, prior, n_randomizations=50, context=ctx).to_numpy()
     assert _err(res[None], res["1"]) < 1e-7
     assert np.array_equal(res[None] == 0.0, res["1"] == 0.0)
+
+
+def test_warp_per_gene_softmax_is_bit_identical_to_warp_per_boot(ctx, monkeypatch):
+    """softmax_i8_warp_kernel adds the normalised boot rows in the same order with the same roundings as
+    softmax_i8_kernel (SCDE_B200_SOFTMAX_OLD=1); 137 randomizations = two passes of 104 boots with a ragged last group"""
+    w = synth.make_workload(3, n_genes=150, n_cells=48, seed=4)
+    counts = np.array(w.counts, copy=True)
+    counts[:20] = np.random.default_rng(2).integers(0, 30000, size=counts[:20].shape)
+    res = {}
+    for old in ("1", None):
+        if old:
+            monkeypatch.setenv("SCDE_B200_SOFTMAX_OLD", old)
+        else:
+            monkeypatch.delenv("SCDE_B200_SOFTMAX_OLD", raising=False)
+        res[old] = api.scde_posteriors(w.models, counts, w.prior, n_randomizations=137, context=ctx).to_numpy()
+    assert np.array_equal(res[None], res["1"])

@@ -23,7 +23,11 @@ namespace {
 constexpr int DEDUP_THREADS = 1024;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr int BM_WORDS = 2048;            // bitmap of the counts 0 .. 65535
-constexpr int BM_STRIDE = BM_WORDS + 8;   // words per cell in the global bitmap scratch; word BM_WORDS = "has a count >= 65536"
+constexpr int BM_STRIDE = BM_WORDS + 8;   // words per cell in the global bitmap scratch: the bitmap, then word BM_WORDS =
+                                          // "hash kernel needed", word BM_WORDS + 1 = number of distinct counts >= 65536,
+                                          // words BM_WORDS + 2 .. + 7 = those counts, ascending (at most OV_MAX)
+constexpr int OV_MAX = 6;                 // distinct counts >= 65536 a cell may have and stay with the bitmap kernels
+constexpr int OV_RAW = 32;                // occurrences collected in pass 1 before they are sorted and made unique
 constexpr int BM_CPB = 8;                 // cells per CTA = one 32-byte sector of ridx per gene
 constexpr int BM_THREADS = 512;
 
@@ -136,11 +140,14 @@ __global__ void __launch_bounds__(BM_THREADS)
 dedup_bitmap_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells,
                           uint32_t *__restrict__ bits, int32_t *__restrict__ n_unique, int32_t *err_flag) {
     extern __shared__ uint32_t s_bm[];  // [BM_CPB][BM_WORDS]
-    __shared__ int s_big[BM_CPB], s_cnt[BM_CPB];
+    __shared__ int s_big[BM_CPB], s_ovn[BM_CPB];
+    __shared__ uint32_t s_ov[BM_CPB][OV_RAW];
     const int c0 = blockIdx.x * BM_CPB;
     const int nc = min(BM_CPB, n_cells - c0);
     for (int i = threadIdx.x; i < BM_CPB * BM_WORDS; i += BM_THREADS) s_bm[i] = (i % BM_WORDS) == 0 ? 1u : 0u;  // count 0
-    if (threadIdx.x < BM_CPB) s_big[threadIdx.x] = s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < BM_CPB) s_big[threadIdx.x] = s_ovn[threadIdx.x] = 0;
+    // EMPTY is not a count: a slot that is claimed but not yet written never matches
+    for (int i = threadIdx.x; i < BM_CPB * OV_RAW; i += BM_THREADS) s_ov[i / OV_RAW][i % OV_RAW] = EMPTY;
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += BM_THREADS) {
         int32_t x[BM_CPB];
@@ -151,7 +158,15 @@ dedup_bitmap_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g
             if (x[j] < 0) {
                 atomicOr(err_flag, 1);
             } else if (x[j] >= 32 * BM_WORDS) {
-                s_big[j] = 1;
+                // a handful of counts per cell at most: collected (with repeats) in a short list, sorted below
+                const int n_seen = min(s_ovn[j], OV_RAW);
+                bool seen = false;
+                for (int i = 0; i < n_seen; ++i) seen = seen || s_ov[j][i] == (uint32_t)x[j];
+                if (!seen) {
+                    const int slot = atomicAdd(&s_ovn[j], 1);
+                    if (slot < OV_RAW) s_ov[j][slot] = (uint32_t)x[j];
+                    else s_big[j] = 1;
+                }
             } else {
                 uint32_t *w = s_bm + j * BM_WORDS + (x[j] >> 5);
                 const uint32_t b = 1u << (x[j] & 31);
@@ -172,8 +187,30 @@ dedup_bitmap_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
         if (lane == 0) {
+            // (a slot claimed by atomicAdd is written before the barrier above, so the list is complete here)
+            int n_ov = 0;
+            uint32_t ov[OV_RAW];
+            if (!s_big[j]) {
+                const int raw = min(s_ovn[j], OV_RAW);
+                for (int i = 0; i < raw; ++i) {  // insertion sort, repeats dropped
+                    const uint32_t v = s_ov[j][i];
+                    int p = n_ov;
+                    bool dup = false;
+                    for (int q = 0; q < n_ov; ++q) dup = dup || ov[q] == v;
+                    if (dup) continue;
+                    while (p > 0 && ov[p - 1] > v) {
+                        ov[p] = ov[p - 1];
+                        --p;
+                    }
+                    ov[p] = v;
+                    ++n_ov;
+                }
+                if (n_ov > OV_MAX) s_big[j] = 1;
+            }
             dst[BM_WORDS] = (uint32_t)s_big[j];
-            n_unique[c0 + j] = s_big[j] ? 0 : n;  // flagged cells are counted by the hash kernel
+            dst[BM_WORDS + 1] = s_big[j] ? 0u : (uint32_t)n_ov;
+            for (int i = 0; i < OV_MAX; ++i) dst[BM_WORDS + 2 + i] = (!s_big[j] && i < n_ov) ? ov[i] : 0u;
+            n_unique[c0 + j] = s_big[j] ? 0 : n + n_ov;  // flagged cells are counted by the hash kernel
         }
     }
 }
@@ -185,7 +222,8 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
     extern __shared__ uint32_t s_bm[];                                               // [BM_CPB][BM_WORDS]
     uint16_t *s_pre = reinterpret_cast<uint16_t *>(s_bm + BM_CPB * BM_WORDS);        // [BM_CPB][BM_WORDS] ranks of the words
     __shared__ int s_part[BM_CPB][BM_THREADS / BM_CPB];
-    __shared__ int s_base[BM_CPB], s_big[BM_CPB];
+    __shared__ int s_base[BM_CPB], s_big[BM_CPB], s_ovn[BM_CPB], s_tot[BM_CPB];
+    __shared__ uint32_t s_ov[BM_CPB][OV_MAX];
     const int c0 = blockIdx.x * BM_CPB;
     const int nc = min(BM_CPB, n_cells - c0);
     for (int i = threadIdx.x; i < BM_CPB * BM_WORDS; i += BM_THREADS) {
@@ -195,6 +233,8 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
     if (threadIdx.x < BM_CPB) {
         const int j = threadIdx.x;
         s_big[j] = j < nc ? (int)bits[(size_t)(c0 + j) * BM_STRIDE + BM_WORDS] : 1;
+        s_ovn[j] = j < nc ? (int)bits[(size_t)(c0 + j) * BM_STRIDE + BM_WORDS + 1] : 0;
+        for (int i = 0; i < OV_MAX; ++i) s_ov[j][i] = j < nc ? bits[(size_t)(c0 + j) * BM_STRIDE + BM_WORDS + 2 + i] : 0u;
         s_base[j] = j < nc ? row_off[c0 + j] : 0;
     }
     __syncthreads();
@@ -214,11 +254,16 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
             s_part[cj][t] = run;
             run += v;
         }
+        s_tot[cj] = run;
+        // the counts >= 65536 follow the bitmap's values (they are larger than all of them), ascending
+        if (cj < nc && !s_big[cj] && blockIdx.y == 0)
+            for (int i = 0; i < s_ovn[cj]; ++i)
+                if ((int64_t)s_base[cj] + run + i < row_cap) row_x[(int64_t)s_base[cj] + run + i] = (int32_t)s_ov[cj][i];
     }
     __syncthreads();
     {
         int run = s_part[cj][ct];
-        const bool emit = cj < nc && !s_big[cj];
+        const bool emit = cj < nc && !s_big[cj] && blockIdx.y == 0;
         const int64_t base = s_base[cj];
         for (int w = 0; w < WPT; ++w) {
             uint32_t v = mine[w];
@@ -234,7 +279,11 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
     __syncthreads();
     const bool all8 = nc == BM_CPB && (ld_ridx % 4) == 0 && (reinterpret_cast<uintptr_t>(ridx + c0) % 16) == 0 && !s_big[0] &&
                       !s_big[1] && !s_big[2] && !s_big[3] && !s_big[4] && !s_big[5] && !s_big[6] && !s_big[7];
-    for (int g = threadIdx.x; g < G; g += BM_THREADS) {
+    // blockIdx.y: a slice of the genes (a launch over few cells -- one chunk of the pipelined front -- has too few groups of
+    // eight cells to fill the GPU; the bitmaps and ranks are then rebuilt by every slice, which is cheap next to the mapping)
+    const int g_per = (G + gridDim.y - 1) / gridDim.y;
+    const int g_lo = blockIdx.y * g_per, g_hi = min(G, g_lo + g_per);
+    for (int g = g_lo + threadIdx.x; g < g_hi; g += BM_THREADS) {
         int32_t x[BM_CPB], r[BM_CPB];
 #pragma unroll
         for (int j = 0; j < BM_CPB; ++j) x[j] = j < nc ? counts[(size_t)(c0 + j) * ldc + g0 + g] : 0;
@@ -243,6 +292,11 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
             const uint32_t xv = x[j] < 0 ? 0u : (uint32_t)x[j];
             const uint32_t w = min(xv >> 5, (uint32_t)(BM_WORDS - 1));
             r[j] = s_base[j] + (int)s_pre[j * BM_WORDS + w] + __popc(s_bm[j * BM_WORDS + w] & ((1u << (xv & 31)) - 1u));
+            if (xv >= 32u * BM_WORDS) {  // rare: one of the cell's few counts beyond the bitmap
+                int i = 0;
+                while (i < OV_MAX - 1 && s_ov[j][i] != xv) ++i;
+                r[j] = s_base[j] + s_tot[j] + i;
+            }
         }
         int32_t *dst = ridx + (size_t)g * ld_ridx + c0;
         if (all8) {
@@ -341,7 +395,10 @@ cudaError_t launch_dedup_emit(const int32_t *counts, int64_t ld_counts, int g0, 
     const size_t bsmem = (sizeof(uint32_t) + sizeof(uint16_t)) * BM_CPB * BM_WORDS;
     cudaError_t e = cudaFuncSetAttribute(dedup_bitmap_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
     if (e != cudaSuccess) return e;
-    dedup_bitmap_emit_kernel<<<(n_cells + BM_CPB - 1) / BM_CPB, BM_THREADS, bsmem, st>>>(
+    const int groups = (n_cells + BM_CPB - 1) / BM_CPB;
+    int slices = (2 * 148 + groups - 1) / groups;
+    slices = slices < 1 ? 1 : (slices > 4 ? 4 : slices);
+    dedup_bitmap_emit_kernel<<<dim3(groups, slices), BM_THREADS, bsmem, st>>>(
         counts, ld_counts, g0, G, n_cells, scratch, row_off, row_x, ridx, ld_ridx, row_cap);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

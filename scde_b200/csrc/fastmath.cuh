@@ -59,4 +59,35 @@ __device__ __forceinline__ double log1p_unit(double w) {
     return (z + z) * p;
 }
 
+// log(y) for 0 < y < 2^-900 (normal or denormal): y is scaled by 2^64 (exact), split into m 2^e with m in
+// [sqrt(1/2), sqrt 2), and log m = 2 atanh((m - 1) / (m + 1)) is summed to z^18 / 19 (z^2 <= 0.0295: truncation 1e-15).
+// Used on exp(a) for a in [-746, -708], where the reference's log(exp(a)) sees the denormal rounding of exp().
+__device__ __forceinline__ double log_tiny(double y) {
+    const double ys = y * 18446744073709551616.0;  // 2^64
+    int hi = __double2hiint(ys);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000FFFFF) | 0x3FF00000;  // mantissa in [1, 2)
+    if (hi >= 0x3FF6A09F) {               // above sqrt 2 (to within 1e-6: the series covers both sides)
+        hi -= 0x00100000;
+        e += 1;
+    }
+    const double m = __hiloint2double(hi, __double2loint(ys));
+    const double t = m + 1.0;
+    double r = (double)__frcp_rn((float)t);
+    r = r * fma(-t, r, 2.0);
+    const double z = (m - 1.0) * r, w = z * z;
+    double p = 1.0 / 19.0;
+    p = fma(p, w, 1.0 / 17.0);
+    p = fma(p, w, 1.0 / 15.0);
+    p = fma(p, w, 1.0 / 13.0);
+    p = fma(p, w, 1.0 / 11.0);
+    p = fma(p, w, 1.0 / 9.0);
+    p = fma(p, w, 1.0 / 7.0);
+    p = fma(p, w, 1.0 / 5.0);
+    p = fma(p, w, 1.0 / 3.0);
+    p = fma(p, w, 1.0);
+    const double E = (double)(e - 64);
+    return fma(E, 6.93147180369123816490e-01, fma(E, 1.90821492927058770002e-10, (z + z) * p));
+}
+
 }  // namespace scde

@@ -787,8 +787,8 @@ struct QrCell {
 };
 constexpr int QR_SMEM_WARP = 4 * Q_PIECE + 2 * (int)sizeof(QrHeaders) + (int)sizeof(QrCell);
 
-template <bool FULL, int MINB>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
-__global__ void __launch_bounds__(QR_WARPS * 32, MINB)
+template <bool FULL>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
+__global__ void __launch_bounds__(QR_WARPS * 32, 3)
 lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                  const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
@@ -967,8 +967,17 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                             const uint32_t hh = (uint32_t)__double2hiint(hi[q]);
                             const uint32_t hd = (uint32_t)__double2hiint(d[q]);
                             if (hh <= H_DEAD && !(hh < H_LOW && (hd & 0x7fffffffu) > H_BAND)) {
-                                hi[q] = lp_slow_element(a[q], e[q], 0.0, sentinel);
-                                if (!(hi[q] > sentinel)) alive &= ~(1u << q);
+                                if ((hd & 0x7fffffffu) > H_BAND) {
+                                    // gradual-underflow band, one term: the other exponential is exactly 0 (it lies 37.5
+                                    // below a value under -708), so the reference's element is log(exp(hi)) with exp()
+                                    // rounded to a denormal -- or log 0
+                                    const double y = exp_nonpos<true>(hi[q]);
+                                    hi[q] = log_tiny(y);
+                                    if (!(y > 0.0)) alive &= ~(1u << q);
+                                } else {
+                                    hi[q] = lp_slow_element(a[q], e[q], 0.0, sentinel);
+                                    if (!(hi[q] > sentinel)) alive &= ~(1u << q);
+                                }
                             }
                         }
                     }
@@ -1011,8 +1020,14 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                 const uint32_t hh = (uint32_t)__double2hiint(hi);
                 bool live = hh <= H_DEAD;
                 if (live && !(hh < H_LOW && (hd & 0x7fffffffu) > H_BAND)) {
-                    hi = lp_slow_element(a, e, 0.0, sentinel);
-                    live = hi > sentinel;
+                    if ((hd & 0x7fffffffu) > H_BAND) {
+                        const double y = exp_nonpos<true>(hi);
+                        hi = log_tiny(y);
+                        live = y > 0.0;
+                    } else {
+                        hi = lp_slow_element(a, e, 0.0, sentinel);
+                        live = hi > sentinel;
+                    }
                 }
                 const long long yb = __double_as_longlong(fma(hi - cell->Z[2 * QR_MAIN][lane].x, SCALE, MAGICB));
                 const uint32_t am = live ? 0xFFFFFFFFu : 0u;
@@ -1114,17 +1129,15 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
         if (which == 2 && qtable && !write_f64 && !row_mode && zero_row && based && prep.ld >= K && !getenv("SCDE_B200_LP_OLD")) {
             // fixed-point rows only: the register-resident kernel; one contiguous run of rows per warp
             const size_t smem = (size_t)QR_WARPS * QR_SMEM_WARP;
-            const int minb = getenv("SCDE_B200_LP_MINB") ? atoi(getenv("SCDE_B200_LP_MINB")) : 3;
             auto launch_q = [&](auto kernel) -> cudaError_t {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                kernel<<<148 * minb, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
+                kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
                                                              (const double4 *)row_const, row_snap, prep, K, sentinel, table,
                                                              ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
                 return cudaGetLastError();
             };
-            if (K < 4 * 32 * QR_MAIN) return launch_q(lp_rows_q_kernel<false, 3>);
-            return minb == 4 ? launch_q(lp_rows_q_kernel<true, 4>) : launch_q(lp_rows_q_kernel<true, 3>);
+            return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);
         }
         auto launch =[&](auto kernel, int rpw) -> cudaError_t {
             const size_t smem = (size_t)ROW_WARPS * rpw * (sizeof(double) * KP_TILED + 4 * Q_PIECE);

@@ -110,7 +110,6 @@ __device__ double d_qnorm_upper(double p) {
 __global__ void __launch_bounds__(R_THREADS) ratio_summary_kernel(const RatioArgs a) {
     extern __shared__ double sm[];
     const int n = a.n, nout = 2 * n - 1;
-    double *p1 = sm, *p2 = sm + n, *out = sm + 2 * n;  // out: nout values
     __shared__ double s_hi[R_THREADS / 32], s_lo[R_THREADS / 32];
     __shared__ double s_bv[R_THREADS / 32];
     __shared__ int s_bi[R_THREADS / 32];
@@ -119,6 +118,18 @@ __global__ void __launch_bounds__(R_THREADS) ratio_summary_kernel(const RatioArg
     const int64_t g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // Staging.  The sliding product below gives FOUR ADJACENT lags to a thread, so that a loaded p1[j] serves four
+    // products and the four p2 values it meets are a window sliding along p2 (one new load per j): two shared-memory
+    // loads per four multiply-adds instead of eight.  Adjacent threads then walk p1 / p2 at a stride of four doubles,
+    // which would be an eight-way bank conflict; both vectors are therefore stored de-interleaved, q[u][m] = p[4 m + u - off],
+    // so that the threads of a warp read consecutive words of one sub-array.  Zero padding on both sides stands for
+    // the out-of-range terms: a product with +0 adds +0, which leaves the (non-negative) partial sums bit-identical to
+    // the reference's shorter loops.
+    const int off2 = 8 + ((4 - ((n - 1) & 3)) & 3);  // p2 index shift: (j + n - 1 - 4 g + off2) % 4 == j % 4 for every group g
+    const int M1 = (n + 11) >> 2, M2 = (n + off2 + 11) >> 2;
+    double *q1 = sm, *q2 = sm + 4 * M1, *out = sm + 4 * M1 + 4 * M2;  // out: nout values
+    for (int i = tid; i < 4 * M1 + 4 * M2; i += R_THREADS) sm[i] = 0.0;
+    __syncthreads();
     for (int j = tid; j < n; j += R_THREADS) {
         double x = a.p1[g * a.ld + j], y = a.p2[g * a.ld + j];
         if (a.prior) {
@@ -126,25 +137,56 @@ __global__ void __launch_bounds__(R_THREADS) ratio_summary_kernel(const RatioArg
             x = __dmul_rn(x, w);
             y = __dmul_rn(y, w);
         }
-        p1[j] = x;
-        p2[j] = y;
+        q1[(j & 3) * M1 + (j >> 2)] = x;
+        q2[((j + off2) & 3) * M2 + ((j + off2) >> 2)] = y;
     }
     if (tid < 2) s_cnt[tid] = 0;
     __syncthreads();
 
-    // sliding product: lag index L in [0, 2n-2]; fold-change shift t = L - (n-1)
-    for (int L = tid; L < nout; L += R_THREADS) {
-        double acc = 0.0;
-        if (L <= n - 2) {  // left half: sum_{j=0..L} m1[j] * m2[n-1-L+j]
-            const double *y = p2 + (n - 1 - L);
-            for (int j = 0; j <= L; ++j) acc = __dadd_rn(acc, __dmul_rn(p1[j], y[j]));
-        } else {  // right half: sum_{j=0..n-1-s} m1[s+j] * m2[j], s = L-(n-1)
-            const int s = L - (n - 1);
-            const double *x = p1 + s;
-            for (int j = 0; j <= n - 1 - s; ++j) acc = __dadd_rn(acc, __dmul_rn(x[j], p2[j]));
+    // sliding product: lag index L in [0, 2n-2]; out[L] = sum_j p1[j] p2[j + n-1-L] over the j where both exist, j
+    // ascending, multiply and add rounded separately (src/matSlideMult.cpp:13-21).  Group gi = lags 4 gi .. 4 gi + 3; its
+    // j range is [max(0, 4 gi - (n-1)) rounded down to a multiple of 4, min(n-1, 4 gi + 3)], walked four j per
+    // iteration.  Short and long groups are paired (gi, gi + ceil(NG/2)) so that every thread does about the same
+    // number of iterations.
+    {
+        const int NG = (nout + 3) >> 2, half = (NG + 1) >> 1;
+        for (int t = tid; t < half; t += R_THREADS) {
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                const int gi = t + which * half;
+                if (gi >= NG) break;
+                const int L0 = 4 * gi;
+                int j0 = L0 - (n - 1);
+                j0 = j0 > 0 ? (j0 & ~3) : 0;
+                const int j1 = min(n - 1, L0 + 3);
+                const int iters = (j1 - j0 + 4) >> 2;
+                const int i2 = j0 + (n - 1) - L0 + off2;  // shifted p2 index met by lag L0 at j0: a multiple of 4, >= 5
+                const double *a1 = q1 + (j0 >> 2), *b2 = q2 + (i2 >> 2);
+                // window: p2 values met by lags L0 + 1, + 2, + 3 at j0 (shifted indices i2 - 1, - 2, - 3)
+                double w1 = q2[3 * M2 + ((i2 - 4) >> 2)], w2 = q2[2 * M2 + ((i2 - 4) >> 2)], w3 = q2[1 * M2 + ((i2 - 4) >> 2)];
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double x = a1[u * M1 + it], y = b2[u * M2 + it];
+                        acc0 = __dadd_rn(acc0, __dmul_rn(x, y));
+                        acc1 = __dadd_rn(acc1, __dmul_rn(x, w1));
+                        acc2 = __dadd_rn(acc2, __dmul_rn(x, w2));
+                        acc3 = __dadd_rn(acc3, __dmul_rn(x, w3));
+                        w3 = w2;
+                        w2 = w1;
+                        w1 = y;
+                    }
+                }
+                const double r[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (L0 + i < nout) {
+                        out[L0 + i] = r[i];
+                        if (a.raw) a.raw[g * a.ld_post + L0 + i] = r[i];
+                    }
+            }
         }
-        out[L] = acc;
-        if (a.raw) a.raw[g * a.ld_post + L] = acc;
     }
     __syncthreads();
     if (!a.idx && !a.z && !a.post) return;
@@ -255,7 +297,8 @@ __global__ void magnitude_kernel(const int32_t *__restrict__ counts, int64_t n, 
 
 cudaError_t launch_ratio_summary(const RatioArgs &a, cudaStream_t st) {
     if (a.n_genes <= 0) return cudaSuccess;
-    size_t smem = sizeof(double) * ((size_t)2 * a.n + 2 * a.n - 1);
+    const int off2 = 8 + ((4 - ((a.n - 1) & 3)) & 3);
+    size_t smem = sizeof(double) * ((size_t)4 * ((a.n + 11) >> 2) + 4 * ((a.n + off2 + 11) >> 2) + 2 * a.n - 1);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ratio_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

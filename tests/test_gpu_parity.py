@@ -516,6 +516,11 @@ def test_dedup_bitmap_and_hash_cells_mixed(ctx):
     counts[:30, 3] = rng.integers(65536, 400000, size=30)   # cell 3 and cell 17 leave the bitmap range
     counts[5, 17] = 65536
     counts[:, 9] = 0                                         # a cell with the single distinct count 0
+    # a few distinct counts beyond the bitmap stay with the bitmap kernels (overflow list, at most six per cell): one value
+    # repeated in many genes, and four values up to the largest the count type holds, next to small counts
+    counts[40:100, 12] = 70000
+    counts[:4, 14] = [65536, 1_000_000, 65537, 2_000_000_000]
+    counts[4:11, 15] = [65536, 65537, 65538, 65539, 65540, 65541, 65542]  # seven: one too many, the hash kernel again
     counts[7, 20] = 65535                                    # the last value the bitmap holds
     mm, lt, sq = api.pack_models(w.models)
     mag = api.marginals_from_prior(w.prior)

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(R_THREADS) ratio_summary_kernel(const RatioArg
     __shared__ double s_bv[R_THREADS / 32];
     __shared__ int s_bi[R_THREADS / 32];
     __shared__ int s_cnt[2];
-    __shared__ double s_chunk_hi[R_THREADS], s_chunk_lo[R_THREADS];
+    __shared__ double s_chunk_hi[R_THREADS / 32], s_chunk_lo[R_THREADS / 32];
     const int64_t g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -233,11 +233,27 @@ __global__ void __launch_bounds__(R_THREADS) ratio_summary_kernel(const RatioArg
     const int c0 = tid * chunk, c1 = min(nout, c0 + chunk);
     dd run = {0.0, 0.0};
     for (int L = c0; L < c1; ++L) run = dd_add(run, out[L]);
-    s_chunk_hi[tid] = run.hi;
-    s_chunk_lo[tid] = run.lo;
+    // exclusive scan of the chunk totals (double-double): shuffles within the warp, then the warps' totals in order.
+    // (A serial sum over the lower threads' totals cost 128 double-double additions per thread on average -- more FP64
+    // work than the sliding product itself.)
+    dd incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const dd other = {__shfl_up_sync(0xffffffffu, incl.hi, o), __shfl_up_sync(0xffffffffu, incl.lo, o)};
+        if (lane >= o) incl = dd_add(other, incl);
+    }
+    if (lane == 31) {
+        s_chunk_hi[warp] = incl.hi;
+        s_chunk_lo[warp] = incl.lo;
+    }
+    dd off = {__shfl_up_sync(0xffffffffu, incl.hi, 1), __shfl_up_sync(0xffffffffu, incl.lo, 1)};
+    if (lane == 0) off = dd{0.0, 0.0};
     __syncthreads();
-    dd off = {0.0, 0.0};
-    for (int t = 0; t < tid; ++t) off = dd_add(off, dd{s_chunk_hi[t], s_chunk_lo[t]});
+    {
+        dd woff = {0.0, 0.0};
+        for (int w = 0; w < warp; ++w) woff = dd_add(woff, dd{s_chunk_hi[w], s_chunk_lo[w]});
+        off = dd_add(woff, off);
+    }
     int n_lt = 0, n_le = 0;
     run = off;
     for (int L = c0; L < c1; ++L) {

@@ -215,7 +215,7 @@ dedup_bitmap_count_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g
     }
 }
 
-__global__ void __launch_bounds__(BM_THREADS)
+__global__ void __launch_bounds__(BM_THREADS, 2)  // 96 KB of shared memory: two CTAs per SM, so at most 64 registers
 dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0, int G, int n_cells,
                          const uint32_t *__restrict__ bits, const int32_t *__restrict__ row_off,
                          int32_t *__restrict__ row_x, int32_t *__restrict__ ridx, int ld_ridx, int64_t row_cap) {
@@ -287,15 +287,24 @@ dedup_bitmap_emit_kernel(const int32_t *__restrict__ counts, int64_t ldc, int g0
         int32_t x[BM_CPB], r[BM_CPB];
 #pragma unroll
         for (int j = 0; j < BM_CPB; ++j) x[j] = j < nc ? counts[(size_t)(c0 + j) * ldc + g0 + g] : 0;
+        bool big = false;
 #pragma unroll
         for (int j = 0; j < BM_CPB; ++j) {
             const uint32_t xv = x[j] < 0 ? 0u : (uint32_t)x[j];
             const uint32_t w = min(xv >> 5, (uint32_t)(BM_WORDS - 1));
             r[j] = s_base[j] + (int)s_pre[j * BM_WORDS + w] + __popc(s_bm[j * BM_WORDS + w] & ((1u << (xv & 31)) - 1u));
-            if (xv >= 32u * BM_WORDS) {  // rare: one of the cell's few counts beyond the bitmap
-                int i = 0;
-                while (i < OV_MAX - 1 && s_ov[j][i] != xv) ++i;
-                r[j] = s_base[j] + s_tot[j] + i;
+            big = big || xv >= 32u * BM_WORDS;
+        }
+        if (big) {  // rare: some cell's count lies beyond the bitmap -- it is one of the cell's few listed values
+#pragma unroll
+            for (int j = 0; j < BM_CPB; ++j) {
+                const int32_t xr = j < nc ? counts[(size_t)(c0 + j) * ldc + g0 + g] : 0;  // re-read: keeps the hot loop lean
+                const uint32_t xv = xr < 0 ? 0u : (uint32_t)xr;
+                if (xv >= 32u * BM_WORDS) {
+                    int i = 0;
+                    while (i < OV_MAX - 1 && s_ov[j][i] != xv) ++i;
+                    r[j] = s_base[j] + s_tot[j] + i;
+                }
             }
         }
         int32_t *dst = ridx + (size_t)g * ld_ridx + c0;

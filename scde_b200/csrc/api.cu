@@ -1128,7 +1128,8 @@ struct scde_b200_diff_job {
     StageTimer timer;
     int64_t contract_cells = 0;
     bool ran = false;
-    int copy_chunks = 0, copy_chunk_cells = 0;  // chunked H2D of the counts in flight on the context's copy stream
+    int copy_chunks = 0;             // chunked H2D of the counts in flight on the context's copy stream:
+    std::vector<int> copy_bounds;    // chunk i holds the cells [copy_bounds[i], copy_bounds[i + 1])
     std::vector<int32_t> ids[2];                 // cells of the two groups
     std::vector<int32_t> gen[4];                 // generated draws, alive until their uploads have completed
     const scde_b200_diff_args *deferred_args = nullptr;  // one-shot call: the draws are still to be generated and uploaded
@@ -1209,17 +1210,32 @@ int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t 
     // the copy stream may overwrite the counts buffer only after earlier work on the compute stream is done with it
     SCDE_CUDA(cudaEventRecord(ctx->copy_events[N_COUNT_CHUNKS], ctx->stream));
     SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_COUNT_CHUNKS], 0));
-    const int chunk = round_up((C + N_COUNT_CHUNKS - 1) / N_COUNT_CHUNKS, 32);
+    // Chunk sizes: the front ends at max(last copy + the last chunk's kernels, first chunk's arrival + all kernels), so
+    // the first and the last chunk are small (1/20 and 1/16 of the cells) and the ones between share the rest.
+    std::vector<int> &bounds = j->copy_bounds;
+    bounds.assign(1, 0);
+    if (N_COUNT_CHUNKS >= 4 && C >= 64 * N_COUNT_CHUNKS && !getenv("SCDE_B200_UNIFORM_CHUNKS")) {
+        const int first = round_up(C / 20, 32), last = round_up(C / 16, 32);
+        const int mid = round_up((C - first - last + N_COUNT_CHUNKS - 3) / (N_COUNT_CHUNKS - 2), 32);
+        bounds.push_back(first);
+        for (int i = 0; i < N_COUNT_CHUNKS - 2 && bounds.back() + mid < C - last; ++i) bounds.push_back(bounds.back() + mid);
+        if (bounds.back() < C - last) bounds.push_back(C - last - ((C - last) % 32));
+        if (bounds.back() <= bounds[bounds.size() - 2]) bounds.pop_back();
+        bounds.push_back(C);
+    } else {
+        const int chunk = round_up((C + N_COUNT_CHUNKS - 1) / N_COUNT_CHUNKS, 32);
+        for (int c0 = chunk; c0 < C; c0 += chunk) bounds.push_back(c0);
+        bounds.push_back(C);
+    }
     int n_ch = 0;
-    for (int c0 = 0; c0 < C; c0 += chunk, ++n_ch) {
-        const int n = (C - c0) < chunk ? (C - c0) : chunk;
+    for (; n_ch + 1 < (int)bounds.size(); ++n_ch) {
+        const int c0 = bounds[n_ch], n = bounds[n_ch + 1] - c0;
         SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p + (size_t)c0 * G, sizeof(int32_t) * G, counts_host + (size_t)c0 * ld_host,
                                     sizeof(int32_t) * (size_t)ld_host, sizeof(int32_t) * G, n, cudaMemcpyHostToDevice,
                                     ctx->copy_stream));
         SCDE_CUDA(cudaEventRecord(ctx->copy_events[n_ch], ctx->copy_stream));
     }
     j->copy_chunks = n_ch;
-    j->copy_chunk_cells = chunk;
     return SCDE_B200_OK;
 }
 
@@ -1390,7 +1406,6 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
     t.ld_ridx = C;
     TablePlan pl = plan_table(t, j->local_theta);
     // the copies are already in flight (start_count_copies); every path below waits for them on the compute stream
-    const int chunk = j->copy_chunk_cells;
     const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * j->copy_chunks && !getenv("SCDE_B200_NO_PIPELINE");
     if (!pipelined) {
         for (int i = 0; i < j->copy_chunks; ++i) SCDE_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
@@ -1425,8 +1440,8 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
     tm.end(SCDE_B200_T_LPTABLE, e0, st, 1);
     int64_t cap = 0;
     int i = 0;
-    for (int c0 = 0; c0 < C; c0 += chunk, ++i) {
-        const int n = (C - c0) < chunk ? (C - c0) : chunk;
+    for (; i < j->copy_chunks; ++i) {
+        const int c0 = j->copy_bounds[i], n = j->copy_bounds[i + 1] - c0;
         const int32_t *cnt = j->ws->counts.p + (size_t)c0 * G;
         FCUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
         e0 = tm.begin(st);

@@ -61,6 +61,24 @@ def test_bh_cz_matches_oracle():
     np.testing.assert_allclose(cz, want, rtol=1e-13, atol=1e-15)
 
 
+def test_bh_cz_ties_and_degenerate_sizes():
+    """long runs of saturated Z (equal p-values: the stable order decides nothing observable, the running minimum
+    stays flat), all-equal input, n = 0 / 1 (R/functions.R:5051 on a one-gene data frame)"""
+    rng = np.random.default_rng(2)
+    z = rng.normal(size=3000) * 2.5
+    z[::3], z[1::7], z[5::11] = 7.160813, -7.160813, 1e-9
+    for zz in (z, np.full(17, 2.5), np.array([3.0]), np.empty(0)):
+        zz = np.ascontiguousarray(zz, dtype=np.float64)
+        cz = np.empty_like(zz)
+        _lib.check(_lib.lib().scde_b200_bh_cz(_lib.p_f64(zz), len(zz), _lib.p_f64(cz)))
+        if len(zz) == 0:
+            continue
+        pa = O.p_adjust_bh(np.array([O.pnorm_upper(abs(v)) for v in zz]))
+        want = np.sign(zz) * np.array([O.qnorm_upper(p) for p in pa])
+        np.testing.assert_allclose(cz, want, rtol=1e-13, atol=1e-15)
+        assert (np.abs(cz) <= np.abs(zz) + 1e-12).all()  # the correction never makes a gene more significant
+
+
 def test_fold_change_grid_and_zero_index():
     x = np.linspace(0, 4.8, 401)
     d = api.fold_change_grid(x)

@@ -44,15 +44,20 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genes", type=int, default=30000)
-    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--genes", type=int, default=None, help="default: the config's size (3: 20000, 4 and 5: 30000)")
+    ap.add_argument("--cells", type=int, default=None, help="default: the config's size (3: 2000, 4 and 5: 10000)")
     ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5])
     ap.add_argument("--cpu-sample-genes-per-thread", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--kernel", type=int, default=0,
                     help="contraction kernel: 0 auto (tcgen05 int8 fixed point), 1 generic FP64, 2 tiled FP64 (DMMA), 3 tcgen05")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.genes is None:
+        args.genes = 20000 if args.config == 3 else 30000  # BASELINE.json configs[2] / configs[3], configs[4]
+    if args.cells is None:
+        args.cells = 2000 if args.config == 3 else 10000
+    return args
 
 
 class ClockSampler(threading.Thread):

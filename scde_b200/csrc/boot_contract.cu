@@ -146,27 +146,67 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
     }
 }
 
-// heaviest genes first: one CTA, bitonic sort of (0xFFFF - len) << 16 | gene
-__global__ void sort_genes_kernel(const int32_t *__restrict__ len, int n_genes, int n_pow2, int32_t *__restrict__ order) {
-    extern __shared__ uint32_t s_key[];
-    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x)
-        s_key[i] = i < n_genes ? ((uint32_t)(0xFFFF - min(len[i], 0xFFFF)) << 16) | (uint32_t)i : 0xFFFFFFFFu;
+// heaviest genes first: a stable counting sort on the list length by one CTA (the order is only a schedule -- results
+// are stored per gene and do not depend on it -- but a fixed schedule keeps run-to-run timing and L2 behaviour equal).
+// Histogram and scan by 1024 threads; the stable placement walks the genes in order, 32 at a time, in one warp
+// (match.any gives a lane its rank among the tile's genes of the same length).  ~0.07 ms for 30 000 genes; the
+// single-CTA bitonic sort it replaces took 0.35 ms per joint with 147 SMs idle, and was limited to 32 768 genes.
+__global__ void __launch_bounds__(1024) order_genes_kernel(const int32_t *__restrict__ len, int n_genes, int n_bins,
+                                                          int32_t *__restrict__ order) {
+    extern __shared__ int32_t s_cnt[];                                 // [n_bins]: bin = n_bins - 1 - len
+    uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_cnt + n_bins);    // [n_genes]
+    __shared__ int32_t s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n_bins; i += 1024) s_cnt[i] = 0;
     __syncthreads();
-    for (int k = 2; k <= n_pow2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const uint32_t a = s_key[i], b = s_key[l];
-                    if ((a > b) == ((i & k) == 0)) {
-                        s_key[i] = b;
-                        s_key[l] = a;
-                    }
-                }
-            }
-            __syncthreads();
+    for (int i = tid; i < n_genes; i += 1024) {
+        const int b = n_bins - 1 - min(max(len[i], 0), n_bins - 1);
+        s_bin[i] = (uint16_t)b;
+        atomicAdd(&s_cnt[b], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the bins: thread t owns `per` consecutive bins
+    const int per = (n_bins + 1023) / 1024, b_lo = min(n_bins, tid * per), b_hi = min(n_bins, b_lo + per);
+    int mine = 0;
+    for (int b = b_lo; b < b_hi; ++b) mine += s_cnt[b];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
         }
-    for (int i = threadIdx.x; i < n_genes; i += blockDim.x) order[i] = (int32_t)(s_key[i] & 0xFFFFu);
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + incl - mine;
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int c = s_cnt[b];
+        s_cnt[b] = run;
+        run += c;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    for (int base = 0; base < n_genes; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < n_genes;
+        const int b = valid ? (int)s_bin[i] : -1 - lane;  // lanes beyond the end: keys of their own
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int pos = valid ? s_cnt[b] + rank : 0;
+        __syncwarp();
+        if (valid && rank == 0) s_cnt[b] += __popc(peers);
+        __syncwarp();
+        if (valid) order[pos] = i;
+    }
 }
 
 __global__ void iota_kernel(int32_t *out, int n) {
@@ -802,14 +842,12 @@ cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *
                                                                       total_entries);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    // processing order: heaviest genes first when the packed 16+16-bit sort key applies, else identity
-    if (zero_row && n_genes <= 32768 && n_list < 65535) {
-        int n2 = 32;
-        while (n2 < n_genes) n2 <<= 1;
-        const size_t smem = sizeof(uint32_t) * n2;
-        e = cudaFuncSetAttribute(sort_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // processing order: heaviest genes first when the counting sort's bins and keys fit in shared memory, else identity
+    const size_t smem = sizeof(int32_t) * ((size_t)n_list + 2) + sizeof(uint16_t) * (size_t)n_genes;
+    if (zero_row && n_list < 65535 && smem <= 200 * 1024) {
+        e = cudaFuncSetAttribute(order_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        sort_genes_kernel<<<1, 1024, smem, st>>>(out.len, n_genes, n2, out.order);
+        order_genes_kernel<<<1, 1024, smem, st>>>(out.len, n_genes, n_list + 1, out.order);
     } else {
         iota_kernel<<<(n_genes + 255) / 256, 256, 0, st>>>(out.order, n_genes);
     }

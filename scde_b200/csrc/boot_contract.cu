@@ -118,22 +118,34 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
     if (g >= n_genes) return;
     const int lane = threadIdx.x & 31;
     int pos = 0;
-    for (int base = 0; base < n_list; base += 32) {
-        const int c = base + lane;
-        bool keep = false;
-        int32_t r = 0;
-        if (c < n_list) {
+    // four 32-cell groups per round: their loads are independent, so a warp keeps 512 bytes of ridx in flight instead
+    // of 128 (one group per round ran at 1.5 TB/s, the latency of one load per warp at a time)
+    constexpr int U = 4;
+    for (int base = 0; base < n_list; base += 32 * U) {
+        int32_t r[U], zr[U], bs[U];
+        bool keep[U];
+        // all loads of the round first, on clamped indices and without branches between them (a test per group made the
+        // compiler wait for each group's loads before it issued the next group's)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = min(base + 32 * u + lane, n_list - 1);
             const int col = cell_ids ? cell_ids[c] : c;
-            r = ridx[g * ld_ridx + col];
-            keep = !zero_row || !based[col] || r != zero_row[col];
+            r[u] = ridx[g * ld_ridx + col];
+            zr[u] = zero_row ? zero_row[col] : -1;
+            bs[u] = zero_row ? based[col] : 0;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int o = pos + __popc(m & ((1u << lane) - 1));
-            lst_row[g * ld_lst + o] = r;
-            lst_cell[g * ld_lst + o] = c;
+#pragma unroll
+        for (int u = 0; u < U; ++u) keep[u] = base + 32 * u + lane < n_list && (bs[u] == 0 || r[u] != zr[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+            if (keep[u]) {
+                const int o = pos + __popc(m & ((1u << lane) - 1));
+                lst_row[g * ld_lst + o] = r[u];
+                lst_cell[g * ld_lst + o] = base + 32 * u + lane;
+            }
+            pos += __popc(m);
         }
-        pos += __popc(m);
     }
     const int padded = (pos + 31) & ~31;  // whole stages of both tiled kernels (8 and 32 entries)
     if (pos + lane < padded) {
@@ -195,17 +207,24 @@ __global__ void __launch_bounds__(1024) order_genes_kernel(const int32_t *__rest
     }
     __syncthreads();
     if (warp != 0) return;
+    // the next tile's keys and peer masks do not depend on the counters: they are taken one tile ahead, so that the
+    // serial chain per tile is only counter read -> counter update
+    auto tile_key = [&](int base) { return base + lane < n_genes ? (int)s_bin[base + lane] : -1 - lane; };  // beyond the end: keys of their own
+    int b = tile_key(0);
+    unsigned peers = __match_any_sync(0xffffffffu, b);
     for (int base = 0; base < n_genes; base += 32) {
         const int i = base + lane;
         const bool valid = i < n_genes;
-        const int b = valid ? (int)s_bin[i] : -1 - lane;  // lanes beyond the end: keys of their own
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int nb = tile_key(base + 32);
+        const unsigned npeers = __match_any_sync(0xffffffffu, nb);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         const int pos = valid ? s_cnt[b] + rank : 0;
         __syncwarp();
         if (valid && rank == 0) s_cnt[b] += __popc(peers);
         __syncwarp();
         if (valid) order[pos] = i;
+        b = nb;
+        peers = npeers;
     }
 }
 

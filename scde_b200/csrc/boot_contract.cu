@@ -160,27 +160,31 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
 
 // heaviest genes first: a stable counting sort on the list length by one CTA (the order is only a schedule -- results
 // are stored per gene and do not depend on it -- but a fixed schedule keeps run-to-run timing and L2 behaviour equal).
-// Histogram and scan by 1024 threads; the stable placement walks the genes in order, 32 at a time, in one warp
-// (match.any gives a lane its rank among the tile's genes of the same length).  ~0.07 ms for 30 000 genes; the
-// single-CTA bitonic sort it replaces took 0.35 ms per joint with 147 SMs idle, and was limited to 32 768 genes.
-__global__ void __launch_bounds__(1024) order_genes_kernel(const int32_t *__restrict__ len, int n_genes, int n_bins,
+// The genes are cut into n_seg contiguous segments with a counter array each: histogram and scan (bin-major, segment-minor,
+// which is the stable order) by 1024 threads, then one warp per segment walks its genes in order, 32 at a time
+// (match.any gives a lane its rank among the tile's genes of the same length; the tile's counter updates are the only
+// serial chain).  0.07 ms for 30 000 genes with four segments; the single-CTA bitonic sort it replaces took 0.35 ms per
+// joint with 147 SMs idle, and was limited to 32 768 genes.
+__global__ void __launch_bounds__(1024) order_genes_kernel(const int32_t *__restrict__ len, int n_genes, int n_bins, int n_seg,
                                                           int32_t *__restrict__ order) {
-    extern __shared__ int32_t s_cnt[];                                 // [n_bins]: bin = n_bins - 1 - len
-    uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_cnt + n_bins);    // [n_genes]
+    extern __shared__ int32_t s_cnt[];                                        // [n_seg][n_bins]: bin = n_bins - 1 - len
+    uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_cnt + n_seg * n_bins);   // [n_genes]
     __shared__ int32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n_bins; i += 1024) s_cnt[i] = 0;
+    const int seg_len = (((n_genes + n_seg - 1) / n_seg) + 31) & ~31;
+    for (int i = tid; i < n_seg * n_bins; i += 1024) s_cnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < n_genes; i += 1024) {
         const int b = n_bins - 1 - min(max(len[i], 0), n_bins - 1);
         s_bin[i] = (uint16_t)b;
-        atomicAdd(&s_cnt[b], 1);
+        atomicAdd(&s_cnt[(i / seg_len) * n_bins + b], 1);
     }
     __syncthreads();
-    // exclusive scan of the bins: thread t owns `per` consecutive bins
+    // exclusive scan: thread t owns `per` consecutive bins (all segments of a bin before the next bin)
     const int per = (n_bins + 1023) / 1024, b_lo = min(n_bins, tid * per), b_hi = min(n_bins, b_lo + per);
     int mine = 0;
-    for (int b = b_lo; b < b_hi; ++b) mine += s_cnt[b];
+    for (int b = b_lo; b < b_hi; ++b)
+        for (int sg = 0; sg < n_seg; ++sg) mine += s_cnt[sg * n_bins + b];
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -200,29 +204,31 @@ __global__ void __launch_bounds__(1024) order_genes_kernel(const int32_t *__rest
     }
     __syncthreads();
     int run = s_warp[warp] + incl - mine;
-    for (int b = b_lo; b < b_hi; ++b) {
-        const int c = s_cnt[b];
-        s_cnt[b] = run;
-        run += c;
-    }
+    for (int b = b_lo; b < b_hi; ++b)
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const int c = s_cnt[sg * n_bins + b];
+            s_cnt[sg * n_bins + b] = run;
+            run += c;
+        }
     __syncthreads();
-    if (warp != 0) return;
-    // the next tile's keys and peer masks do not depend on the counters: they are taken one tile ahead, so that the
-    // serial chain per tile is only counter read -> counter update
-    auto tile_key = [&](int base) { return base + lane < n_genes ? (int)s_bin[base + lane] : -1 - lane; };  // beyond the end: keys of their own
-    int b = tile_key(0);
+    if (warp >= n_seg) return;
+    int32_t *cnt = s_cnt + warp * n_bins;
+    const int g_lo = warp * seg_len, g_hi = min(n_genes, g_lo + seg_len);
+    // the next tile's keys and peer masks do not depend on the counters: they are taken one tile ahead
+    auto tile_key = [&](int base) { return base + lane < g_hi ? (int)s_bin[base + lane] : -1 - lane; };  // beyond the end: keys of their own
+    int b = tile_key(g_lo);
     unsigned peers = __match_any_sync(0xffffffffu, b);
-    for (int base = 0; base < n_genes; base += 32) {
+    for (int base = g_lo; base < g_hi; base += 32) {
         const int i = base + lane;
-        const bool valid = i < n_genes;
+        const bool valid = i < g_hi;
         const int nb = tile_key(base + 32);
         const unsigned npeers = __match_any_sync(0xffffffffu, nb);
         const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int pos = valid ? s_cnt[b] + rank : 0;
+        const int first = valid ? cnt[b] : 0;
         __syncwarp();
-        if (valid && rank == 0) s_cnt[b] += __popc(peers);
+        if (valid && rank == 0) cnt[b] = first + __popc(peers);
         __syncwarp();
-        if (valid) order[pos] = i;
+        if (valid) order[first + rank] = i;
         b = nb;
         peers = npeers;
     }
@@ -862,11 +868,14 @@ cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // processing order: heaviest genes first when the counting sort's bins and keys fit in shared memory, else identity
-    const size_t smem = sizeof(int32_t) * ((size_t)n_list + 2) + sizeof(uint16_t) * (size_t)n_genes;
+    const size_t bins_bytes = sizeof(int32_t) * ((size_t)n_list + 1), keys_bytes = sizeof(uint16_t) * ((size_t)n_genes + 2);
+    int n_seg = 8;  // as many gene segments (warps placing concurrently) as fit
+    while (n_seg > 1 && (n_seg * bins_bytes + keys_bytes > 200 * 1024 || n_genes < 64 * n_seg)) n_seg >>= 1;
+    const size_t smem = n_seg * bins_bytes + keys_bytes;
     if (zero_row && n_list < 65535 && smem <= 200 * 1024) {
         e = cudaFuncSetAttribute(order_genes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        order_genes_kernel<<<1, 1024, smem, st>>>(out.len, n_genes, n_list + 1, out.order);
+        order_genes_kernel<<<1, 1024, smem, st>>>(out.len, n_genes, n_list + 1, n_seg, out.order);
     } else {
         iota_kernel<<<(n_genes + 255) / 256, 256, 0, st>>>(out.order, n_genes);
     }

@@ -191,6 +191,27 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: run on the CPUs NVML names as local to the GPU, so that the pinned count matrix (first
+    touch) and the host thread that feeds the copies sit on the GPU's NUMA node -- with eight ranks on two sockets half
+    of the 1.2 GB uploads otherwise cross the socket link.  Returns the CPU list, or None when NVML does not say."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +220,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("SCDE_B200_NO_AFFINITY") else None
 
     import torch
     import torch.distributed as dist
@@ -412,6 +436,7 @@ def main():
         "config": {"workload": f"cfg{args.config}: {G} genes x {C} cells per GPU, 2 groups of {n_groups[0]}/{n_groups[1]}, "
                                f"B={N_BOOT}, K={K_GRID}" + (", batch-corrected" if batch is not None else ""),
                    "genes_total": total_genes, "sharding": "genes, one shard per rank, NCCL all_gather of Z/indices at the end",
+                   "host_affinity": ("GPU-local CPUs (NVML), %d" % len(numa)) if numa else "unchanged",
                    "l2": "inputs larger than L2 (counts %.1f GB, lp table %.1f GB)" % (
                        counts.nbytes / 1e9, stats_acc[-1]["table_rows"] * (2048 if args.kernel in (0, 3) else 416 * 8) / 1e9)},
         "clocks": clocks,
@@ -423,6 +448,7 @@ def main():
 
     # ---------------- parity spot-check + CPU baseline on a bounded gene sample (rank 0) ----------------
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again (the OpenMP runtime loads below)
         from oracle import oracle as O
 
         O.build()

@@ -128,6 +128,8 @@ struct scde_b200_ctx {
     DBuf<unsigned long long> epi_dbg;       // SCDE_B200_EPI_TIMING: cycle counters of the tcgen05 kernel's epilogue
     cudaStream_t copy_stream = nullptr;     // H2D of the count matrix in cell chunks, overlapped with the table build
     std::vector<cudaEvent_t> copy_events;   // one per chunk (+ 1: "the compute stream has released the counts buffer")
+    int32_t *h_draws = nullptr;             // mapped pinned staging of the bootstrap draws of the one-shot call: the W build
+    size_t h_draws_cap = 0;                 // reads them in place, so they never queue behind the count copies
 };
 
 namespace {
@@ -582,6 +584,7 @@ void scde_b200_destroy(scde_b200_ctx *ctx) {
         cudaStreamDestroy(ctx->copy_stream);
     }
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->h_draws) cudaFreeHost(ctx->h_draws);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx->ws;
     delete ctx;
@@ -1130,6 +1133,11 @@ struct scde_b200_diff_job {
     bool ran = false;
     int copy_chunks = 0;             // chunked H2D of the counts in flight on the context's copy stream:
     std::vector<int> copy_bounds;    // chunk i holds the cells [copy_bounds[i], copy_bounds[i + 1])
+    int split_chunks = 0;            // > 0: the chunks [0, split_chunks) hold every cell of the first group, whose joint
+                                     // runs before the rest of the front (so it hides the second half of the upload)
+    int64_t front_cap = 0;           // row capacity chosen by the chunked front
+    TablePlan front_plan;            // the front's table plan (buffers bound in its first phase)
+    const int32_t *boot_ptr[4] = {nullptr, nullptr, nullptr, nullptr};  // draws as the device reads them
     std::vector<int32_t> ids[2];                 // cells of the two groups
     std::vector<int32_t> gen[4];                 // generated draws, alive until their uploads have completed
     const scde_b200_diff_args *deferred_args = nullptr;  // one-shot call: the draws are still to be generated and uploaded
@@ -1138,7 +1146,9 @@ struct scde_b200_diff_job {
 // Bootstrap draws of the group joints (local indices) and, with a batch factor, of the composition-sampled joints (global
 // cell ids): the caller's, or generated from the seed (src/jpmatLogBoot.cpp:221,254-257 / :467-481).  The uploads are
 // queued on the context stream; the host vectors live in the job.
-int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_args *a) {
+// pinned: the draws go to the context's mapped pinned staging and are read in place (one-shot call with a split front:
+// an H2D copy would queue behind the count matrix on the copy engine, and the first joint starts before that has landed).
+int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_args *a, bool pinned = false) {
     cudaStream_t st = ctx->stream;
     const int C = j->C;
     const int32_t *src[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1184,7 +1194,32 @@ int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff
             j->D[2 + i] = D;
         }
     }
-    for (int i = 0; i < (j->has_batch ? 4 : 2); ++i) TRY(upload(j->boot[i], src[i], (size_t)a->n_boot * j->D[i], st));
+    const int n_sets = j->has_batch ? 4 : 2;
+    if (pinned) {
+        size_t total = 0;
+        for (int i = 0; i < n_sets; ++i) total += (size_t)a->n_boot * j->D[i];
+        if (total > ctx->h_draws_cap) {
+            if (ctx->h_draws) cudaFreeHost(ctx->h_draws);
+            ctx->h_draws = nullptr;
+            ctx->h_draws_cap = 0;
+            SCDE_CUDA(cudaHostAlloc((void **)&ctx->h_draws, sizeof(int32_t) * total, cudaHostAllocMapped));
+            ctx->h_draws_cap = total;
+        }
+        int32_t *dev = nullptr;
+        SCDE_CUDA(cudaHostGetDevicePointer((void **)&dev, ctx->h_draws, 0));
+        size_t off = 0;
+        for (int i = 0; i < n_sets; ++i) {
+            const size_t n = (size_t)a->n_boot * j->D[i];
+            memcpy(ctx->h_draws + off, src[i], sizeof(int32_t) * n);
+            j->boot_ptr[i] = dev + off;
+            off += n;
+        }
+        return SCDE_B200_OK;
+    }
+    for (int i = 0; i < n_sets; ++i) {
+        TRY(upload(j->boot[i], src[i], (size_t)a->n_boot * j->D[i], st));
+        j->boot_ptr[i] = j->boot[i].p;
+    }
     SCDE_CUDA(cudaStreamSynchronize(st));  // the caller's (or the job's) host arrays have been read
     return SCDE_B200_OK;
 }
@@ -1212,20 +1247,52 @@ int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t 
     SCDE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[N_COUNT_CHUNKS], 0));
     // Chunk sizes: the front ends at max(last copy + the last chunk's kernels, first chunk's arrival + all kernels), so
     // the first and the last chunk are small (1/20 and 1/16 of the cells) and the ones between share the rest.
+    // Split front: when every cell of the first group lies in the leading part of the matrix (the usual layout: cells
+    // ordered by group), a chunk boundary is put right behind that group's last cell.  The first group's joint then
+    // runs as soon as those chunks are processed -- under the upload of the rest, which is what bounds the call when
+    // several ranks share the host's PCIe bandwidth (eight ranks: 35-50 ms for the 1.2 GB instead of 22).
     std::vector<int> &bounds = j->copy_bounds;
     bounds.assign(1, 0);
+    j->split_chunks = 0;
+    auto add_equal = [&](int lo, int hi, int n) {  // n chunks over [lo, hi), boundaries on multiples of 32, hi included
+        n = n < 1 ? 1 : n;
+        const int step = round_up((hi - lo + n - 1) / n, 32);
+        for (int c = lo + step; c < hi; c += step) bounds.push_back(c);
+        bounds.push_back(hi);
+    };
+    int split = 0;
+    if (!j->ids[0].empty() && !getenv("SCDE_B200_NO_SPLIT_FRONT")) {
+        int last0 = 0;
+        for (int c : j->ids[0]) last0 = c > last0 ? c : last0;
+        split = round_up(last0 + 1, 32);
+    }
     if (N_COUNT_CHUNKS >= 4 && C >= 64 * N_COUNT_CHUNKS && !getenv("SCDE_B200_UNIFORM_CHUNKS")) {
         const int first = round_up(C / 20, 32), last = round_up(C / 16, 32);
-        const int mid = round_up((C - first - last + N_COUNT_CHUNKS - 3) / (N_COUNT_CHUNKS - 2), 32);
-        bounds.push_back(first);
-        for (int i = 0; i < N_COUNT_CHUNKS - 2 && bounds.back() + mid < C - last; ++i) bounds.push_back(bounds.back() + mid);
-        if (bounds.back() < C - last) bounds.push_back(C - last - ((C - last) % 32));
-        if (bounds.back() <= bounds[bounds.size() - 2]) bounds.pop_back();
-        bounds.push_back(C);
+        if (split >= 2 * first && split <= C - 2 * last && split <= (C / 4) * 3) {
+            int nA = (int)((double)N_COUNT_CHUNKS * split / C + 0.5);
+            nA = nA < 2 ? 2 : (nA > N_COUNT_CHUNKS - 2 ? N_COUNT_CHUNKS - 2 : nA);
+            bounds.push_back(first);
+            add_equal(first, split, nA - 1);
+            j->split_chunks = (int)bounds.size() - 1;
+            add_equal(split, C - last - ((C - last) % 32), N_COUNT_CHUNKS - nA - 1);
+            bounds.push_back(C);
+        } else {
+            const int mid = round_up((C - first - last + N_COUNT_CHUNKS - 3) / (N_COUNT_CHUNKS - 2), 32);
+            bounds.push_back(first);
+            for (int i = 0; i < N_COUNT_CHUNKS - 2 && bounds.back() + mid < C - last; ++i) bounds.push_back(bounds.back() + mid);
+            if (bounds.back() < C - last) bounds.push_back(C - last - ((C - last) % 32));
+            if (bounds.back() <= bounds[bounds.size() - 2]) bounds.pop_back();
+            bounds.push_back(C);
+        }
     } else {
         const int chunk = round_up((C + N_COUNT_CHUNKS - 1) / N_COUNT_CHUNKS, 32);
         for (int c0 = chunk; c0 < C; c0 += chunk) bounds.push_back(c0);
         bounds.push_back(C);
+    }
+    while ((int)ctx->copy_events.size() < (int)bounds.size() + 1) {
+        cudaEvent_t e;
+        SCDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
     }
     int n_ch = 0;
     for (; n_ch + 1 < (int)bounds.size(); ++n_ch) {
@@ -1395,7 +1462,9 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
 // device; the row-level kernels read their bounds there (CellRange), so nothing waits for the host except one 4-byte read
 // after the first chunk: its row count sizes the buffers (x 1.25).  If the estimate turns out too small the kernels stop
 // at the capacity and *done stays false: the caller rebuilds index and table the classic way from the resident counts.
-static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) {
+// phase 0: the chunks [0, split_chunks) -- all of them without a split; phase 1: the rest (split front only).  A phase
+// returns with the compute stream idle and its rows checked against the capacity, so the caller may queue a joint on them.
+static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, int phase, bool *done) {
     *done = false;
     LpTable &t = j->ws->table;
     const int G = j->G, C = j->C;
@@ -1404,18 +1473,18 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
     t.n_cells = C;
     t.n_genes = G;
     t.ld_ridx = C;
-    TablePlan pl = plan_table(t, j->local_theta);
+    if (phase == 0) j->front_plan = plan_table(t, j->local_theta);
+    TablePlan &pl = j->front_plan;  // prepare_cells and reserve_rows bind its buffers in phase 0
     // the copies are already in flight (start_count_copies); every path below waits for them on the compute stream
     const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * j->copy_chunks && !getenv("SCDE_B200_NO_PIPELINE");
     if (!pipelined) {
+        j->split_chunks = 0;
         for (int i = 0; i < j->copy_chunks; ++i) SCDE_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
         return SCDE_B200_OK;
     }
-    SCDE_CUDA(t.n_unique.ensure(C));
-    SCDE_CUDA(t.row_off.ensure((size_t)C + 1));
-    SCDE_CUDA(t.err.ensure(1));
-    SCDE_CUDA(t.ridx.ensure((size_t)G * C));
-    SCDE_CUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
+    const bool split = j->split_chunks > 0 && j->split_chunks < j->copy_chunks;
+    const int ch_lo = phase == 0 ? 0 : j->split_chunks, ch_hi = (phase == 0 && split) ? j->split_chunks : j->copy_chunks;
+    const bool last_phase = ch_hi == j->copy_chunks;
     auto drain = [&](int r) {  // never return while the copy engine may still read the caller's buffer
         cudaStreamSynchronize(ctx->copy_stream);
         return r;
@@ -1434,13 +1503,21 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
     const auto tf0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count(); };
     double tr_first = 0, tr_queued = 0, tr_draws = 0, tr_front = 0, tr_copy = 0;
-    FCUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
-    int e0 = tm.begin(st);
-    FTRY(prepare_cells(ctx, t, pl, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit));
-    tm.end(SCDE_B200_T_LPTABLE, e0, st, 1);
-    int64_t cap = 0;
-    int i = 0;
-    for (; i < j->copy_chunks; ++i) {
+    int e0 = 0;
+    if (phase == 0) {
+        FCUDA(t.n_unique.ensure(C));
+        FCUDA(t.row_off.ensure((size_t)C + 1));
+        FCUDA(t.err.ensure(1));
+        FCUDA(t.ridx.ensure((size_t)G * C));
+        FCUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
+        FCUDA(cudaMemsetAsync(t.err.p, 0, sizeof(int32_t), st));
+        e0 = tm.begin(st);
+        FTRY(prepare_cells(ctx, t, pl, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit));
+        tm.end(SCDE_B200_T_LPTABLE, e0, st, 1);
+        j->front_cap = 0;
+    }
+    int64_t cap = j->front_cap;
+    for (int i = ch_lo; i < ch_hi; ++i) {
         const int c0 = j->copy_bounds[i], n = j->copy_bounds[i + 1] - c0;
         const int32_t *cnt = j->ws->counts.p + (size_t)c0 * G;
         FCUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
@@ -1459,6 +1536,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
             if (cap > 0x7fffffff) cap = 0x7fffffff;
             FTRY(reserve_rows(t, pl, (size_t)cap));
             FCUDA(t.row_x.ensure((size_t)cap));
+            j->front_cap = cap;
         }
         FCUDA(launch_dedup_emit(cnt, G, 0, G, n, t.row_off.p + c0, t.row_x.p, t.ridx.p + c0, t.ld_ridx, t.err.p, cap, bits,
                                 st));
@@ -1469,32 +1547,34 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool *done) 
         tm.end(SCDE_B200_T_LPTABLE, e0, st, nl);
     }
     tr_queued = since();
-    if (trace) {
+    if (trace && last_phase) {
         cudaStreamSynchronize(ctx->copy_stream);
         tr_copy = since();
     }
     if (j->deferred_args) {  // the bootstrap draws: host RNG work while the kernels queued above run
         const scde_b200_diff_args *da = j->deferred_args;
         j->deferred_args = nullptr;
-        FTRY(upload_draws(ctx, j, da));
+        FTRY(upload_draws(ctx, j, da, split));
     }
     tr_draws = since();
     int32_t total = 0, err = 0;
-    FCUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FCUDA(cudaMemcpyAsync(&total, t.row_off.p + j->copy_bounds[ch_hi], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FCUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FCUDA(cudaStreamSynchronize(st));
-    FCUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if (last_phase) FCUDA(cudaStreamSynchronize(ctx->copy_stream));
     tr_front = since();
     if (trace)
-        fprintf(stderr, "[scde_b200] front: first chunk counted %.2f ms, all chunks queued %.2f, copies done %.2f, draws uploaded (incl. wait) %.2f, front done %.2f\n",
-                tr_first, tr_queued, tr_copy, tr_draws, tr_front);
+        fprintf(stderr, "[scde_b200] front%s: first chunk counted %.2f ms, chunks queued %.2f, copies done %.2f, draws staged (incl. wait) %.2f, done %.2f\n",
+                !split ? "" : (phase == 0 ? " (first group's chunks)" : " (rest)"), tr_first, tr_queued, tr_copy, tr_draws, tr_front);
 #undef FTRY
 #undef FCUDA
     if (err & 1) {
+        cudaStreamSynchronize(ctx->copy_stream);
         set_error("negative count in the count matrix");
         return SCDE_B200_EINVAL;
     }
     if (err & 2) {
+        cudaStreamSynchronize(ctx->copy_stream);
         set_error("a cell has >= 32768 distinct count values among the processed genes (hash capacity)");
         return SCDE_B200_ELIMIT;
     }
@@ -1535,8 +1615,26 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
     j->ws->table.want_modes = false;
     TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
-    bool front_done = false;
-    if (chunked_counts) TRY(front_chunked(ctx, j, &front_done));
+    bool front_done = false, joint0_done = false;
+    auto group_joint = [&](int i) {  // cells of one factor level, draws are local indices (R/functions.R:372-374)
+        return run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot_ptr[i], j->n_boot, j->D[i],
+                         (double)j->n_boot, j->ws->jp[i].p, ld, j->ws->scr, &tm, true);
+    };
+    if (chunked_counts) {
+        TRY(front_chunked(ctx, j, 0, &front_done));
+        if (front_done && j->split_chunks > 0 && j->split_chunks < j->copy_chunks) {
+            // split front: every row of the first group's cells is built and within the capacity -- its joint runs
+            // while the rest of the count matrix is still arriving
+            TRY(group_joint(0));
+            joint0_done = true;
+            TRY(front_chunked(ctx, j, 1, &front_done));
+            if (!front_done) {  // the table is rebuilt below: row ids change, the first joint is repeated
+                joint0_done = false;
+                SCDE_CUDA(cudaMemsetAsync(j->ws->scr.total.p, 0, sizeof(unsigned long long), st));
+            }
+        }
+        if (!front_done && ctx->copy_stream) SCDE_CUDA(cudaStreamSynchronize(ctx->copy_stream));  // the counts must be resident
+    }
     if (j->deferred_args) {  // not done by the chunked front (small problem or fallback)
         const scde_b200_diff_args *da = j->deferred_args;
         j->deferred_args = nullptr;
@@ -1546,14 +1644,12 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
         TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
         TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
     }
-    // group joints: cells of one factor level, draws are local indices (R/functions.R:372-374)
     for (int i = 0; i < 2; ++i)
-        TRY(run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot[i].p, j->n_boot, j->D[i], (double)j->n_boot,
-                      j->ws->jp[i].p, ld, j->ws->scr, &tm, true));
+        if (!(i == 0 && joint0_done)) TRY(group_joint(i));
     // batch joints: all cells, composition-sampled draws are global cell ids (R/functions.R:355-357)
     if (j->has_batch)
         for (int i = 0; i < 2; ++i)
-            TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot[2 + i].p, j->n_boot, j->D[2 + i], (double)j->n_boot,
+            TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot_ptr[2 + i], j->n_boot, j->D[2 + i], (double)j->n_boot,
                           j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, true));
     int e0 = tm.begin(st);
     int nl = 0;

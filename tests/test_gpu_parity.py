@@ -507,6 +507,55 @@ def test_one_shot_call_gene_shard_and_row_estimate_fallback(ctx):
         assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])
 
 
+def _assert_same(one, two):
+    assert one["stats"]["table_rows"] == two["stats"]["table_rows"]
+    assert np.array_equal(one["idx"], two["idx"])
+    assert np.array_equal(one["z"], two["z"])
+    for i in range(2):
+        assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])
+
+
+def test_one_shot_call_split_front_overflow_after_first_joint():
+    """split front: the first group's cells hold a handful of distinct counts, so their rows fit the estimate and the first
+    joint runs early; the second group's cells hold hundreds, the rest of the front hits the capacity, the table is
+    rebuilt from the resident counts and the first joint is repeated on the new row ids -- same results as the job path"""
+    w = synth.make_workload(3, n_genes=200, n_cells=640, seed=23)
+    counts = np.array(w.counts, dtype=np.int32, order="F")
+    counts[:, :320] = np.minimum(counts[:, :320], 2)
+    counts[:, 320:] += np.arange(200, dtype=np.int32)[:, None] * 37
+    ctx = _lib.Context(0)  # a fresh workspace: no row buffers left over from a larger problem
+    one, two = _call_and_job(ctx, w, counts)
+    assert one["stats"]["table_rows"] > 20000
+    _assert_same(one, two)
+
+
+def test_one_shot_call_group_layouts(ctx):
+    """where the first group's cells lie decides whether the front is split: interleaved groups (no split), the first
+    group in the trailing cells (no split), a short first group (split after a quarter), cells outside both groups"""
+    w = synth.make_workload(3, n_genes=120, n_cells=640, seed=24)
+    counts = np.asarray(w.counts, dtype=np.int32, order="F")
+    base = np.asarray(w.groups.codes, dtype=np.int32)
+    layouts = {
+        "interleaved": (np.arange(640) % 2).astype(np.int32),
+        "reversed": (1 - base).astype(np.int32),
+        "short_first": np.where(np.arange(640) < 150, 0, 1).astype(np.int32),
+        "with_na": np.where(np.arange(640) % 7 == 3, -1, base).astype(np.int32),
+    }
+    mm, lt, sq = api.pack_models(w.models)
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    zi = api._zero_index(api.fold_change_grid(x), 0.0)
+    for name, codes in layouts.items():
+        one = api.expression_difference_call(ctx, counts, mm, x, y, codes, 100, 1, zero_index=zi, local_theta=lt, sqlogit=sq,
+                                             joint_posteriors=True)
+        job = api.DifferenceJob(ctx, counts, mm, x, y, codes, 100, 1, zero_index=zi, local_theta=lt, sqlogit=sq)
+        try:
+            job.run()
+            two = job.download(joint_posteriors=True)
+        finally:
+            job.close()
+        _assert_same(one, two)
+
+
 def test_dedup_bitmap_and_hash_cells_mixed(ctx):
     """cells whose counts all lie below 65536 are indexed by the bitmap kernels (eight cells per CTA), cells with a larger
     count by the hash kernels; both kinds side by side, a ragged last group of cells, against the oracle"""

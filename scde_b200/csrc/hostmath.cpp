@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <numeric>
 #include <vector>
 
@@ -87,23 +89,44 @@ static double qnorm_upper(double p) {  // Wichura AS 241 (PPND16), upper tail
     return q < 0.0 ? -val : val;
 }
 
+// runs f(lo, hi) over [0, n) on up to 16 host threads (one for small n): the p-values and the quantiles of the BH
+// correction are independent per gene, and with eight ranks gathered on rank 0 they are 240 000 erfc + qnorm evaluations
+static void parallel_ranges(int n, const std::function<void(int, int)> &f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? hw : 1);
+    nt = nt > 16 ? 16 : nt;
+    if (nt > n / 4096) nt = n / 4096;
+    if (nt <= 1) {
+        f(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) th.emplace_back(f, t * per < n ? t * per : n, (t + 1) * per < n ? (t + 1) * per : n);
+    f(0, per < n ? per : n);
+    for (auto &x : th) x.join();
+}
+
 void bh_cz(const double *z, int n, double *cz) {
     // p = pnorm(|Z|, upper), then order(p, decreasing = TRUE) as a stable LSD radix sort (six 11-bit digits) of the
     // complemented bit patterns: p >= 0, so its bits order like the value, and equal p keep their input order as R's
     // order() does.  30 000 genes: 0.5 ms instead of the 4 ms of an indirect std::stable_sort.
     std::vector<uint64_t> key(n), key2(n);
     std::vector<int> o(n), o2(n);
-    std::vector<double> p(n);
+    std::vector<double> p(n), pa(n);
     constexpr int BITS = 11, PASSES = 6, RADIX = 1 << BITS;
     std::vector<uint32_t> hist((size_t)PASSES * RADIX, 0u);
-    for (int i = 0; i < n; ++i) {
-        p[i] = 0.5 * std::erfc(std::fabs(z[i]) * M_SQRT1_2);
-        uint64_t b;
-        std::memcpy(&b, &p[i], sizeof b);
-        key[i] = ~b;
-        o[i] = i;
+    parallel_ranges(n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            p[i] = 0.5 * std::erfc(std::fabs(z[i]) * M_SQRT1_2);
+            uint64_t b;
+            std::memcpy(&b, &p[i], sizeof b);
+            key[i] = ~b;
+            o[i] = i;
+        }
+    });
+    for (int i = 0; i < n; ++i)
         for (int d = 0; d < PASSES; ++d) ++hist[(size_t)d * RADIX + ((key[i] >> (d * BITS)) & (RADIX - 1))];
-    }
     for (int d = 0; d < PASSES; ++d) {
         uint32_t *h = &hist[(size_t)d * RADIX];
         if (n > 0 && h[(key[0] >> (d * BITS)) & (RADIX - 1)] == (uint32_t)n) continue;  // all keys share this digit
@@ -121,21 +144,27 @@ void bh_cz(const double *z, int n, double *cz) {
         key.swap(key2);
         o.swap(o2);
     }
-    // cummin(n / rank * p) in decreasing order of p; qnorm only where the running minimum moves (Z saturates at
-    // +-7.16 for every clearly different gene, so long runs of ranks share one adjusted p)
-    double cm = INFINITY, last_pa = -1.0, last_q = 0.0;
+    // cummin(n / rank * p) in decreasing order of p
+    double cm = INFINITY;
     for (int r = 0; r < n; ++r) {
-        const int i = o[r];
-        const double v = (double)n / (double)(n - r) * p[i];
+        const double v = (double)n / (double)(n - r) * p[o[r]];
         if (v < cm) cm = v;
-        const double pa = cm < 1 ? cm : 1;
-        if (pa != last_pa) {
-            last_pa = pa;
-            last_q = qnorm_upper(pa);
-        }
-        const double sgn = (z[i] > 0) - (z[i] < 0);
-        cz[i] = sgn * last_q;
+        pa[r] = cm < 1 ? cm : 1;
     }
+    // qnorm only where the running minimum moves (Z saturates at +-7.16 for every clearly different gene, so long runs
+    // of ranks share one adjusted p)
+    parallel_ranges(n, [&](int lo, int hi) {
+        double last_pa = -1.0, last_q = 0.0;
+        for (int r = lo; r < hi; ++r) {
+            const int i = o[r];
+            if (pa[r] != last_pa) {
+                last_pa = pa[r];
+                last_q = qnorm_upper(pa[r]);
+            }
+            const double sgn = (z[i] > 0) - (z[i] < 0);
+            cz[i] = sgn * last_q;
+        }
+    });
 }
 
 }  // namespace scde

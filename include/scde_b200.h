@@ -213,7 +213,9 @@ typedef struct {
     int64_t contract_cells;  /* list entries (gene x cell pairs) the contraction visited, summed over all joints */
 } scde_b200_stats;
 
-/* One-shot: host buffers in, host buffers out (uploads, runs, downloads). */
+/* One-shot: host buffers in, host buffers out (uploads, runs, downloads).  The count matrix goes up in cell chunks that are
+ * processed as they land; when the cells of group 0 lead the matrix (cells ordered by group) that group's joint
+ * posterior is computed while the rest is still uploading.  Any cell order gives the same results. */
 SCDE_B200_API int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_args *args,
                                     const scde_b200_diff_out *out, scde_b200_stats *stats);
 

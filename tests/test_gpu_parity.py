@@ -556,6 +556,22 @@ def test_one_shot_call_group_layouts(ctx):
         _assert_same(one, two)
 
 
+def test_one_shot_call_split_front_with_batch(ctx):
+    """batch-corrected call through the split front: the two composition-sampled joints need every cell and run after the
+    whole front; every array the call returns equals the job path's, bit for bit"""
+    w = synth.make_workload(5, n_genes=100, n_cells=640, seed=25)
+    counts = np.asarray(w.counts, dtype=np.int32, order="F")
+    bcodes = np.asarray(w.batch.codes, dtype=np.int32)
+    kw = dict(batch_codes=bcodes, n_batch_levels=int(bcodes.max()) + 1)
+    one, two = _call_and_job(ctx, w, counts, **kw)
+    n_cmp = 0
+    for k, v in one.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, two[k]), k
+            n_cmp += 1
+    assert n_cmp >= 4
+
+
 def test_dedup_bitmap_and_hash_cells_mixed(ctx):
     """cells whose counts all lie below 65536 are indexed by the bitmap kernels (eight cells per CTA), cells with a larger
     count by the hash kernels; both kinds side by side, a ragged last group of cells, against the oracle"""

@@ -81,6 +81,44 @@ SCDE_B200_API void *scde_b200_stream(scde_b200_ctx *ctx);
 /* blocks until all work queued on the context's stream has finished */
 SCDE_B200_API int scde_b200_synchronize(scde_b200_ctx *ctx);
 
+/*
+ * A context over several CUDA devices of one node: the reference's `n.cores` (R/functions.R:304,566 -- gene chunks over
+ * forked workers, :606-617) becomes "n devices".  scde_b200_expression_difference on such a context shards the genes
+ * into contiguous ranges, one per device, runs every shard on its own host thread with the n.cores = 1 draw semantics
+ * (Seed as given, one draw set for all genes, so the result does not depend on the number of devices), and the shards'
+ * results land in the caller's buffers by device-to-host copies -- no inter-GPU traffic.  devices == NULL: devices
+ * 0 .. n_devices-1.  Every other entry point uses the first device of the list.
+ */
+SCDE_B200_API int scde_b200_create_multi(int n_devices, const int *devices, scde_b200_ctx **out);
+/* number of devices of the context (1 for scde_b200_create) */
+SCDE_B200_API int scde_b200_n_devices(const scde_b200_ctx *ctx);
+
+/*
+ * Behavioural switches of a context (the reference has function arguments only -- no global
+ * options, no environment variables -- so neither has the library).  scde_b200_get_options fills the defaults (or the
+ * current values); scde_b200_set_options applies to every later call on the context (and on its per-device children).
+ */
+typedef struct {
+    int32_t contract_kernel;    /* 0 auto (tcgen05 fixed point where it applies), 1 generic FP64, 2 tiled FP64 (DMMA), 3 tcgen05 */
+    int32_t zero_base;          /* 1: rows hold lp(x) - lp(0), the contraction visits non-zero counts only */
+    int32_t fused_fixed_point;  /* 1: the row kernel emits the fixed-point planes itself (FP64 rows of non-zero counts not stored) */
+    int32_t lp_rows_kernel;     /* 0: register-resident row kernel (default); 1: the per-element kernel it replaced (tests) */
+    int32_t count_chunks;       /* one-shot call: the count matrix goes up in this many cell chunks (default 8, 1..64) */
+    int32_t split_front;        /* 1: the first group's joint runs under the upload of the second group's cells */
+    int32_t uniform_chunks;     /* 1: equal chunks instead of a small first and last one */
+    int32_t pipeline_front;     /* 1: chunks are processed as they land; 0: wait for the whole matrix */
+    int32_t item_order;         /* tcgen05 contraction: 0 = the pieces of a gene on neighbouring SMs, 1 = piece-major */
+    int32_t hot_rank;           /* table rows whose rank within their cell is <= hot_rank are loaded with the L2 evict_last
+                                   policy; < 0: no cache hints */
+    int32_t cold_evict_first;   /* with hot_rank >= 0: the other rows are loaded evict_first (1) or without a priority (0) */
+    int32_t trace;              /* 1: host wall-clock of the phases of the one-shot call on stderr */
+    int32_t epilogue_timing;    /* 1: cycle counters of the tcgen05 kernel's epilogue on stderr */
+    int32_t debug_contract;     /* FP64 tiled kernel: diagnostic mode (0 = off) */
+    int32_t reserved[7];
+} scde_b200_options;
+SCDE_B200_API int scde_b200_get_options(const scde_b200_ctx *ctx, scde_b200_options *opt);
+SCDE_B200_API int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt);
+
 /* ---- bootstrap draws (host; glibc TYPE_3 additive-feedback rand() restated) ---------------- */
 /* Reproduces `srand(seed); for b<n_boot, j<n: while(n <= (rj = rand()/(RAND_MAX/n)));`
  * (src/jpmatLogBoot.cpp:221,254-257) without touching libc's global state.  out[b*n + j], draw order. */

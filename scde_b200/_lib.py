@@ -59,8 +59,17 @@ class Stats(C.Structure):
                 "table_rows": int(self.table_rows), "contract_cells": int(self.contract_cells)}
 
 
+class Options(C.Structure):
+    """scde_b200_options (include/scde_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "contract_kernel", "zero_base", "fused_fixed_point", "lp_rows_kernel", "count_chunks", "split_front",
+        "uniform_chunks", "pipeline_front", "item_order", "hot_rank", "cold_evict_first", "trace", "epilogue_timing",
+        "debug_contract")] + [("reserved", C.c_int32 * 7)]
+
+
 # every symbol include/scde_b200.h declares
 EXPORTED = [
+    "scde_b200_create_multi", "scde_b200_n_devices", "scde_b200_get_options", "scde_b200_set_options",
     "scde_b200_version", "scde_b200_last_error", "scde_b200_device_count", "scde_b200_create", "scde_b200_destroy",
     "scde_b200_stream", "scde_b200_synchronize", "scde_b200_boot_indices", "scde_b200_batch_boot_indices",
     "scde_b200_log_boot_posterior", "scde_b200_log_boot_batch_posterior", "scde_b200_jpmat_log_boot",
@@ -97,6 +106,10 @@ def lib():
                                                       C.POINTER(Stats)]
         L.scde_b200_measure_fp64_peak.argtypes = [C.c_void_p, f64p]
         L.scde_b200_set_contract_kernel.argtypes = [C.c_void_p, C.c_int32]
+        L.scde_b200_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        L.scde_b200_n_devices.argtypes = [C.c_void_p]
+        L.scde_b200_get_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.scde_b200_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
         _lib = L
     return _lib
 
@@ -123,12 +136,39 @@ def i32(a, order="F"):
 
 
 class Context:
-    """One CUDA device + stream (scde_b200_ctx)."""
+    """One CUDA device + stream (scde_b200_ctx), or -- `devices` a list -- a multi-device context
+    (scde_b200_create_multi): scde_b200_expression_difference then shards the genes over the devices."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self._h = C.c_void_p()
-        check(lib().scde_b200_create(int(device), C.byref(self._h)))
-        self.device = int(device)
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib().scde_b200_create_multi(len(devices), devs, C.byref(self._h)))
+            self.device = int(devices[0])
+            self.devices = [int(d) for d in devices]
+        else:
+            check(lib().scde_b200_create(int(device), C.byref(self._h)))
+            self.device = int(device)
+            self.devices = [self.device]
+
+    def options(self) -> "Options":
+        o = Options()
+        check(lib().scde_b200_get_options(self._h, C.byref(o)))
+        return o
+
+    def set_options(self, **kw) -> "Options":
+        """Change the named scde_b200_options fields; returns the previous options (for restoring)."""
+        old = self.options()
+        new = self.options()
+        for k, v in kw.items():
+            if not hasattr(new, k):
+                raise AttributeError(f"scde_b200_options has no field {k}")
+            setattr(new, k, int(v))
+        check(lib().scde_b200_set_options(self._h, C.byref(new)))
+        return old
+
+    def restore_options(self, old: "Options"):
+        check(lib().scde_b200_set_options(self._h, C.byref(old)))
 
     @property
     def handle(self):

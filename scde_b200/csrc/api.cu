@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 namespace scde {
@@ -116,11 +117,30 @@ namespace {
 struct DiffWorkspace;
 }
 
+static scde_b200_options default_options() {
+    scde_b200_options o;
+    memset(&o, 0, sizeof(o));
+    o.contract_kernel = 0;
+    o.zero_base = 1;
+    o.fused_fixed_point = 1;
+    o.lp_rows_kernel = 0;
+    o.count_chunks = 8;
+    o.split_front = 1;
+    o.uniform_chunks = 0;
+    o.pipeline_front = 1;
+    o.item_order = 0;
+    o.hot_rank = -1;
+    o.cold_evict_first = 1;
+    return o;
+}
+
 struct scde_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int n_sm = 148;
-    int contract_kernel = 0;  // 0 auto (tcgen05 int8 where supported), 1 generic, 2 tiled FP64 (DMMA), 3 tcgen05 int8
+    scde_b200_options opt = default_options();  // opt.contract_kernel: 0 auto (tcgen05 int8 where supported), 1 generic,
+                                                // 2 tiled FP64 (DMMA), 3 tcgen05 int8
+    std::vector<scde_b200_ctx *> children;      // scde_b200_create_multi: the contexts of the other devices of the list
     DBuf<int32_t> flags;      // device status word of the int8 path: 1 = a multiplicity > 127, 2 = kernel watchdog,
                               // 4 = sentinel ranges need the FP64 kernel
     DiffWorkspace *ws = nullptr;  // large device buffers of the differential-expression path, kept across calls
@@ -181,11 +201,11 @@ struct TablePlan {
     uint32_t *qr = nullptr;
 };
 
-TablePlan plan_table(const LpTable &t, int local_theta) {
+TablePlan plan_table(const scde_b200_ctx *ctx, const LpTable &t, int local_theta) {
     TablePlan pl;
     pl.fast = t.fast_theta && !local_theta && t.K <= KP_TILED;
     pl.q_any = t.want_q && t.zero_base && t.ld == KP_TILED && t.K <= Q_MAX_K;
-    pl.q_fused = pl.q_any && pl.fast && !getenv("SCDE_B200_Q_SEPARATE");
+    pl.q_fused = pl.q_any && pl.fast && ctx->opt.fused_fixed_point;
     return pl;
 }
 
@@ -257,7 +277,7 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                  t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
-                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st));
+                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1));
         *nl += 4;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
@@ -272,7 +292,7 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
 int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_models, const double *mag_dev,
                int local_theta, int sqlogit, StageTimer *tm) {
     cudaStream_t st = ctx->stream;
-    TablePlan pl = plan_table(t, local_theta);
+    TablePlan pl = plan_table(ctx, t, local_theta);
     TRY(reserve_rows(t, pl, (size_t)t.n_rows));
     int e0 = tm ? tm->begin(st) : -1;
     int nl = 1;
@@ -290,7 +310,7 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     return SCDE_B200_OK;
 }
 
-inline bool want_i8(const scde_b200_ctx *ctx) { return ctx->contract_kernel == 0 || ctx->contract_kernel == 3; }
+inline bool want_i8(const scde_b200_ctx *ctx) { return ctx->opt.contract_kernel == 0 || ctx->opt.contract_kernel == 3; }
 
 // unique-count indices from raw counts (device, column-major, leading dimension ldc, genes [g0, g0+G))
 int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev, int64_t ldc, int g0, int G, int C,
@@ -371,16 +391,17 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     SCDE_CUDA(launch_build_w(boot_idx_dev, n_boot, D, n_list, scr.W.p, n_w_rows, st));
     SCDE_CUDA(cudaMemsetAsync(jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
     GeneLists lists{scr.lst_row.p, scr.lst_cell.p, scr.lst_len.p, scr.order.p, ld_lst};
-    SCDE_CUDA(launch_build_lists(t.ridx.p, t.ld_ridx, cell_ids_dev, n_list, t.n_genes, zb ? t.zero_row.p : nullptr,
-                                 zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st));
-    if (zb)
-        SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
-                                  scr.Z.p, scr.zpart.p, st));
     const bool i8 = zb && t.has_q && want_i8(ctx) && contract_i8_supported(t.K, t.ld, ld_lst, D);
-    if (ctx->contract_kernel == 3 && !i8) {
+    if (ctx->opt.contract_kernel == 3 && !i8) {
         set_error("tcgen05 int8 contraction forced but unsupported here (K=%d, zero-base form %d)", t.K, (int)zb);
         return SCDE_B200_EINVAL;
     }
+    const int hot_rank = i8 ? ctx->opt.hot_rank : -1;  // only the tcgen05 kernel's producers know the hot bit
+    SCDE_CUDA(launch_build_lists(t.ridx.p, t.ld_ridx, cell_ids_dev, n_list, t.n_genes, zb ? t.zero_row.p : nullptr,
+                                 zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st, hot_rank));
+    if (zb)
+        SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
+                                  scr.Z.p, scr.zpart.p, st));
     if (i8) {
         SCDE_CUDA(scr.W8.ensure((size_t)passes * n_w_rows * Q_WB));
         SCDE_CUDA(ctx->flags.ensure(1));
@@ -405,7 +426,10 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.ld_jp = ld_jp;
         q.err = ctx->flags.p;
         q.dbg = nullptr;
-        if (getenv("SCDE_B200_EPI_TIMING")) {
+        q.item_order = ctx->opt.item_order;
+        q.hot_rank = hot_rank;
+        q.cold_evict_first = ctx->opt.cold_evict_first;
+        if (ctx->opt.epilogue_timing) {
             SCDE_CUDA(ctx->epi_dbg.ensure(3));
             SCDE_CUDA(cudaMemsetAsync(ctx->epi_dbg.p, 0, 3 * sizeof(unsigned long long), st));
             q.dbg = ctx->epi_dbg.p;
@@ -455,9 +479,10 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     a.K = t.K;
     a.jp = jp_dev;
     a.ld_jp = ld_jp;
+    a.debug = ctx->opt.debug_contract;
     bool tiled = contract_tiled_supported(a);
-    if (ctx->contract_kernel == 1) tiled = false;
-    if (ctx->contract_kernel >= 2 && !tiled) {
+    if (ctx->opt.contract_kernel == 1) tiled = false;
+    if (ctx->opt.contract_kernel >= 2 && !tiled) {
         set_error("tiled contraction kernel forced but unsupported for K=%d", t.K);
         return SCDE_B200_EINVAL;
     }
@@ -577,6 +602,8 @@ int scde_b200_create(int device, scde_b200_ctx **out) {
 
 void scde_b200_destroy(scde_b200_ctx *ctx) {
     if (!ctx) return;
+    for (auto *c : ctx->children) scde_b200_destroy(c);
+    ctx->children.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) {
@@ -600,7 +627,57 @@ int scde_b200_synchronize(scde_b200_ctx *ctx) {
 
 int scde_b200_set_contract_kernel(scde_b200_ctx *ctx, int32_t which) {
     if (!ctx || which < 0 || which > 3) return SCDE_B200_EINVAL;
-    ctx->contract_kernel = which;
+    ctx->opt.contract_kernel = which;
+    for (auto *c : ctx->children) c->opt.contract_kernel = which;
+    return SCDE_B200_OK;
+}
+
+int scde_b200_get_options(const scde_b200_ctx *ctx, scde_b200_options *opt) {
+    if (!opt) return SCDE_B200_EINVAL;
+    *opt = ctx ? ctx->opt : default_options();
+    return SCDE_B200_OK;
+}
+
+int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt) {
+    if (!ctx || !opt) return SCDE_B200_EINVAL;
+    if (opt->contract_kernel < 0 || opt->contract_kernel > 3 || opt->count_chunks < 0 || opt->count_chunks > 64 ||
+        opt->item_order < 0 || opt->item_order > 1) {
+        set_error("set_options: value out of range");
+        return SCDE_B200_EINVAL;
+    }
+    ctx->opt = *opt;
+    for (auto *c : ctx->children) c->opt = *opt;
+    return SCDE_B200_OK;
+}
+
+int scde_b200_n_devices(const scde_b200_ctx *ctx) { return ctx ? 1 + (int)ctx->children.size() : 0; }
+
+int scde_b200_create_multi(int n_devices, const int *devices, scde_b200_ctx **out) {
+    if (!out) return SCDE_B200_EINVAL;
+    *out = nullptr;
+    if (n_devices < 1) {
+        set_error("create_multi: n_devices must be >= 1");
+        return SCDE_B200_EINVAL;
+    }
+    for (int i = 0; i < n_devices; ++i)
+        for (int k = 0; k < i; ++k)
+            if (devices && devices[i] == devices[k]) {
+                set_error("create_multi: device %d listed twice", devices[i]);
+                return SCDE_B200_EINVAL;
+            }
+    scde_b200_ctx *parent = nullptr;
+    TRY(scde_b200_create(devices ? devices[0] : 0, &parent));
+    for (int i = 1; i < n_devices; ++i) {
+        scde_b200_ctx *c = nullptr;
+        const int r = scde_b200_create(devices ? devices[i] : i, &c);
+        if (r != SCDE_B200_OK) {
+            scde_b200_destroy(parent);
+            return r;
+        }
+        parent->children.push_back(c);
+    }
+    cudaSetDevice(parent->device);
+    *out = parent;
     return SCDE_B200_OK;
 }
 
@@ -709,7 +786,7 @@ static int log_boot_impl(scde_b200_ctx *ctx, const double *models, int32_t n_cel
     const double minlogprob = -DBL_MAX / n_cells / 1.1;  // src/jpmatLogBoot.cpp:127,372
     t.sentinel = -DBL_MAX / (double)(D > n_cells ? D : n_cells) / 1.1;
     t.fast_theta = !local_theta && theta_all_regular(models, n_cells, n_cells);
-    t.zero_base = !post_flag && !ensemble && t.ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
+    t.zero_base = !post_flag && !ensemble && t.ld <= KP_TILED && ctx->opt.zero_base;
     t.want_q = want_i8(ctx) && n_boot > 0;
     t.want_modes = modes_flag != 0;
     TRY(reset_flags(ctx));
@@ -780,12 +857,12 @@ static int log_boot_common(scde_b200_ctx *ctx, const double *models, int32_t n_c
     int rerun = 0;
     TRY(read_flags(ctx, &rerun));
     if (rerun) {  // a cell drawn more than 127 times in one randomization: outside the int8 operand range
-        const int keep = ctx->contract_kernel;
-        ctx->contract_kernel = 2;
+        const int keep = ctx->opt.contract_kernel;
+        ctx->opt.contract_kernel = 2;
         r = log_boot_impl(ctx, models, n_cells, ucl_flat, ucl_offsets, uci, n_genes, magnitudes, n_grid, n_boot, boot_idx, D,
                           return_individual, local_theta, square_logit_conc, ensemble, modes_flag, post_flag, jp, modes,
                           post);
-        ctx->contract_kernel = keep;
+        ctx->opt.contract_kernel = keep;
     }
     return r;
 }
@@ -1095,6 +1172,9 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.jp = nullptr;
     q.ld_jp = 0;
     q.err = ctx->flags.p;
+    q.item_order = ctx->opt.item_order;
+    q.hot_rank = -1;
+    q.cold_evict_first = 0;
     SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
     SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
     SCDE_CUDA(launch_finalize_t(q, n_genes, d_t.p, d_sr.p, st));
@@ -1225,9 +1305,8 @@ int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff
 }
 
 constexpr int N_COUNT_CHUNKS_DEFAULT = 8;
-static int n_count_chunks() {
-    const char *e = getenv("SCDE_B200_CHUNKS");
-    const int n = e ? atoi(e) : N_COUNT_CHUNKS_DEFAULT;
+static int n_count_chunks(const scde_b200_ctx *ctx) {
+    const int n = ctx->opt.count_chunks > 0 ? ctx->opt.count_chunks : N_COUNT_CHUNKS_DEFAULT;
     return n < 1 ? 1 : (n > 64 ? 64 : n);
 }
 
@@ -1235,7 +1314,7 @@ static int n_count_chunks() {
 // the 22 ms of PCIe time at config 4 run under the front kernels.
 int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t *counts_host, int64_t ld_host) {
     const int G = j->G, C = j->C;
-    const int N_COUNT_CHUNKS = n_count_chunks();
+    const int N_COUNT_CHUNKS = n_count_chunks(ctx);
     if (!ctx->copy_stream) SCDE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->copy_events.size() < N_COUNT_CHUNKS + 1) {
         cudaEvent_t e;
@@ -1261,12 +1340,12 @@ int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t 
         bounds.push_back(hi);
     };
     int split = 0;
-    if (!j->ids[0].empty() && !getenv("SCDE_B200_NO_SPLIT_FRONT")) {
+    if (!j->ids[0].empty() && ctx->opt.split_front) {
         int last0 = 0;
         for (int c : j->ids[0]) last0 = c > last0 ? c : last0;
         split = round_up(last0 + 1, 32);
     }
-    if (N_COUNT_CHUNKS >= 4 && C >= 64 * N_COUNT_CHUNKS && !getenv("SCDE_B200_UNIFORM_CHUNKS")) {
+    if (N_COUNT_CHUNKS >= 4 && C >= 64 * N_COUNT_CHUNKS && !ctx->opt.uniform_chunks) {
         const int first = round_up(C / 20, 32), last = round_up(C / 16, 32);
         if (split >= 2 * first && split <= C - 2 * last && split <= (C / 4) * 3) {
             int nA = (int)((double)N_COUNT_CHUNKS * split / C + 0.5);
@@ -1305,10 +1384,6 @@ int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t 
     j->copy_chunks = n_ch;
     return SCDE_B200_OK;
 }
-
-extern "C" {
-
-}  // extern "C"
 
 // defer_counts: the count matrix is not copied here (the one-shot call overlaps its upload with the table build)
 static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, int32_t want_posteriors,
@@ -1381,7 +1456,7 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
     j->n_levels = has_batch ? a->n_batch_levels : 0;
     j->n_zero = a->n_zero;
     // counts shard: rows [g0, g1) of every column
-    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;
+    const bool trace = ctx->opt.trace != 0;
     const auto tu0 = std::chrono::steady_clock::now();
     JCUDA(j->ws->counts.ensure((size_t)G * C));
     const auto tu1 = std::chrono::steady_clock::now();
@@ -1445,7 +1520,7 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
     j->ws->table.ld = ld;
     j->ws->table.sentinel = -DBL_MAX / C / 1.1;
     j->ws->table.fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
-    j->ws->table.zero_base = ld <= KP_TILED && !getenv("SCDE_B200_NO_ZERO_BASE");
+    j->ws->table.zero_base = ld <= KP_TILED && ctx->opt.zero_base;
     j->ws->table.want_q = want_i8(ctx);
     JCUDA(cudaStreamSynchronize(st));
     // last: the small uploads above share the one H2D copy engine with these 1.2 GB and would queue behind them
@@ -1473,10 +1548,10 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, int phase, b
     t.n_cells = C;
     t.n_genes = G;
     t.ld_ridx = C;
-    if (phase == 0) j->front_plan = plan_table(t, j->local_theta);
+    if (phase == 0) j->front_plan = plan_table(ctx, t, j->local_theta);
     TablePlan &pl = j->front_plan;  // prepare_cells and reserve_rows bind its buffers in phase 0
     // the copies are already in flight (start_count_copies); every path below waits for them on the compute stream
-    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * j->copy_chunks && !getenv("SCDE_B200_NO_PIPELINE");
+    const bool pipelined = pl.q_fused && t.zero_base && C >= 64 * j->copy_chunks && ctx->opt.pipeline_front;
     if (!pipelined) {
         j->split_chunks = 0;
         for (int i = 0; i < j->copy_chunks; ++i) SCDE_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[i], 0));
@@ -1499,7 +1574,7 @@ static int front_chunked(scde_b200_ctx *ctx, scde_b200_diff_job *j, int phase, b
         cudaError_t _e = (x);                                                       \
         if (_e != cudaSuccess) return drain(cuda_fail(_e, #x, __FILE__, __LINE__));  \
     } while (0)
-    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;
+    const bool trace = ctx->opt.trace != 0;
     const auto tf0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count(); };
     double tr_first = 0, tr_queued = 0, tr_draws = 0, tr_front = 0, tr_copy = 0;
@@ -1708,19 +1783,26 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
     return SCDE_B200_OK;
 }
 
-extern "C" {
+// Where a job's per-gene results go in the caller's (column-major) output matrices: row `row0` of matrices with `ld`
+// rows.  A single-device call writes whole matrices (ld = the job's genes, row0 = 0); the shards of a multi-device call
+// write their gene range of the same buffers.
+struct OutPlace {
+    int64_t ld, row0;
+};
 
-static int download_matrix(scde_b200_ctx *ctx, scde_b200_diff_job *j, const double *src, int ld_src, int cols, double *dst) {
+static int download_matrix(scde_b200_ctx *ctx, scde_b200_diff_job *j, const double *src, int ld_src, int cols, double *dst,
+                           OutPlace pl) {
     cudaStream_t st = ctx->stream;
     SCDE_CUDA(j->ws->tbuf.ensure((size_t)j->G * cols));
     SCDE_CUDA(launch_transpose_out(src, ld_src, j->G, cols, j->ws->tbuf.p, st));
-    SCDE_CUDA(cudaMemcpyAsync(dst, j->ws->tbuf.p, sizeof(double) * (size_t)j->G * cols, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaMemcpy2DAsync(dst + pl.row0, sizeof(double) * (size_t)pl.ld, j->ws->tbuf.p, sizeof(double) * (size_t)j->G,
+                                sizeof(double) * (size_t)j->G, cols, cudaMemcpyDeviceToHost, st));
     SCDE_CUDA(cudaStreamSynchronize(st));
     return SCDE_B200_OK;
 }
 
-int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_out *o,
-                            scde_b200_stats *stats) {
+static int diff_download_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_out *o,
+                              scde_b200_stats *stats, OutPlace pl) {
     CHECK_CTX(ctx);
     if (!j || !j->ran) {
         set_error("diff_download: job has not been run");
@@ -1734,47 +1816,51 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
         int rerun = 0;
         TRY(read_flags(ctx, &rerun));
         if (rerun) {  // a multiplicity above 127: repeat the run on the FP64 contraction kernel
-            const int keep = ctx->contract_kernel;
-            ctx->contract_kernel = 2;
+            const int keep = ctx->opt.contract_kernel;
+            ctx->opt.contract_kernel = 2;
             const int r = scde_b200_diff_run(ctx, j);
-            ctx->contract_kernel = keep;
+            ctx->opt.contract_kernel = keep;
             if (r != SCDE_B200_OK) return r;
             SCDE_CUDA(cudaStreamSynchronize(st));
         }
     }
     if (o) {
-        if (o->idx) SCDE_CUDA(cudaMemcpyAsync(o->idx, j->idx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
-        if (o->z) SCDE_CUDA(cudaMemcpyAsync(o->z, j->z.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+        auto get_idx = [&](int32_t *dst, const int32_t *src) {  // [3][G] on the device -> rows row0.. of an ld x 3 matrix
+            return cudaMemcpy2DAsync(dst + pl.row0, sizeof(int32_t) * (size_t)pl.ld, src, sizeof(int32_t) * (size_t)G,
+                                     sizeof(int32_t) * (size_t)G, 3, cudaMemcpyDeviceToHost, st);
+        };
+        auto get_z = [&](double *dst, const double *src) {
+            return cudaMemcpyAsync(dst + pl.row0, src, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st);
+        };
+        if (o->idx) SCDE_CUDA(get_idx(o->idx, j->idx.p));
+        if (o->z) SCDE_CUDA(get_z(o->z, j->z.p));
         if (j->has_batch) {
-            if (o->batch_idx)
-                SCDE_CUDA(cudaMemcpyAsync(o->batch_idx, j->bidx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
-            if (o->batch_z) SCDE_CUDA(cudaMemcpyAsync(o->batch_z, j->bz.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
-            if (o->adjusted_idx)
-                SCDE_CUDA(cudaMemcpyAsync(o->adjusted_idx, j->aidx.p, sizeof(int32_t) * 3 * (size_t)G, cudaMemcpyDeviceToHost, st));
-            if (o->adjusted_z)
-                SCDE_CUDA(cudaMemcpyAsync(o->adjusted_z, j->az.p, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+            if (o->batch_idx) SCDE_CUDA(get_idx(o->batch_idx, j->bidx.p));
+            if (o->batch_z) SCDE_CUDA(get_z(o->batch_z, j->bz.p));
+            if (o->adjusted_idx) SCDE_CUDA(get_idx(o->adjusted_idx, j->aidx.p));
+            if (o->adjusted_z) SCDE_CUDA(get_z(o->adjusted_z, j->az.p));
         }
         SCDE_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < 2; ++i) {
-            if (o->joint_posteriors[i]) TRY(download_matrix(ctx, j, j->ws->jp[i].p, ld, K, o->joint_posteriors[i]));
+            if (o->joint_posteriors[i]) TRY(download_matrix(ctx, j, j->ws->jp[i].p, ld, K, o->joint_posteriors[i], pl));
             if (j->has_batch && o->batch_joint_posteriors[i])
-                TRY(download_matrix(ctx, j, j->ws->jp[2 + i].p, ld, K, o->batch_joint_posteriors[i]));
+                TRY(download_matrix(ctx, j, j->ws->jp[2 + i].p, ld, K, o->batch_joint_posteriors[i], pl));
         }
         if (o->difference_posterior) {
             if (!j->ws->post.p) {
                 set_error("difference_posterior requested but the job was uploaded without want_posteriors");
                 return SCDE_B200_EINVAL;
             }
-            TRY(download_matrix(ctx, j, j->ws->post.p, ldo, nout, o->difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->post.p, ldo, nout, o->difference_posterior, pl));
         }
         if (j->has_batch && o->batch_difference_posterior)
-            TRY(download_matrix(ctx, j, j->ws->bpost.p, ldo, nout, o->batch_difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->bpost.p, ldo, nout, o->batch_difference_posterior, pl));
         if (j->has_batch && o->adjusted_difference_posterior) {
             if (!j->ws->apost.p) {
                 set_error("adjusted posterior requested but the job was uploaded without want_posteriors");
                 return SCDE_B200_EINVAL;
             }
-            TRY(download_matrix(ctx, j, j->ws->apost.p, lda, nadj, o->adjusted_difference_posterior));
+            TRY(download_matrix(ctx, j, j->ws->apost.p, lda, nadj, o->adjusted_difference_posterior, pl));
         }
     }
     SCDE_CUDA(cudaStreamSynchronize(st));
@@ -1788,18 +1874,26 @@ int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scd
     return SCDE_B200_OK;
 }
 
+extern "C" {
+
+int scde_b200_diff_download(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff_out *o, scde_b200_stats *stats) {
+    return diff_download_impl(ctx, j, o, stats, OutPlace{j ? j->G : 0, 0});
+}
+
 void scde_b200_diff_free(scde_b200_ctx *ctx, scde_b200_diff_job *job) {
     if (ctx) cudaSetDevice(ctx->device);
     if (job && job->owner) job->owner->ws_busy = false;
     delete job;
 }
 
-int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_args *args, const scde_b200_diff_out *out,
-                                    scde_b200_stats *stats) {
+}  // extern "C"
+
+// one device: upload (chunked, overlapped), run, download into the caller's buffers at `pl`
+static int expression_difference_single(scde_b200_ctx *ctx, const scde_b200_diff_args *args, const scde_b200_diff_out *out,
+                                        scde_b200_stats *stats, const OutPlace *place) {
     CHECK_CTX(ctx);
-    if (!args || !out) return SCDE_B200_EINVAL;
     const int want_post = out->difference_posterior || out->adjusted_difference_posterior;
-    const bool trace = getenv("SCDE_B200_TRACE") != nullptr;  // host wall-clock of the three phases on stderr
+    const bool trace = ctx->opt.trace != 0;  // host wall-clock of the three phases on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
@@ -1812,13 +1906,78 @@ int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_arg
     r = diff_run_impl(ctx, job, true);
     if (r != SCDE_B200_OK && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     const auto t2 = now();
-    if (r == SCDE_B200_OK) r = scde_b200_diff_download(ctx, job, out, stats);
+    if (r == SCDE_B200_OK) r = diff_download_impl(ctx, job, out, stats, place ? *place : OutPlace{job->G, 0});
     const auto t3 = now();
     scde_b200_diff_free(ctx, job);
     if (trace)
-        fprintf(stderr, "[scde_b200] expression_difference: upload %.2f ms, run (queued) %.2f ms, download (incl. wait) %.2f ms, free %.2f ms\n",
-                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
+        fprintf(stderr, "[scde_b200] expression_difference (device %d): upload %.2f ms, run (queued) %.2f ms, download (incl. wait) %.2f ms, free %.2f ms\n",
+                ctx->device, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
     return r;
+}
+
+// Several devices: contiguous gene ranges, one per device (the split the reference's chunk() makes for n.cores,
+// R/functions.R:606), one host thread per device, every shard with the same Seed and therefore the same draws -- the
+// n.cores = 1 semantics, so the result does not depend on the number of devices.  No inter-GPU traffic: every shard's
+// results go to its rows of the caller's buffers by device-to-host copies (north_star: "or by a host copy").
+static int expression_difference_multi(scde_b200_ctx *ctx, const scde_b200_diff_args *args, const scde_b200_diff_out *out,
+                                       scde_b200_stats *stats) {
+    int g0 = args->gene_begin, g1 = args->gene_end;
+    if (g0 == 0 && g1 == 0) g1 = args->n_genes;
+    if (g0 < 0 || g1 > args->n_genes || g0 >= g1) {
+        set_error("gene range [%d, %d) invalid for %d genes", g0, g1, args->n_genes);
+        return SCDE_B200_EINVAL;
+    }
+    std::vector<scde_b200_ctx *> devs;
+    devs.push_back(ctx);
+    for (auto *c : ctx->children) devs.push_back(c);
+    const int n = g1 - g0;
+    const int n_use = (int)devs.size() < n ? (int)devs.size() : n;
+    std::vector<int> rc(n_use, SCDE_B200_OK);
+    std::vector<std::string> msg(n_use);
+    std::vector<scde_b200_stats> sst(n_use);
+    std::vector<std::thread> th;
+    const int base = n / n_use, rem = n % n_use;
+    for (int i = 0; i < n_use; ++i) {
+        const int b = g0 + i * base + (i < rem ? i : rem), e = b + base + (i < rem ? 1 : 0);
+        th.emplace_back([&, i, b, e] {
+            scde_b200_diff_args a = *args;
+            a.gene_begin = b;
+            a.gene_end = e;
+            const OutPlace pl{n, b - g0};
+            memset(&sst[i], 0, sizeof(scde_b200_stats));
+            rc[i] = expression_difference_single(devs[i], &a, out, &sst[i], &pl);
+            if (rc[i] != SCDE_B200_OK) msg[i] = g_err;  // the error text is thread-local
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < n_use; ++i)
+        if (rc[i] != SCDE_B200_OK) {
+            set_error("device %d (shard %d of %d): %s", devs[i]->device, i, n_use, msg[i].c_str());
+            return rc[i];
+        }
+    if (stats) {  // stage times: the slowest shard; counters: summed
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < n_use; ++i) {
+            for (int k = 0; k < SCDE_B200_T_COUNT; ++k) {
+                if (sst[i].ms[k] > stats->ms[k]) stats->ms[k] = sst[i].ms[k];
+                stats->launches[k] += sst[i].launches[k];
+            }
+            stats->table_rows += sst[i].table_rows;
+            stats->contract_cells += sst[i].contract_cells;
+        }
+    }
+    return SCDE_B200_OK;
+}
+
+extern "C" {
+
+int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_args *args, const scde_b200_diff_out *out,
+                                    scde_b200_stats *stats) {
+    CHECK_CTX(ctx);
+    if (!args || !out) return SCDE_B200_EINVAL;
+    if (!ctx->children.empty()) return expression_difference_multi(ctx, args, out, stats);
+    return expression_difference_single(ctx, args, out, stats, nullptr);
 }
 
 }  // extern "C"

@@ -86,9 +86,6 @@ __device__ __forceinline__ void st_peer_f64(const void *p, uint32_t peer, double
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(peer));
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // W build: multiplicities from the draw lists
@@ -113,7 +110,7 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
                                    int n_list, int n_genes, const int32_t *__restrict__ zero_row,
                                    const int32_t *__restrict__ based, int pad_row, int32_t *__restrict__ lst_row,
                                    int32_t *__restrict__ lst_cell, int32_t *__restrict__ lst_len, int64_t ld_lst,
-                                   unsigned long long *total_entries) {
+                                   unsigned long long *total_entries, int hot_rank) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n_genes) return;
     const int lane = threadIdx.x & 31;
@@ -142,7 +139,9 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
             if (keep[u]) {
                 const int o = pos + __popc(m & ((1u << lane) - 1));
                 lst_row[g * ld_lst + o] = r[u];
-                lst_cell[g * ld_lst + o] = base + 32 * u + lane;
+                // rows of a cell are in ascending count order behind its zero-count row: a small distance = a small count
+                const bool hot = hot_rank >= 0 && zr[u] >= 0 && r[u] - zr[u] <= hot_rank;
+                lst_cell[g * ld_lst + o] = (base + 32 * u + lane) | (hot ? LIST_HOT_BIT : 0);
             }
             pos += __popc(m);
         }
@@ -859,12 +858,12 @@ cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_lis
 
 cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
                                const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
-                               unsigned long long *total_entries, cudaStream_t st) {
+                               unsigned long long *total_entries, cudaStream_t st, int hot_rank) {
     if (n_genes <= 0) return cudaSuccess;
     const int wpb = 8;
     build_lists_kernel<<<(n_genes + wpb - 1) / wpb, wpb * 32, 0, st>>>(ridx, ld_ridx, cell_ids, n_list, n_genes, zero_row,
                                                                       based, pad_row, out.row, out.cell, out.len, out.ld,
-                                                                      total_entries);
+                                                                      total_entries, hot_rank);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // processing order: heaviest genes first when the counting sort's bins and keys fit in shared memory, else identity
@@ -914,15 +913,12 @@ size_t contract_tiled_scratch_doubles(int n_genes) {
 
 cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, double *t_scratch, cudaStream_t st, int *n_launches) {
     if (a.n_genes <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {  // function attributes are per device: set on every launch (a process may hold contexts on several GPUs)
         cudaError_t e = cudaFuncSetAttribute(contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(MmaSmem));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int passes = (a.n_boot + WP_TILED - 1) / WP_TILED;
-    const char *dbg = getenv("SCDE_B200_DEBUG_CONTRACT");
     for (int g0 = 0; g0 < a.n_genes; g0 += TILED_MAX_GENES_PER_LAUNCH) {
         const int n_pos = (a.n_genes - g0) < TILED_MAX_GENES_PER_LAUNCH ? (a.n_genes - g0) : TILED_MAX_GENES_PER_LAUNCH;
         for (int ps = 0; ps < passes; ++ps) {
@@ -937,7 +933,7 @@ cudaError_t launch_contract_tiled(const ContractArgs &a, int n_sm, double *t_scr
             p.Z = a.Z ? a.Z + (size_t)ps * WP_TILED * KP_TILED : nullptr;
             p.T = t_scratch;
             p.n_pos = n_pos;
-            p.debug = dbg ? atoi(dbg) : 0;
+            p.debug = a.debug;
             int grid = n_sm < 2 * n_pos ? n_sm : 2 * n_pos;
             contract_mma_kernel<<<grid, T_THREADS, sizeof(MmaSmem), st>>>(p);
             cudaError_t e = cudaGetLastError();

@@ -60,7 +60,8 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st);
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0);
+// legacy_q_rows: build fixed-point-only rows with the per-element kernel the register-resident one replaced (tests)
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
@@ -104,7 +105,9 @@ struct GeneLists {
 cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
                                const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
                                unsigned long long *total_entries /* += sum of list lengths, may be NULL */,
-                               cudaStream_t st);
+                               cudaStream_t st, int hot_rank = -1);
+// hot_rank >= 0 (tcgen05 kernel only): entries whose table row is at most hot_rank rows above the cell's zero-count row
+// -- the cell's smallest counts, rows are in ascending count order -- carry LIST_HOT_BIT in out.cell
 // Z[pass*104 + b][k] = sum over based cells of the joint of W[cell][b] * table[zero_row[cell]][k]; scratch holds
 // base_sum_scratch_doubles() doubles.  Two deterministic passes (partials per cell chunk, then a fixed-order reduction).
 size_t base_sum_scratch_doubles(int n_boot, int ld_table);
@@ -123,6 +126,7 @@ struct ContractArgs {
     int n_genes, K;
     double *jp;  // [n_genes][ld_jp], must be zeroed by the caller
     int ld_jp;
+    int debug = 0;  // tiled kernel: diagnostic mode (scde_b200_options::debug_contract)
 };
 cudaError_t launch_contract_generic(const ContractArgs &a, cudaStream_t st, int *n_launches);
 // requires K <= 416 and ld_table == 416; t_scratch holds contract_tiled_scratch_doubles(n_genes) doubles (the raw
@@ -187,7 +191,13 @@ struct ContractI8Args {
     int ld_jp;
     int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired, |= 4 if the sentinel ranges need the FP64 kernel
     unsigned long long *dbg;  // optional [3] cycle counters of the epilogue (see contract_i8.cu), or NULL
+    int item_order;    // 0: item = (gene, piece), a gene's pieces on neighbouring SMs; 1: piece-major (all SMs walk the same
+                       // 512-byte piece of the rows at the same time, so rows shared between genes are L2 hits more often)
+    int hot_rank;      // >= 0: list entries carry bit 30 of `cell` when the row's rank within its cell is <= hot_rank; such
+                       // rows are loaded with the L2 evict_last policy, the others evict_first.  < 0: no hints
+    int cold_evict_first;  // with hot_rank >= 0: 1 = the other rows are loaded evict_first, 0 = without a priority
 };
+constexpr int32_t LIST_HOT_BIT = 1 << 30;  // in GeneLists::cell (W row ids are < 65536)
 // n_draws: draws per randomization (the plane sums are combined pairwise in 32 bits: 257 * 128 * draws < 2^31)
 bool contract_i8_supported(int K, int ld_table, int ld_lst, int n_draws);
 size_t contract_i8_range_words(int n_genes);  // uint32 words of the (gene, boot) sentinel-range scratch

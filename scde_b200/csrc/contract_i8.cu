@@ -31,7 +31,7 @@
 //   * MMA (1 thread): per stage two tcgen05.mma (M = 128 boots, N = 256, K = 32 entries), then tcgen05.commit onto the
 //     stage's "empty" barrier; after the last stage a commit onto the accumulator barrier.
 //   * epilogue (4 warps, one per 32-lane quarter of tensor memory): tcgen05.ld the five planes of 8 grid points at a
-//     time, recombine into one 64-bit integer per (boot, grid point) and store it; softmax_i8_kernel finishes the gene
+//     time, recombine into one 64-bit integer per (boot, grid point) and store it; softmax_i8_warp_kernel finishes the gene
 //     (conversion, zero-count base Z[b, k], sentinel ranges, soft-max, average).  Producers keep prefetching the next
 //     item meanwhile.
 // Roofline: HBM gather bandwidth (512 bytes per visited (gene, cell) pair and piece; tools/gather_bench.cu measures
@@ -88,6 +88,8 @@ struct I8Params {
     int32_t *err;        // device flag: 2 = watchdog abort
     unsigned long long *dbg;  // optional diagnostics: [0] += cycles between "accumulators ready" and "tensor memory released",
                               // [1] += items, [2] += cycles the MMA thread waited for the release (epilogue warp 0 / MMA thread)
+    int piece_major;     // item order: 0 = (gene, piece) with the piece fastest, 1 = (piece, gene) with the gene fastest
+    int cold_evict_first;  // HINT kernels: rows without the hot bit are loaded evict_first (else without a hint)
 };
 
 __device__ __forceinline__ bool wait_or_abort(I8Smem &sm, uint64_t *bar, uint32_t parity) {
@@ -103,19 +105,27 @@ __device__ __forceinline__ bool wait_or_abort(I8Smem &sm, uint64_t *bar, uint32_
     return true;
 }
 
-// item -> (gene position, piece); the pieces of one gene go to neighbouring CTAs of the same round, so the W rows and
-// list entries they share are L2 hits for three of the four
+// item -> (gene position, piece).  Gene-major order: the pieces of one gene go to neighbouring CTAs of the same round, so
+// the W rows and list entries they share are L2 hits for three of the four.  Piece-major order: all CTAs work on the same
+// 512-byte piece of the table rows at the same time -- four times as many genes in flight per piece, and a quarter of
+// the table as the working set of a phase, so the rows of small counts (shared by thousands of genes) are L2 hits more
+// often; the lists and W rows are re-read once per phase (8 + 128 B per entry against the piece's 512 B).
 struct Item {
     int pos, piece;
 };
 __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
     Item it;
-    it.pos = item / p.n_pieces;
-    it.piece = item - it.pos * p.n_pieces;
+    if (p.piece_major) {
+        it.piece = item / p.n_pos;
+        it.pos = item - it.piece * p.n_pos;
+    } else {
+        it.pos = item / p.n_pieces;
+        it.piece = item - it.pos * p.n_pieces;
+    }
     return it;
 }
 __device__ __forceinline__ int64_t item_gene(const I8Params &p, int item) {
-    const int pos = item / p.n_pieces;
+    const int pos = p.piece_major ? item % p.n_pos : item / p.n_pieces;
     return p.order ? p.order[pos] : pos;
 }
 
@@ -136,8 +146,25 @@ template <int DOFF, int SOFF>
 __device__ __forceinline__ void cp_async16_at(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst_smem), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
 }
-template <int Q_PGROUPS>
+template <int DOFF, int SOFF>
+__device__ __forceinline__ void cp_async16_hint_at(uint32_t dst_smem, const void *src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0+%2], [%1+%3], 16, %4;" ::"r"(dst_smem), "l"(src), "n"(DOFF), "n"(SOFF),
+                 "l"(policy)
+                 : "memory");
+}
+// HINT: list entries carry LIST_HOT_BIT in `cell` when the row is one of the first few of its cell (a small count: such a
+// row is shared by thousands of genes); its pieces are loaded with the L2 evict_last policy, the others evict_first (or
+// unhinted), so that the stream of rows that are used once does not push the shared ones out of the L2.
+template <int Q_PGROUPS, bool HINT>
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
+    uint64_t pol_hot = 0, pol_cold = 0;
+    if (HINT) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+        if (p.cold_evict_first)
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+        else
+            asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
+    }
     const int grp = warp >> 2, kg = warp & 3;
     const int l7 = lane & 7, l3 = lane >> 3;
     // entry kk = l3 (and l3 + 4): line kk of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
@@ -195,19 +222,34 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
                     const uint32_t sB0 = sA + Q_A_BYTES + d0, sB1 = sA + Q_A_BYTES + d1;
                     const int8_t *src0 = qbase + (int64_t)row0 * p.ldq;
                     const int8_t *src1 = qbase + (int64_t)row1 * p.ldq;
-                    const int8_t *w0 = wbase + (int64_t)cel0 * Q_WB;
-                    const int8_t *w1 = wbase + (int64_t)cel1 * Q_WB;
+                    const int8_t *w0 = wbase + (int64_t)(cel0 & ~LIST_HOT_BIT) * Q_WB;
+                    const int8_t *w1 = wbase + (int64_t)(cel1 & ~LIST_HOT_BIT) * Q_WB;
                     if (fill > 0 && !wait_or_abort(sm, &sm.empty[slot], (fill - 1) & 1u)) return;
-                    cp_async16_at<0, 0>(sB0, src0);
-                    cp_async16_at<0, 0>(sB1, src1);
-                    cp_async16_at<4096, 128>(sB0, src0);
-                    cp_async16_at<4096, 128>(sB1, src1);
-                    cp_async16_at<8192, 256>(sB0, src0);
-                    cp_async16_at<8192, 256>(sB1, src1);
-                    cp_async16_at<12288, 384>(sB0, src0);
-                    cp_async16_at<12288, 384>(sB1, src1);
-                    cp_async16_at<0, 0>(sA + d0, w0);
-                    cp_async16_at<0, 0>(sA + d1, w1);
+                    if (HINT) {
+                        const uint64_t pol0 = (cel0 & LIST_HOT_BIT) ? pol_hot : pol_cold;
+                        const uint64_t pol1 = (cel1 & LIST_HOT_BIT) ? pol_hot : pol_cold;
+                        cp_async16_hint_at<0, 0>(sB0, src0, pol0);
+                        cp_async16_hint_at<0, 0>(sB1, src1, pol1);
+                        cp_async16_hint_at<4096, 128>(sB0, src0, pol0);
+                        cp_async16_hint_at<4096, 128>(sB1, src1, pol1);
+                        cp_async16_hint_at<8192, 256>(sB0, src0, pol0);
+                        cp_async16_hint_at<8192, 256>(sB1, src1, pol1);
+                        cp_async16_hint_at<12288, 384>(sB0, src0, pol0);
+                        cp_async16_hint_at<12288, 384>(sB1, src1, pol1);
+                        cp_async16_hint_at<0, 0>(sA + d0, w0, pol_hot);
+                        cp_async16_hint_at<0, 0>(sA + d1, w1, pol_hot);
+                    } else {
+                        cp_async16_at<0, 0>(sB0, src0);
+                        cp_async16_at<0, 0>(sB1, src1);
+                        cp_async16_at<4096, 128>(sB0, src0);
+                        cp_async16_at<4096, 128>(sB1, src1);
+                        cp_async16_at<8192, 256>(sB0, src0);
+                        cp_async16_at<8192, 256>(sB1, src1);
+                        cp_async16_at<12288, 384>(sB0, src0);
+                        cp_async16_at<12288, 384>(sB1, src1);
+                        cp_async16_at<0, 0>(sA + d0, w0);
+                        cp_async16_at<0, 0>(sA + d1, w1);
+                    }
                     cp_async_mbar_arrive_noinc(&sm.full[slot]);
                     slot += Q_PGROUPS;
                     if (slot >= Q_NS) {
@@ -275,7 +317,7 @@ __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t 
 // per (boot, grid point) and store it with streaming stores -- no loads, no floating point.  |sum_p| <= 128 * draws < 2^23
 // (draws <= 65000 is checked by the launcher), so a = s0 + 256 s1 and b = s2 + 256 s3 fit 32 bits and the value is
 // a + 2^16 b + 2^32 s4.  Conversion to FP64, the zero-count base Z and the sentinel ranges are applied by
-// softmax_i8_kernel when it reads T.  (An epilogue that did all of that took 16 800 cycles per item -- 8.9 us, of which
+// softmax_i8_warp_kernel when it reads T.  (An epilogue that did all of that took 16 800 cycles per item -- 8.9 us, of which
 // the ring hides 3 -- and cost a quarter of the kernel: SCDE_B200_EPI_TIMING, profiles/r01x.)
 __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint32_t xbuf, uint32_t tmem, int n_items, int ewarp,
                                              int lane) {
@@ -351,7 +393,7 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
     }
 }
 
-template <int Q_PGROUPS>
+template <int Q_PGROUPS, bool HINT>
 __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(const I8Params p) {
     constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -379,7 +421,7 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     const int n_items = p.n_pos * p.n_pieces;
 
     if (warp < Q_PRODUCER_WARPS)
-        run_producer<Q_PGROUPS>(p, sm, stage0, n_items, warp, lane);
+        run_producer<Q_PGROUPS, HINT>(p, sm, stage0, n_items, warp, lane);
     else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
         run_epilogue(p, sm, xbuf, tmem, n_items, warp - Q_PRODUCER_WARPS, lane);
     else if (lane == 0)
@@ -421,7 +463,7 @@ __global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__re
         cell = 0;
         if (e < len) {
             rr = __ldg(row_range + lr[e]);
-            cell = lc[e];
+            cell = lc[e] & ~LIST_HOT_BIT;
         }
     };
     uint32_t rr_n = full;
@@ -486,89 +528,17 @@ __global__ void __launch_bounds__(256) sentinel_range_kernel(const int32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// softmax_i8_kernel + softmax_i8_reduce_kernel: jp[gene, k] (+)= sum_b softmax_k(T[b, :])[k] / scale from the integer T tiles
-// of contract_i8_kernel (src/jpmatLogBoot.cpp:264-269).  T[b, k] = 2^-29 * integer + Z[b, k], "log 0" (excluded from the
-// soft-max) outside the (gene, boot) sentinel range.
-// A CTA owns one group of 13 boots -- one boot per warp, so the warp keeps its row of the zero-count base Z in registers
-// for all the genes it walks (read from every gene's CTA, Z cost as much L2 traffic as T costs HBM traffic).  Per gene a
-// warp reads its T row once (13 grid points per lane), takes the log-sum-exp pieces by shuffles (exp_nonpos, skipped
-// warp-wide where a 32-point stretch lies > 746 nats below the row maximum: a joint posterior is sharply peaked), and the
-// 13 normalised rows are added in ascending boot order through shared memory.  The eight groups' partial sums are added
-// in group order by the reduce kernel: the result is deterministic.
+// softmax_i8_warp_kernel + softmax_i8_reduce_kernel: jp[gene, k] (+)= sum_b softmax_k(T[b, :])[k] / scale from the integer
+// T tiles of contract_i8_kernel (src/jpmatLogBoot.cpp:264-269).  T[b, k] = 2^-29 * integer + Z[b, k], "log 0" (excluded
+// from the soft-max) outside the (gene, boot) sentinel range.  A CTA owns one group of 13 boots; the eight groups' partial
+// sums are added in group order by the reduce kernel: the result is deterministic.
 constexpr int SP_GROUPS = 8, SP_ROWS = WP_TILED / SP_GROUPS;
 static_assert(SP_GROUPS * SP_ROWS == WP_TILED && SP_ROWS * 32 == KP_TILED, "13 warps x 32 lanes = the 416 grid slots");
-__global__ void __launch_bounds__(SP_ROWS * 32)
-softmax_i8_kernel(const long long *__restrict__ T, const double *__restrict__ Z, const uint32_t *__restrict__ SR, int K,
-                  int n_boot_pass, double scale, double *__restrict__ part, int n_pos) {
-    constexpr int NJ = KP_TILED / 32;
-    __shared__ double s_acc[SP_ROWS][KP_TILED];
-    const int group = blockIdx.x % SP_GROUPS, batch = blockIdx.x / SP_GROUPS, n_batch = gridDim.x / SP_GROUPS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = group * SP_ROWS + warp;
-    const bool active = b < n_boot_pass;
-    double zr[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) zr[j] = (Z && active) ? Z[(int64_t)b * KP_TILED + lane + 32 * j] : 0.0;
-    const double q = 1.0 / (double)(1ll << Q_FRAC);
-    // the next gene's row is pulled into the L2 while the current one is processed (26 lines of 128 bytes, one per lane):
-    // a CTA is otherwise bound by one HBM latency per gene
-    auto prefetch_row = [&](int pos) {
-        if (active && lane < (KP_TILED * 8) / 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(T + ((int64_t)pos * WP_TILED + b) * KP_TILED + lane * 16));
-    };
-    for (int pos = batch; pos < n_pos; pos += n_batch) {
-        double v[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) v[j] = 0.0;
-        if (pos + n_batch < n_pos) prefetch_row(pos + n_batch);
-        if (active) {
-            const long long *row = T + ((int64_t)pos * WP_TILED + b) * KP_TILED;
-            const uint32_t sr = SR ? SR[(int64_t)pos * Q_WB + b] : 0xFFFF0000u;
-            const int klo = (int)(sr & 0xFFFFu), khi = (int)(sr >> 16);
-            double m = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int k = lane + 32 * j;
-                // some drawn row is "log 0" outside [klo, khi]: the reference's T is a multiple of the sentinel there
-                v[j] = (k < K && k >= klo && k <= khi) ? fma((double)__ldcs(row + k), q, zr[j]) : -INFINITY;
-                m = fmax(m, v[j]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-            double sum = 0.0;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const double d = v[j] - m;
-                v[j] = 0.0;
-                if (__any_sync(0xffffffffu, d > -746.0)) v[j] = d > -INFINITY ? exp_nonpos(d) : 0.0;
-                sum += v[j];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const double inv = 1.0 / (sum * scale);
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) v[j] *= inv;
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) s_acc[warp][lane + 32 * j] = v[j];
-        __syncthreads();
-        {
-            const int k = threadIdx.x;  // 416 threads = 416 grid slots
-            double r = 0.0;
-#pragma unroll
-            for (int w = 0; w < SP_ROWS; ++w) r += s_acc[w][k];
-            part[((int64_t)group * n_pos + pos) * KP_TILED + k] = r;
-        }
-        __syncthreads();
-    }
-}
-
-// softmax_i8_warp_kernel: the same result with a warp per gene instead of a warp per boot.  A CTA still owns one group
-// of 13 boots, whose Z rows it keeps in shared memory (43 KB); each of its warps walks genes on its own and, for a gene,
-// the 13 boots in ascending order: T row (the next boot's row is already in flight), soft-max pieces by shuffles, and the
-// normalised row is added to 13 accumulators per lane -- the same additions in the same order as the shared-memory
-// column sums of softmax_i8_kernel, without the two CTA barriers per gene, the 13 x 416 shared-memory stores and loads,
-// and with the skipped stretches (a joint posterior is sharply peaked) skipped in the accumulation too.
+// softmax_i8_warp_kernel: a warp per gene.  A CTA owns one group of 13 boots, whose Z rows it keeps in shared memory
+// (43 KB); each of its warps walks genes on its own and, for a gene, the 13 boots in ascending order: T row (the next
+// boot's row is already in flight), soft-max pieces by shuffles (exp_nonpos, skipped warp-wide where a 32-point stretch
+// lies > 746 nats below the row maximum: a joint posterior is sharply peaked), and the normalised row is added to 13
+// accumulators per lane in ascending boot order.
 constexpr int SW_WARPS = 8;
 __global__ void __launch_bounds__(SW_WARPS * 32, 2)
 softmax_i8_warp_kernel(const long long *__restrict__ T, const double *__restrict__ Z, const uint32_t *__restrict__ SR, int K,
@@ -782,6 +752,8 @@ static I8Params make_params(const ContractI8Args &a, int g0, int n_pos, int pass
     p.n_pieces = q_pieces(a.K);
     p.err = a.err;
     p.dbg = a.dbg;
+    p.piece_major = a.item_order == 1;
+    p.cold_evict_first = a.cold_evict_first;
     return p;
 }
 
@@ -802,17 +774,17 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
     // two producer groups: a third one (12 producer warps) measured 1 % slower -- the producers already wait on free
     // ring slots most of the time (profiles/r01w)
     constexpr int PG = 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_i8_kernel<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     const I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
-    contract_i8_kernel<PG><<<grid, q_threads(PG), Q_SMEM_BYTES, st>>>(p);
-    return cudaGetLastError();
+    // function attributes are per device: set on every launch (a process may hold contexts on several GPUs)
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, q_threads(PG), Q_SMEM_BYTES, st>>>(p);
+        return cudaGetLastError();
+    };
+    return a.hot_rank >= 0 ? launch(contract_i8_kernel<PG, true>) : launch(contract_i8_kernel<PG, false>);
 }
 
 size_t softmax_i8_scratch_doubles(int n_pos) { return (size_t)SP_GROUPS * (n_pos > 0 ? n_pos : 1) * KP_TILED; }
@@ -823,25 +795,15 @@ cudaError_t launch_softmax_i8(const ContractI8Args &a, int g0, int n_pos, int pa
     if (a.row_range && !sr) return cudaErrorInvalidValue;
     const int nb = (a.n_boot - pass * WP_TILED) < WP_TILED ? (a.n_boot - pass * WP_TILED) : WP_TILED;
     const double *Z = a.Z ? a.Z + (size_t)pass * WP_TILED * KP_TILED : nullptr;
-    int batches = n_sm * 4 / SP_GROUPS;  // four CTAs of 416 threads per SM
-    if (batches > n_pos) batches = n_pos;
-    if (batches < 1) batches = 1;
-    cudaError_t e;
-    if (getenv("SCDE_B200_SOFTMAX_OLD")) {
-        softmax_i8_kernel<<<batches * SP_GROUPS, SP_ROWS * 32, 0, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
+    const size_t smem = sizeof(double) * SP_ROWS * KP_TILED;
+    cudaError_t e = cudaFuncSetAttribute(softmax_i8_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int wb = n_sm * 2 / SP_GROUPS;  // two CTAs of eight warps per SM
+    if (wb * SW_WARPS > n_pos) wb = (n_pos + SW_WARPS - 1) / SW_WARPS;
+    if (wb < 1) wb = 1;
+    softmax_i8_warp_kernel<<<wb * SP_GROUPS, SW_WARPS * 32, smem, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
                                                                         a.row_range ? sr : nullptr, a.K, nb, a.scale,
                                                                         part_scratch, n_pos);
-    } else {
-        const size_t smem = sizeof(double) * SP_ROWS * KP_TILED;
-        e = cudaFuncSetAttribute(softmax_i8_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int wb = n_sm * 2 / SP_GROUPS;  // two CTAs of eight warps per SM
-        if (wb * SW_WARPS > n_pos) wb = (n_pos + SW_WARPS - 1) / SW_WARPS;
-        if (wb < 1) wb = 1;
-        softmax_i8_warp_kernel<<<wb * SP_GROUPS, SW_WARPS * 32, smem, st>>>(reinterpret_cast<const long long *>(t_scratch), Z,
-                                                                            a.row_range ? sr : nullptr, a.K, nb, a.scale,
-                                                                            part_scratch, n_pos);
-    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t n = (int64_t)n_pos * KP_TILED;

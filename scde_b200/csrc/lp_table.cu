@@ -1117,7 +1117,7 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st) {
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
@@ -1126,7 +1126,7 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
     if (qtable && (!row_range || K > Q_MAX_K)) return cudaErrorInvalidValue;
     if (prep.cfp && prep.scfp && row_const && !local_theta && K <= KP_TILED && ld_table >= round_up(K, 16)) {
         if (!row_snap) return cudaErrorInvalidValue;
-        if (which == 2 && qtable && !write_f64 && !row_mode && zero_row && based && prep.ld >= K && !getenv("SCDE_B200_LP_OLD")) {
+        if (which == 2 && qtable && !write_f64 && !row_mode && zero_row && based && prep.ld >= K && !legacy_q_rows) {
             // fixed-point rows only: the register-resident kernel; one contiguous run of rows per warp
             const size_t smem = (size_t)QR_WARPS * QR_SMEM_WARP;
             auto launch_q = [&](auto kernel) -> cudaError_t {

@@ -133,9 +133,9 @@ def test_multiplicity_above_127_falls_back_to_fp64(ctx):
 
 
 @pytest.mark.parametrize("length_out", [400, 200, 407])
-def test_register_resident_row_kernel_equals_per_element_kernel(ctx, monkeypatch, length_out):
+def test_register_resident_row_kernel_equals_per_element_kernel(ctx, length_out):
     """lp_rows_q_kernel (cell vectors in registers, 13 grid points per lane) against lp_rows_fast_kernel (the same rows
-    built with per-element loads; SCDE_B200_LP_OLD=1): the fixed-point tables may differ by one unit of 2^-29 where a
+    built with per-element loads; scde_b200_options.lp_rows_kernel = 1): the fixed-point tables may differ by one unit of 2^-29 where a
     value sits on a rounding boundary (the row sum is associated differently), so the joint posteriors agree to 1e-7;
     counts up to 60000 exercise the snap point on every part of the grid, the sentinel ranges and the slow band; grids
     of 201 and 408 points exercise the lanes without a point of their own and the largest grid of the fixed-point form."""
@@ -146,27 +146,30 @@ def test_register_resident_row_kernel_equals_per_element_kernel(ctx, monkeypatch
     counts[:30] = rng.integers(0, 60000, size=counts[:30].shape)
     counts[30:50] = rng.integers(0, 40, size=counts[30:50].shape)
     res = {}
-    for old in ("1", None):
-        if old:
-            monkeypatch.setenv("SCDE_B200_LP_OLD", old)
-        else:
-            monkeypatch.delenv("SCDE_B200_LP_OLD", raising=False)
-        res[old] = api.scde_posteriors(w.models, counts, prior, n_randomizations=50, context=ctx).to_numpy()
-    assert _err(res[None], res["1"]) < 1e-7
-    assert np.array_equal(res[None] == 0.0, res["1"] == 0.0)
+    for old in (1, 0):
+        keep = ctx.set_options(lp_rows_kernel=old)
+        try:
+            res[old] = api.scde_posteriors(w.models, counts, prior, n_randomizations=50, context=ctx).to_numpy()
+        finally:
+            ctx.restore_options(keep)
+    assert _err(res[0], res[1]) < 1e-7
+    assert np.array_equal(res[0] == 0.0, res[1] == 0.0)
 
 
-def test_warp_per_gene_softmax_is_bit_identical_to_warp_per_boot(ctx, monkeypatch):
-    """softmax_i8_warp_kernel adds the normalised boot rows in the same order with the same roundings as
-    softmax_i8_kernel (SCDE_B200_SOFTMAX_OLD=1); 137 randomizations = two passes of 104 boots with a ragged last group"""
+def test_item_order_and_l2_hints_do_not_change_results(ctx):
+    """The tcgen05 kernel's schedule (gene-major or piece-major items) and the L2 eviction hints on the table loads
+    (scde_b200_options.item_order / hot_rank / cold_evict_first) are performance knobs: the integer sums, and therefore
+    the posteriors, are bit-identical.  137 randomizations = two passes of 104 boots with a ragged last group."""
     w = synth.make_workload(3, n_genes=150, n_cells=48, seed=4)
     counts = np.array(w.counts, copy=True)
     counts[:20] = np.random.default_rng(2).integers(0, 30000, size=counts[:20].shape)
-    res = {}
-    for old in ("1", None):
-        if old:
-            monkeypatch.setenv("SCDE_B200_SOFTMAX_OLD", old)
-        else:
-            monkeypatch.delenv("SCDE_B200_SOFTMAX_OLD", raising=False)
-        res[old] = api.scde_posteriors(w.models, counts, w.prior, n_randomizations=137, context=ctx).to_numpy()
-    assert np.array_equal(res[None], res["1"])
+    res = []
+    for kw in (dict(item_order=0, hot_rank=-1), dict(item_order=1, hot_rank=-1), dict(item_order=1, hot_rank=8),
+               dict(item_order=0, hot_rank=2, cold_evict_first=0)):
+        keep = ctx.set_options(**kw)
+        try:
+            res.append(api.scde_posteriors(w.models, counts, w.prior, n_randomizations=137, context=ctx).to_numpy())
+        finally:
+            ctx.restore_options(keep)
+    for r in res[1:]:
+        assert np.array_equal(res[0], r)

@@ -361,17 +361,19 @@ def test_na_group_cells_and_per_gene_expectation(ctx):
     np.testing.assert_allclose(got[["lb", "mle", "ub", "ce"]].to_numpy(), want["results"][:, :4], rtol=1e-12, atol=1e-300)
 
 
-def test_zero_base_equals_dense_form(ctx, monkeypatch):
+def test_zero_base_equals_dense_form(ctx):
     """The zero-base contraction (visit only non-zero-count cells) against the dense form on the same device."""
     w = synth.make_workload(3, n_genes=300, n_cells=120, seed=4)
     ctx.set_contract_kernel(2)  # both forms on the FP64 kernel: they differ by rounding only
     try:
         a = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
                                            return_posteriors=True, context=ctx)
-        monkeypatch.setenv("SCDE_B200_NO_ZERO_BASE", "1")
-        b = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
-                                           return_posteriors=True, context=ctx)
-        monkeypatch.delenv("SCDE_B200_NO_ZERO_BASE")
+        keep = ctx.set_options(zero_base=0)
+        try:
+            b = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, n_randomizations=100,
+                                               return_posteriors=True, context=ctx)
+        finally:
+            ctx.restore_options(keep)
     finally:
         ctx.set_contract_kernel(0)
     assert a["stats"]["contract_cells"] < 0.8 * b["stats"]["contract_cells"]
@@ -609,3 +611,93 @@ def test_dedup_bitmap_and_hash_cells_mixed(ctx):
         ok, worst = _logp_close(res["joint_posteriors"][lev], wj)
         assert ok, worst
     assert want.shape == (120, len(mag))
+
+
+def _oracle_diff(w, nboot=100, batch_codes=None):
+    codes = np.asarray(w.groups.codes)
+    return O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=nboot, seed=1,
+                                   batch_codes=batch_codes)
+
+
+def test_gene_shard_against_oracle(ctx):
+    """the shard path (gene_begin / gene_end of the one-shot call and of the job) against the ORACLE's rows of the same
+    genes -- not against the library's own unsharded run: genes are independent, the draws are those of Seed = 1 whatever
+    the range (n.cores = 1 semantics)"""
+    w = synth.make_workload(3, n_genes=230, n_cells=96, seed=31)
+    want = _oracle_diff(w)
+    mm, lt, sq = api.pack_models(w.models)
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    codes = np.asarray(w.groups.codes, dtype=np.int32)
+    for g0, g1 in ((0, 77), (77, 154), (154, 230), (229, 230)):
+        one = api.expression_difference_call(ctx, w.counts, mm, x, y, codes, 100, 1, local_theta=lt, sqlogit=sq,
+                                             gene_range=(g0, g1), want_posteriors=True)
+        assert np.array_equal(one["idx"], want["idx"][g0:g1])
+        _z_close(one["z"], want["results"][g0:g1, 4])
+        ok, worst = _logp_close(one["difference_posterior"], want["difference.posterior"][g0:g1])
+        assert ok, worst
+        job = api.DifferenceJob(ctx, w.counts, mm, x, y, codes, 100, 1, local_theta=lt, sqlogit=sq, gene_range=(g0, g1))
+        try:
+            job.run()
+            two = job.download()
+        finally:
+            job.close()
+        assert np.array_equal(two["idx"], one["idx"]) and np.array_equal(two["z"], one["z"])
+
+
+def _multi_ctx(n):
+    if _lib.lib().scde_b200_device_count() < n:
+        pytest.skip(f"needs {n} CUDA devices")
+    return _lib.Context(devices=list(range(n)))
+
+
+@pytest.mark.parametrize("batch", [False, True])
+def test_multi_device_call_equals_single_device(ctx, batch):
+    """scde_b200_create_multi: the one-shot call shards the genes over two devices on two host threads and writes every
+    shard's rows of the caller's buffers; bit-identical to the one-device call (the reference's n.cores > 1 would reseed
+    per chunk, R/functions.R:613 -- the library keeps the n.cores = 1 draws), and within tolerance of the oracle."""
+    mctx = _multi_ctx(2)
+    w = synth.make_workload(5 if batch else 3, n_genes=301, n_cells=128, seed=41, batch=batch)
+    mm, lt, sq = api.pack_models(w.models)
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    codes = np.asarray(w.groups.codes, dtype=np.int32)
+    bc = np.asarray(w.batch.codes, dtype=np.int32) if batch else None
+    kw = dict(batch_codes=bc, n_batch_levels=2 if batch else 0, local_theta=lt, sqlogit=sq, want_posteriors=True)
+    if batch:
+        kw["zero_index_adjusted"] = [2 * len(x) - 1]
+    one = api.expression_difference_call(ctx, w.counts, mm, x, y, codes, 100, 1, **kw)
+    two = api.expression_difference_call(mctx, w.counts, mm, x, y, codes, 100, 1, **kw)
+    keys = ["idx", "z", "difference_posterior"] + (["adjusted_idx", "adjusted_z", "batch_idx", "batch_z",
+                                                   "adjusted_difference_posterior"] if batch else [])
+    for k in keys:
+        assert np.array_equal(one[k], two[k]), k
+    for i in range(2):
+        assert np.array_equal(one["joint_posteriors"][i], two["joint_posteriors"][i])
+    want = _oracle_diff(w, batch_codes=bc)
+    assert np.array_equal(two["idx"], want["idx"])
+    _z_close(two["z"], want["results"][:, 4])
+    # a sub-range of the genes on the multi-device context, and fewer genes than devices
+    sub = api.expression_difference_call(mctx, w.counts, mm, x, y, codes, 100, 1, gene_range=(100, 233), **kw)
+    assert np.array_equal(sub["idx"], one["idx"][100:233]) and np.array_equal(sub["z"], one["z"][100:233])
+    tiny = api.expression_difference_call(mctx, w.counts, mm, x, y, codes, 100, 1, gene_range=(300, 301), **kw)
+    assert np.array_equal(tiny["z"], one["z"][300:301])
+    mctx.close()
+
+
+def test_second_device_runs_every_kernel(ctx):
+    """function attributes (dynamic shared memory opt-in) are per device: a context on device 1 must be able to launch the
+    tcgen05 and the FP64 contraction kernels after device 0 has (static attr_set)"""
+    if _lib.lib().scde_b200_device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    w = synth.make_workload(3, n_genes=64, n_cells=40, seed=9)
+    c1 = _lib.Context(1)
+    for kernel in (0, 2, 1):
+        res = []
+        for c in (ctx, c1):
+            c.set_contract_kernel(kernel)
+            try:
+                res.append(api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=20, context=c).to_numpy())
+            finally:
+                c.set_contract_kernel(0)
+        assert np.array_equal(res[0], res[1])
+    c1.close()

@@ -1,7 +1,8 @@
 """ctypes binding of the CPU oracle (``oracle/scde_oracle.c``).
 
 TEST INFRASTRUCTURE ONLY: imported by ``tests/``, ``__graft_entry__.smoke()`` and the CPU legs of
-``bench.py``; never by the product package ``scde_b200``.  "parity unpinned" caveat: see the header of
+``bench.py``; never by the product package ``scde_b200``.  Parity status (pinned bit for bit against the reference's own
+C++ compiled against a header shim, ``oracle/ref.py``; R nmath / R-level code stay restated): see the header of
 ``scde_oracle.c`` and DESIGN.md.
 
 All matrices follow R's column-major convention, expressed here as Fortran-ordered numpy arrays.

@@ -5,12 +5,19 @@
  * import or call this file; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, and there only as the checker / CPU arm.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference ships
- * no assertions (tests/tests.R only checks that nothing throws) and
- * cannot be built here (no R, Rcpp, RcppArmadillo, libRmath in the image).  The oracle is
- * pinned instead by (a) glibc srand/rand known answers, (b) mpmath 50-digit values for
- * dnbinom/dpois/qnorm/pnorm, (c) numpy.correlate for the sliding product, (d) the printed
- * rows of vignettes/diffexp.md:113-119 as a loose end-to-end smoke pin (tests/).
+ * PARITY STATUS: pinned against THE REFERENCE'S OWN C++ compiled here.  The reference ships no
+ * assertions (tests/tests.R only checks that nothing throws) and its build
+ * needs R, Rcpp, RcppArmadillo (absent from the image) -- but its two translation units of this
+ * path, src/jpmatLogBoot.cpp and src/matSlideMult.cpp, compile UNMODIFIED against the header shim
+ * oracle/shim/RcppArmadillo.h (the part of R / Rcpp / Armadillo they use, restated; Makefile target
+ * `ref` -> oracle/_ref/libscde_ref.so).  tests/test_ref.py holds every entry point of this file to
+ * that library BIT FOR BIT (all returnpost forms, batch, ensemble, no-bootstrap, local theta, legacy
+ * forms, matSlideMult, the rand() rejection loop), and tests/golden/ref_fixtures.npz carries its
+ * outputs to machines without /root/reference.  What stays restated -- "parity unpinned" in the
+ * strict sense -- is R itself: nmath's dnbinom / dpois (used by BOTH sides through Rf_dnbinom /
+ * Rf_dpois of the shim), qnorm / pnorm / p.adjust and the R-level ratio-posterior / summary code
+ * (R/functions.R), pinned by (a) mpmath 50-digit values, (b) scipy ndtri, (c) numpy.correlate,
+ * (d) glibc srand/rand known answers, (e) the printed rows of vignettes/diffexp.md:113-119.
  *
  * This is a plain-C, FP64, single-threaded (per gene chunk) restatement, in the reference's
  * loop order, of
@@ -34,6 +41,7 @@
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off, R's default optimisation level,
  * no FMA contraction so results match an x86-64 R build without -march flags).
  */
+#define _GNU_SOURCE /* qsort_r */
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
@@ -258,6 +266,21 @@ void orc_batch_boot_indices(int seed, int nlevels, const int *pool_off, const in
 /* ------------------------------------------------------------------------------------ */
 /* per-cell log-posterior table, src/jpmatLogBoot.cpp:128-211 (batch: :373-457)          */
 
+/* Armadillo's sum() of contiguous memory -- sum(vector) and every column of sum(M, 0) -- is arrayops::accumulate: two
+ * interleaved partial sums, acc1 over the even and acc2 over the odd positions, returned as acc1 + acc2.  Restated
+ * because the order decides the last bit; checked bit for bit against the reference compiled against the header shim
+ * (oracle/_ref, tests/test_ref.py). */
+static double arma_accumulate(const double *src, int n) {
+    double acc1 = 0.0, acc2 = 0.0;
+    int j;
+    for (j = 1; j < n; j += 2) {
+        acc1 += *src++;
+        acc2 += *src++;
+    }
+    if ((j - 1) < n) acc1 += *src;
+    return acc1 + acc2;
+}
+
 /* Fill pm[K x ncounts] (column j = grid vector for unique count uc[j], contiguous) and, if maxi != NULL,
  * the per-column argmax (first maximum, taken BEFORE the lower clamp as in :198-204). */
 static void cell_table(const double *models, int ncells_total, int i, const int *uc, int ncounts, const double *mag,
@@ -316,11 +339,9 @@ static void cell_table(const double *models, int ncells_total, int i, const int 
         for (int k = 1; k < K; k++)
             if (nbp[k] > maxp) maxp = nbp[k];
         if (maxp < (maxcfp + fp)) maxp = maxcfp + fp;
-        double sd = 0; /* arma::sum accumulates in double (its internal pairing of partial sums is not restated) */
-        for (int k = 0; k < K; k++) { /* :193 */
+        for (int k = 0; k < K; k++) /* :193 */
             nbp[k] = exp(nbp[k] - maxp) + exp(cfp[k] + fp - maxp);
-            sd += nbp[k];
-        }
+        const double sd = arma_accumulate(nbp, K); /* :194 sum(nbp) */
         for (int k = 0; k < K; k++) nbp[k] = log(nbp[k] / sd); /* :194-195 */
         if (maxi) {                                             /* :198-202 first maximum */
             int mi = 0;
@@ -383,11 +404,8 @@ static void softmax_accumulate(double *tjp, double *jp, int K, int ngenes, doubl
         double m = col[0];
         for (int k = 1; k < K; k++)
             if (col[k] > m) m = col[k];
-        double s = 0;
-        for (int k = 0; k < K; k++) {
-            col[k] = exp(col[k] - m);
-            s += col[k];
-        }
+        for (int k = 0; k < K; k++) col[k] = exp(col[k] - m);
+        double s = arma_accumulate(col, K); /* sum(tjp, 0) */
         s *= scale;
         double *out = jp + (size_t)g * K;
         for (int k = 0; k < K; k++) out[k] += col[k] / s;
@@ -432,11 +450,8 @@ int orc_log_boot_posterior(const double *models, int ncells, const int *ucl_flat
             int nc = ucl_off[j + 1] - ucl_off[j];
             double *cp = (double *)malloc(sizeof(double) * (size_t)K * (nc > 0 ? nc : 1));
             for (int u = 0; u < nc; u++) {
-                double s = 0;
-                for (int k = 0; k < K; k++) {
-                    cp[(size_t)u * K + k] = exp(t.pm[j][(size_t)u * K + k]);
-                    s += cp[(size_t)u * K + k];
-                }
+                for (int k = 0; k < K; k++) cp[(size_t)u * K + k] = exp(t.pm[j][(size_t)u * K + k]);
+                const double s = arma_accumulate(cp + (size_t)u * K, K); /* sum(cellucpost, 0) */
                 for (int k = 0; k < K; k++) cp[(size_t)u * K + k] /= s;
             }
             for (int g = 0; g < ngenes; g++) {
@@ -446,8 +461,7 @@ int orc_log_boot_posterior(const double *models, int ncells, const int *ucl_flat
             free(cp);
         }
         for (int g = 0; g < ngenes; g++) {
-            double s = 0;
-            for (int k = 0; k < K; k++) s += jpt[(size_t)g * K + k];
+            const double s = arma_accumulate(jpt + (size_t)g * K, K); /* sum(jp, 0) */
             for (int k = 0; k < K; k++) jpt[(size_t)g * K + k] /= s;
         }
     } else if (nboot == 0) { /* :239-249 */

@@ -54,3 +54,34 @@ def es_mef_inputs(variant: str = "tests"):
     cd = cd.loc[:, list(ifm.index)]
     groups = pd.Categorical([("ESC" if n.startswith("ESC") else "MEF") for n in ifm.index], categories=["ESC", "MEF"])
     return cd, ifm, prior, groups
+
+
+# ---- inputs of tests/golden/ref_fixtures.npz (outputs of the reference's own C++, tests/golden/make_ref_fixtures.py) ----
+VIGNETTE_GENES = ["Dppa5a", "Pou5f1", "Gm13242", "Tdh", "Ift46", "4930509G22Rik"]
+
+
+def ref_fixtures():
+    return np.load(os.path.join(GOLD, "ref_fixtures.npz"))
+
+
+def ref_cfg1_inputs():
+    """(counts of the selected genes, models, prior, groups, selected row numbers): 64 genes spread over the es.mef.small
+    matrix (tests/tests.R filter) plus the six genes of vignettes/diffexp.md:113-119"""
+    cd, ifm, prior, groups = es_mef_inputs("tests")
+    names = list(cd.index)
+    sel = sorted(set(np.linspace(0, len(names) - 1, 64).astype(int)) | {names.index(g) for g in VIGNETTE_GENES if g in names})
+    return cd.iloc[sel], ifm, prior, groups, np.array(sel, dtype=np.int32)
+
+
+def ref_knn_inputs():
+    knn = knn_models().iloc[:12]
+    rng = np.random.default_rng(3)
+    counts = rng.negative_binomial(0.8, 0.02, size=(40, len(knn))).astype(np.int32)
+    counts[rng.uniform(size=counts.shape) < 0.4] = 0
+    return knn, np.asfortranarray(counts)
+
+
+def ref_batch_inputs():
+    from scde_b200 import synth
+
+    return synth.make_workload(5, n_genes=48, n_cells=36, seed=3, batch=True)

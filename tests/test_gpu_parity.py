@@ -701,3 +701,50 @@ def test_second_device_runs_every_kernel(ctx):
                 c.set_contract_kernel(0)
         assert np.array_equal(res[0], res[1])
     c1.close()
+
+
+def test_cuda_path_against_reference_fixtures(ctx):
+    """The CUDA path against outputs of THE REFERENCE'S OWN C++ (tests/golden/ref_fixtures.npz: src/jpmatLogBoot.cpp and
+    src/matSlideMult.cpp compiled unmodified, tests/golden/make_ref_fixtures.py) -- no oracle in between.  Config 1's
+    data incl. the vignette's six genes, a batch case, the 12-column knn models.  Log-posteriors 1e-6 relative, modes
+    exact, matSlideMult bit-exact."""
+    fx = helpers.ref_fixtures()
+    sub, ifm, prior, groups, sel = helpers.ref_cfg1_inputs()
+    codes = np.asarray(groups.codes)
+    jps = []
+    for lev in (0, 1):
+        ii = np.nonzero(codes == lev)[0]
+        r = api.scde_posteriors(ifm.iloc[ii], sub.iloc[:, ii], prior, n_randomizations=100,
+                                return_individual_posterior_modes=True, context=ctx)
+        ok, worst = _logp_close(r["jp"].to_numpy(), fx[f"cfg1_jp{lev}"])
+        assert ok, worst
+        assert np.array_equal(r["modes"].to_numpy(), fx[f"cfg1_modes{lev}"])
+        jps.append(fx[f"cfg1_jp{lev}"])
+    py = prior["y"].to_numpy()
+    got = api.mat_slide_mult(jps[0] * py[None, :], jps[1] * py[None, :], context=ctx)
+    assert np.array_equal(got, fx["cfg1_slide"])
+    # the fused call on the same genes: joint posteriors of both groups against the reference's
+    res = api.scde_expression_difference(ifm, sub, prior, groups=groups, n_randomizations=100, return_posteriors=True,
+                                         context=ctx)
+    for lev, name in enumerate(["ESC", "MEF"]):
+        ok, worst = _logp_close(res["joint.posteriors"][name].to_numpy(), fx[f"cfg1_jp{lev}"])
+        assert ok, worst
+    w = helpers.ref_batch_inputs()
+    res = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=w.batch, n_randomizations=100,
+                                         return_posteriors=True, context=ctx)
+    for lev, name in enumerate(["g1", "g2"]):
+        ok, worst = _logp_close(res["joint.posteriors"][name].to_numpy(), fx[f"batch_jp{lev}"])
+        assert ok, worst
+    codes, bc = np.asarray(w.groups.codes), np.asarray(w.batch.codes)
+    for lev in (0, 1):
+        comp = np.bincount(bc[codes == lev], minlength=2).astype(np.int32)
+        bj = api.scde_posteriors(w.models, w.counts, w.prior, n_randomizations=100, batch=w.batch, composition=comp,
+                                 context=ctx)
+        ok, worst = _logp_close(bj.to_numpy(), fx[f"batch_bjp{lev}"])
+        assert ok, worst
+    knn, counts = helpers.ref_knn_inputs()
+    prior = pd.DataFrame({"x": np.linspace(0, 4.8, 401), "y": np.full(401, 1.0 / 401)})
+    r = api.scde_posteriors(knn, counts, prior, n_randomizations=50, return_individual_posterior_modes=True, context=ctx)
+    ok, worst = _logp_close(r["jp"].to_numpy(), fx["knn_jp"])
+    assert ok, worst
+    assert np.array_equal(r["modes"].to_numpy(), fx["knn_modes"])

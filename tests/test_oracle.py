@@ -164,3 +164,46 @@ def test_oracle_reproduces_committed_golden_slice():
     out = O.expression_difference(ifm, cd.to_numpy()[sel], prior.x.to_numpy(), prior.y.to_numpy(),
                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1)
     np.testing.assert_allclose(out["results"][:, :5], res[sel, :5], rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_matches_reference_fixtures():
+    """tests/golden/ref_fixtures.npz holds outputs of the reference's own C++ (src/jpmatLogBoot.cpp, src/matSlideMult.cpp
+    compiled unmodified, tests/golden/make_ref_fixtures.py).  The oracle reproduces them BIT FOR BIT on config 1's data
+    (es.mef.small + o.ifm, incl. the vignette's six genes), a batch case and the 12-column knn models -- this is what
+    pins the oracle where /root/reference (and oracle/_ref) is absent."""
+    fx = helpers.ref_fixtures()
+    sub, ifm, prior, groups, sel = helpers.ref_cfg1_inputs()
+    assert np.array_equal(sel, fx["cfg1_genes"])
+    mm, lt, sq = O.pack_models(ifm)
+    mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+    codes = np.asarray(groups.codes)
+    jps = []
+    for lev in (0, 1):
+        ii = np.nonzero(codes == lev)[0]
+        flat, off, uci = O.unique_counts(np.asfortranarray(sub.to_numpy()[:, ii]))
+        r = O.log_boot_posterior(np.asfortranarray(mm[ii]), flat, off, uci, mag, 100, seed=1, returnpost=1)
+        assert np.array_equal(r["jp"], fx[f"cfg1_jp{lev}"])
+        assert np.array_equal(r["modes"], fx[f"cfg1_modes{lev}"])
+        jps.append(r["jp"])
+    py = prior["y"].to_numpy()
+    assert np.array_equal(O.mat_slide_mult(jps[0] * py[None, :], jps[1] * py[None, :]), fx["cfg1_slide"])
+    w = helpers.ref_batch_inputs()
+    mm, lt, sq = O.pack_models(w.models)
+    mag = O.marginals_from_prior_x(w.prior["x"].to_numpy())
+    codes, bc = np.asarray(w.groups.codes), np.asarray(w.batch.codes)
+    pools = [np.nonzero(bc == l)[0].astype(np.int32) for l in range(2)]
+    flat_all, off_all, uci_all = O.unique_counts(w.counts)
+    for lev in (0, 1):
+        ii = np.nonzero(codes == lev)[0]
+        flat, off, uci = O.unique_counts(np.asfortranarray(w.counts[:, ii]))
+        assert np.array_equal(O.log_boot_posterior(np.asfortranarray(mm[ii]), flat, off, uci, mag, 100, seed=1)["jp"],
+                              fx[f"batch_jp{lev}"])
+        comp = np.bincount(bc[ii], minlength=2).astype(np.int32)
+        assert np.array_equal(O.log_boot_batch_posterior(mm, flat_all, off_all, uci_all, mag, pools, comp, 100, seed=1)["jp"],
+                              fx[f"batch_bjp{lev}"])
+    knn, counts = helpers.ref_knn_inputs()
+    mm, lt, sq = O.pack_models(knn)
+    flat, off, uci = O.unique_counts(counts)
+    r = O.log_boot_posterior(mm, flat, off, uci, O.marginals_from_prior_x(np.linspace(0, 4.8, 401)), 50, seed=1,
+                             returnpost=1, localtheta=lt, sqlogit=sq)
+    assert np.array_equal(r["jp"], fx["knn_jp"]) and np.array_equal(r["modes"], fx["knn_modes"])

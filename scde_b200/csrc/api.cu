@@ -312,9 +312,12 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
 
 inline bool want_i8(const scde_b200_ctx *ctx) { return ctx->opt.contract_kernel == 0 || ctx->opt.contract_kernel == 3; }
 
-// unique-count indices from raw counts (device, column-major, leading dimension ldc, genes [g0, g0+G))
+// unique-count indices from raw counts (device, column-major, leading dimension ldc, genes [g0, g0+G)).
+// known_cap > 0: the row buffers already hold known_cap rows (an earlier run of the same job) -- nothing is read back, the
+// emit pass and the row kernels take their bounds from row_off on the device and stop at the capacity; the caller
+// checks row_off[C] <= known_cap once the stream has drained (diff_download_impl) and repeats the run if not.
 int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev, int64_t ldc, int g0, int G, int C,
-                      StageTimer *tm) {
+                      StageTimer *tm, int64_t known_cap = 0) {
     cudaStream_t st = ctx->stream;
     t.n_cells = C;
     t.n_genes = G;
@@ -328,22 +331,26 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
     SCDE_CUDA(t.dedup_bits.ensure(dedup_scratch_words(C)));
     SCDE_CUDA(launch_dedup_count(counts_dev, ldc, g0, G, C, t.n_unique.p, t.err.p, t.dedup_bits.p, st));
     SCDE_CUDA(launch_exclusive_scan(t.n_unique.p, t.row_off.p, C, nullptr, st));
-    int32_t total = 0, err = 0;
-    SCDE_CUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SCDE_CUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SCDE_CUDA(cudaStreamSynchronize(st));  // the table is sized by the number of distinct (cell, count) pairs
-    if (err & 1) {
-        set_error("negative count in the count matrix");
-        return SCDE_B200_EINVAL;
+    int64_t cap = known_cap;
+    if (known_cap <= 0) {
+        int32_t total = 0, err = 0;
+        SCDE_CUDA(cudaMemcpyAsync(&total, t.row_off.p + C, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SCDE_CUDA(cudaMemcpyAsync(&err, t.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SCDE_CUDA(cudaStreamSynchronize(st));  // the table is sized by the number of distinct (cell, count) pairs
+        if (err & 1) {
+            set_error("negative count in the count matrix");
+            return SCDE_B200_EINVAL;
+        }
+        if (err & 2) {
+            set_error("a cell has >= 32768 distinct count values among the processed genes (hash capacity)");
+            return SCDE_B200_ELIMIT;
+        }
+        cap = total;
     }
-    if (err & 2) {
-        set_error("a cell has >= 32768 distinct count values among the processed genes (hash capacity)");
-        return SCDE_B200_ELIMIT;
-    }
-    t.n_rows = total;
-    SCDE_CUDA(t.row_x.ensure((size_t)total));
-    SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p,
-                                (int64_t)total, t.dedup_bits.p, st));
+    t.n_rows = cap;
+    SCDE_CUDA(t.row_x.ensure((size_t)cap));
+    SCDE_CUDA(launch_dedup_emit(counts_dev, ldc, g0, G, C, t.row_off.p, t.row_x.p, t.ridx.p, t.ld_ridx, t.err.p, cap,
+                                t.dedup_bits.p, st));
     if (tm) tm->end(SCDE_B200_T_DEDUP, e0, st, 5);
     return SCDE_B200_OK;
 }
@@ -1211,6 +1218,9 @@ struct scde_b200_diff_job {
     StageTimer timer;
     int64_t contract_cells = 0;
     bool ran = false;
+    int64_t known_rows = 0;          // table rows of the last completed run of this job (0: unknown): the next run needs no
+                                     // size read-back -- same counts, same rows
+    bool rows_unchecked = false;     // the last run used known_rows as the capacity; download verifies it
     int copy_chunks = 0;             // chunked H2D of the counts in flight on the context's copy stream:
     std::vector<int> copy_bounds;    // chunk i holds the cells [copy_bounds[i], copy_bounds[i + 1])
     int split_chunks = 0;            // > 0: the chunks [0, split_chunks) hold every cell of the first group, whose joint
@@ -1718,8 +1728,12 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
         j->deferred_args = nullptr;
         TRY(upload_draws(ctx, j, da));
     }
+    j->rows_unchecked = false;
     if (!front_done) {
-        TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm));
+        // a repeated run of a resident job: the buffers of the last run are exactly large enough, no host round trip
+        const int64_t known = (!chunked_counts && want_i8(ctx)) ? j->known_rows : 0;
+        TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm, known));
+        j->rows_unchecked = known > 0;
         TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
     }
     for (int i = 0; i < 2; ++i)
@@ -1813,6 +1827,20 @@ static int diff_download_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, const s
     const int ld = j->ws->table.ld, nout = 2 * K - 1, ldo = round_up(nout, 8), nadj = 2 * nout - 1, lda = round_up(nadj, 8);
     {
         SCDE_CUDA(cudaStreamSynchronize(st));
+        if (j->rows_unchecked) {  // the run took its row capacity from the previous run: confirm, else repeat with a read-back
+            int32_t total = 0, err = 0;
+            SCDE_CUDA(cudaMemcpy(&total, j->ws->table.row_off.p + j->C, sizeof(int32_t), cudaMemcpyDeviceToHost));
+            SCDE_CUDA(cudaMemcpy(&err, j->ws->table.err.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+            j->rows_unchecked = false;
+            if (err || total < 0 || (int64_t)total > j->known_rows) {
+                j->known_rows = 0;
+                TRY(scde_b200_diff_run(ctx, j));
+                SCDE_CUDA(cudaStreamSynchronize(st));
+            } else {
+                j->ws->table.n_rows = total;
+            }
+        }
+        j->known_rows = j->ws->table.n_rows;
         int rerun = 0;
         TRY(read_flags(ctx, &rerun));
         if (rerun) {  // a multiplicity above 127: repeat the run on the FP64 contraction kernel

@@ -279,6 +279,39 @@ def expression_magnitude(counts, corr_b, corr_a):
     return out
 
 
+def density_gaussian(x, w, bw, n, lo_from, hi_to):
+    """stats::density(x, bw = bw, weights = w, n = n, from = lo_from, to = hi_to) -> (x grid, y); published algorithm
+    restated (R is not in the reference tree)."""
+    x, w = _f64(x), _f64(w)
+    xo, yo = np.empty(n), np.empty(n)
+    lib().orc_density_gaussian(_d(x), _d(w), C.c_long(len(x)), C.c_double(bw), C.c_int(n), C.c_double(lo_from),
+                               C.c_double(hi_to), _d(xo), _d(yo))
+    return xo, yo
+
+
+def failure_probability(mag, conc_a, conc_b, conc_a2=None):
+    """scde.failure.probability with a genes x cells magnitude matrix (R/functions.R:736-748)."""
+    mag = _f64(mag)
+    G, Cn = mag.shape
+    out = np.empty((G, Cn), dtype=np.float64, order="F")
+    a2 = None if conc_a2 is None else _f64(conc_a2)
+    lib().orc_failure_probability(_d(mag), C.c_int(G), C.c_int(Cn), _d(_f64(conc_a)), _d(_f64(conc_b)), _d(a2), _d(out))
+    return out
+
+
+def expression_prior(models_df, counts, length_out=400, pseudo_count=1.0, bw=0.1, max_quantile=1.0, max_value=None):
+    """scde.expression.prior (R/functions.R:225-254) -> dict(x, y, lp, grid.weight)."""
+    counts = _i32(counts)
+    G, Cn = counts.shape
+    mm, lt, sq = pack_models(models_df)
+    K = length_out + 1
+    x, y, lp, gw = (np.empty(K) for _ in range(4))
+    lib().orc_expression_prior(_i(counts), C.c_int(G), C.c_int(Cn), _d(mm), C.c_int(sq), C.c_int(length_out),
+                               C.c_double(pseudo_count), C.c_double(bw), C.c_double(max_quantile),
+                               C.c_double(np.nan if max_value is None else max_value), _d(x), _d(y), _d(lp), _d(gw))
+    return {"x": x, "y": y, "lp": lp, "grid.weight": gw}
+
+
 def posteriors_chunked(models, counts, mag, nboot, boot_idx, nthreads, return_times=False):
     """Gene-chunked CPU arm (R/functions.R:606-617 semantics with shared boot_idx)."""
     models = _f64(models)

@@ -947,3 +947,198 @@ int orc_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* scde.expression.prior (R/functions.R:225-254) and what it calls: scde.failure.probability (:725-750) and R's
+ * stats::density.default (gaussian kernel, bw and weights given).  density.default is R code around two native
+ * pieces -- BinDist (linear binning, src/library/stats/src/massdist.c) and fft() -- and approx(); R is not in
+ * /root/reference, so this restates the published algorithm:
+ *   n <- max(n, 512); if (n > 512) n <- 2^ceiling(log2(n));  lo <- from - 4 bw;  up <- to + 4 bw
+ *   y <- BinDist(x, weights, lo, up, n)                       (2n values, the upper half zero)
+ *   kords <- seq(0, 2 (up - lo), length.out = 2n);  kords[(n+2):(2n)] <- -kords[n:2];  kords <- dnorm(kords, sd = bw)
+ *   kords <- fft(fft(y) * Conj(fft(kords)), inverse = TRUE);  kords <- pmax(0, Re(kords)[1:n] / length(y))
+ *   approx(seq(lo, up, length.out = n), kords, seq(from, to, length.out = n.user))
+ * The FFT here is a plain radix-2 transform (2n is a power of two); R's is Singleton's mixed-radix routine: equal up to
+ * rounding (1e-16 of the largest value), which is why the tests compare the prior at 1e-12, not bit for bit. */
+static void fft_radix2(double *re, double *im, int n, int inverse) {
+    for (int i = 1, j = 0; i < n; i++) { /* bit reversal */
+        int bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) {
+            double t = re[i]; re[i] = re[j]; re[j] = t;
+            t = im[i]; im[i] = im[j]; im[j] = t;
+        }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        const double ang = 2 * M_PI / len * (inverse ? 1 : -1); /* R: forward transform uses exp(-2 pi i jk/n) */
+        for (int i = 0; i < n; i += len)
+            for (int k = 0; k < len / 2; k++) {
+                const double wr = cos(ang * k), wi = sin(ang * k);
+                const int a = i + k, b = i + k + len / 2;
+                const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] += xr; im[a] += xi;
+            }
+    }
+}
+
+/* x, w: nx weighted points (non-finite x are skipped as BinDist does); xout, yout: n_user values */
+void orc_density_gaussian(const double *x, const double *w, long nx, double bw, int n_user, double from, double to,
+                          double *xout, double *yout) {
+    int n = n_user > 512 ? n_user : 512;
+    if (n > 512) {
+        int p = 1;
+        while (p < n) p <<= 1;
+        n = p;
+    }
+    const double lo = from - 4 * bw, up = to + 4 * bw;
+    const int n2 = 2 * n;
+    double *y = (double *)calloc((size_t)n2 * 4, sizeof(double));
+    double *yi = y + n2, *kr = yi + n2, *ki = kr + n2;
+    const int ixmin = 0, ixmax = n - 2;
+    const double xdelta = (up - lo) / (n - 1);
+    for (long i = 0; i < nx; i++) { /* BinDist */
+        if (!isfinite(x[i])) continue;
+        const double xpos = (x[i] - lo) / xdelta;
+        const int ix = (int)floor(xpos);
+        const double fx = xpos - ix, wi = w[i];
+        if (ixmin <= ix && ix <= ixmax) {
+            y[ix] += wi * (1 - fx);
+            y[ix + 1] += wi * fx;
+        } else if (ix == -1)
+            y[0] += wi * fx;
+        else if (ix == ixmax + 1)
+            y[ix] += wi * (1 - fx);
+    }
+    for (int i = 0; i < n2; i++) { /* seq.int(0, 2*(up-lo), length.out = 2n): from + i*by */
+        kr[i] = 0 + i * ((2 * (up - lo) - 0) / (n2 - 1));
+    }
+    kr[n2 - 1] = 2 * (up - lo);
+    for (int i = n + 1; i < n2; i++) kr[i] = -kr[n2 - i]; /* kords[(n+2):(2n)] <- -kords[n:2] */
+    for (int i = 0; i < n2; i++) kr[i] = exp(-0.5 * (kr[i] / bw) * (kr[i] / bw)) / (bw * sqrt(2 * M_PI)); /* dnorm */
+    fft_radix2(y, yi, n2, 0);
+    fft_radix2(kr, ki, n2, 0);
+    for (int i = 0; i < n2; i++) { /* fft(y) * Conj(fft(kords)) */
+        const double a = y[i], b = yi[i], c = kr[i], d = -ki[i];
+        y[i] = a * c - b * d;
+        yi[i] = a * d + b * c;
+    }
+    fft_radix2(y, yi, n2, 1); /* R's inverse transform is unnormalised */
+    for (int i = 0; i < n; i++) {
+        const double v = y[i] / n2;
+        kr[i] = v > 0 ? v : 0; /* pmax.int(0, Re(kords)[1:n] / length(y)) */
+    }
+    /* approx(xords, kords, xout): linear interpolation, xords = seq.int(lo, up, length.out = n) */
+    const double xby = (up - lo) / (n - 1), oby = n_user > 1 ? (to - from) / (n_user - 1) : 0;
+    for (int i = 0; i < n_user; i++) {
+        const double xo = (i == n_user - 1 && n_user > 1) ? to : from + i * oby;
+        xout[i] = xo;
+        /* R's approx1: binary search for the interval, then v[i] + (v[j] - v[i]) * ((x - x[i]) / (x[j] - x[i])) */
+        int a = 0, b = n - 1;
+        if (xo < lo || xo > up) {
+            yout[i] = NAN;
+            continue;
+        }
+        while (a < b - 1) {
+            const int m = (a + b) / 2;
+            const double xm = (m == n - 1) ? up : lo + m * xby;
+            if (xo < xm) b = m; else a = m;
+        }
+        const double xa = (a == n - 1) ? up : lo + a * xby, xb = (b == n - 1) ? up : lo + b * xby;
+        if (xo == xb) yout[i] = kr[b];
+        else if (xo == xa) yout[i] = kr[a];
+        else yout[i] = kr[a] + (kr[b] - kr[a]) * ((xo - xa) / (xb - xa));
+    }
+    free(y);
+}
+
+static int cmp_double(const void *a, const void *b) {
+    const double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+/* scde.failure.probability with per-cell magnitudes (the matrix branch, R/functions.R:736-741); NaN -> 0 (:748) */
+void orc_failure_probability(const double *mag, int G, int C, const double *conc_a, const double *conc_b,
+                             const double *conc_a2, double *out) {
+    for (int c = 0; c < C; c++)
+        for (int g = 0; g < G; g++) {
+            const size_t e = (size_t)c * G + g;
+            double eta = mag[e] * conc_a[c];
+            if (conc_a2) eta += mag[e] * mag[e] * conc_a2[c];
+            eta += conc_b[c];
+            double v = 1 / (exp(eta) + 1);
+            if (isnan(v)) v = 0;
+            out[e] = v;
+        }
+}
+
+/* scde.expression.prior.  models: C x 12 column-major (conc.a2 used when has_a2); max_value NaN = NULL (use the
+ * max.quantile quantile, type 7, of the finite magnitudes).  Outputs x, y, lp, gw: length_out + 1 values each. */
+void orc_expression_prior(const int *counts, int G, int C, const double *models, int has_a2, int length_out,
+                          double pseudo_count, double bw, double max_quantile, double max_value, double *x, double *y,
+                          double *lp, double *gw) {
+    const size_t N = (size_t)G * C;
+    double *fpkm = (double *)malloc(sizeof(double) * N * 4); /* fpkm, then the mirrored points and weights */
+    double *wts = fpkm + N, *xx = wts + N;                   /* xx: 2N points; ww aliases after */
+    double *mag = (double *)malloc(sizeof(double) * N);
+    orc_expression_magnitude(counts, G, C, models + (size_t)CORRB_I * C, models + (size_t)CORRA_I * C, mag); /* :226 */
+    orc_failure_probability(mag, G, C, models + (size_t)CONCA_I * C, models + (size_t)CONCB_I * C,
+                            has_a2 ? models + (size_t)CONCA2_I * C : NULL, wts); /* :227 */
+    long double ws = 0; /* R's sum() accumulates in long double */
+    for (size_t i = 0; i < N; i++) {
+        fpkm[i] = log10(exp(mag[i]) + 1); /* :228 */
+        wts[i] = 1 - wts[i];              /* :229 */
+        ws += wts[i];
+    }
+    for (size_t i = 0; i < N; i++) wts[i] /= (double)ws; /* :230 */
+    if (isnan(max_value)) { /* :233-236 quantile(x[x < Inf], p = max.quantile), type 7 */
+        size_t m = 0;
+        for (size_t i = 0; i < N; i++)
+            if (fpkm[i] < INFINITY) mag[m++] = fpkm[i];
+        qsort(mag, m, sizeof(double), cmp_double);
+        const double index = 1 + (m - 1) * max_quantile, fuzz = 4 * DBL_EPSILON;
+        const double lo = floor(index + fuzz), hi = ceil(index - fuzz);
+        const double qlo = mag[(size_t)lo - 1], qhi = mag[(size_t)hi - 1];
+        double h = index - lo;
+        if (fabs(h) < fuzz) h = 0;
+        max_value = (h == 0) ? qlo : (1 - h) * qlo + h * qhi;
+    }
+    free(mag);
+    /* :237 density(c(-fpkm, fpkm), weights = c(wts/2, wts/2)) */
+    double *x2 = (double *)malloc(sizeof(double) * N * 4);
+    double *w2 = x2 + 2 * N;
+    for (size_t i = 0; i < N; i++) {
+        x2[i] = -1 * fpkm[i];
+        x2[N + i] = fpkm[i];
+        w2[i] = w2[N + i] = wts[i] / 2;
+    }
+    const int n_user = 2 * length_out + 1;
+    double *dx = (double *)malloc(sizeof(double) * n_user * 2), *dy = dx + n_user;
+    orc_density_gaussian(x2, w2, (long)(2 * N), bw, n_user, -1 * max_value, max_value, dx, dy);
+    const int K = length_out + 1;
+    long double ys = 0;
+    for (int k = 0; k < K; k++) { /* :239-241 */
+        x[k] = dx[length_out + k];
+        double v = dy[length_out + k];
+        if (isnan(v)) v = 0;
+        y[k] = v + pseudo_count / G;
+        ys += y[k];
+    }
+    for (int k = 0; k < K; k++) {
+        y[k] /= (double)ys; /* :242 */
+        lp[k] = log(y[k]);  /* :247 */
+    }
+    /* :250 grid.weight = diff(10^c(x[1], x + c(diff(x)/2, 0)) - 1) */
+    double prev = pow(10.0, x[0]) - 1;
+    for (int k = 0; k < K; k++) {
+        const double edge = x[k] + (k < K - 1 ? (x[k + 1] - x[k]) / 2 : 0);
+        const double cur = pow(10.0, edge) - 1;
+        gw[k] = cur - prev;
+        prev = cur;
+    }
+    free(x2);
+    free(dx);
+    free(fpkm);
+    (void)xx;
+}

@@ -107,7 +107,7 @@ typedef struct {
     int32_t split_front;        /* 1: the first group's joint runs under the upload of the second group's cells */
     int32_t uniform_chunks;     /* 1: equal chunks instead of a small first and last one */
     int32_t pipeline_front;     /* 1: chunks are processed as they land; 0: wait for the whole matrix */
-    int32_t item_order;         /* tcgen05 contraction: 0 = the pieces of a gene on neighbouring SMs, 1 = piece-major */
+    int32_t item_order;         /* tcgen05 contraction: 0 = the pieces of a gene on neighbouring SMs, 1 = piece-major (default) */
     int32_t hot_rank;           /* table rows whose rank within their cell is <= hot_rank are loaded with the L2 evict_last
                                    policy; < 0: no cache hints */
     int32_t cold_evict_first;   /* with hot_rank >= 0: the other rows are loaded evict_first (1) or without a priority (0) */

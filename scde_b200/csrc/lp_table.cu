@@ -835,7 +835,6 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
     int cur_c = -1;
     int64_t cur_zero = -1;
     double maxcfp = 0.0;
-    uint32_t dirty = 0u;  // bit j: this lane's staging slots of round j hold non-zero digits (of the previous row)
     const double DEAD_FILL = -1.0e300;  // points beyond the grid: far below every threshold, never the maximum
 
     auto fetch_headers = [&](int64_t base, int slot) {  // one row per lane
@@ -907,41 +906,16 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
             const double R = rc.x, asnap = rc.z, fp = rc.w;
             // ---- sweep 1: the row maximum.  The snapped value (mu~ = x maximises the NB term) replaces a_ks and is not
             // below it, so max(regular values, snapped value) is the maximum of the row as the reference builds it.
-            double vmax = asnap, rmx[QR_MAIN];  // rmx[j]: the lane's largest regular value of round j
+            double vmax = asnap;
 #pragma unroll
-            for (int j = 0; j < QR_MAIN; ++j) {
-                double m = fma(x, L[4 * j], R) + A[4 * j];
-#pragma unroll
-                for (int q = 1; q < 4; ++q) {
-                    const double a = fma(x, L[4 * j + q], R) + A[4 * j + q];
-                    m = a > m ? a : m;
-                }
-                rmx[j] = m;
-                vmax = m > vmax ? m : vmax;
-            }
-            {
-                const double a = fma(x, L[4 * QR_MAIN], R) + A[4 * QR_MAIN];
+            for (int p = 0; p < 4 * QR_MAIN + 1; ++p) {
+                const double a = fma(x, L[p], R) + A[p];
                 vmax = a > vmax ? a : vmax;
             }
             vmax = warp_max_redux(vmax);
             const double alt = maxcfp + fp;
             const double maxp = vmax > alt ? vmax : alt;
             const double Rm = R - maxp, fm = fp - maxp, asn = asnap - maxp;
-            // Rounds (128 consecutive grid points) whose every element is "log 0": a row of a large count is dead on most
-            // of the grid (x = 2000: all but the last ~30 points), and three quarters of the rows are such rows.  A round
-            // is skipped when the drop-out term is dead on the whole grid (max_k E_k + f - M < -750) and no lane holds a
-            // regular value within 750 of the row maximum (the snap point's round is always processed): every element of
-            // it would take the "dead" branch below (hi < -746) and store zero digits -- which is what the skipped
-            // round's slots of the staging buffer hold (a lane zeroes the slots it last wrote non-zero digits to).
-            uint32_t live_rounds = (1u << QR_MAIN) - 1u;
-            if (maxcfp + fm < -750.0) {
-                const double thr = maxp - 750.0;
-                live_rounds = 0u;
-#pragma unroll
-                for (int j = 0; j < QR_MAIN; ++j)
-                    live_rounds |= __any_sync(0xffffffffu, !(rmx[j] < thr)) ? (1u << j) : 0u;
-                if (ks >= 0 && (ks >> 7) < QR_MAIN) live_rounds |= 1u << (ks >> 7);
-            }
             // ---- sweep 2: values, digits.  hi = max(a, e) (both relative to the row maximum, so hi <= 0 up to rounding).
             // The classes of lp_rows_fast_kernel's sweep 3 are decided on the high words of hi and of d = a - e, on the safe
             // side: "dead" (hi < -746: log 0) only when the high word alone proves it, "easy" (hi >= -708 and
@@ -953,21 +927,6 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
             const bool snap_lane = lane == (qs & 31);
 #pragma unroll
             for (int j = 0; j < QR_MAIN; ++j) {
-                if (!(live_rounds & (1u << j))) {  // warp-uniform
-                    if (dirty & (1u << j)) {
-                        dirty &= ~(1u << j);
-                        const int k0 = 4 * (lane + 32 * j);
-                        if (FULL || k0 < K) {
-#pragma unroll
-                            for (int p = 0; p < Q_NV; ++p) st_shared_u16(off[j][0] + p * Q_PW, 0u);
-                        }
-                        if (FULL || k0 + 2 < K) {
-#pragma unroll
-                            for (int p = 0; p < Q_NV; ++p) st_shared_u16(off[j][1] + p * Q_PW, 0u);
-                        }
-                    }
-                    continue;
-                }
                 double a[4], e[4], hi[4], z[4];
                 {
                     const double2 e0 = cell->E[2 * j][lane], e1 = cell->E[2 * j + 1][lane];
@@ -1024,7 +983,6 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                     }
                 }
                 okmask |= alive << (4 * j);
-                dirty = alive ? (dirty | (1u << j)) : (dirty & ~(1u << j));  // what this lane's slots of the round hold now
                 uint32_t lo[4], hw[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

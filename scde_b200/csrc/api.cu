@@ -436,6 +436,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.item_order = ctx->opt.item_order;
         q.hot_rank = hot_rank;
         q.cold_evict_first = ctx->opt.cold_evict_first;
+        q.ring_stages = ctx->opt.ring_stages;
         if (ctx->opt.epilogue_timing) {
             SCDE_CUDA(ctx->epi_dbg.ensure(3));
             SCDE_CUDA(cudaMemsetAsync(ctx->epi_dbg.p, 0, 3 * sizeof(unsigned long long), st));
@@ -648,7 +649,8 @@ int scde_b200_get_options(const scde_b200_ctx *ctx, scde_b200_options *opt) {
 int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt) {
     if (!ctx || !opt) return SCDE_B200_EINVAL;
     if (opt->contract_kernel < 0 || opt->contract_kernel > 3 || opt->count_chunks < 0 || opt->count_chunks > 64 ||
-        opt->item_order < 0 || opt->item_order > 1) {
+        opt->item_order < 0 || opt->item_order > 1 ||
+        !(opt->ring_stages == 0 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10)) {
         set_error("set_options: value out of range");
         return SCDE_B200_EINVAL;
     }
@@ -1182,6 +1184,7 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.item_order = ctx->opt.item_order;
     q.hot_rank = -1;
     q.cold_evict_first = 0;
+    q.ring_stages = ctx->opt.ring_stages;
     SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
     SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
     SCDE_CUDA(launch_finalize_t(q, n_genes, d_t.p, d_sr.p, st));

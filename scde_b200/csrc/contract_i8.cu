@@ -49,7 +49,7 @@ namespace {
 using namespace ptx;
 
 constexpr int Q_ES = 32;                         // list entries per stage = K of one tcgen05.mma.kind::i8
-constexpr int Q_NS = 10;                         // ring depth
+constexpr int Q_NS = 10;                         // ring depth (largest; the kernel takes the depth as a template parameter)
 constexpr int Q_A_BYTES = Q_ES * Q_WB;           // W tile of a stage: 4096
 constexpr int Q_B_BYTES = Q_ES * Q_PIECE;        // table tile of a stage: 16384
 constexpr int Q_STAGE_BYTES = Q_A_BYTES + Q_B_BYTES;  // 20480, a multiple of the 1024-byte swizzle atom
@@ -73,7 +73,7 @@ struct I8Smem {
     volatile int abort;
 };
 constexpr int Q_XBUF_BYTES = Q_EPILOGUE_WARPS * 2048;  // per epilogue warp: one [32 boots][8 grid points] tile of 64-bit sums
-constexpr size_t Q_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)Q_NS * Q_STAGE_BYTES + Q_XBUF_BYTES + sizeof(I8Smem);
+constexpr size_t q_smem_bytes(int ns) { return 1024 /* alignment slack */ + (size_t)ns * Q_STAGE_BYTES + Q_XBUF_BYTES + sizeof(I8Smem); }
 
 struct I8Params {
     const int8_t *qtable;  // [rows][ldq]: row = [piece][plane][102] (+ 2)
@@ -155,7 +155,7 @@ __device__ __forceinline__ void cp_async16_hint_at(uint32_t dst_smem, const void
 // HINT: list entries carry LIST_HOT_BIT in `cell` when the row is one of the first few of its cell (a small count: such a
 // row is shared by thousands of genes); its pieces are loaded with the L2 evict_last policy, the others evict_first (or
 // unhinted), so that the stream of rows that are used once does not push the shared ones out of the L2.
-template <int Q_PGROUPS, bool HINT>
+template <int Q_PGROUPS, bool HINT, int NS>
 __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint32_t stage0, int n_items, int warp, int lane) {
     uint64_t pol_hot = 0, pol_cold = 0;
     if (HINT) {
@@ -206,8 +206,8 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
         load_block(1, r0b, r1b, c0b, c1b);
         int slot = slot_b + grp;
         uint32_t fill = fill_b;
-        if (slot >= Q_NS) {
-            slot -= Q_NS;
+        if (slot >= NS) {
+            slot -= NS;
             ++fill;
         }
         for (int t = 0; grp + Q_PGROUPS * 8 * t < nst; ++t) {
@@ -252,8 +252,8 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
                     }
                     cp_async_mbar_arrive_noinc(&sm.full[slot]);
                     slot += Q_PGROUPS;
-                    if (slot >= Q_NS) {
-                        slot -= Q_NS;
+                    if (slot >= NS) {
+                        slot -= NS;
                         ++fill;
                     }
                 }
@@ -264,16 +264,17 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
             c1a = c1b;
             load_block(t + 2, r0b, r1b, c0b, c1b);
         }
-        slot_b += nst % Q_NS;
-        fill_b += (uint32_t)(nst / Q_NS);
-        if (slot_b >= Q_NS) {
-            slot_b -= Q_NS;
+        slot_b += nst % NS;
+        fill_b += (uint32_t)(nst / NS);
+        if (slot_b >= NS) {
+            slot_b -= NS;
             ++fill_b;
         }
     }
 }
 
 // ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
+template <int NS>
 __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t stage0, uint32_t tmem, int n_items) {
     const uint32_t idesc = umma_idesc_s8_mn(128, 256);
     int slot = 0;
@@ -299,7 +300,7 @@ __device__ __forceinline__ void run_mma(const I8Params &p, I8Smem &sm, uint32_t 
             umma_s8(tmem, da, umma_desc_sw128(sB, 4096u, 1024u), idesc, s > 0);                      // runs 0, 1
             umma_s8(tmem + 256u, da, umma_desc_sw128(sB + 2u * 4096u, 4096u, 1024u), idesc, s > 0);  // runs 2, 3
             umma_commit(&sm.empty[slot]);  // frees the slot once these MMAs have read it
-            if (++slot == Q_NS) {
+            if (++slot == NS) {
                 slot = 0;
                 ++fill;
             }
@@ -393,18 +394,19 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
     }
 }
 
-template <int Q_PGROUPS, bool HINT>
+template <int Q_PGROUPS, bool HINT, int NS>
 __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(const I8Params p) {
+    static_assert(NS >= 2 && NS <= Q_NS, "ring depth");
     constexpr int Q_PRODUCER_WARPS = 4 * Q_PGROUPS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // stage buffers on a 1024-byte boundary (the swizzle pattern is a function of the shared-memory address bits)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t stage0 = (raw + 1023u) & ~1023u;
-    const uint32_t xbuf = stage0 + (uint32_t)Q_NS * Q_STAGE_BYTES;
-    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw + (stage0 - raw) + (size_t)Q_NS * Q_STAGE_BYTES + Q_XBUF_BYTES);
+    const uint32_t xbuf = stage0 + (uint32_t)NS * Q_STAGE_BYTES;
+    I8Smem &sm = *reinterpret_cast<I8Smem *>(smem_raw + (stage0 - raw) + (size_t)NS * Q_STAGE_BYTES + Q_XBUF_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Q_NS; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&sm.full[s], 4 * 32);                 // one cp.async completion arrival per thread of a producer group
             mbar_init(&sm.empty[s], 1);                     // one tcgen05.commit
         }
@@ -421,11 +423,11 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     const int n_items = p.n_pos * p.n_pieces;
 
     if (warp < Q_PRODUCER_WARPS)
-        run_producer<Q_PGROUPS, HINT>(p, sm, stage0, n_items, warp, lane);
+        run_producer<Q_PGROUPS, HINT, NS>(p, sm, stage0, n_items, warp, lane);
     else if (warp < Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS)
         run_epilogue(p, sm, xbuf, tmem, n_items, warp - Q_PRODUCER_WARPS, lane);
     else if (lane == 0)
-        run_mma(p, sm, stage0, tmem, n_items);
+        run_mma<NS>(p, sm, stage0, tmem, n_items);
 
     tc_fence_before_sync();
     __syncthreads();
@@ -778,13 +780,18 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
     // function attributes are per device: set on every launch (a process may hold contexts on several GPUs)
-    auto launch = [&](auto kernel) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+    auto launch = [&](auto kernel, int ns) -> cudaError_t {
+        const size_t smem = q_smem_bytes(ns);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, q_threads(PG), Q_SMEM_BYTES, st>>>(p);
+        kernel<<<grid, q_threads(PG), smem, st>>>(p);
         return cudaGetLastError();
     };
-    return a.hot_rank >= 0 ? launch(contract_i8_kernel<PG, true>) : launch(contract_i8_kernel<PG, false>);
+    if (a.hot_rank >= 0) return launch(contract_i8_kernel<PG, true, Q_NS>, Q_NS);
+    // the shallow ring leaves 69 KB of shared memory and a third of the register file to a co-resident kernel
+    if (a.ring_stages == 7) return launch(contract_i8_kernel<PG, false, 7>, 7);
+    if (a.ring_stages == 8) return launch(contract_i8_kernel<PG, false, 8>, 8);
+    return launch(contract_i8_kernel<PG, false, Q_NS>, Q_NS);
 }
 
 size_t softmax_i8_scratch_doubles(int n_pos) { return (size_t)SP_GROUPS * (n_pos > 0 ? n_pos : 1) * KP_TILED; }

@@ -203,12 +203,14 @@ typedef struct {
     const double *prior_x;   /* n_grid: prior$x (log10(FPM+1) grid) */
     const double *prior_y;   /* n_grid: prior$y */
     const int32_t *group;    /* n_cells: 0 = first factor level, 1 = second, <0 = NA (ignored) */
-    const int32_t *batch;    /* n_cells batch level codes 0..n_batch_levels-1, or NULL (no correction) */
+    const int32_t *batch;    /* n_cells batch level codes 0..n_batch_levels-1 (< 0 = NA: in no pool, not in the
+                                composition, as tapply / table drop NA), or NULL (no correction) */
     int32_t n_batch_levels;
     int32_t n_boot;          /* n.randomizations */
     int32_t seed;            /* Seed handed to srand(); 1 reproduces n.cores = 1 */
     /* optional explicit draws; NULL = generate from `seed`.  [0],[1]: group joints (local indices into the
-     * group's cells, n_boot x |group|); [2],[3]: batch joints (global cell ids, n_boot x |group|). */
+     * group's cells, n_boot x |group|); [2],[3]: batch joints (global cell ids, n_boot x number of the group's cells with
+     * a non-NA batch). */
     const int32_t *boot_idx[4];
     const int32_t *zero_index; /* 1-based H0 grid position(s) on the 2K-1 fold-change grid */
     int32_t n_zero;            /* 1 or n_genes */
@@ -216,6 +218,10 @@ typedef struct {
     int32_t local_theta, square_logit_conc;
     int32_t gene_begin, gene_end; /* process genes [gene_begin, gene_end) of `counts` (0,0 = all): the
                                      multi-GPU gene shard; outputs are indexed from gene_begin */
+    /* batch.models (R/functions.R:304,356): the error models of the two composition-sampled joints, n_cells x 12, rows in
+     * the order of `models`; NULL = the same models (the reference's default).  With their own column-presence flags. */
+    const double *batch_models;
+    int32_t batch_local_theta, batch_square_logit_conc;
 } scde_b200_diff_args;
 
 typedef struct {

@@ -353,11 +353,12 @@ def pack_models(models_df):
 
 
 def expression_difference(models_df, counts, prior_x, prior_y, group_idx, nboot=100, seed=1, batch_codes=None,
-                          expectation=0.0):
+                          expectation=0.0, batch_models_df=None):
     """scde.expression.difference with n.cores = 1 (R/functions.R:304-408) on numpy inputs.
 
     counts: G x C (cells ordered as model rows); group_idx: (idx0, idx1) integer arrays of the two factor levels;
-    batch_codes: optional per-cell integer batch level codes (0..L-1).
+    batch_codes: optional per-cell integer batch level codes (0..L-1; negative = NA, dropped from the pools and the
+    composition as tapply / table do); batch_models_df: batch.models (default: the same models).
     """
     counts = _i32(counts)
     mm, lt, sq = pack_models(models_df)
@@ -378,10 +379,12 @@ def expression_difference(models_df, counts, prior_x, prior_y, group_idx, nboot=
         pools = [np.nonzero(batch_codes == l)[0].astype(np.int32) for l in range(L)]
         flat, off, uci = unique_counts(counts)
         bjpl = []
+        bmm, blt, bsq = (mm, lt, sq) if batch_models_df is None else pack_models(batch_models_df)
         for ii in group_idx:
-            comp = np.bincount(batch_codes[ii], minlength=L).astype(np.int32)
-            bjpl.append(log_boot_batch_posterior(mm, flat, off, uci, mag, pools, comp, nboot, seed=seed,
-                                                 localtheta=lt, sqlogit=sq)["jp"])
+            bc = batch_codes[ii]
+            comp = np.bincount(bc[bc >= 0], minlength=L).astype(np.int32)
+            bjpl.append(log_boot_batch_posterior(bmm, flat, off, uci, mag, pools, comp, nboot, seed=seed,
+                                                 localtheta=blt, sqlogit=bsq)["jp"])
         bb = ratio_posterior(bjpl[0], bjpl[1], prior_y)
         bres, bidx = distribution_summary(bb, diffv, 0.0)
         ab = ratio_posterior(bdiffp, bb, None)

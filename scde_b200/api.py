@@ -253,6 +253,34 @@ def jpmat_log_batch_boot(matll, comp, nboot: int, seed: int, boot_idx=None, cont
     return jp
 
 
+def fisher_test_p_value(table: np.ndarray) -> float:
+    """Two-sided p-value of fisher.test (R/functions.R:339) for the groups x batch contingency table: the total
+    probability, under fixed margins, of the tables that are not more probable than the observed one (R's relative
+    tolerance 1e-7).  2 x 2 tables are summed here (hypergeometric); larger ones go to scipy's exact r x c routine."""
+    from math import lgamma
+
+    t = np.asarray(table, dtype=np.int64)
+    t = t[t.sum(axis=1) > 0][:, t.sum(axis=0) > 0]
+    if t.shape[0] < 2 or t.shape[1] < 2:
+        return 1.0
+    if t.shape == (2, 2):
+        r1, r2, c1 = int(t[0].sum()), int(t[1].sum()), int(t[:, 0].sum())
+        lo, hi = max(0, c1 - r2), min(r1, c1)
+
+        def lchoose(n, k):
+            return lgamma(n + 1) - lgamma(k + 1) - lgamma(n - k + 1)
+
+        ks = np.arange(lo, hi + 1)
+        lp = np.array([lchoose(r1, k) + lchoose(r2, c1 - k) - lchoose(r1 + r2, c1) for k in ks])
+        p = np.exp(lp - lp.max())
+        p /= p.sum()
+        obs = p[int(t[0, 0]) - lo]
+        return float(min(1.0, p[p <= obs * (1 + 1e-7)].sum()))
+    from scipy.stats import fisher_exact
+
+    return float(fisher_exact(t).pvalue)
+
+
 def _zero_index(diffv: np.ndarray, expectation) -> np.ndarray:
     """which.min(abs(mvs - expectation/log2(10))), 1-based (R/functions.R:3519,3524,5050)."""
     ex = np.atleast_1d(np.asarray(expectation, dtype=np.float64)) / np.log2(10.0)
@@ -312,7 +340,8 @@ def quick_distribution_summary(pmat1, pmat2, prior, expectation=0.0, skip_prior_
 
 # ------------------------------------------------------------------------------------------------
 def _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes, n_batch_levels, zero_index,
-               zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range):
+               zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range, batch_mm=None, batch_local_theta=0,
+               batch_sqlogit=0):
     """scde_b200_diff_args for the C ABI; returns (args, the host arrays it points into, processed genes, K, has_batch)."""
     keep_alive = []
 
@@ -342,6 +371,9 @@ def _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_co
     a.zero_index_adjusted = p_i32(zia)
     a.local_theta, a.square_logit_conc = int(local_theta), int(sqlogit)
     a.gene_begin, a.gene_end = int(gene_range[0]), int(gene_range[1])
+    if batch_mm is not None:
+        a.batch_models = p_f64(keep(f64(batch_mm)))
+        a.batch_local_theta, a.batch_square_logit_conc = int(batch_local_theta), int(batch_sqlogit)
     G = (gene_range[1] - gene_range[0]) if tuple(gene_range) != (0, 0) else G_all
     return a, keep_alive, G, K, has_batch
 
@@ -379,12 +411,13 @@ def _diff_out(G, K, has_batch, want_posteriors, joint_posteriors):
 def expression_difference_call(ctx: _lib.Context, counts: np.ndarray, mm: np.ndarray, prior_x, prior_y, group_codes,
                                n_boot: int, seed: int = 1, batch_codes=None, n_batch_levels: int = 0, zero_index=None,
                                zero_index_adjusted=None, local_theta: int = 0, sqlogit: int = 0, boot_idx=(None,) * 4,
-                               gene_range=(0, 0), want_posteriors: bool = False, joint_posteriors: bool = False):
+                               gene_range=(0, 0), want_posteriors: bool = False, joint_posteriors: bool = False,
+                               batch_mm=None, batch_local_theta: int = 0, batch_sqlogit: int = 0):
     """The one-shot C-ABI call (scde_b200_expression_difference): host buffers in, host buffers out.  The count matrix is
     uploaded in cell chunks while the table rows of the chunks already on the device are being built."""
     a, keep_alive, G, K, has_batch = _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes,
                                                 n_batch_levels, zero_index, zero_index_adjusted, local_theta, sqlogit,
-                                                boot_idx, gene_range)
+                                                boot_idx, gene_range, batch_mm, batch_local_theta, batch_sqlogit)
     o, res = _diff_out(G, K, has_batch, want_posteriors, joint_posteriors)
     st = _lib.Stats()
     check(lib().scde_b200_expression_difference(ctx.handle, C.byref(a), C.byref(o), C.byref(st)))
@@ -399,11 +432,12 @@ class DifferenceJob:
     def __init__(self, ctx: _lib.Context, counts: np.ndarray, mm: np.ndarray, prior_x, prior_y, group_codes,
                  n_boot: int, seed: int = 1, batch_codes=None, n_batch_levels: int = 0, zero_index=None,
                  zero_index_adjusted=None, local_theta: int = 0, sqlogit: int = 0, boot_idx=(None,) * 4,
-                 gene_range=(0, 0), want_posteriors: bool = False):
+                 gene_range=(0, 0), want_posteriors: bool = False, batch_mm=None, batch_local_theta: int = 0,
+                 batch_sqlogit: int = 0):
         self.ctx = ctx
         a, keep_alive, self.G, self.K, self.has_batch = _diff_args(
             counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes, n_batch_levels, zero_index,
-            zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range)
+            zero_index_adjusted, local_theta, sqlogit, boot_idx, gene_range, batch_mm, batch_local_theta, batch_sqlogit)
         self.want_posteriors = bool(want_posteriors)
         self._job = C.c_void_p()
         check(lib().scde_b200_diff_upload(ctx.handle, C.byref(a), int(want_posteriors), C.byref(self._job)))
@@ -443,8 +477,6 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
     ``difference.posterior``, ``batch.adjusted.difference.posterior``, ``joint.posteriors``).
     """
     cm, genes = _counts_for_models(models, counts)
-    if batch_models is not None and batch_models is not models:
-        raise NotImplementedError("batch.models different from models is not supported by the fused device path")
     if groups is None:
         groups = models.attrs.get("groups")
         if groups is None:
@@ -461,9 +493,25 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
             correct_batch = True
         elif verbose:
             sys.stdout.write("WARNING: only one batch level detected. Nothing to correct for.")
-    if correct_batch and verbose:
-        sys.stdout.write("controlling for batch effects. interaction:\n")
-        sys.stdout.write(str(pd.crosstab(pd.Series(gcodes, name="groups"), pd.Series(bcodes, name="batch"))) + "\n")
+    bmm, blt, bsq = None, 0, 0
+    if correct_batch and batch_models is not None and batch_models is not models:
+        # batch.models (R/functions.R:304,356): the error models of the composition-sampled joints, same cells as `models`
+        if list(batch_models.index) != list(models.index):
+            if not all(c in batch_models.index for c in models.index):
+                _stop("batch.models does not cover all of the cells specified in the model matrix")
+            batch_models = batch_models.loc[list(models.index)]
+        bmm, blt, bsq = pack_models(batch_models)
+    if correct_batch:
+        # check batch-group interactions (R/functions.R:336-349): table(groups, batch), fisher.test, warning below 1e-3
+        bgti = pd.crosstab(pd.Series(np.asarray(gcodes), name="groups"), pd.Series(np.asarray(bcodes), name="batch"))
+        bgti = bgti.loc[[i for i in bgti.index if i >= 0], [c for c in bgti.columns if c >= 0]]
+        if verbose:
+            sys.stdout.write("controlling for batch effects. interaction:\n")
+            sys.stdout.write(str(bgti) + "\n")
+        pval = fisher_test_p_value(bgti.to_numpy())
+        if pval < 1e-3:
+            sys.stdout.write("WARNING: strong interaction between groups and batches! Correction may be ineffective:\n")
+            sys.stdout.write(f"Fisher's Exact Test for Count Data: p-value = {pval:.4g}\n")
     elif verbose:
         sys.stdout.write("comparing groups:\n")
         sys.stdout.write(str(pd.Series([glev[c] for c in gcodes if c >= 0]).value_counts().sort_index()) + "\n")
@@ -483,7 +531,8 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
                                      batch_codes=bcodes if correct_batch else None,
                                      n_batch_levels=len(blev) if correct_batch else 0, zero_index=zi,
                                      zero_index_adjusted=zia, local_theta=lt, sqlogit=sq, boot_idx=boot_idx,
-                                     want_posteriors=return_posteriors)
+                                     want_posteriors=return_posteriors, batch_mm=bmm, batch_local_theta=blt,
+                                     batch_sqlogit=bsq)
     if verbose:
         sys.stdout.write("summarizing differences\n")
     bdiffp_rep = _summary_frame(res["idx"], res["z"], diffv, genes)
@@ -528,8 +577,8 @@ def scde_test_gene_expression_difference(gene, models: pd.DataFrame, counts: pd.
     """
     if gene not in counts.index:
         _stop(f"specified gene ({gene}) is not found in the count data")
-    if batch_models is not None and batch_models is not models:
-        raise NotImplementedError("batch.models different from models")
+    if batch_models is None:
+        batch_models = models
     sub = counts.loc[[gene], list(models.index)]
     if groups is None:
         groups = models.attrs.get("groups")
@@ -557,7 +606,7 @@ def scde_test_gene_expression_difference(gene, models: pd.DataFrame, counts: pd.
         for lev in range(2):
             ii = np.nonzero(gcodes == lev)[0]
             comp = np.bincount(bcodes[ii][bcodes[ii] >= 0], minlength=len(blev)).astype(np.int32)
-            bjpl.append(scde_posteriors(models, sub, prior, n_randomizations=n_randomizations, batch=batch,
+            bjpl.append(scde_posteriors(batch_models, sub, prior, n_randomizations=n_randomizations, batch=batch,
                                         composition=comp, seed=seed, context=ctx))
         bb = calculate_ratio_posterior(bjpl[0], bjpl[1], prior, context=ctx)
         uni = {"x": diffv, "y": np.full(len(diffv), 1.0 / len(diffv))}

@@ -942,6 +942,10 @@ static int jpmat_common(scde_b200_ctx *ctx, const double *matl, int n_mat, int n
         return SCDE_B200_EINVAL;
     }
     if (n_rows == 0) return SCDE_B200_OK;
+    if ((int64_t)n_mat * n_rows > 0x7fffffffll) {  // table rows are addressed with 32-bit ids
+        set_error("jpmat_log_boot: n_mat * n_rows = %lld exceeds 2^31 - 1", (long long)n_mat * n_rows);
+        return SCDE_B200_ELIMIT;
+    }
     TRY(validate_index(boot_idx, (size_t)n_boot * D, 0, n_mat, "boot_idx"));
     LpTable t;
     t.n_cells = n_mat;
@@ -1212,6 +1216,9 @@ struct scde_b200_diff_job {
     DiffWorkspace *ws = nullptr;
     scde_b200_ctx *owner = nullptr;
     DBuf<double> models, mag, prior_y;
+    DBuf<double> bmodels;       // batch.models when they differ from models (else empty)
+    int b_local_theta = 0, b_sqlogit = 0;
+    bool fast_theta = false, b_fast_theta = false;
     DBuf<int32_t> cell_ids[2];  // group cell lists
     DBuf<int32_t> boot[4];
     int D[4] = {0, 0, 0, 0};
@@ -1257,25 +1264,32 @@ int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff
         j->D[i] = n;
     }
     if (j->has_batch) {
+        // batch[c] < 0 = NA: the reference's tapply(seq_len(n) - 1, batch, I) (R/functions.R:570) and table(batch[ii])
+        // (:356) both drop NA entries -- such a cell is in no pool and does not count towards the composition
         const int L = a->n_batch_levels;
         std::vector<int32_t> off(L + 1, 0), cells;
         for (int c = 0; c < C; ++c) {
-            if (a->batch[c] < 0 || a->batch[c] >= L) {
-                set_error("batch[%d] = %d outside [0, %d)", c, a->batch[c], L);
+            if (a->batch[c] >= L) {
+                set_error("batch[%d] = %d outside [0, %d) (negative = NA)", c, a->batch[c], L);
                 return SCDE_B200_EINVAL;
             }
-            off[a->batch[c] + 1]++;
+            if (a->batch[c] >= 0) off[a->batch[c] + 1]++;
         }
         for (int l = 0; l < L; ++l) off[l + 1] += off[l];
-        cells.resize(C);
+        cells.resize(off[L] > 0 ? off[L] : 1);  // (never NULL: scde_b200_batch_boot_indices checks its pointers)
         {
             std::vector<int32_t> pos(off.begin(), off.end() - 1);
-            for (int c = 0; c < C; ++c) cells[pos[a->batch[c]]++] = c;  // tapply(0:(n-1), batch, I): ascending
+            for (int c = 0; c < C; ++c)
+                if (a->batch[c] >= 0) cells[pos[a->batch[c]]++] = c;  // tapply(0:(n-1), batch, I): ascending
         }
         for (int i = 0; i < 2; ++i) {
             std::vector<int32_t> comp(L, 0);  // table(batch[ii])
-            for (int c : j->ids[i]) comp[a->batch[c]]++;
-            const int D = j->n_group[i];
+            int D = 0;
+            for (int c : j->ids[i])
+                if (a->batch[c] >= 0) {
+                    comp[a->batch[c]]++;
+                    ++D;
+                }
             src[2 + i] = a->boot_idx[2 + i];
             if (!src[2 + i]) {
                 j->gen[2 + i].resize((size_t)a->n_boot * D);
@@ -1283,7 +1297,7 @@ int upload_draws(scde_b200_ctx *ctx, scde_b200_diff_job *j, const scde_b200_diff
                                                  j->gen[2 + i].data()));
                 src[2 + i] = j->gen[2 + i].data();
             }
-            TRY(validate_index(src[2 + i], (size_t)a->n_boot * D, 0, C, "batch boot_idx"));
+            if (D > 0) TRY(validate_index(src[2 + i], (size_t)a->n_boot * D, 0, C, "batch boot_idx"));
             j->D[2 + i] = D;
         }
     }
@@ -1386,15 +1400,17 @@ int start_count_copies(scde_b200_ctx *ctx, scde_b200_diff_job *j, const int32_t 
         SCDE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->copy_events.push_back(e);
     }
-    int n_ch = 0;
-    for (; n_ch + 1 < (int)bounds.size(); ++n_ch) {
+    j->copy_chunks = 0;
+    for (int n_ch = 0; n_ch + 1 < (int)bounds.size(); ++n_ch) {
         const int c0 = bounds[n_ch], n = bounds[n_ch + 1] - c0;
+        // counted before it is queued: if a later call fails, the caller (fail() of diff_upload_impl) drains the copy stream
+        // whenever copy_chunks != 0 -- the copy engine must not read the caller's buffer after the call has returned
+        j->copy_chunks = n_ch + 1;
         SCDE_CUDA(cudaMemcpy2DAsync(j->ws->counts.p + (size_t)c0 * G, sizeof(int32_t) * G, counts_host + (size_t)c0 * ld_host,
                                     sizeof(int32_t) * (size_t)ld_host, sizeof(int32_t) * G, n, cudaMemcpyHostToDevice,
                                     ctx->copy_stream));
         SCDE_CUDA(cudaEventRecord(ctx->copy_events[n_ch], ctx->copy_stream));
     }
-    j->copy_chunks = n_ch;
     return SCDE_B200_OK;
 }
 
@@ -1484,6 +1500,12 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
                 std::chrono::duration<double, std::milli>(tu2 - tu1).count());
     }
     JTRY(upload(j->models, a->models, (size_t)C * 12, st));
+    if (has_batch && a->batch_models && a->batch_models != a->models) {
+        JTRY(upload(j->bmodels, a->batch_models, (size_t)C * 12, st));
+        j->b_local_theta = a->batch_local_theta;
+        j->b_sqlogit = a->batch_square_logit_conc;
+        j->b_fast_theta = !a->batch_local_theta && theta_all_regular(a->batch_models, C, C);
+    }
     JTRY(upload(j->prior_y, a->prior_y, (size_t)K, st));
     std::vector<double> mag(K);
     for (int k = 0; k < K; ++k) {  // R/functions.R:575-577
@@ -1532,7 +1554,8 @@ static int diff_upload_impl(scde_b200_ctx *ctx, const scde_b200_diff_args *a, in
     j->ws->table.K = K;
     j->ws->table.ld = ld;
     j->ws->table.sentinel = -DBL_MAX / C / 1.1;
-    j->ws->table.fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
+    j->fast_theta = !a->local_theta && theta_all_regular(a->models, C, C);
+    j->ws->table.fast_theta = j->fast_theta;
     j->ws->table.zero_base = ld <= KP_TILED && ctx->opt.zero_base;
     j->ws->table.want_q = want_i8(ctx);
     JCUDA(cudaStreamSynchronize(st));
@@ -1742,10 +1765,18 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
     for (int i = 0; i < 2; ++i)
         if (!(i == 0 && joint0_done)) TRY(group_joint(i));
     // batch joints: all cells, composition-sampled draws are global cell ids (R/functions.R:355-357)
-    if (j->has_batch)
+    if (j->has_batch) {
+        if (j->bmodels.p) {
+            // batch.models differ from models: the table rows are rebuilt from them (same row ids -- the counts have not
+            // changed -- so the index matrix stays); the group joints above are done with the first table
+            j->ws->table.fast_theta = j->b_fast_theta;
+            TRY(fill_table(ctx, j->ws->table, j->bmodels.p, C, j->mag.p, j->b_local_theta, j->b_sqlogit, &tm));
+            j->ws->table.fast_theta = j->fast_theta;
+        }
         for (int i = 0; i < 2; ++i)
             TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot_ptr[2 + i], j->n_boot, j->D[2 + i], (double)j->n_boot,
                           j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, true));
+    }
     int e0 = tm.begin(st);
     int nl = 0;
     RatioArgs r{};

@@ -916,10 +916,6 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
             const double alt = maxcfp + fp;
             const double maxp = vmax > alt ? vmax : alt;
             const double Rm = R - maxp, fm = fp - maxp, asn = asnap - maxp;
-            // Rows of counts above ~130 (85 % of the rows): the drop-out term lies more than 750 below the row maximum at
-            // every grid point (max_k E_k + f - M < -750), so wherever the NB term is above -708 it wins by more than 37.5 and
-            // the element is "easy" with hi = a -- decided on the high word of a alone, without E, a - e and the band tests.
-            const bool e_dead = maxcfp + fm < -750.0;
             // ---- sweep 2: values, digits.  hi = max(a, e) (both relative to the row maximum, so hi <= 0 up to rounding).
             // The classes of lp_rows_fast_kernel's sweep 3 are decided on the high words of hi and of d = a - e, on the safe
             // side: "dead" (hi < -746: log 0) only when the high word alone proves it, "easy" (hi >= -708 and
@@ -933,7 +929,9 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
             for (int j = 0; j < QR_MAIN; ++j) {
                 double a[4], e[4], hi[4], z[4];
                 {
+                    const double2 e0 = cell->E[2 * j][lane], e1 = cell->E[2 * j + 1][lane];
                     const double2 z0 = cell->Z[2 * j][lane], z1 = cell->Z[2 * j + 1][lane];
+                    e[0] = e0.x + fm, e[1] = e0.y + fm, e[2] = e1.x + fm, e[3] = e1.y + fm;
                     z[0] = z0.x, z[1] = z0.y, z[2] = z1.x, z[3] = z1.y;
                 }
 #pragma unroll
@@ -946,34 +944,17 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                 // per element only inside the branch
                 uint32_t alive = 0u, hh_max = 0u, band_min = 0xffffffffu;
                 double d[4];
-                bool all_easy = false;
-                if (e_dead) {  // warp-uniform
-                    uint32_t am4 = 0u;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) am4 = max(am4, (uint32_t)__double2hiint(a[q]));
-                    // every a of the round in (-708, +tiny]: hi = a, all four alive (the general code below would find
-                    // exactly that: a - e > 42, hi >= -708)
-                    all_easy = __all_sync(0xffffffffu, am4 < H_LOW);
+                for (int q = 0; q < 4; ++q) {
+                    d[q] = a[q] - e[q];
+                    const uint32_t hd = (uint32_t)__double2hiint(d[q]);
+                    hi[q] = (int32_t)hd >= 0 ? a[q] : e[q];  // a >= e (for a - e == -0 the two are equal)
+                    const uint32_t hh = (uint32_t)__double2hiint(hi[q]);
+                    alive |= hh <= H_DEAD ? (1u << q) : 0u;
+                    hh_max = max(hh_max, hh);
+                    band_min = min(band_min, hd & 0x7fffffffu);
                 }
-                if (all_easy) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) hi[q] = a[q];
-                    alive = 0xFu;
-                } else {
-                    const double2 e0 = cell->E[2 * j][lane], e1 = cell->E[2 * j + 1][lane];
-                    e[0] = e0.x + fm, e[1] = e0.y + fm, e[2] = e1.x + fm, e[3] = e1.y + fm;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        d[q] = a[q] - e[q];
-                        const uint32_t hd = (uint32_t)__double2hiint(d[q]);
-                        hi[q] = (int32_t)hd >= 0 ? a[q] : e[q];  // a >= e (for a - e == -0 the two are equal)
-                        const uint32_t hh = (uint32_t)__double2hiint(hi[q]);
-                        alive |= hh <= H_DEAD ? (1u << q) : 0u;
-                        hh_max = max(hh_max, hh);
-                        band_min = min(band_min, hd & 0x7fffffffu);
-                    }
-                }
-                if (!all_easy && alive != 0u && !(hh_max < H_LOW && band_min > H_BAND)) {
+                if (alive != 0u && !(hh_max < H_LOW && band_min > H_BAND)) {
                     if (hh_max < H_LOW) {
                         // cross-over band only, no exponential underflows: log(exp(a) + exp(e)) = hi + log1p(exp(-|d|)) to
                         // 1e-13 (for the quad's elements outside the band the correction is below their last bit)

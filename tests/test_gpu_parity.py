@@ -748,3 +748,30 @@ def test_cuda_path_against_reference_fixtures(ctx):
     ok, worst = _logp_close(r["jp"].to_numpy(), fx["knn_jp"])
     assert ok, worst
     assert np.array_equal(r["modes"].to_numpy(), fx["knn_modes"])
+
+
+def test_batch_models_and_na_batch_cells(ctx):
+    """batch.models different from models (R/functions.R:304,356: the composition-sampled joints use their own error
+    models) and NA entries in the batch factor (dropped from the pools and from the composition, as tapply / table do)
+    against the oracle; the group joints must not change."""
+    w = synth.make_workload(5, n_genes=90, n_cells=60, seed=17, batch=True)
+    rng = np.random.default_rng(3)
+    bm = w.models.copy()
+    bm["corr.b"] = bm["corr.b"] + rng.uniform(-0.3, 0.3, len(bm))
+    bm["conc.b"] = bm["conc.b"] - 0.5
+    bcodes = np.asarray(w.batch.codes).copy()
+    bcodes[[3, 17, 44]] = -1
+    batch = pd.Categorical.from_codes(bcodes, categories=list(w.batch.categories))
+    codes = np.asarray(w.groups.codes)
+    want = O.expression_difference(w.models, w.counts, w.prior["x"].to_numpy(), w.prior["y"].to_numpy(),
+                                   (np.nonzero(codes == 0)[0], np.nonzero(codes == 1)[0]), nboot=100, seed=1,
+                                   batch_codes=bcodes, batch_models_df=bm)
+    got = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=batch, batch_models=bm,
+                                         n_randomizations=100, return_posteriors=True, context=ctx)
+    for k, ref in (("results", want["results"]), ("batch.effect", want["batch.effect"]), ("batch.adjusted", want["batch.adjusted"])):
+        _z_close(got[k]["Z"].to_numpy(), ref[:, 4])
+        np.testing.assert_allclose(got[k][["lb", "mle", "ub"]].to_numpy(), ref[:, :3], rtol=1e-12, atol=1e-300)
+    plain = api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=batch, n_randomizations=100,
+                                           context=ctx)
+    assert np.array_equal(plain["results"].to_numpy(), got["results"].to_numpy())
+    assert not np.array_equal(plain["batch.effect"]["Z"].to_numpy(), got["batch.effect"]["Z"].to_numpy())

@@ -151,3 +151,42 @@ def test_synthetic_generator_is_deterministic():
     b = synth.make_workload(3, n_genes=50, n_cells=10)
     assert np.array_equal(a.counts, b.counts) and a.counts.flags["F_CONTIGUOUS"] and a.counts.dtype == np.int32
     assert 0.2 < (a.counts == 0).mean() < 0.8
+
+
+def test_fisher_test_p_value():
+    """fisher.test (R/functions.R:339): known answers -- R's documentation example (Agresti's tea tasting, p = 0.4857) and
+    scipy's exact 2 x 2 routine; a 2 x 3 table goes through scipy's r x c code"""
+    from scipy.stats import fisher_exact
+
+    assert abs(api.fisher_test_p_value(np.array([[3, 1], [1, 3]])) - 0.4857142857142857) < 1e-12
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        t = rng.integers(0, 40, size=(2, 2))
+        if t.sum(axis=0).min() == 0 or t.sum(axis=1).min() == 0:
+            continue
+        assert abs(api.fisher_test_p_value(t) - fisher_exact(t).pvalue) < 1e-9
+    assert 0.0 < api.fisher_test_p_value(np.array([[10, 3, 5], [4, 12, 7]])) < 0.1
+    assert api.fisher_test_p_value(np.array([[5000, 0], [0, 5000]])) < 1e-300 or api.fisher_test_p_value(np.array([[5000, 0], [0, 5000]])) == 0.0
+
+
+def test_strong_group_batch_interaction_warns(capsys, monkeypatch):
+    """the reference prints a WARNING when groups and batches are confounded (p < 1e-3, R/functions.R:345-348); checked
+    at the host layer with the device call stubbed out"""
+    w = synth.make_workload(5, n_genes=4, n_cells=40, seed=2, batch=True)
+    confounded = pd.Categorical(np.where(np.arange(40) < 20, "b1", "b2"))
+
+    class Stop(Exception):
+        pass
+
+    def boom(*a, **k):
+        raise Stop()
+
+    monkeypatch.setattr(api, "expression_difference_call", boom)
+    monkeypatch.setattr(api._lib, "default_context", lambda *a, **k: None)
+    with pytest.raises(Stop):
+        api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=confounded)
+    assert "strong interaction between groups and batches" in capsys.readouterr().out
+    balanced = pd.Categorical(np.where(np.arange(40) % 2 == 0, "b1", "b2"))
+    with pytest.raises(Stop):
+        api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=balanced)
+    assert "strong interaction" not in capsys.readouterr().out

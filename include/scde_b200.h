@@ -279,6 +279,21 @@ SCDE_B200_API void scde_b200_diff_free(scde_b200_ctx *ctx, scde_b200_diff_job *j
 SCDE_B200_API int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, int32_t n_genes, int32_t n_cells,
                                    const double *corr_b, const double *corr_a, double *out);
 
+/* ---- input preparation next to the path ---------------------------------------------------- */
+/* scde.failure.probability (R/functions.R:725-750) for a genes x cells matrix: drop-out probability of every (gene, cell)
+ * at the cell's magnitude -- taken from `magnitudes` (n_genes x n_cells, natural log) or, when that is NULL, from `counts`
+ * as scde.expression.magnitude gives it.  models: n_cells x 12 (conc.a2 used when square_logit_conc).  NaN -> 0. */
+SCDE_B200_API int scde_b200_failure_probability(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *counts,
+                                  const double *magnitudes, int32_t n_genes, int32_t square_logit_conc, double *out);
+/* scde.expression.prior (R/functions.R:225-254): magnitudes and drop-out weights of every (gene, cell), the max.quantile
+ * quantile (type 7) of the finite magnitudes when max_value is NaN ("NULL"), stats::density (gaussian kernel, bandwidth
+ * bw, weights, n = 2 length_out + 1, from -max_value to max_value) of the mirrored points, pseudo-count, normalisation.
+ * Outputs, length_out + 1 values each: x (log10 scale), y, lp = log(y), grid_weight.  The O(genes x cells) work runs on
+ * the device; the 2048-point kernel smoothing is host work. */
+SCDE_B200_API int scde_b200_expression_prior(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *counts,
+                               int32_t n_genes, int32_t square_logit_conc, int32_t length_out, double pseudo_count, double bw,
+                               double max_quantile, double max_value, double *x, double *y, double *lp, double *grid_weight);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* One cell's log-posterior table (the reference's ucposteriors[[i]]): out[n_grid * n_counts], grid index
  * fastest; modes[n_counts] (may be NULL).  n_cells_for_clamp sets the lower clamp -DBL_MAX/n/1.1. */

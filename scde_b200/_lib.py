@@ -78,6 +78,7 @@ EXPORTED = [
     "scde_b200_bh_cz", "scde_b200_expression_difference", "scde_b200_diff_upload", "scde_b200_diff_run",
     "scde_b200_diff_download", "scde_b200_diff_free", "scde_b200_expression_magnitude", "scde_b200_cell_table",
     "scde_b200_measure_fp64_peak", "scde_b200_set_contract_kernel", "scde_b200_probe_contract_i8",
+    "scde_b200_failure_probability", "scde_b200_expression_prior",
 ]
 
 _lib = None
@@ -107,6 +108,9 @@ def lib():
                                                       C.POINTER(Stats)]
         L.scde_b200_measure_fp64_peak.argtypes = [C.c_void_p, f64p]
         L.scde_b200_set_contract_kernel.argtypes = [C.c_void_p, C.c_int32]
+        L.scde_b200_failure_probability.argtypes = [C.c_void_p, f64p, C.c_int32, i32p, f64p, C.c_int32, C.c_int32, f64p]
+        L.scde_b200_expression_prior.argtypes = [C.c_void_p, f64p, C.c_int32, i32p, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_double, C.c_double, C.c_double, C.c_double, f64p, f64p, f64p, f64p]
         L.scde_b200_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
         L.scde_b200_n_devices.argtypes = [C.c_void_p]
         L.scde_b200_get_options.argtypes = [C.c_void_p, C.POINTER(Options)]

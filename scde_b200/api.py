@@ -67,11 +67,12 @@ def marginals_from_prior(prior) -> np.ndarray:
         return np.log(m)
 
 
-def pack_models(models: pd.DataFrame):
-    """12-column matrix with NaN for absent columns (R/functions.R:601-604) after the slope clamp (:579-583)."""
+def pack_models(models: pd.DataFrame, clamp: bool = True):
+    """12-column matrix with NaN for absent columns (R/functions.R:601-604) after the slope clamp (:579-583;
+    clamp = False: the models as they are, for scde.expression.prior / scde.failure.probability, which do not clamp)."""
     models = models.copy()
     ca = np.asarray(models["corr.a"], dtype=np.float64)
-    bad = ca < MIN_SLOPE
+    bad = (ca < MIN_SLOPE) & clamp
     if bad.any():
         sys.stdout.write("WARNING: the following cells have negatively-correlated or 0-slope fits:  "
                          + " ".join(map(str, models.index[bad])) + " . Setting slopes to 1e-10.\n")

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscde_b200.so")
-SOURCES = ["api.cu", "lp_table.cu", "dedup.cu", "boot_contract.cu", "contract_i8.cu", "ratio_summary.cu", "hostmath.cpp"]
+SOURCES = ["api.cu", "lp_table.cu", "dedup.cu", "boot_contract.cu", "contract_i8.cu", "ratio_summary.cu", "prior.cu", "hostmath.cpp"]
 HEADERS = ["common.cuh", "ptx_sm100.cuh", "fastmath.cuh", "hostmath.h", os.path.join("..", "..", "include", "scde_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared", "-cudart", "static"]

@@ -1134,6 +1134,148 @@ int scde_b200_expression_magnitude(scde_b200_ctx *ctx, const int32_t *counts, in
     return SCDE_B200_OK;
 }
 
+int scde_b200_failure_probability(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *counts,
+                                  const double *magnitudes, int32_t n_genes, int32_t square_logit_conc, double *out) {
+    CHECK_CTX(ctx);
+    if (!models || (!counts && !magnitudes) || !out || n_cells < 1 || n_genes < 0) {
+        set_error("failure_probability: bad arguments (either magnitudes or counts should be provided)");
+        return SCDE_B200_EINVAL;
+    }
+    const size_t n = (size_t)n_genes * n_cells;
+    if (n == 0) return SCDE_B200_OK;
+    cudaStream_t st = ctx->stream;
+    DBuf<double> d_models, d_mag, d_out;
+    DBuf<int32_t> d_counts;
+    TRY(upload(d_models, models, (size_t)n_cells * 12, st));
+    if (magnitudes)
+        TRY(upload(d_mag, magnitudes, n, st));
+    else
+        TRY(upload(d_counts, counts, n, st));
+    SCDE_CUDA(d_out.ensure(n));
+    SCDE_CUDA(launch_failure_probability(magnitudes ? nullptr : d_counts.p, magnitudes ? d_mag.p : nullptr, (int64_t)n, n_genes,
+                                         d_models.p, n_cells, square_logit_conc, d_out.p, st));
+    SCDE_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    return SCDE_B200_OK;
+}
+
+int scde_b200_expression_prior(scde_b200_ctx *ctx, const double *models, int32_t n_cells, const int32_t *counts,
+                               int32_t n_genes, int32_t square_logit_conc, int32_t length_out, double pseudo_count, double bw,
+                               double max_quantile, double max_value, double *x, double *y, double *lp, double *grid_weight) {
+    CHECK_CTX(ctx);
+    if (!models || !counts || !x || !y || n_cells < 1 || n_genes < 1 || length_out < 1 || !(bw > 0) ||
+        !(max_quantile >= 0 && max_quantile <= 1)) {
+        set_error("expression_prior: bad arguments");
+        return SCDE_B200_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    const int64_t n = (int64_t)n_genes * n_cells;
+    DBuf<double> d_models, d_v, d_w, d_part;
+    DBuf<int32_t> d_counts;
+    DBuf<unsigned long long> d_scal, d_hist, d_bins;
+    TRY(upload(d_models, models, (size_t)n_cells * 12, st));
+    TRY(upload(d_counts, counts, (size_t)n, st));
+    SCDE_CUDA(d_v.ensure((size_t)n));
+    SCDE_CUDA(d_w.ensure((size_t)n));
+    const int nb = prior_pass1_blocks(n);
+    SCDE_CUDA(d_part.ensure((size_t)nb));
+    SCDE_CUDA(d_scal.ensure(2));
+    SCDE_CUDA(cudaMemsetAsync(d_scal.p, 0, 2 * sizeof(unsigned long long), st));
+    SCDE_CUDA(launch_prior_pass1(d_counts.p, n, n_genes, d_models.p, n_cells, square_logit_conc, d_v.p, d_w.p, d_part.p, d_scal.p,
+                                 d_scal.p + 1, st));
+    std::vector<double> part((size_t)nb);
+    unsigned long long scal[2] = {0, 0};
+    SCDE_CUDA(cudaMemcpyAsync(part.data(), d_part.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaMemcpyAsync(scal, d_scal.p, sizeof(scal), cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    long double wsum = 0;  // R's sum() accumulates in long double
+    for (int i = 0; i < nb; ++i) wsum += part[i];
+    const int64_t m = (int64_t)scal[1];
+    if (std::isnan(max_value)) {  // quantile(x[x < Inf], p = max.quantile), type 7 (:233-236)
+        if (m < 1) {
+            set_error("expression_prior: no finite expression magnitude");
+            return SCDE_B200_EINVAL;
+        }
+        if (max_quantile >= 1.0) {
+            max_value = prior_key_to_double(scal[0]);
+        } else {
+            SCDE_CUDA(d_hist.ensure(256));
+            auto kth = [&](int64_t rank, double *out) -> int {  // rank-th smallest (0-based) finite value: 8-pass radix select
+                unsigned long long prefix = 0;
+                for (int shift = 56; shift >= 0; shift -= 8) {
+                    unsigned long long h[256];
+                    SCDE_CUDA(cudaMemsetAsync(d_hist.p, 0, sizeof(h), st));
+                    SCDE_CUDA(launch_select_hist(d_v.p, n, prefix, shift, d_hist.p, st));
+                    SCDE_CUDA(cudaMemcpyAsync(h, d_hist.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+                    SCDE_CUDA(cudaStreamSynchronize(st));
+                    int b = 0;
+                    for (; b < 255 && rank >= (int64_t)h[b]; ++b) rank -= (int64_t)h[b];
+                    prefix |= (unsigned long long)b << shift;
+                }
+                *out = prior_key_to_double(prefix);
+                return SCDE_B200_OK;
+            };
+            const double index = 1 + (double)(m - 1) * max_quantile, fuzz = 4 * DBL_EPSILON;
+            const double lo = std::floor(index + fuzz), hi = std::ceil(index - fuzz);
+            double qlo = 0, qhi = 0;
+            TRY(kth((int64_t)lo - 1, &qlo));
+            double h = index - lo;
+            if (std::fabs(h) < fuzz) h = 0;
+            if (h != 0) {
+                TRY(kth((int64_t)hi - 1, &qhi));
+                max_value = (1 - h) * qlo + h * qhi;
+            } else {
+                max_value = qlo;
+            }
+        }
+    }
+    // density.default: n <- max(n, 512); if (n > 512) n <- 2^ceiling(log2(n)); lo <- from - 4 bw; up <- to + 4 bw
+    const int n_user = 2 * length_out + 1;
+    int nbin = n_user > 512 ? n_user : 512;
+    if (nbin > 512) {
+        int p2 = 1;
+        while (p2 < nbin) p2 <<= 1;
+        nbin = p2;
+    }
+    if (nbin > 16384) {
+        set_error("expression_prior: length_out %d too large (working grid of %d points)", length_out, nbin);
+        return SCDE_B200_ELIMIT;
+    }
+    const double from = -1 * max_value, to = max_value, lo = from - 4 * bw, up = to + 4 * bw;
+    SCDE_CUDA(d_bins.ensure((size_t)nbin));
+    SCDE_CUDA(cudaMemsetAsync(d_bins.p, 0, sizeof(unsigned long long) * nbin, st));
+    SCDE_CUDA(launch_prior_bins(d_v.p, d_w.p, n, 1.0 / (double)wsum, lo, (up - lo) / (nbin - 1), nbin, d_bins.p, st));
+    std::vector<unsigned long long> hb((size_t)nbin);
+    SCDE_CUDA(cudaMemcpyAsync(hb.data(), d_bins.p, sizeof(unsigned long long) * nbin, cudaMemcpyDeviceToHost, st));
+    SCDE_CUDA(cudaStreamSynchronize(st));
+    std::vector<double> yb((size_t)nbin), dx((size_t)n_user), dy((size_t)n_user);
+    for (int i = 0; i < nbin; ++i) yb[i] = (double)(long long)hb[i] / 4611686018427387904.0;
+    density_from_bins(yb.data(), nbin, lo, up, bw, n_user, from, to, dx.data(), dy.data());
+    const int K = length_out + 1;
+    long double ys = 0;
+    for (int k = 0; k < K; ++k) {  // :239-241
+        x[k] = dx[length_out + k];
+        double v = dy[length_out + k];
+        if (std::isnan(v)) v = 0;
+        y[k] = v + pseudo_count / n_genes;
+        ys += y[k];
+    }
+    for (int k = 0; k < K; ++k) {
+        y[k] /= (double)ys;  // :242
+        if (lp) lp[k] = std::log(y[k]);  // :247
+    }
+    if (grid_weight) {  // :250 diff(10^c(x[1], x + c(diff(x)/2, 0)) - 1)
+        double prev = std::pow(10.0, x[0]) - 1;
+        for (int k = 0; k < K; ++k) {
+            const double edge = x[k] + (k < K - 1 ? (x[k + 1] - x[k]) / 2 : 0);
+            const double cur = std::pow(10.0, edge) - 1;
+            grid_weight[k] = cur - prev;
+            prev = cur;
+        }
+    }
+    return SCDE_B200_OK;
+}
+
 int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_t n_rows, int32_t n_grid,
                                 const uint32_t *row_range, const int8_t *w8, int32_t n_w_rows, const int32_t *lst_row,
                                 const int32_t *lst_cell, const int32_t *lst_len, int32_t n_genes, int32_t ld_lst,

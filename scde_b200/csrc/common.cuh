@@ -237,4 +237,19 @@ cudaError_t launch_ratio_summary(const RatioArgs &a, cudaStream_t st);
 cudaError_t launch_magnitude(const int32_t *counts, int64_t n, int G, const double *corr_b, const double *corr_a,
                              double *out, cudaStream_t st);
 
+
+// ---- prior.cu (scde.expression.prior / scde.failure.probability) -----------------------------------
+int prior_pass1_blocks(int64_t n);
+// out[e] = drop-out probability of element e of a G x C matrix; magnitudes from `mag` (G x C) or, when NULL, from counts
+cudaError_t launch_failure_probability(const int32_t *counts, const double *mag, int64_t n, int G, const double *models, int C,
+                                       int sq, double *out, cudaStream_t st);
+cudaError_t launch_prior_pass1(const int32_t *counts, int64_t n, int G, const double *models, int C, int sq, double *v, double *w,
+                               double *part /* [prior_pass1_blocks(n)] */, unsigned long long *vmax_key,
+                               unsigned long long *n_finite, cudaStream_t st);
+cudaError_t launch_select_hist(const double *v, int64_t n, unsigned long long prefix, int shift, unsigned long long *hist,
+                               cudaStream_t st);
+cudaError_t launch_prior_bins(const double *v, const double *w, int64_t n, double inv_sum, double lo, double xdelta, int nbin,
+                              unsigned long long *bins, cudaStream_t st);
+double prior_key_to_double(unsigned long long k);
+
 }  // namespace scde

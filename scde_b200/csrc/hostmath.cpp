@@ -169,6 +169,54 @@ void bh_cz(const double *z, int n, double *cz) {
 
 }  // namespace scde
 
+namespace scde {
+
+void density_from_bins(const double *y, int n, double lo, double up, double bw, int n_user, double from, double to,
+                       double *xout, double *yout) {
+    const int n2 = 2 * n;
+    std::vector<double> k((size_t)n2), conv((size_t)n);
+    // kords <- seq.int(0, 2 * (up - lo), length.out = 2n); kords[(n + 2):(2n)] <- -kords[n:2]; dnorm(kords, sd = bw)
+    const double kby = (2 * (up - lo)) / (n2 - 1);
+    for (int i = 0; i < n2; ++i) k[i] = i * kby;
+    k[n2 - 1] = 2 * (up - lo);
+    for (int i = n + 1; i < n2; ++i) k[i] = -k[n2 - i];
+    const double norm = bw * std::sqrt(2 * M_PI);
+    for (int i = 0; i < n2; ++i) k[i] = std::exp(-0.5 * (k[i] / bw) * (k[i] / bw)) / norm;
+    // Re(fft(fft(y) * Conj(fft(kords)), inverse = TRUE))[1:n] / length(y) = sum_j y[j] kords[(j - i) mod 2n], summed directly
+    // (n^2 = 1e6 products) -- equal to the FFT result up to rounding
+    for (int i = 0; i < n; ++i) {
+        double acc = 0;
+        for (int j = 0; j < n; ++j) {
+            int m = j - i;
+            if (m < 0) m += n2;
+            acc += y[j] * k[m];
+        }
+        conv[i] = acc > 0 ? acc : 0;  // pmax.int(0, .)
+    }
+    // approx(seq.int(lo, up, length.out = n), kords, seq.int(from, to, length.out = n.user))
+    const double xby = (up - lo) / (n - 1), oby = n_user > 1 ? (to - from) / (n_user - 1) : 0;
+    auto xord = [&](int m) { return m == n - 1 ? up : lo + m * xby; };
+    for (int i = 0; i < n_user; ++i) {
+        const double xo = (i == n_user - 1 && n_user > 1) ? to : from + i * oby;
+        xout[i] = xo;
+        if (!(xo >= lo && xo <= up)) {
+            yout[i] = NAN;
+            continue;
+        }
+        int a = 0, b = n - 1;
+        while (a < b - 1) {
+            const int m = (a + b) / 2;
+            if (xo < xord(m)) b = m; else a = m;
+        }
+        const double xa = xord(a), xb = xord(b);
+        if (xo == xb) yout[i] = conv[b];
+        else if (xo == xa) yout[i] = conv[a];
+        else yout[i] = conv[a] + (conv[b] - conv[a]) * ((xo - xa) / (xb - xa));
+    }
+}
+
+}  // namespace scde
+
 extern "C" {
 
 int scde_b200_boot_indices(int32_t seed, int32_t n, int32_t n_boot, int32_t *out) {

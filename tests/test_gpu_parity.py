@@ -775,3 +775,40 @@ def test_batch_models_and_na_batch_cells(ctx):
                                            context=ctx)
     assert np.array_equal(plain["results"].to_numpy(), got["results"].to_numpy())
     assert not np.array_equal(plain["batch.effect"]["Z"].to_numpy(), got["batch.effect"]["Z"].to_numpy())
+
+
+def test_expression_prior_and_failure_probability_on_device(ctx):
+    """scde.expression.prior / scde.failure.probability through the C ABI (csrc/prior.cu: magnitudes, weights, radix-select
+    quantile and fixed-point BinDist on the device) against the oracle's restatement of R's density.default.  1e-9: the
+    bins are 2^-62 fixed point (deterministic), the reference sums doubles sequentially."""
+    from scde_b200 import prior as prior_mod
+
+    cd = helpers.es_mef_raw()
+    ifm = helpers.o_ifm()
+    cd = cd[cd.sum(axis=1) > 0]
+    cd = cd.loc[:, cd.sum(axis=0) > 1e4]
+    ifm = ifm[ifm["corr.a"] > 0]
+    cd = cd.loc[:, list(ifm.index)]
+    for kw in (dict(), dict(max_quantile=0.999), dict(max_quantile=0.5), dict(max_value=5.0, bw=0.2, pseudo_count=3, length_out=250)):
+        want = O.expression_prior(ifm, cd.to_numpy(), **kw)
+        got = prior_mod.scde_expression_prior(ifm, cd, context=ctx, **kw)
+        again = prior_mod.scde_expression_prior(ifm, cd, context=ctx, **kw)
+        for k in ("x", "y", "lp", "grid.weight"):
+            np.testing.assert_allclose(got[k].to_numpy(), want[k], rtol=1e-9, atol=1e-300, err_msg=f"{kw} {k}")
+            assert np.array_equal(got[k].to_numpy(), again[k].to_numpy())  # integer bins: reproducible bit for bit
+    # the prior the es.mef tests use (host twin, CPU fixtures) is the same prior
+    _cd, _ifm, prior_host, _g = helpers.es_mef_inputs("tests")
+    got = prior_mod.scde_expression_prior(ifm, cd, context=ctx)
+    np.testing.assert_allclose(got["y"].to_numpy(), prior_host["y"].to_numpy(), rtol=1e-9)
+    assert np.array_equal(got["x"].to_numpy(), prior_host["x"].to_numpy())
+    # scde.failure.probability: counts form, magnitude-matrix form, common-vector form; 12-column models (conc.a2)
+    sub = cd.iloc[:500]
+    mag = O.expression_magnitude(sub.to_numpy(), ifm["corr.b"].to_numpy(), ifm["corr.a"].to_numpy())
+    want = O.failure_probability(mag, ifm["conc.a"].to_numpy(), ifm["conc.b"].to_numpy())
+    np.testing.assert_allclose(prior_mod.scde_failure_probability(ifm, counts=sub, context=ctx), want, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(prior_mod.scde_failure_probability(ifm, magnitudes=mag, context=ctx), want, rtol=1e-13, atol=1e-300)
+    knn = helpers.knn_models().iloc[:12]
+    mags = np.array([1.0, 1.5, 2.0, -np.inf])
+    m2 = np.repeat(mags[:, None], 12, axis=1)
+    want = O.failure_probability(m2, knn["conc.a"].to_numpy(), knn["conc.b"].to_numpy(), knn["conc.a2"].to_numpy())
+    np.testing.assert_allclose(prior_mod.scde_failure_probability(knn, magnitudes=mags, context=ctx), want, rtol=1e-13, atol=1e-300)

@@ -190,3 +190,20 @@ def test_strong_group_batch_interaction_warns(capsys, monkeypatch):
     with pytest.raises(Stop):
         api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=balanced)
     assert "strong interaction" not in capsys.readouterr().out
+
+
+def test_prior_host_twin_against_oracle():
+    """scde.expression.prior: the numpy twin (np.fft) against the oracle's C restatement of density.default (own radix-2
+    FFT, BinDist, approx) on the es.mef.small data -- default, max.quantile = 0.999 (the vignette's setting) and explicit
+    max.value / bw / pseudo.count"""
+    cd = helpers.es_mef_raw()
+    ifm = helpers.o_ifm()
+    cd = cd[cd.sum(axis=1) > 0]
+    cd = cd.loc[:, cd.sum(axis=0) > 1e4]
+    ifm = ifm[ifm["corr.a"] > 0]
+    cd = cd.loc[:, list(ifm.index)].iloc[::7]
+    for kw in (dict(), dict(max_quantile=0.999), dict(max_value=5.0, bw=0.2, pseudo_count=3, length_out=250)):
+        a = O.expression_prior(ifm, cd.to_numpy(), **kw)
+        b = prior_mod.scde_expression_prior_host(ifm, cd, **kw)
+        for k in ("x", "y", "lp", "grid.weight"):
+            np.testing.assert_allclose(b[k].to_numpy(), a[k], rtol=1e-11, atol=1e-300)

@@ -419,6 +419,10 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    // Programmatic dependent launch: once every CTA of this grid is resident and has passed this point, a kernel queued
+    // behind it with the programmatic-stream-serialization attribute may start and share the SMs (api.cu queues the
+    // issue-bound lp_rows_q_kernel of the other group's cells behind this memory-bound kernel).  A no-op otherwise.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
     const int n_items = p.n_pos * p.n_pieces;
 

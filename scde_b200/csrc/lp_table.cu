@@ -1117,7 +1117,8 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows) {
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows,
+                           int pdl_secondary) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
@@ -1132,10 +1133,19 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
             auto launch_q = [&](auto kernel) -> cudaError_t {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
-                                                             (const double4 *)row_const, row_snap, prep, K, sentinel, table,
-                                                             ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
-                return cudaGetLastError();
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(148 * 3);
+                cfg.blockDim = dim3(QR_WARPS * 32);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = pdl_secondary ? 1 : 0;
+                return cudaLaunchKernelEx(&cfg, kernel, models, ld_models, cr, row_off, row_cell_map, row_x,
+                                          (const double4 *)row_const, row_snap, prep, K, sentinel, (const double *)table, ld_table,
+                                          zero_row, based, qtable, q_row_bytes(K), row_range);
             };
             return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);
         }

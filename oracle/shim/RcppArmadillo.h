@@ -34,6 +34,7 @@
 #include <algorithm>
 #include <iostream>
 #include <iterator>
+#include <stdexcept>
 
 /* ---- R API ------------------------------------------------------------------------------------------------------ */
 enum { SHIM_INTSXP = 13, SHIM_REALSXP = 14, SHIM_VECSXP = 19 };
@@ -401,6 +402,8 @@ class IntegerVector {
     IntegerVector(SEXP x) : s(x) {}
     int size() const { return (int)s->ival.size(); }
     int operator[](std::ptrdiff_t i) const { return s->ival[(size_t)i]; }
+    int *begin() { return s->ival.data(); }
+    int *end() { return s->ival.data() + s->ival.size(); }
 };
 class IntegerMatrix {
   public:
@@ -409,7 +412,20 @@ class IntegerMatrix {
     int nrow() const { return s->nrow; }
     int ncol() const { return s->ncol; }
     int operator()(std::ptrdiff_t i, std::ptrdiff_t j) const { return s->ival[(size_t)(i + (std::ptrdiff_t)s->nrow * j)]; }
+    int *begin() { return s->ival.data(); }
 };
+class NumericVector {
+  public:
+    SEXP s;
+    NumericVector(SEXP x) : s(x) {}
+    int size() const { return (int)s->dval.size(); }
+    double operator[](std::ptrdiff_t i) const { return s->dval[(size_t)i]; }
+    double *begin() { return s->dval.data(); }
+};
+struct ShimStop : public std::runtime_error { /* Rcpp::stop: an R error; here a C++ exception the entry wrapper reports */
+    explicit ShimStop(const std::string &m) : std::runtime_error(m) {}
+};
+inline void stop(const std::string &msg) { throw ShimStop(msg); }
 class NumericMatrix {
   public:
     SEXP s;
@@ -422,8 +438,10 @@ class NumericMatrix {
     }
     int nrow() const { return s->nrow; }
     int ncol() const { return s->ncol; }
+    int size() const { return (int)s->dval.size(); }
     double *begin() { return s->dval.data(); }
     double &operator()(std::ptrdiff_t i, std::ptrdiff_t j) { return s->dval[(size_t)(i + (std::ptrdiff_t)s->nrow * j)]; }
+    operator SEXP() const { return s; }
 };
 
 template <class T>
@@ -443,6 +461,10 @@ struct AsImpl<IntegerMatrix> {
 template <>
 struct AsImpl<NumericMatrix> {
     static NumericMatrix get(SEXP x) { return NumericMatrix(x); }
+};
+template <>
+struct AsImpl<NumericVector> {
+    static NumericVector get(SEXP x) { return NumericVector(x); }
 };
 template <>
 struct AsImpl<arma::mat> {
@@ -489,6 +511,10 @@ class List {
         }
         Slot &operator=(const arma::Mat &m) {
             *p = wrap(m);
+            return *this;
+        }
+        Slot &operator=(const NumericMatrix &m) {
+            *p = m.s;
             return *this;
         }
     };

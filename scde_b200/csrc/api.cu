@@ -266,6 +266,7 @@ enum { ROWS_ALL = 0, ROWS_PRE = 1, ROWS_MAIN_PDL = 2 };
 int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl, CellRange cr, const double *models_dev,
                       int ld_models, int local_theta, int *nl, int part = ROWS_ALL) {
     cudaStream_t st = ctx->stream;
+    unsigned long long *probe = (part == ROWS_MAIN_PDL && ctx->opt.epilogue_timing && ctx->epi_dbg.p) ? ctx->epi_dbg.p + 5 : nullptr;
     const int n = cr.c1 - cr.c0;
     if (part != ROWS_MAIN_PDL) {
         SCDE_CUDA(launch_row_cell(t.row_off.p, cr, t.row_cell.p, st));
@@ -289,7 +290,7 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
             SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                      t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
                                      pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1,
-                                     part == ROWS_MAIN_PDL));
+                                     part == ROWS_MAIN_PDL, probe));
             ++*nl;
         }
     } else if (part != ROWS_MAIN_PDL) {
@@ -467,9 +468,12 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.hot_rank = hot_rank;
         q.cold_evict_first = ctx->opt.cold_evict_first;
         q.ring_stages = ctx->opt.ring_stages;
+        q.producer_groups = ctx->opt.producer_groups;
         if (ctx->opt.epilogue_timing) {
-            SCDE_CUDA(ctx->epi_dbg.ensure(3));
-            SCDE_CUDA(cudaMemsetAsync(ctx->epi_dbg.p, 0, 3 * sizeof(unsigned long long), st));
+            SCDE_CUDA(ctx->epi_dbg.ensure(8));
+            const unsigned long long init[8] = {0, 0, 0, ~0ull, 0, ~0ull, 0, 0};  // [3]/[5]: minima
+            SCDE_CUDA(cudaMemcpyAsync(ctx->epi_dbg.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            SCDE_CUDA(cudaStreamSynchronize(st));
             q.dbg = ctx->epi_dbg.p;
         }
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
@@ -484,10 +488,14 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
                 if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
                 const bool co = co_launch && g0 == 0 && ps == 0;
-                if (co && q.ring_stages == 0) q.ring_stages = 7;  // leaves room for one CTA of the row kernel on every SM
+                if (co) {  // leaves shared memory and registers for one CTA of the row kernel on every SM
+                    q.ring_stages = 7;
+                    q.producer_groups = 1;
+                }
                 SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
                 if (co) {
                     q.ring_stages = ctx->opt.ring_stages;
+                    q.producer_groups = ctx->opt.producer_groups;
                     TRY((*co_launch)());
                 }
                 if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, co ? 2 : 1);
@@ -497,12 +505,17 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
             }
         }
         if (q.dbg) {
-            unsigned long long h[3];
+            unsigned long long h[8];
             SCDE_CUDA(cudaMemcpyAsync(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
             SCDE_CUDA(cudaStreamSynchronize(st));
             fprintf(stderr, "[scde_b200] tcgen05 epilogue: %llu items, %.0f cycles from accumulators ready to tensor memory released, "
                     "MMA thread waited %.0f cycles per item for the release\n", h[1], h[1] ? (double)h[0] / h[1] : 0.0,
                     h[1] ? (double)h[2] / h[1] : 0.0);
+            if (h[5] != ~0ull)
+                fprintf(stderr, "[scde_b200] contraction kernels ran %.3f ms (first CTA start .. last CTA end of the joint's launches); "
+                        "co-launched row kernel started %.3f ms after the first contraction CTA and ended %.3f ms %s the last\n",
+                        (h[4] - h[3]) * 1e-6, ((double)h[5] - (double)h[3]) * 1e-6, std::fabs((double)h[6] - (double)h[4]) * 1e-6,
+                        h[6] > h[4] ? "after" : "before");
         }
         return SCDE_B200_OK;
     }
@@ -687,7 +700,8 @@ int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt) {
     if (!ctx || !opt) return SCDE_B200_EINVAL;
     if (opt->contract_kernel < 0 || opt->contract_kernel > 3 || opt->count_chunks < 0 || opt->count_chunks > 64 ||
         opt->item_order < 0 || opt->item_order > 1 ||
-        !(opt->ring_stages == 0 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10)) {
+        !(opt->ring_stages == 0 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10) ||
+        opt->producer_groups < 0 || opt->producer_groups > 2) {
         set_error("set_options: value out of range");
         return SCDE_B200_EINVAL;
     }
@@ -1368,6 +1382,7 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.hot_rank = -1;
     q.cold_evict_first = 0;
     q.ring_stages = ctx->opt.ring_stages;
+    q.producer_groups = ctx->opt.producer_groups;
     SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
     SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
     SCDE_CUDA(launch_finalize_t(q, n_genes, d_t.p, d_sr.p, st));

@@ -812,3 +812,59 @@ def test_expression_prior_and_failure_probability_on_device(ctx):
     m2 = np.repeat(mags[:, None], 12, axis=1)
     want = O.failure_probability(m2, knn["conc.a"].to_numpy(), knn["conc.b"].to_numpy(), knn["conc.a2"].to_numpy())
     np.testing.assert_allclose(prior_mod.scde_failure_probability(knn, magnitudes=mags, context=ctx), want, rtol=1e-13, atol=1e-300)
+
+
+def test_r_shim_symbols_against_reference_fixtures(ctx):
+    """integration/scde_b200_shim.cpp -- the file an scde maintainer puts into src/ in place of jpmatLogBoot.cpp and
+    matSlideMult.cpp -- compiled against the header shim of the Rcpp API and driven through the same SEXP-building
+    wrappers that drive the reference's own C++ (oracle/shim/ref_entry.cpp): .Call-shaped arguments -> shim ->
+    libscde_b200.so, i.e. the code path of an R session minus R.  Compared with the reference fixtures / the oracle."""
+    import ctypes
+    import os
+
+    from oracle import ref as R
+
+    path = os.path.join(helpers.GOLD, "..", "..", "integration", "_build", "libscde_shim.so")
+    if not os.path.exists(path):
+        pytest.skip("integration/_build/libscde_shim.so not built (make -C integration; needs the reference headers)")
+    shim = ctypes.CDLL(os.path.abspath(path))
+    keep, R._lib = R._lib, shim  # the oracle.ref binding, pointed at the shim build of the same five entry points
+    try:
+        fx = helpers.ref_fixtures()
+        sub, ifm, prior, groups, sel = helpers.ref_cfg1_inputs()
+        mm, lt, sq = O.pack_models(ifm)
+        mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+        codes = np.asarray(groups.codes)
+        jps = []
+        for lev in (0, 1):
+            ii = np.nonzero(codes == lev)[0]
+            flat, off, uci = O.unique_counts(np.asfortranarray(sub.to_numpy()[:, ii]))
+            r = R.log_boot_posterior(np.asfortranarray(mm[ii]), flat, off, uci, mag, 100, seed=1, returnpost=3)
+            ok, worst = _logp_close(r["jp"], fx[f"cfg1_jp{lev}"])
+            assert ok, worst
+            assert np.array_equal(r["modes"], fx[f"cfg1_modes{lev}"])
+            want = O.log_boot_posterior(np.asfortranarray(mm[ii]), flat, off, uci, mag, 100, seed=1, returnpost=2)["post"]
+            for a, b in zip(r["post"], want):
+                _rows_close(np.asarray(a), np.asarray(b))
+            jps.append(fx[f"cfg1_jp{lev}"])
+        py = prior["y"].to_numpy()
+        assert np.array_equal(R.mat_slide_mult(jps[0] * py[None, :], jps[1] * py[None, :]), fx["cfg1_slide"])
+        w = helpers.ref_batch_inputs()
+        mm, lt, sq = O.pack_models(w.models)
+        mag = O.marginals_from_prior_x(w.prior["x"].to_numpy())
+        codes, bc = np.asarray(w.groups.codes), np.asarray(w.batch.codes)
+        pools = [np.nonzero(bc == l)[0].astype(np.int32) for l in range(2)]
+        flat, off, uci = O.unique_counts(w.counts)
+        for lev in (0, 1):
+            comp = np.bincount(bc[codes == lev], minlength=2).astype(np.int32)
+            r = R.log_boot_batch_posterior(mm, flat, off, uci, mag, pools, comp, 100, seed=1, returnpost=1)
+            ok, worst = _logp_close(r["jp"], fx[f"batch_bjp{lev}"])
+            assert ok, worst
+        rng = np.random.default_rng(11)
+        matl = [np.asfortranarray(-rng.gamma(2.0, 3.0, size=(13, 29))) for _ in range(9)]
+        np.testing.assert_allclose(R.jpmat_log_boot(matl, 40, seed=3), O.jpmat_log_boot(matl, 40, seed=3), rtol=1e-9)
+        comp = np.array([3, 6], dtype=np.int32)
+        np.testing.assert_allclose(R.jpmat_log_batch_boot([matl[:4], matl[4:]], comp, 25, seed=2),
+                                   O.jpmat_log_batch_boot([matl[:4], matl[4:]], comp, 25, seed=2), rtol=1e-9)
+    finally:
+        R._lib = keep

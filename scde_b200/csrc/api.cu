@@ -290,7 +290,7 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
             SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                      t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
                                      pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1,
-                                     part == ROWS_MAIN_PDL, probe));
+                                     part == ROWS_MAIN_PDL ? (ctx->opt.debug_contract == 77 ? 2 : 1) : 0, probe));
             ++*nl;
         }
     } else if (part != ROWS_MAIN_PDL) {
@@ -489,7 +489,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
                 e0 = tm ? tm->begin(st) : -1;
                 const bool co = co_launch && g0 == 0 && ps == 0;
                 if (co) {  // leaves shared memory and registers for one CTA of the row kernel on every SM
-                    q.ring_stages = 7;
+                    q.ring_stages = ctx->opt.ring_stages == 4 ? 4 : 7;
                     q.producer_groups = 1;
                 }
                 SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
@@ -700,7 +700,7 @@ int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt) {
     if (!ctx || !opt) return SCDE_B200_EINVAL;
     if (opt->contract_kernel < 0 || opt->contract_kernel > 3 || opt->count_chunks < 0 || opt->count_chunks > 64 ||
         opt->item_order < 0 || opt->item_order > 1 ||
-        !(opt->ring_stages == 0 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10) ||
+        !(opt->ring_stages == 0 || opt->ring_stages == 4 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10) ||
         opt->producer_groups < 0 || opt->producer_groups > 2) {
         set_error("set_options: value out of range");
         return SCDE_B200_EINVAL;

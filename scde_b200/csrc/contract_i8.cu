@@ -810,6 +810,7 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
     if (a.hot_rank >= 0) return launch(contract_i8_kernel<2, true, Q_NS>, 2, Q_NS);
     // the shallow ring leaves 69 KB of shared memory to a co-resident kernel
     if (a.producer_groups == 1) {
+        if (a.ring_stages == 4) return launch(contract_i8_kernel<1, false, 4>, 1, 4);
         if (a.ring_stages == 7) return launch(contract_i8_kernel<1, false, 7>, 1, 7);
         return launch(contract_i8_kernel<1, false, Q_NS>, 1, Q_NS);
     }

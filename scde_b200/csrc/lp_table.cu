@@ -787,8 +787,8 @@ struct QrCell {
 };
 constexpr int QR_SMEM_WARP = 4 * Q_PIECE + 2 * (int)sizeof(QrHeaders) + (int)sizeof(QrCell);
 
-template <bool FULL>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
-__global__ void __launch_bounds__(QR_WARPS * 32, 3)
+template <bool FULL, int MINB = 3>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
+__global__ void __launch_bounds__(QR_WARPS * 32, MINB)
 lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                  const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
@@ -1167,6 +1167,8 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                                           (const double4 *)row_const, row_snap, prep, K, sentinel, (const double *)table, ld_table,
                                           zero_row, based, qtable, q_row_bytes(K), row_range, probe);
             };
+            if (pdl_secondary == 2)  // experiment: a 128-register build (four CTAs per SM)
+                return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true, 4>) : launch_q(lp_rows_q_kernel<false, 4>);
             return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);
         }
         auto launch =[&](auto kernel, int rpw) -> cudaError_t {

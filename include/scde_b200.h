@@ -115,10 +115,7 @@ typedef struct {
     int32_t epilogue_timing;    /* 1: cycle counters of the tcgen05 kernel's epilogue on stderr */
     int32_t debug_contract;     /* FP64 tiled kernel: diagnostic mode (0 = off) */
     int32_t ring_stages;        /* tcgen05 contraction: stages of the shared-memory ring, 0 = default (10); 7 or 8 (experiments) */
-    int32_t overlap_rows;       /* 1 (default): resident job -- the second group's table rows are built under the first group's
-                                   contraction kernel (programmatic dependent launch); 0: one kernel after the other */
-    int32_t producer_groups;    /* tcgen05 contraction: groups of four producer warps, 0 = default (2); 1 = the 13-warp variant */
-    int32_t reserved[4];
+    int32_t reserved[6];
 } scde_b200_options;
 SCDE_B200_API int scde_b200_get_options(const scde_b200_ctx *ctx, scde_b200_options *opt);
 SCDE_B200_API int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt);

@@ -11,7 +11,6 @@
 #include <cstring>
 #include <string>
 #include <chrono>
-#include <functional>
 #include <thread>
 #include <vector>
 
@@ -132,7 +131,6 @@ static scde_b200_options default_options() {
     o.item_order = 1;  // piece-major: measured 5 % faster at config 4 (profiles/r02a_sweep.txt)
     o.hot_rank = -1;
     o.cold_evict_first = 1;
-    o.overlap_rows = 1;
     return o;
 }
 
@@ -259,41 +257,29 @@ int reserve_rows(LpTable &t, TablePlan &pl, size_t rows) {
 }
 
 // the row-level kernels for the cells of `cr` (their rows are read from t.row_off on the device); returns the number of
-// launches through *nl.  part: ROWS_ALL = everything; ROWS_PRE = everything except the big fixed-point row kernel of the
-// non-zero counts; ROWS_MAIN_PDL = only that kernel, queued as a programmatic dependent of the kernel launched immediately
-// before it (zero-base tables only)
-enum { ROWS_ALL = 0, ROWS_PRE = 1, ROWS_MAIN_PDL = 2 };
+// launches through *nl
 int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl, CellRange cr, const double *models_dev,
-                      int ld_models, int local_theta, int *nl, int part = ROWS_ALL) {
+                      int ld_models, int local_theta, int *nl) {
     cudaStream_t st = ctx->stream;
-    unsigned long long *probe = (part == ROWS_MAIN_PDL && ctx->opt.epilogue_timing && ctx->epi_dbg.p) ? ctx->epi_dbg.p + 5 : nullptr;
     const int n = cr.c1 - cr.c0;
-    if (part != ROWS_MAIN_PDL) {
-        SCDE_CUDA(launch_row_cell(t.row_off.p, cr, t.row_cell.p, st));
+    SCDE_CUDA(launch_row_cell(t.row_off.p, cr, t.row_cell.p, st));
+    ++*nl;
+    if (pl.fast) {
+        SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_off.p, cr, t.row_cell.p, t.row_x.p, pl.rowc, t.row_snap.p,
+                                    pl.prep, t.K, st));
         ++*nl;
-        if (pl.fast) {
-            SCDE_CUDA(launch_row_consts(models_dev, ld_models, t.row_off.p, cr, t.row_cell.p, t.row_x.p, pl.rowc, t.row_snap.p,
-                                        pl.prep, t.K, st));
-            ++*nl;
-        }
     }
     if (t.zero_base) {
-        if (part != ROWS_MAIN_PDL) {
-            SCDE_CUDA(launch_zero_rows(t.row_off.p + cr.c0, t.row_x.p, n, t.zero_row.p + cr.c0, cr.row_cap, st));
-            SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
-                                     t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, t.row_snap.p, 1, pl.qf, pl.qr,
-                                     st));
-            SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
-            *nl += 3;
-        }
-        if (part != ROWS_PRE) {
-            SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
-                                     t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
-                                     pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1,
-                                     part == ROWS_MAIN_PDL ? (ctx->opt.debug_contract == 77 ? 2 : 1) : 0, probe));
-            ++*nl;
-        }
-    } else if (part != ROWS_MAIN_PDL) {
+        SCDE_CUDA(launch_zero_rows(t.row_off.p + cr.c0, t.row_x.p, n, t.zero_row.p + cr.c0, cr.row_cap, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, t.row_snap.p, 1, pl.qf, pl.qr,
+                                 st));
+        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
+        SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
+                                 t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
+                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1));
+        *nl += 4;
+    } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                  t.sentinel, t.table.p, t.ld, pl.rmode, 0, nullptr, nullptr, pl.rowc, t.row_snap.p, 1, nullptr, nullptr,
                                  st));
@@ -302,14 +288,9 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
     return SCDE_B200_OK;
 }
 
-// rows of the table from the per-cell model rows; t.row_off / t.row_x / t.n_rows must be set.
-// defer_from in (0, n_cells): the fixed-point rows of the cells [defer_from, n_cells) are NOT built here -- the caller
-// queues them (launch_table_rows(.., ROWS_MAIN_PDL) with *plan_out) behind the first group's contraction kernel, which is
-// memory-bound and leaves the issue slots of the SMs to this issue-bound kernel (only honoured for the fused fixed-point
-// table; *deferred says whether it was).
+// rows of the table from the per-cell model rows; t.row_off / t.row_x / t.n_rows must be set
 int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_models, const double *mag_dev,
-               int local_theta, int sqlogit, StageTimer *tm, int defer_from = 0, TablePlan *plan_out = nullptr,
-               bool *deferred = nullptr) {
+               int local_theta, int sqlogit, StageTimer *tm) {
     cudaStream_t st = ctx->stream;
     TablePlan pl = plan_table(ctx, t, local_theta);
     TRY(reserve_rows(t, pl, (size_t)t.n_rows));
@@ -318,16 +299,7 @@ int fill_table(scde_b200_ctx *ctx, LpTable &t, const double *models_dev, int ld_
     TRY(prepare_cells(ctx, t, pl, models_dev, ld_models, mag_dev, local_theta, sqlogit));
     // fixed-point planes for the tcgen05 contraction: emitted by the fast row kernel itself (the FP64 rows of non-zero
     // counts are then not stored at all), by a separate pass over the FP64 table for the general kernel
-    const bool defer = plan_out && deferred && defer_from > 0 && defer_from < t.n_cells && pl.q_fused && t.zero_base;
-    if (defer) {
-        TRY(launch_table_rows(ctx, t, pl, CellRange{0, defer_from, (int64_t)t.n_rows}, models_dev, ld_models, local_theta, &nl));
-        TRY(launch_table_rows(ctx, t, pl, CellRange{defer_from, t.n_cells, (int64_t)t.n_rows}, models_dev, ld_models, local_theta,
-                              &nl, ROWS_PRE));
-    } else {
-        TRY(launch_table_rows(ctx, t, pl, CellRange{0, t.n_cells, (int64_t)t.n_rows}, models_dev, ld_models, local_theta, &nl));
-    }
-    if (plan_out) *plan_out = pl;
-    if (deferred) *deferred = defer;
+    TRY(launch_table_rows(ctx, t, pl, CellRange{0, t.n_cells, (int64_t)t.n_rows}, models_dev, ld_models, local_theta, &nl));
     t.has_q = pl.q_any;
     t.f64_rows = !(pl.q_fused && t.zero_base);
     if (pl.q_any && !pl.q_fused) {
@@ -404,12 +376,9 @@ struct DiffWorkspace {
 };
 
 // jp_dev[G][ld_jp] = joint posterior of the listed cells under the draws boot_idx_dev (n_boot x D, device).
-// co_launch (optional): kernels the caller wants to run UNDER this joint's first contraction launch (the deferred table
-// rows of the other group, see fill_table): called right after that launch with nothing queued in between, or -- when the
-// joint does not go to the tcgen05 kernel -- before the contraction, as ordinary launches.
 int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev, int n_list,
               const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
-              JointScratch &scr, StageTimer *tm, bool count_entries, const std::function<int()> *co_launch = nullptr) {
+              JointScratch &scr, StageTimer *tm, bool count_entries) {
     cudaStream_t st = ctx->stream;
     const int n_w_rows = round_up(n_list + 1, 16);  // at least one all-zero row after the cells (list padding)
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
@@ -468,12 +437,9 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         q.hot_rank = hot_rank;
         q.cold_evict_first = ctx->opt.cold_evict_first;
         q.ring_stages = ctx->opt.ring_stages;
-        q.producer_groups = ctx->opt.producer_groups;
         if (ctx->opt.epilogue_timing) {
-            SCDE_CUDA(ctx->epi_dbg.ensure(8));
-            const unsigned long long init[8] = {0, 0, 0, ~0ull, 0, ~0ull, 0, 0};  // [3]/[5]: minima
-            SCDE_CUDA(cudaMemcpyAsync(ctx->epi_dbg.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-            SCDE_CUDA(cudaStreamSynchronize(st));
+            SCDE_CUDA(ctx->epi_dbg.ensure(3));
+            SCDE_CUDA(cudaMemsetAsync(ctx->epi_dbg.p, 0, 3 * sizeof(unsigned long long), st));
             q.dbg = ctx->epi_dbg.p;
         }
         SCDE_CUDA(scr.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
@@ -487,35 +453,20 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
                 SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps, scr.SR.p, st));
                 if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
-                const bool co = co_launch && g0 == 0 && ps == 0;
-                if (co) {  // leaves shared memory and registers for one CTA of the row kernel on every SM
-                    q.ring_stages = ctx->opt.ring_stages == 4 ? 4 : 7;
-                    q.producer_groups = 1;
-                }
                 SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
-                if (co) {
-                    q.ring_stages = ctx->opt.ring_stages;
-                    q.producer_groups = ctx->opt.producer_groups;
-                    TRY((*co_launch)());
-                }
-                if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, co ? 2 : 1);
+                if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_softmax_i8(q, g0, n_pos, ps, scr.T.p, scr.SR.p, scr.spart.p, ctx->n_sm, st));
                 if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, 2);
             }
         }
         if (q.dbg) {
-            unsigned long long h[8];
+            unsigned long long h[3];
             SCDE_CUDA(cudaMemcpyAsync(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
             SCDE_CUDA(cudaStreamSynchronize(st));
             fprintf(stderr, "[scde_b200] tcgen05 epilogue: %llu items, %.0f cycles from accumulators ready to tensor memory released, "
                     "MMA thread waited %.0f cycles per item for the release\n", h[1], h[1] ? (double)h[0] / h[1] : 0.0,
                     h[1] ? (double)h[2] / h[1] : 0.0);
-            if (h[5] != ~0ull)
-                fprintf(stderr, "[scde_b200] contraction kernels ran %.3f ms (first CTA start .. last CTA end of the joint's launches); "
-                        "co-launched row kernel started %.3f ms after the first contraction CTA and ended %.3f ms %s the last\n",
-                        (h[4] - h[3]) * 1e-6, ((double)h[5] - (double)h[3]) * 1e-6, std::fabs((double)h[6] - (double)h[4]) * 1e-6,
-                        h[6] > h[4] ? "after" : "before");
         }
         return SCDE_B200_OK;
     }
@@ -523,7 +474,6 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         set_error("internal: the table was built in fixed point only but the FP64 contraction kernel was selected");
         return SCDE_B200_EINVAL;
     }
-    if (co_launch) TRY((*co_launch)());
     ContractArgs a;
     a.table = t.table.p;
     a.ld_table = t.ld;
@@ -700,8 +650,7 @@ int scde_b200_set_options(scde_b200_ctx *ctx, const scde_b200_options *opt) {
     if (!ctx || !opt) return SCDE_B200_EINVAL;
     if (opt->contract_kernel < 0 || opt->contract_kernel > 3 || opt->count_chunks < 0 || opt->count_chunks > 64 ||
         opt->item_order < 0 || opt->item_order > 1 ||
-        !(opt->ring_stages == 0 || opt->ring_stages == 4 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10) ||
-        opt->producer_groups < 0 || opt->producer_groups > 2) {
+        !(opt->ring_stages == 0 || opt->ring_stages == 7 || opt->ring_stages == 8 || opt->ring_stages == 10)) {
         set_error("set_options: value out of range");
         return SCDE_B200_EINVAL;
     }
@@ -1382,7 +1331,6 @@ int scde_b200_probe_contract_i8(scde_b200_ctx *ctx, const int8_t *qtable, int32_
     q.hot_rank = -1;
     q.cold_evict_first = 0;
     q.ring_stages = ctx->opt.ring_stages;
-    q.producer_groups = ctx->opt.producer_groups;
     SCDE_CUDA(launch_sentinel_ranges(q, 0, n_genes, 0, d_sr.p, st));
     SCDE_CUDA(launch_contract_i8_pass(q, 0, n_genes, 0, ctx->n_sm, d_t.p, st));
     SCDE_CUDA(launch_finalize_t(q, n_genes, d_t.p, d_sr.p, st));
@@ -1924,14 +1872,9 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
     TRY(reset_flags(ctx));
     int t_all = tm.begin(st);
     bool front_done = false, joint0_done = false;
-    const std::function<int()> *co_rows = nullptr;  // deferred table rows to run under the first group's contraction
-    std::function<int()> co_fn;
-    TablePlan defer_plan;
     auto group_joint = [&](int i) {  // cells of one factor level, draws are local indices (R/functions.R:372-374)
-        const std::function<int()> *co = i == 0 ? co_rows : nullptr;
-        if (i == 0) co_rows = nullptr;
         return run_joint(ctx, j->ws->table, j->cell_ids[i].p, j->n_group[i], j->boot_ptr[i], j->n_boot, j->D[i],
-                         (double)j->n_boot, j->ws->jp[i].p, ld, j->ws->scr, &tm, true, co);
+                         (double)j->n_boot, j->ws->jp[i].p, ld, j->ws->scr, &tm, true);
     };
     if (chunked_counts) {
         TRY(front_chunked(ctx, j, 0, &front_done));
@@ -1959,23 +1902,7 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
         const int64_t known = (!chunked_counts && want_i8(ctx)) ? j->known_rows : 0;
         TRY(index_from_counts(ctx, j->ws->table, j->ws->counts.p, G, 0, G, C, &tm, known));
         j->rows_unchecked = known > 0;
-        // Overlap of the two complementary stages: the rows of the cells behind the first group's last cell are not needed
-        // by that group's joint; their fixed-point row kernel (issue-bound) is queued behind the group's contraction kernel
-        // (memory-bound, issue slots 21 % busy) as a programmatic dependent launch and shares the SMs with it.
-        int last0 = -1;
-        for (int c : j->ids[0]) last0 = c > last0 ? c : last0;
-        const int defer_from = (ctx->opt.overlap_rows && want_i8(ctx)) ? last0 + 1 : 0;
-        bool deferred = false;
-        TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm, defer_from, &defer_plan,
-                       &deferred));
-        if (deferred) {
-            co_fn = [ctx, j, defer_from, C, &defer_plan]() -> int {
-                int nl = 0;
-                return launch_table_rows(ctx, j->ws->table, defer_plan, CellRange{defer_from, C, (int64_t)j->ws->table.n_rows},
-                                         j->models.p, C, j->local_theta, &nl, ROWS_MAIN_PDL);
-            };
-            co_rows = &co_fn;
-        }
+        TRY(fill_table(ctx, j->ws->table, j->models.p, C, j->mag.p, j->local_theta, j->sqlogit, &tm));
     }
     for (int i = 0; i < 2; ++i)
         if (!(i == 0 && joint0_done)) TRY(group_joint(i));

@@ -60,12 +60,8 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0,
-                           int pdl_secondary = 0, unsigned long long *probe = nullptr);
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0);
 // legacy_q_rows: build fixed-point-only rows with the per-element kernel the register-resident one replaced (tests)
-// pdl_secondary: launch the fixed-point row kernel with the programmatic-stream-serialization attribute, so that it may
-// start while the kernel queued immediately before it on the stream is still running (once that kernel has executed
-// griddepcontrol.launch_dependents in every CTA); the caller guarantees that the two are independent
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
@@ -201,7 +197,6 @@ struct ContractI8Args {
                        // rows are loaded with the L2 evict_last policy, the others evict_first.  < 0: no hints
     int cold_evict_first;  // with hot_rank >= 0: 1 = the other rows are loaded evict_first, 0 = without a priority
     int ring_stages;       // 0 / 10: the full 10-stage ring (200 KB in flight per SM); 7 or 8: a shallower one
-    int producer_groups;   // 0 / 2: two groups of four producer warps; 1: one group (13 warps: the co-residency variant)
 };
 constexpr int32_t LIST_HOT_BIT = 1 << 30;  // in GeneLists::cell (W row ids are < 65536)
 // n_draws: draws per randomization (the plane sums are combined pairwise in 32 bits: 257 * 128 * draws < 2^31)

@@ -419,15 +419,6 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    // Programmatic dependent launch: once every CTA of this grid is resident and has passed this point, a kernel queued
-    // behind it with the programmatic-stream-serialization attribute may start and share the SMs (api.cu queues the
-    // issue-bound lp_rows_q_kernel of the other group's cells behind this memory-bound kernel).  A no-op otherwise.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (p.dbg && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMin(p.dbg + 3, t);
-    }
     const uint32_t tmem = sm.tmem_base;
     const int n_items = p.n_pos * p.n_pieces;
 
@@ -441,11 +432,6 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    if (p.dbg && threadIdx.x == 0) {  // [3]: first CTA start, [4]: last CTA end (globaltimer ns)
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMax(p.dbg + 4, t);
-    }
     if (sm.abort && p.err && threadIdx.x == 0) atomicExch(p.err, 2);
     if (warp == Q_PRODUCER_WARPS + Q_EPILOGUE_WARPS) tmem_dealloc(tmem, Q_TMEM_COLS);
 }
@@ -788,35 +774,24 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
                                     cudaStream_t st) {
     if (n_pos <= 0) return cudaSuccess;
     // two producer groups: a third one (12 producer warps) measured 1 % slower -- the producers already wait on free
-    // ring slots most of the time (profiles/r01w).  One group (13 warps in all) is the co-residency variant: the register
-    // file is four 16 K partitions, one per scheduler; with 17 warps of 80 registers one partition holds five of them and
-    // has 3 584 registers left -- less than one warp of lp_rows_q_kernel (168 x 32 = 5 376) -- so that kernel's CTA does
-    // not fit beside this one; with 13 warps every partition keeps 6 144.
+    // ring slots most of the time (profiles/r01w)
+    constexpr int PG = 2;
     const I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;
     // function attributes are per device: set on every launch (a process may hold contexts on several GPUs)
-    auto launch = [&](auto kernel, int pg, int ns) -> cudaError_t {
+    auto launch = [&](auto kernel, int ns) -> cudaError_t {
         const size_t smem = q_smem_bytes(ns);
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        // the SM's shared-memory carve-out is chosen when a kernel starts on an idle SM: ask for the largest one, so that a
-        // co-resident kernel still finds shared memory beside a shallow ring
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        kernel<<<grid, q_threads(pg), smem, st>>>(p);
+        kernel<<<grid, q_threads(PG), smem, st>>>(p);
         return cudaGetLastError();
     };
-    if (a.hot_rank >= 0) return launch(contract_i8_kernel<2, true, Q_NS>, 2, Q_NS);
-    // the shallow ring leaves 69 KB of shared memory to a co-resident kernel
-    if (a.producer_groups == 1) {
-        if (a.ring_stages == 4) return launch(contract_i8_kernel<1, false, 4>, 1, 4);
-        if (a.ring_stages == 7) return launch(contract_i8_kernel<1, false, 7>, 1, 7);
-        return launch(contract_i8_kernel<1, false, Q_NS>, 1, Q_NS);
-    }
-    if (a.ring_stages == 7) return launch(contract_i8_kernel<2, false, 7>, 2, 7);
-    if (a.ring_stages == 8) return launch(contract_i8_kernel<2, false, 8>, 2, 8);
-    return launch(contract_i8_kernel<2, false, Q_NS>, 2, Q_NS);
+    if (a.hot_rank >= 0) return launch(contract_i8_kernel<PG, true, Q_NS>, Q_NS);
+    // the shallow ring leaves 69 KB of shared memory and a third of the register file to a co-resident kernel
+    if (a.ring_stages == 7) return launch(contract_i8_kernel<PG, false, 7>, 7);
+    if (a.ring_stages == 8) return launch(contract_i8_kernel<PG, false, 8>, 8);
+    return launch(contract_i8_kernel<PG, false, Q_NS>, Q_NS);
 }
 
 size_t softmax_i8_scratch_doubles(int n_pos) { return (size_t)SP_GROUPS * (n_pos > 0 ? n_pos : 1) * KP_TILED; }

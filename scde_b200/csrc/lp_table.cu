@@ -787,33 +787,15 @@ struct QrCell {
 };
 constexpr int QR_SMEM_WARP = 4 * Q_PIECE + 2 * (int)sizeof(QrHeaders) + (int)sizeof(QrCell);
 
-template <bool FULL, int MINB = 3>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
-__global__ void __launch_bounds__(QR_WARPS * 32, MINB)
+template <bool FULL>  // FULL: K >= 384, every quad of the three rounds lies inside the grid
+__global__ void __launch_bounds__(QR_WARPS * 32, 3)
 lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const int32_t *__restrict__ row_off,
                  const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
                  double sentinel, const double *__restrict__ table, int ld_table, const int32_t *__restrict__ zero_row,
-                 const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range,
-                 unsigned long long *probe /* optional [2]: first CTA start / last CTA end (globaltimer ns) */) {
+                 const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][QR_SMEM_WARP]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    struct ProbeGuard {  // scde_b200_options::trace: when did this grid run (co-residency with the contraction kernel)
-        unsigned long long *p;
-        __device__ ProbeGuard(unsigned long long *q) : p(q) {
-            if (p && threadIdx.x == 0) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                atomicMin(p, t);
-            }
-        }
-        __device__ ~ProbeGuard() {
-            if (p && threadIdx.x == 0) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                atomicMax(p + 1, t);
-            }
-        }
-    } probe_guard(probe);
     uint8_t *sq = s_dyn + warp * QR_SMEM_WARP;
     QrHeaders *hdr = reinterpret_cast<QrHeaders *>(sq + 4 * Q_PIECE);
     QrCell *cell = reinterpret_cast<QrCell *>(sq + 4 * Q_PIECE + 2 * sizeof(QrHeaders));
@@ -1135,8 +1117,7 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows,
-                           int pdl_secondary, unsigned long long *probe) {
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
@@ -1151,24 +1132,11 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
             auto launch_q = [&](auto kernel) -> cudaError_t {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-                if (e != cudaSuccess) return e;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(148 * 3);
-                cfg.blockDim = dim3(QR_WARPS * 32);
-                cfg.dynamicSmemBytes = smem;
-                cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr;
-                cfg.numAttrs = pdl_secondary ? 1 : 0;
-                return cudaLaunchKernelEx(&cfg, kernel, models, ld_models, cr, row_off, row_cell_map, row_x,
-                                          (const double4 *)row_const, row_snap, prep, K, sentinel, (const double *)table, ld_table,
-                                          zero_row, based, qtable, q_row_bytes(K), row_range, probe);
+                kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
+                                                             (const double4 *)row_const, row_snap, prep, K, sentinel, table,
+                                                             ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
+                return cudaGetLastError();
             };
-            if (pdl_secondary == 2)  // experiment: a 128-register build (four CTAs per SM)
-                return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true, 4>) : launch_q(lp_rows_q_kernel<false, 4>);
             return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);
         }
         auto launch =[&](auto kernel, int rpw) -> cudaError_t {

@@ -868,3 +868,35 @@ def test_r_shim_symbols_against_reference_fixtures(ctx):
                                    O.jpmat_log_batch_boot([matl[:4], matl[4:]], comp, 25, seed=2), rtol=1e-9)
     finally:
         R._lib = keep
+
+
+def test_config2_posteriors_all_cells_and_magnitude(ctx):
+    """BASELINE.json config 2: scde.posteriors(o.ifm, cd, o.prior) -- the joint posterior of ALL 40 es.mef.small cells as
+    one group, every gene (13 788 x 40, tests/tests.R filter), 100 randomizations -- and scde.expression.magnitude on the
+    same matrix, against the oracle (threaded over gene chunks with the Seed = 1 draws) and, for a spread gene sample
+    with per-cell modes, against the oracle's full logBootPosterior."""
+    cd, ifm, prior, groups = helpers.es_mef_inputs("tests")
+    got = api.scde_posteriors(ifm, cd, prior, n_randomizations=100, context=ctx)
+    assert got.shape == (cd.shape[0], 401)
+    mm, lt, sq = O.pack_models(ifm)
+    mag = O.marginals_from_prior_x(prior["x"].to_numpy())
+    bi = O.boot_indices(1, len(ifm), 100)
+    want = O.posteriors_chunked(mm, np.asfortranarray(cd.to_numpy()), mag, 100, bi, O.max_threads())
+    ok, worst = _logp_close(got.to_numpy(), want)
+    assert ok, worst
+    np.testing.assert_allclose(got.to_numpy().sum(axis=1), 1.0, rtol=1e-12)
+    sel = np.linspace(0, cd.shape[0] - 1, 48).astype(int)
+    sub = cd.iloc[sel]
+    r = api.scde_posteriors(ifm, sub, prior, n_randomizations=100, return_individual_posterior_modes=True, context=ctx)
+    flat, off, uci = O.unique_counts(np.asfortranarray(sub.to_numpy()))
+    w = O.log_boot_posterior(mm, flat, off, uci, mag, 100, seed=1, returnpost=1)
+    ok, worst = _logp_close(r["jp"].to_numpy(), w["jp"])
+    assert ok, worst
+    assert np.array_equal(r["modes"].to_numpy(), w["modes"])
+    ok, worst = _logp_close(r["jp"].to_numpy(), got.to_numpy()[sel])  # a gene's posterior does not depend on the other genes
+    assert ok, worst
+    m = api.scde_expression_magnitude(ifm, cd).to_numpy()
+    wm = O.expression_magnitude(cd.to_numpy(), ifm["corr.b"].to_numpy(), ifm["corr.a"].to_numpy())
+    fin = np.isfinite(wm)
+    assert np.array_equal(np.isneginf(m), np.isneginf(wm))
+    np.testing.assert_allclose(m[fin], wm[fin], rtol=1e-14, atol=1e-14)

@@ -165,6 +165,7 @@ struct LpTable {
     DBuf<int8_t> q;      // fixed-point planes of the table (contract_i8.cu), [n_rows][q_row_bytes(K)]
     DBuf<uint32_t> qrange;  // [n_rows] non-sentinel range of every row (klo | khi << 16)
     DBuf<uint32_t> dedup_bits;  // per-cell bitmaps between the two dedup passes
+    DBuf<unsigned long long> work_counter;  // chunk counter of the fixed-point row kernel
     bool want_q = false, has_q = false;
     bool f64_rows = true;  // false: the FP64 rows of non-zero counts were not stored (planes only)
     bool want_modes = true;  // row_mode (argmax of every row) is needed: only for return.individual.posterior.modes
@@ -248,6 +249,7 @@ int reserve_rows(LpTable &t, TablePlan &pl, size_t rows) {
     if (pl.q_any) {
         SCDE_CUDA(t.q.ensure(rows * q_row_bytes(t.K)));
         SCDE_CUDA(t.qrange.ensure(rows));
+        SCDE_CUDA(t.work_counter.ensure(1));
     }
     pl.rowc = pl.fast ? (void *)t.rowc.p : nullptr;
     pl.rmode = t.want_modes ? t.row_mode.p : nullptr;
@@ -277,7 +279,7 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
         SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                  t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
-                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1));
+                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1, t.work_counter.p));
         *nl += 4;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,

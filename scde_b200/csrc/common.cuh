@@ -60,8 +60,11 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0);
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0,
+                           unsigned long long *work_counter = nullptr);
 // legacy_q_rows: build fixed-point-only rows with the per-element kernel the register-resident one replaced (tests)
+// work_counter: one device word the register-resident row kernel hands its row chunks out from (zeroed by the launcher;
+// required whenever that kernel is chosen, i.e. qtable != NULL with which == 2 on the constant-theta path)
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row

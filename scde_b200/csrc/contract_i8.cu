@@ -23,7 +23,7 @@
 // Kernel: persistent, one CTA per SM, three warp roles, no CTA-wide barrier in the steady state.
 //   * work item = (gene, piece): one 512-byte piece of the gene's table rows = 102 grid points x 5 planes.  The item
 //     accumulates D[boot (128 lanes, 104 real)][plane * 102 + i] in all 512 tensor-memory columns of the SM.
-//   * producers (Q_PGROUPS x 4 warps): gather the list entries' pieces (512 contiguous, 512-byte-aligned bytes per
+//   * producers (Q_PGROUPS x 4 warps; Q_PGROUPS = 1, see launch_contract_i8_pass): gather the list entries' pieces (512 contiguous, 512-byte-aligned bytes per
 //     entry) and W rows (128 bytes) with 16-byte cp.async straight into the canonical 128-byte-swizzle layout of an
 //     MN-major operand; completion is signalled by cp.async.mbarrier.arrive; a 10-stage ring of 32 entries (20 KB per
 //     stage) keeps up to 200 KB in flight per SM.  The loop is branch-free per stage: constant offsets, slot / phase
@@ -773,9 +773,14 @@ cudaError_t launch_sentinel_ranges(const ContractI8Args &a, int g0, int n_pos, i
 cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, int pass, int n_sm, double *t_scratch,
                                     cudaStream_t st) {
     if (n_pos <= 0) return cudaSuccess;
-    // two producer groups: a third one (12 producer warps) measured 1 % slower -- the producers already wait on free
-    // ring slots most of the time (profiles/r01w)
-    constexpr int PG = 2;
+    // ONE producer group (four warps, one per k-group of a stage).  Round 1 used two groups that took alternate stages:
+    // no faster (74.37 against 74.34 ms per step at config 4, profiles/r02_experiments.txt) and unsafe -- a group that has
+    // no stage of its own in a run of short items (lists of <= 32 entries) does not wait on anything, runs arbitrarily far
+    // ahead of the MMA thread, and its next parity wait on a slot's "empty" barrier can then be satisfied by a phase two
+    // uses back; with the piece-major item order (short items at the end of every phase, long ones at the start of the
+    // next) that deadlocked scde.posteriors over 40 cells (tests: test_config2_..., test_short_and_long_lists_mixed...).
+    // With one group every producer warp touches every stage, so the ring itself bounds its lead.
+    constexpr int PG = 1;
     const I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
     const int n_items = n_pos * p.n_pieces;
     const int grid = n_sm < n_items ? n_sm : n_items;

@@ -759,6 +759,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
 using namespace ptx;
 constexpr int QR_WARPS = 4;
 constexpr int QR_MAIN = 3;  // quads per lane
+constexpr int QR_CHUNK = 64;  // rows per work chunk (two header batches)
 
 __device__ __forceinline__ double warp_max_redux(double v) {
     // order-preserving map double -> (hi, lo) unsigned, maximum by two 32-bit redux.sync
@@ -793,7 +794,8 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                  const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
                  double sentinel, const double *__restrict__ table, int ld_table, const int32_t *__restrict__ zero_row,
-                 const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
+                 const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range,
+                 unsigned long long *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][QR_SMEM_WARP]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *sq = s_dyn + warp * QR_SMEM_WARP;
@@ -804,10 +806,14 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
     const int64_t row0 = (int64_t)row_off[cr.c0];
     const int64_t row1 = min((int64_t)row_off[cr.c1], cr.row_cap);
     const int64_t n_rows = row1 > row0 ? row1 - row0 : 0;
-    const int64_t n_warps = (int64_t)gridDim.x * QR_WARPS, gw = (int64_t)blockIdx.x * QR_WARPS + warp;
-    const int64_t per_warp = (n_rows + n_warps - 1) / n_warps;
-    const int64_t r_begin = row0 + min(n_rows, gw * per_warp), r_end = row0 + min(n_rows, (gw + 1) * per_warp);
-    if (r_begin >= r_end) return;
+    // Rows are handed out in chunks of QR_CHUNK consecutive rows from a global counter (zeroed by the launcher): a warp
+    // that starts late -- its CTA waited for room on an SM that another stream's kernel (the NCCL gather of the previous
+    // step) was using -- or that meets slow rows simply takes fewer chunks.  With a static split of the rows over the
+    // warps the slowest warp set the kernel's time (7.4 ms instead of 5.9 ms per rank at eight ranks).  Consecutive
+    // chunks mostly belong to the same cell, whose grid vectors stay in registers across chunks.
+    if (n_rows <= 0) return;
+    const int64_t n_chunks = (n_rows + QR_CHUNK - 1) / QR_CHUNK;
+    int64_t r_begin = 0, r_end = 0;
 
     // this lane's grid points and where their digits go in the staged row (shared-memory byte addresses)
     const int kt = 4 * 32 * QR_MAIN + lane;  // the single point
@@ -852,6 +858,13 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
     const double SCALE = (double)(1ll << Q_FRAC);
     const double MAGICB = 6755399441055744.0 + 551911719040.0;  // 1.5 2^52 + 0x8080808080
     constexpr uint32_t H_DEAD = 0xC0875000u, H_LOW = 0xC0862000u, H_BAND = 0x4042C000u;  // high words of -746, -708, 37.5
+    for (;;) {
+    unsigned long long ch = 0;
+    if (lane == 0) ch = atomicAdd(work_counter, 1ull);
+    ch = __shfl_sync(0xffffffffu, ch, 0);
+    if ((int64_t)ch >= n_chunks) break;
+    r_begin = row0 + (int64_t)ch * QR_CHUNK;
+    r_end = min(row0 + n_rows, r_begin + QR_CHUNK);
     fetch_headers(r_begin, 0);
     int slot = 0;
     for (int64_t base = r_begin; base < r_end; base += 32, slot ^= 1) {
@@ -1072,6 +1085,7 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
         }
         __syncwarp();  // the headers of this slot are overwritten by the next iteration's fetch
     }
+    }  // chunk loop
 }
 
 }  // namespace
@@ -1117,7 +1131,8 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            const int32_t *row_cell_map, const int32_t *row_x, CellPrep prep, int K,
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
-                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows) {
+                           int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows,
+                           unsigned long long *work_counter) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
@@ -1132,9 +1147,13 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
             auto launch_q = [&](auto kernel) -> cudaError_t {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
+                if (!work_counter) return cudaErrorInvalidValue;
+                e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+                if (e != cudaSuccess) return e;
                 kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
                                                              (const double4 *)row_const, row_snap, prep, K, sentinel, table,
-                                                             ld_table, zero_row, based, qtable, q_row_bytes(K), row_range);
+                                                             ld_table, zero_row, based, qtable, q_row_bytes(K), row_range,
+                                                             work_counter);
                 return cudaGetLastError();
             };
             return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);

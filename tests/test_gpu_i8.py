@@ -173,3 +173,26 @@ def test_item_order_and_l2_hints_do_not_change_results(ctx):
             ctx.restore_options(keep)
     for r in res[1:]:
         assert np.array_equal(res[0], r)
+
+
+@pytest.mark.parametrize("item_order", [0, 1])
+def test_short_and_long_lists_mixed_in_any_order(ctx, item_order):
+    """Genes whose entry lists take 0, 1, 2 and 3 ring stages (0 .. 70 non-zero cells), shuffled so that the schedule meets
+    them in every succession, in both item orders: with two producer groups the group without a stage of its own in a run
+    of short items ran ahead of the MMA thread and a parity wait aliased (deadlock caught by the kernel's watchdog in
+    round 2); the single producer group cannot.  Results against the FP64 kernel."""
+    w = synth.make_workload(3, n_genes=900, n_cells=72, seed=13)
+    counts = np.array(w.counts, copy=True)
+    rng = np.random.default_rng(7)
+    keep = rng.integers(0, 72, size=900)          # number of non-zero cells per gene: 0 .. 71
+    for g in range(900):
+        zero = rng.permutation(72)[keep[g]:]
+        counts[g, zero] = 0
+    res = {}
+    for kernel in (3, 2):
+        keep_opt = ctx.set_options(item_order=item_order, contract_kernel=kernel)
+        try:
+            res[kernel] = api.scde_posteriors(w.models, counts, w.prior, n_randomizations=60, context=ctx).to_numpy()
+        finally:
+            ctx.restore_options(keep_opt)
+    assert _err(res[3], res[2]) < 1e-6

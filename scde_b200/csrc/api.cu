@@ -173,6 +173,9 @@ struct LpTable {
     // zero-base form: rows of non-zero counts hold lp(x) - lp(0) of their cell, the zero-count rows lp(0) itself, and
     // the contraction only visits the cells whose count is non-zero (boot_contract.cu)
     bool zero_base = false;
+    // the FP64 table holds one row per CELL (its zero-count row, at the cell's index) instead of one per table row: set by
+    // reserve_rows when the fixed-point planes come from the row kernel itself, which stores no other FP64 row
+    bool zero_compact = false;
 };
 
 #define TRY(x)                          \
@@ -239,7 +242,8 @@ int prepare_cells(scde_b200_ctx *ctx, LpTable &t, TablePlan &pl, const double *m
 
 // per-row buffers for `rows` table rows
 int reserve_rows(LpTable &t, TablePlan &pl, size_t rows) {
-    SCDE_CUDA(t.table.ensure(rows * t.ld));
+    t.zero_compact = pl.q_fused && t.zero_base;  // 33 MB instead of 40 GB at config 4
+    SCDE_CUDA(t.table.ensure((t.zero_compact ? (size_t)t.n_cells : rows) * t.ld));
     SCDE_CUDA(t.row_mode.ensure(rows));
     SCDE_CUDA(t.row_cell.ensure(rows));
     if (pl.fast) {
@@ -275,11 +279,13 @@ int launch_table_rows(scde_b200_ctx *ctx, const LpTable &t, const TablePlan &pl,
         SCDE_CUDA(launch_zero_rows(t.row_off.p + cr.c0, t.row_x.p, n, t.zero_row.p + cr.c0, cr.row_cap, st));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                  t.sentinel, t.table.p, t.ld, pl.rmode, 1, t.zero_row.p, nullptr, pl.rowc, t.row_snap.p, 1, pl.qf, pl.qr,
-                                 st));
-        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st));
+                                 st, 0, nullptr, t.zero_compact));
+        SCDE_CUDA(launch_based_flags(t.table.p, t.ld, t.K, t.sentinel, t.zero_row.p + cr.c0, n, t.based.p + cr.c0, st,
+                                     t.zero_compact ? cr.c0 : -1));
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
                                  t.sentinel, t.table.p, t.ld, pl.rmode, 2, t.zero_row.p, t.based.p, pl.rowc, t.row_snap.p,
-                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1, t.work_counter.p));
+                                 pl.q_fused ? 0 : 1, pl.qf, pl.qr, st, ctx->opt.lp_rows_kernel == 1, t.work_counter.p,
+                                 t.zero_compact));
         *nl += 4;
     } else {
         SCDE_CUDA(launch_lp_rows(models_dev, ld_models, cr, t.row_off.p, t.row_cell.p, t.row_x.p, pl.prep, t.K, local_theta,
@@ -410,7 +416,7 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
                                  zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st, hot_rank));
     if (zb)
         SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
-                                  scr.Z.p, scr.zpart.p, st));
+                                  scr.Z.p, scr.zpart.p, st, t.zero_compact));
     if (i8) {
         SCDE_CUDA(scr.W8.ensure((size_t)passes * n_w_rows * Q_WB));
         SCDE_CUDA(ctx->flags.ensure(1));

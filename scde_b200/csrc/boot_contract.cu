@@ -243,7 +243,8 @@ constexpr int Z_CHUNKS = 32, Z_BC = 8;
 __global__ void __launch_bounds__(KP_TILED)
 base_sum_partial_kernel(const double *__restrict__ table, int64_t ld_table, const int32_t *__restrict__ zero_row,
                         const int32_t *__restrict__ based, const int32_t *__restrict__ cell_ids, int n_list,
-                        const double *__restrict__ W, int64_t n_w_rows, int n_bcols, double *__restrict__ part) {
+                        const double *__restrict__ W, int64_t n_w_rows, int n_bcols, double *__restrict__ part,
+                        int zero_compact) {
     const int k = threadIdx.x;                 // blockDim.x == ld_table (<= 416 by construction of the caller)
     const int b0 = blockIdx.x * Z_BC;          // column among passes*104
     const int chunk = blockIdx.y;
@@ -257,7 +258,7 @@ base_sum_partial_kernel(const double *__restrict__ table, int64_t ld_table, cons
     for (int c = c0; c < c1; ++c) {
         const int col = cell_ids ? cell_ids[c] : c;
         if (!based[col]) continue;
-        const double a = table[(int64_t)zero_row[col] * ld_table + k];
+        const double a = table[(int64_t)(zero_compact ? col : zero_row[col]) * ld_table + k];
         const double *w = Wp + (int64_t)c * WS_TILED;
 #pragma unroll
         for (int j = 0; j < Z_BC; ++j) acc[j] = fma(a, w[j], acc[j]);
@@ -888,13 +889,13 @@ size_t base_sum_scratch_doubles(int n_boot, int ld_table) {
 
 cudaError_t launch_base_sum(const double *table, int ld_table, const int32_t *zero_row, const int32_t *based,
                             const int32_t *cell_ids, int n_list, const double *W, int n_w_rows, int n_boot, double *Z,
-                            double *scratch, cudaStream_t st) {
+                            double *scratch, cudaStream_t st, int zero_compact) {
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
     const int n_bcols = passes * WP_TILED;
     if (ld_table > KP_TILED) return cudaErrorInvalidValue;
     dim3 grid(n_bcols / Z_BC, Z_CHUNKS);
     base_sum_partial_kernel<<<grid, ld_table, 0, st>>>(table, ld_table, zero_row, based, cell_ids, n_list, W, n_w_rows,
-                                                      n_bcols, scratch);
+                                                      n_bcols, scratch, zero_compact);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t n = (int64_t)n_bcols * ld_table;

@@ -52,7 +52,10 @@ cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n
                              cudaStream_t st);
 // based[c] = 1 when cell c has a zero-count row and that row holds no "log 0" sentinel (it can be subtracted)
 cudaError_t launch_based_flags(const double *table, int ld_table, int K, double sentinel, const int32_t *zero_row,
-                               int n_cells, int32_t *based, cudaStream_t st);
+                               int n_cells, int32_t *based, cudaStream_t st, int zero_compact_c0 = -1);
+// zero_compact_c0 >= 0: the FP64 table is the COMPACT one -- one row per cell, its zero-count row, at the cell's index --
+// and zero_row / based point at cell zero_compact_c0 (the fused fixed-point path stores no other FP64 row, so the table is
+// n_cells rows instead of one per distinct (cell, count): 33 MB instead of 40 GB at config 4)
 // One warp per table row.  Writes table[r*ld_table + k] (k >= K zero-filled up to ld_table) and row_mode[r] (first
 // argmax, before the clamp).  which: 0 = every row, plain values; 1 = only the zero-count rows (plain values);
 // 2 = every row except the zero-count ones, stored as the difference to the cell's zero-count row when based[cell].
@@ -61,10 +64,12 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
                            int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows = 0,
-                           unsigned long long *work_counter = nullptr);
+                           unsigned long long *work_counter = nullptr, int zero_compact = 0);
 // legacy_q_rows: build fixed-point-only rows with the per-element kernel the register-resident one replaced (tests)
 // work_counter: one device word the register-resident row kernel hands its row chunks out from (zeroed by the launcher;
 // required whenever that kernel is chosen, i.e. qtable != NULL with which == 2 on the constant-theta path)
+// zero_compact: `table` is the compact FP64 table (see launch_based_flags); which == 1 writes a cell's zero-count row at the
+// cell's index, which == 2 reads it there
 // write_f64 = 0: the FP64 row is not stored (table is still read for the zero-count rows); qtable != NULL: also emit the
 // row's fixed-point planes and its non-sentinel range (contract_i8.cu) -- both only on the constant-theta fast path
 // per-row constants of the constant-theta fast path (4 doubles per row), one thread per row
@@ -116,7 +121,7 @@ cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *
 size_t base_sum_scratch_doubles(int n_boot, int ld_table);
 cudaError_t launch_base_sum(const double *table, int ld_table, const int32_t *zero_row, const int32_t *based,
                             const int32_t *cell_ids, int n_list, const double *W, int n_w_rows, int n_boot, double *Z,
-                            double *scratch, cudaStream_t st);
+                            double *scratch, cudaStream_t st, int zero_compact = 0);
 struct ContractArgs {
     const double *table;   // [rows][ld_table]
     int ld_table;

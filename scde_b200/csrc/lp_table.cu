@@ -251,15 +251,18 @@ __global__ void zero_rows_kernel(const int32_t *__restrict__ row_off, const int3
 }
 
 __global__ void based_flags_kernel(const double *__restrict__ table, int ld_table, int K, double sentinel,
-                                   const int32_t *__restrict__ zero_row, int n_cells, int32_t *__restrict__ based) {
+                                   const int32_t *__restrict__ zero_row, int n_cells, int32_t *__restrict__ based,
+                                   int zero_compact_c0) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_cells) return;
     const int lane = threadIdx.x & 31;
     const int zr = zero_row[c];
     bool ok = zr >= 0;
+    // compact form (zero_compact_c0 >= 0): the FP64 table holds one row per CELL -- its zero-count row -- at the cell's index
+    const size_t slot = zero_compact_c0 >= 0 ? (size_t)(zero_compact_c0 + c) : (size_t)(zr >= 0 ? zr : 0);
     if (ok)
         for (int k = lane; k < K; k += 32) {
-            const double v = table[(size_t)zr * ld_table + k];
+            const double v = table[slot * ld_table + k];
             ok = ok && (v > sentinel) && isfinite(v);
         }
     ok = __all_sync(0xffffffffu, ok);
@@ -499,7 +502,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
                     const int32_t *__restrict__ row_cell, const int32_t *__restrict__ row_x,
                     const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
                     double sentinel, double *__restrict__ table, int ld_table, int32_t *__restrict__ row_mode, int which,
-                    const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64,
+                    const int32_t *__restrict__ zero_row, const int32_t *__restrict__ based, int write_f64, int zero_compact,
                     int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range) {
     constexpr int RPW = 32 / LW;  // rows per warp
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -565,7 +568,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         const int c = cur.c;
         bool valid = cur.valid;
         if (which == 2 && zero_row[c] == row) valid = false;
-        const double *zr = (which == 2 && based[c]) ? table + (size_t)zero_row[c] * ld_table : nullptr;
+        const double *zr = (which == 2 && based[c]) ? table + (size_t)(zero_compact ? c : zero_row[c]) * ld_table : nullptr;
         const double x = cur.x;
         const double s = models[(size_t)5 * ldm + c];
         const size_t base = (size_t)c * prep.ld;
@@ -631,7 +634,7 @@ lp_rows_fast_kernel(const double *__restrict__ models, int ldm, CellRange cr, co
         // ---- sweep 3
         double best = -INFINITY;
         int besti = 0x7fffffff;
-        double *out = table + (size_t)row * ld_table;
+        double *out = table + (size_t)((zero_compact && which == 1) ? (int64_t)c : row) * ld_table;  // compact: a row per cell
         uint32_t okmask = 0u;  // bit 4 j + e: grid point 4 l + 4 LW j + e is not "log 0" (j-th quad of this lane)
         int jq = 0;
         for (int k0 = 4 * l; k0 < kp; k0 += 4 * LW, ++jq) {
@@ -795,7 +798,7 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                  const double4 *__restrict__ rowc, const int32_t *__restrict__ row_snap, CellPrep prep, int K,
                  double sentinel, const double *__restrict__ table, int ld_table, const int32_t *__restrict__ zero_row,
                  const int32_t *__restrict__ based, int8_t *__restrict__ qtable, int ldq, uint32_t *__restrict__ row_range,
-                 unsigned long long *__restrict__ work_counter) {
+                 unsigned long long *__restrict__ work_counter, int zero_compact) {
     extern __shared__ __align__(16) unsigned char s_dyn[];  // [QR_WARPS][QR_SMEM_WARP]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *sq = s_dyn + warp * QR_SMEM_WARP;
@@ -888,7 +891,7 @@ lp_rows_q_kernel(const double *__restrict__ models, int ldm, CellRange cr, const
                 cur_zero = zr;
                 const bool bs = zr >= 0 && based[c] != 0;
                 const size_t pb = (size_t)c * prep.ld;
-                const double *zrow = table + (size_t)(zr >= 0 ? zr : 0) * ld_table;
+                const double *zrow = table + (size_t)(zero_compact ? c : (zr >= 0 ? zr : 0)) * ld_table;
                 double Ev[4 * QR_MAIN + 2], Zv[4 * QR_MAIN + 2];
                 Ev[4 * QR_MAIN + 1] = Zv[4 * QR_MAIN + 1] = 0.0;
 #pragma unroll
@@ -1121,9 +1124,10 @@ cudaError_t launch_zero_rows(const int32_t *row_off, const int32_t *row_x, int n
 }
 
 cudaError_t launch_based_flags(const double *table, int ld_table, int K, double sentinel, const int32_t *zero_row,
-                               int n_cells, int32_t *based, cudaStream_t st) {
+                               int n_cells, int32_t *based, cudaStream_t st, int zero_compact_c0) {
     if (n_cells <= 0) return cudaSuccess;
-    based_flags_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(table, ld_table, K, sentinel, zero_row, n_cells, based);
+    based_flags_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(table, ld_table, K, sentinel, zero_row, n_cells, based,
+                                                         zero_compact_c0);
     return cudaGetLastError();
 }
 
@@ -1132,8 +1136,10 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                            int local_theta, double sentinel, double *table, int ld_table, int32_t *row_mode, int which,
                            const int32_t *zero_row, const int32_t *based, void *row_const, const int32_t *row_snap,
                            int write_f64, int8_t *qtable, uint32_t *row_range, cudaStream_t st, int legacy_q_rows,
-                           unsigned long long *work_counter) {
+                           unsigned long long *work_counter, int zero_compact) {
     if (cr.c1 <= cr.c0) return cudaSuccess;
+    // compact FP64 table (one row per cell: its zero-count row): only the zero-count rows may be stored in FP64
+    if (zero_compact && (which == 0 || (which == 2 && write_f64) || local_theta)) return cudaErrorInvalidValue;
     // the number of rows is only known on the device: size the grid for the cells (hundreds of rows each), grid-stride
     int64_t blocks = which == 1 ? ((int64_t)(cr.c1 - cr.c0) + ROW_WARPS - 1) / ROW_WARPS : (int64_t)(cr.c1 - cr.c0) * 8;
     const int64_t cap = 148 * 64;
@@ -1153,7 +1159,7 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
                 kernel<<<148 * 3, QR_WARPS * 32, smem, st>>>(models, ld_models, cr, row_off, row_cell_map, row_x,
                                                              (const double4 *)row_const, row_snap, prep, K, sentinel, table,
                                                              ld_table, zero_row, based, qtable, q_row_bytes(K), row_range,
-                                                             work_counter);
+                                                             work_counter, zero_compact);
                 return cudaGetLastError();
             };
             return K >= 4 * 32 * QR_MAIN ? launch_q(lp_rows_q_kernel<true>) : launch_q(lp_rows_q_kernel<false>);
@@ -1164,7 +1170,7 @@ cudaError_t launch_lp_rows(const double *models, int ld_models, CellRange cr, co
             if (e != cudaSuccess) return e;
             kernel<<<(unsigned)blocks, ROW_WARPS * 32, smem, st>>>(
                 models, ld_models, cr, row_off, row_cell_map, row_x, (const double4 *)row_const, row_snap, prep, K, sentinel,
-                table, ld_table, row_mode, which, zero_row, based, write_f64, qtable, q_row_bytes(K), row_range);
+                table, ld_table, row_mode, which, zero_row, based, write_f64, zero_compact, qtable, q_row_bytes(K), row_range);
             return cudaGetLastError();
         };
         const bool norm = write_f64 != 0;  // rows that exist in fixed point only need no normalising constant

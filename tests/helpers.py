@@ -38,7 +38,8 @@ def es_mef_inputs(variant: str = "tests"):
     variant "vignette": clean.counts(min.lib.size = 1000, min.reads = 1, min.detected = 1) and max.quantile = 0.999
                         -- the settings the printed vignette rows were produced with.
     """
-    from scde_b200.prior import clean_counts, scde_expression_prior_host as scde_expression_prior
+    from prior_host import scde_expression_prior_host as scde_expression_prior
+    from scde_b200.prior import clean_counts
 
     cd = es_mef_raw()
     ifm = o_ifm()

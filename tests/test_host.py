@@ -9,7 +9,8 @@ import pytest
 
 import helpers
 from oracle import oracle as O
-from scde_b200 import _lib, api, prior as prior_mod, synth
+import prior_host as prior_mod
+from scde_b200 import _lib, api, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -196,3 +196,29 @@ def test_short_and_long_lists_mixed_in_any_order(ctx, item_order):
         finally:
             ctx.restore_options(keep_opt)
     assert _err(res[3], res[2]) < 1e-6
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_shapes_tcgen05_against_fp64_kernel(ctx, seed):
+    """Randomised shapes and sparsity patterns (cells 1 .. 200, genes 1 .. 400, 1 .. 137 randomizations, per-gene density
+    anywhere between all-zero and dense, a few huge counts) through the tcgen05 kernel against the FP64 DMMA kernel on
+    the same table: every combination of ring stages per item, empty lists, one- and two-pass runs."""
+    rng = np.random.default_rng(1000 + seed)
+    n_cells = int(rng.integers(1, 201))
+    n_genes = int(rng.integers(1, 401))
+    n_boot = int(rng.choice([1, 7, 100, 104, 105, 137]))
+    w = synth.make_workload(3, n_genes=n_genes, n_cells=max(n_cells, 2), seed=50 + seed)
+    models = w.models.iloc[:n_cells]
+    counts = np.array(w.counts[:, :n_cells], copy=True)
+    dens = rng.uniform(0, 1, size=n_genes)
+    counts[rng.uniform(size=counts.shape) > dens[:, None]] = 0
+    big = rng.uniform(size=counts.shape) < 0.01
+    counts[big] = rng.integers(1, 200000, size=int(big.sum()))
+    res = {}
+    for kernel in (3, 2):
+        keep = ctx.set_options(contract_kernel=kernel)
+        try:
+            res[kernel] = api.scde_posteriors(models, counts, w.prior, n_randomizations=n_boot, context=ctx).to_numpy()
+        finally:
+            ctx.restore_options(keep)
+    assert _err(res[3], res[2]) < 1e-6, (n_cells, n_genes, n_boot)

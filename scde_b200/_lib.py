@@ -65,7 +65,7 @@ class Options(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "contract_kernel", "zero_base", "fused_fixed_point", "lp_rows_kernel", "count_chunks", "split_front",
         "uniform_chunks", "pipeline_front", "item_order", "hot_rank", "cold_evict_first", "trace", "epilogue_timing",
-        "debug_contract", "ring_stages")] + [("reserved", C.c_int32 * 6)]
+        "debug_contract", "ring_stages", "twin_batch_joints")] + [("reserved", C.c_int32 * 5)]
 
 
 # every symbol include/scde_b200.h declares

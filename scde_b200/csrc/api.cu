@@ -131,6 +131,7 @@ static scde_b200_options default_options() {
     o.item_order = 1;  // piece-major: measured 5 % faster at config 4 (profiles/r02a_sweep.txt)
     o.hot_rank = -1;
     o.cold_evict_first = 1;
+    o.twin_batch_joints = 1;
     return o;
 }
 
@@ -378,16 +379,30 @@ struct DiffWorkspace {
     DBuf<int32_t> counts;  // [C][G] (column-major shard)
     LpTable table;
     JointScratch scr;
+    JointScratch scr2;  // the second of two joints computed in one launch (batch-corrected calls)
     DBuf<double> jp[4];
     DBuf<double> post, bpost, apost;  // [G][ld] gene-major ratio posteriors
     DBuf<double> tbuf;                // transposition scratch for downloads
 };
 
+// A second joint over the SAME cells (and therefore the same entry lists) with its own draws, computed in the same
+// launches of the tcgen05 kernel: the two composition-sampled joints of a batch-corrected call (R/functions.R:355-357).
+struct TwinJoint {
+    const int32_t *boot_idx_dev;  // n_boot x D
+    int D;
+    double *jp_dev;
+    JointScratch *scr;            // W, W8, Z, zpart, T, SR, spart of the second joint (the lists are the first joint's)
+};
+
 // jp_dev[G][ld_jp] = joint posterior of the listed cells under the draws boot_idx_dev (n_boot x D, device).
+// twin (optional): see TwinJoint; only honoured on the tcgen05 path (the caller checks the return flag *twin_done and runs
+// the second joint on its own otherwise).
 int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev, int n_list,
               const int32_t *boot_idx_dev, int n_boot, int D, double scale, double *jp_dev, int ld_jp,
-              JointScratch &scr, StageTimer *tm, bool count_entries) {
+              JointScratch &scr, StageTimer *tm, bool count_entries, const TwinJoint *twin = nullptr,
+              bool *twin_done = nullptr) {
     cudaStream_t st = ctx->stream;
+    if (twin_done) *twin_done = false;
     const int n_w_rows = round_up(n_list + 1, 16);  // at least one all-zero row after the cells (list padding)
     const int passes = (n_boot + WP_TILED - 1) / WP_TILED;
     const int ld_lst = round_up(n_list, 32);
@@ -407,22 +422,37 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
     SCDE_CUDA(cudaMemsetAsync(jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
     GeneLists lists{scr.lst_row.p, scr.lst_cell.p, scr.lst_len.p, scr.order.p, ld_lst};
     const bool i8 = zb && t.has_q && want_i8(ctx) && contract_i8_supported(t.K, t.ld, ld_lst, D);
+    const bool tw = twin && i8 && contract_i8_supported(t.K, t.ld, ld_lst, twin->D) && ctx->opt.twin_batch_joints;
     if (ctx->opt.contract_kernel == 3 && !i8) {
         set_error("tcgen05 int8 contraction forced but unsupported here (K=%d, zero-base form %d)", t.K, (int)zb);
         return SCDE_B200_EINVAL;
     }
     const int hot_rank = i8 ? ctx->opt.hot_rank : -1;  // only the tcgen05 kernel's producers know the hot bit
     SCDE_CUDA(launch_build_lists(t.ridx.p, t.ld_ridx, cell_ids_dev, n_list, t.n_genes, zb ? t.zero_row.p : nullptr,
-                                 zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st, hot_rank));
+                                 zb ? t.based.p : nullptr, 0, lists, count_entries ? scr.total.p : nullptr, st, hot_rank,
+                                 tw ? 2 : 1));
     if (zb)
         SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, scr.W.p, n_w_rows, n_boot,
                                   scr.Z.p, scr.zpart.p, st, t.zero_compact));
+    if (tw) {  // the second joint's W, base sums and output
+        JointScratch &s2 = *twin->scr;
+        SCDE_CUDA(s2.W.ensure((size_t)passes * n_w_rows * WS_TILED));
+        SCDE_CUDA(s2.Z.ensure((size_t)passes * WP_TILED * t.ld));
+        SCDE_CUDA(s2.zpart.ensure(base_sum_scratch_doubles(n_boot, t.ld)));
+        SCDE_CUDA(s2.W8.ensure((size_t)passes * n_w_rows * Q_WB));
+        SCDE_CUDA(launch_build_w(twin->boot_idx_dev, n_boot, twin->D, n_list, s2.W.p, n_w_rows, st));
+        SCDE_CUDA(cudaMemsetAsync(twin->jp_dev, 0, sizeof(double) * (size_t)t.n_genes * ld_jp, st));
+        SCDE_CUDA(launch_base_sum(t.table.p, t.ld, t.zero_row.p, t.based.p, cell_ids_dev, n_list, s2.W.p, n_w_rows, n_boot,
+                                  s2.Z.p, s2.zpart.p, st, t.zero_compact));
+        SCDE_CUDA(ctx->flags.ensure(1));
+        SCDE_CUDA(launch_w_to_i8(s2.W.p, n_w_rows, n_boot, s2.W8.p, ctx->flags.p, st));
+    }
     if (i8) {
         SCDE_CUDA(scr.W8.ensure((size_t)passes * n_w_rows * Q_WB));
         SCDE_CUDA(ctx->flags.ensure(1));
         SCDE_CUDA(launch_w_to_i8(scr.W.p, n_w_rows, n_boot, scr.W8.p, ctx->flags.p, st));
     }
-    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, (zb ? 5 : 3) + (i8 ? 1 : 0));
+    if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, (zb ? 5 : 3) + (i8 ? 1 : 0) + (tw ? 5 : 0));
     if (i8) {
         ContractI8Args q{};
         q.qtable = t.q.p;
@@ -454,20 +484,37 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
         const int max_genes = contract_tiled_max_genes();
         SCDE_CUDA(scr.SR.ensure(contract_i8_range_words(t.n_genes < max_genes ? t.n_genes : max_genes)));
         SCDE_CUDA(scr.spart.ensure(softmax_i8_scratch_doubles(t.n_genes < max_genes ? t.n_genes : max_genes)));
+        ContractI8Args q2 = q;  // the twin joint: same table, lists and schedule; its own W, Z, output
+        if (tw) {
+            JointScratch &s2 = *twin->scr;
+            SCDE_CUDA(s2.T.ensure(contract_tiled_scratch_doubles(t.n_genes)));
+            SCDE_CUDA(s2.SR.ensure(contract_i8_range_words(t.n_genes < max_genes ? t.n_genes : max_genes)));
+            SCDE_CUDA(s2.spart.ensure(softmax_i8_scratch_doubles(t.n_genes < max_genes ? t.n_genes : max_genes)));
+            q2.W8 = s2.W8.p;
+            q2.Z = s2.Z.p;
+            q2.jp = twin->jp_dev;
+            q.W8_twin = s2.W8.p;   // one launch of the contraction kernel computes both joints' T tiles
+            q.t_twin = s2.T.p;
+        }
         for (int g0 = 0; g0 < t.n_genes; g0 += max_genes) {
             const int n_pos = (t.n_genes - g0) < max_genes ? (t.n_genes - g0) : max_genes;
             for (int ps = 0; ps < passes; ++ps) {
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps, scr.SR.p, st));
-                if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, 1);
+                if (tw) SCDE_CUDA(launch_sentinel_ranges(q2, g0, n_pos, ps, twin->scr->SR.p, st));
+                if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, tw ? 2 : 1);
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
                 if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_softmax_i8(q, g0, n_pos, ps, scr.T.p, scr.SR.p, scr.spart.p, ctx->n_sm, st));
-                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, 2);
+                if (tw)
+                    SCDE_CUDA(launch_softmax_i8(q2, g0, n_pos, ps, twin->scr->T.p, twin->scr->SR.p, twin->scr->spart.p,
+                                                ctx->n_sm, st));
+                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, tw ? 4 : 2);
             }
         }
+        if (tw && twin_done) *twin_done = true;
         if (q.dbg) {
             unsigned long long h[3];
             SCDE_CUDA(cudaMemcpyAsync(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1923,9 +1970,15 @@ static int diff_run_impl(scde_b200_ctx *ctx, scde_b200_diff_job *j, bool chunked
             TRY(fill_table(ctx, j->ws->table, j->bmodels.p, C, j->mag.p, j->b_local_theta, j->b_sqlogit, &tm));
             j->ws->table.fast_theta = j->fast_theta;
         }
-        for (int i = 0; i < 2; ++i)
-            TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot_ptr[2 + i], j->n_boot, j->D[2 + i], (double)j->n_boot,
-                          j->ws->jp[2 + i].p, ld, j->ws->scr, &tm, true));
+        // the two composition-sampled joints walk the same cells and rows with different draws: one launch of the contraction
+        // kernel for both, items paired on neighbouring SMs, so the table is pulled from DRAM once for the two
+        TwinJoint tw{j->boot_ptr[3], j->D[3], j->ws->jp[3].p, &j->ws->scr2};
+        bool twin_done = false;
+        TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot_ptr[2], j->n_boot, j->D[2], (double)j->n_boot, j->ws->jp[2].p, ld,
+                      j->ws->scr, &tm, true, &tw, &twin_done));
+        if (!twin_done)
+            TRY(run_joint(ctx, j->ws->table, nullptr, C, j->boot_ptr[3], j->n_boot, j->D[3], (double)j->n_boot,
+                          j->ws->jp[3].p, ld, j->ws->scr, &tm, true));
     }
     int e0 = tm.begin(st);
     int nl = 0;

@@ -110,7 +110,7 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
                                    int n_list, int n_genes, const int32_t *__restrict__ zero_row,
                                    const int32_t *__restrict__ based, int pad_row, int32_t *__restrict__ lst_row,
                                    int32_t *__restrict__ lst_cell, int32_t *__restrict__ lst_len, int64_t ld_lst,
-                                   unsigned long long *total_entries, int hot_rank) {
+                                   unsigned long long *total_entries, int hot_rank, int count_times) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n_genes) return;
     const int lane = threadIdx.x & 31;
@@ -153,7 +153,7 @@ __global__ void build_lists_kernel(const int32_t *__restrict__ ridx, int64_t ld_
     }
     if (lane == 0) {
         lst_len[g] = pos;
-        if (total_entries) atomicAdd(total_entries, (unsigned long long)pos);
+        if (total_entries) atomicAdd(total_entries, (unsigned long long)pos * (unsigned long long)count_times);
     }
 }
 
@@ -859,12 +859,12 @@ cudaError_t launch_build_w(const int32_t *boot_idx, int n_boot, int D, int n_lis
 
 cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
                                const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
-                               unsigned long long *total_entries, cudaStream_t st, int hot_rank) {
+                               unsigned long long *total_entries, cudaStream_t st, int hot_rank, int count_times) {
     if (n_genes <= 0) return cudaSuccess;
     const int wpb = 8;
     build_lists_kernel<<<(n_genes + wpb - 1) / wpb, wpb * 32, 0, st>>>(ridx, ld_ridx, cell_ids, n_list, n_genes, zero_row,
                                                                       based, pad_row, out.row, out.cell, out.len, out.ld,
-                                                                      total_entries, hot_rank);
+                                                                      total_entries, hot_rank, count_times);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // processing order: heaviest genes first when the counting sort's bins and keys fit in shared memory, else identity

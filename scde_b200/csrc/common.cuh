@@ -113,7 +113,7 @@ struct GeneLists {
 cudaError_t launch_build_lists(const int32_t *ridx, int ld_ridx, const int32_t *cell_ids, int n_list, int n_genes,
                                const int32_t *zero_row, const int32_t *based, int pad_row, GeneLists out,
                                unsigned long long *total_entries /* += sum of list lengths, may be NULL */,
-                               cudaStream_t st, int hot_rank = -1);
+                               cudaStream_t st, int hot_rank = -1, int count_times = 1);
 // hot_rank >= 0 (tcgen05 kernel only): entries whose table row is at most hot_rank rows above the cell's zero-count row
 // -- the cell's smallest counts, rows are in ascending count order -- carry LIST_HOT_BIT in out.cell
 // Z[pass*104 + b][k] = sum over based cells of the joint of W[cell][b] * table[zero_row[cell]][k]; scratch holds
@@ -199,6 +199,9 @@ struct ContractI8Args {
     int ld_jp;
     int32_t *err;      // device flag, |= 2 if the kernel's watchdog fired, |= 4 if the sentinel ranges need the FP64 kernel
     unsigned long long *dbg;  // optional [3] cycle counters of the epilogue (see contract_i8.cu), or NULL
+    const int8_t *W8_twin;  // twin launch (launch_contract_i8_pass only): a second joint over the SAME cells and lists with its
+    double *t_twin;         // own draws -- its W (layout as W8) and its T scratch; NULL = one joint.  The sentinel ranges
+                            // and the soft-max of the second joint are separate launches with W8 = W8_twin.
     int item_order;    // 0: item = (gene, piece), a gene's pieces on neighbouring SMs; 1: piece-major (all SMs walk the same
                        // 512-byte piece of the rows at the same time, so rows shared between genes are L2 hits more often)
     int hot_rank;      // >= 0: list entries carry bit 30 of `cell` when the row's rank within its cell is <= hot_rank; such

@@ -88,6 +88,10 @@ struct I8Params {
     int32_t *err;        // device flag: 2 = watchdog abort
     unsigned long long *dbg;  // optional diagnostics: [0] += cycles between "accumulators ready" and "tensor memory released",
                               // [1] += items, [2] += cycles the MMA thread waited for the release (epilogue warp 0 / MMA thread)
+    const int8_t *W8b;   // twin launch: the second joint's W (same cells, same lists, other draws), else NULL
+    long long *Tb;       // twin launch: the second joint's T tiles
+    int twin;            // 1: items come in pairs (2 i, 2 i + 1) = the same (gene, piece) for joint 0 and joint 1, so that two
+                         // neighbouring CTAs gather the same table rows at the same time and the second read is an L2 hit
     int piece_major;     // item order: 0 = (gene, piece) with the piece fastest, 1 = (piece, gene) with the gene fastest
     int cold_evict_first;  // HINT kernels: rows without the hot bit are loaded evict_first (else without a hint)
 };
@@ -115,6 +119,7 @@ struct Item {
 };
 __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
     Item it;
+    item >>= p.twin;  // twin launch: bit 0 of the item selects the joint
     if (p.piece_major) {
         it.piece = item / p.n_pos;
         it.pos = item - it.piece * p.n_pos;
@@ -125,6 +130,7 @@ __device__ __forceinline__ Item decode_item(const I8Params &p, int item) {
     return it;
 }
 __device__ __forceinline__ int64_t item_gene(const I8Params &p, int item) {
+    item >>= p.twin;
     const int pos = p.piece_major ? item % p.n_pos : item / p.n_pieces;
     return p.order ? p.order[pos] : pos;
 }
@@ -170,7 +176,6 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
     // entry kk = l3 (and l3 + 4): line kk of this warp's k-group, piece l7 at 16 * (l7 ^ kk)
     const uint32_t d0 = (uint32_t)kg * 1024u + (uint32_t)l3 * 128u + (uint32_t)((l7 ^ l3) << 4);
     const uint32_t d1 = (uint32_t)kg * 1024u + (uint32_t)(l3 + 4) * 128u + (uint32_t)((l7 ^ (l3 + 4)) << 4);
-    const int8_t *wbase = p.W8 + l7 * 16;
     int slot_b = 0;        // ring slot of the first stage of the current item
     uint32_t fill_b = 0;   // how often that slot has been filled before
     int item = blockIdx.x;
@@ -189,6 +194,7 @@ __device__ __forceinline__ void run_producer(const I8Params &p, I8Smem &sm, uint
             len_n = p.lst_len[gene_n];
         }
         const int8_t *qbase = p.qtable + (int64_t)it.piece * Q_PIECE + l7 * 16;
+        const int8_t *wbase = ((p.twin && (item & 1)) ? p.W8b : p.W8) + l7 * 16;
         const int32_t *lrow = p.lst_row + gene * p.ld_lst + kg * 8 + l3;
         const int32_t *lcell = p.lst_cell + gene * p.ld_lst + kg * 8 + l3;
         int32_t r0a = 0, r1a = 0, c0a = 0, c1a = 0, r0b = 0, r1b = 0, c0b = 0, c1b = 0;
@@ -342,7 +348,7 @@ __device__ __forceinline__ void run_epilogue(const I8Params &p, I8Smem &sm, uint
         }
         tc_fence_after_sync();
         const long long t_ready = p.dbg ? clock64() : 0;
-        long long *Tbase = p.T + ((int64_t)it.pos * WP_TILED + qd * 32) * KP_TILED + it.piece * Q_PW;
+        long long *Tbase = ((p.twin && (item & 1)) ? p.Tb : p.T) + ((int64_t)it.pos * WP_TILED + qd * 32) * KP_TILED + it.piece * Q_PW;
         for (int rd = r_begin; rd < r_end; ++rd) {
             const int i0 = rd * 8;
             const int n = Q_PW - i0 < 8 ? Q_PW - i0 : 8;  // 8, or 6 in the last round
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(q_threads(Q_PGROUPS), 1) contract_i8_kernel(co
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = sm.tmem_base;
-    const int n_items = p.n_pos * p.n_pieces;
+    const int n_items = (p.n_pos * p.n_pieces) << p.twin;
 
     if (warp < Q_PRODUCER_WARPS)
         run_producer<Q_PGROUPS, HINT, NS>(p, sm, stage0, n_items, warp, lane);
@@ -754,6 +760,9 @@ static I8Params make_params(const ContractI8Args &a, int g0, int n_pos, int pass
     p.n_pieces = q_pieces(a.K);
     p.err = a.err;
     p.dbg = a.dbg;
+    p.W8b = a.W8_twin ? a.W8_twin + (size_t)pass * a.n_w_rows * Q_WB : nullptr;
+    p.Tb = reinterpret_cast<long long *>(a.t_twin);
+    p.twin = (a.W8_twin && a.t_twin) ? 1 : 0;
     p.piece_major = a.item_order == 1;
     p.cold_evict_first = a.cold_evict_first;
     return p;
@@ -782,8 +791,9 @@ cudaError_t launch_contract_i8_pass(const ContractI8Args &a, int g0, int n_pos, 
     // With one group every producer warp touches every stage, so the ring itself bounds its lead.
     constexpr int PG = 1;
     const I8Params p = make_params(a, g0, n_pos, pass, t_scratch);
-    const int n_items = n_pos * p.n_pieces;
-    const int grid = n_sm < n_items ? n_sm : n_items;
+    const int n_items = (n_pos * p.n_pieces) << p.twin;
+    int grid = n_sm < n_items ? n_sm : n_items;
+    if (p.twin) grid &= ~1;  // an even stride keeps every CTA on one joint and the pairs (2 i, 2 i + 1) together
     // function attributes are per device: set on every launch (a process may hold contexts on several GPUs)
     auto launch = [&](auto kernel, int ns) -> cudaError_t {
         const size_t smem = q_smem_bytes(ns);

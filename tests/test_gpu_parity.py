@@ -900,3 +900,24 @@ def test_config2_posteriors_all_cells_and_magnitude(ctx):
     fin = np.isfinite(wm)
     assert np.array_equal(np.isneginf(m), np.isneginf(wm))
     np.testing.assert_allclose(m[fin], wm[fin], rtol=1e-14, atol=1e-14)
+
+
+def test_twin_batch_joints_equal_separate_launches(ctx):
+    """the two composition-sampled joints of a batch-corrected call computed in one launch of the tcgen05 kernel (paired
+    items on neighbouring SMs, scde_b200_options.twin_batch_joints) against one launch per joint: integer sums, so the
+    results are bit-identical; 137 randomizations = two passes"""
+    w = synth.make_workload(5, n_genes=333, n_cells=90, seed=23, batch=True)
+    res = []
+    for twin in (1, 0):
+        keep = ctx.set_options(twin_batch_joints=twin)
+        try:
+            res.append(api.scde_expression_difference(w.models, w.counts, w.prior, groups=w.groups, batch=w.batch,
+                                                      n_randomizations=137, return_posteriors=True, context=ctx))
+        finally:
+            ctx.restore_options(keep)
+    for k in ("results", "batch.effect", "batch.adjusted"):
+        assert np.array_equal(res[0][k].to_numpy(), res[1][k].to_numpy()), k
+    assert np.array_equal(res[0]["batch.adjusted.difference.posterior"].to_numpy(),
+                          res[1]["batch.adjusted.difference.posterior"].to_numpy())
+    assert res[0]["stats"]["contract_cells"] == res[1]["stats"]["contract_cells"]
+    assert res[0]["stats"]["launches"]["contract"] == res[1]["stats"]["launches"]["contract"] - 2

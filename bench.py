@@ -63,7 +63,11 @@ def parse_args():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="scde_b200_options field (e.g. item_order=1, hot_rank=16); repeatable")
     ap.add_argument("--trace", action="store_true", help="host wall-clock of the one-shot call's phases on stderr")
+    ap.add_argument("--boot", type=int, default=None, help="n.randomizations (default 100, BASELINE.json; R's default is 150)")
     args = ap.parse_args()
+    if args.boot:
+        global N_BOOT
+        N_BOOT = args.boot
     return args
 
 

@@ -115,8 +115,9 @@ typedef struct {
     int32_t epilogue_timing;    /* 1: cycle counters of the tcgen05 kernel's epilogue on stderr */
     int32_t debug_contract;     /* FP64 tiled kernel: diagnostic mode (0 = off) */
     int32_t ring_stages;        /* tcgen05 contraction: stages of the shared-memory ring, 0 = default (10); 7 or 8 (experiments) */
-    int32_t twin_batch_joints;  /* 1 (default): the two composition-sampled joints of a batch-corrected call share the launches
-                                   of the tcgen05 kernel (same cells and rows, two W operands on neighbouring SMs) */
+    int32_t twin_batch_joints;  /* 1 (default): two contractions over the same cells and rows share the launches of the tcgen05
+                                   kernel (paired items on neighbouring SMs): the two composition-sampled joints of a
+                                   batch-corrected call, and the two passes of more than 104 randomizations */
     int32_t reserved[5];
 } scde_b200_options;
 SCDE_B200_API int scde_b200_get_options(const scde_b200_ctx *ctx, scde_b200_options *opt);

@@ -366,8 +366,10 @@ int index_from_counts(scde_b200_ctx *ctx, LpTable &t, const int32_t *counts_dev,
 
 struct JointScratch {
     DBuf<double> W, Z, zpart, T, spart;
+    DBuf<double> T2;    // T tiles of the second pass when two passes of randomizations share a launch
     DBuf<int8_t> W8;
     DBuf<uint32_t> SR;  // sentinel range of every (gene, boot) of one launch of the tcgen05 kernel
+    DBuf<uint32_t> SR2;
     DBuf<int32_t> lst_row, lst_cell, lst_len, order;
     DBuf<unsigned long long> total;  // running sum of list lengths over the joints of one run
 };
@@ -496,22 +498,43 @@ int run_joint(scde_b200_ctx *ctx, const LpTable &t, const int32_t *cell_ids_dev,
             q.W8_twin = s2.W8.p;   // one launch of the contraction kernel computes both joints' T tiles
             q.t_twin = s2.T.p;
         }
+        // More than 104 randomizations (R's default is 150): two passes over the same lists and rows.  Without a twin joint
+        // the passes are paired the same way -- pass ps and ps + 1 in one launch, on neighbouring SMs.
+        const bool pass_pairs = !tw && passes > 1 && ctx->opt.twin_batch_joints;
+        if (pass_pairs) {
+            SCDE_CUDA(scr.T2.ensure(contract_tiled_scratch_doubles(t.n_genes)));
+            SCDE_CUDA(scr.SR2.ensure(contract_i8_range_words(t.n_genes < max_genes ? t.n_genes : max_genes)));
+        }
         for (int g0 = 0; g0 < t.n_genes; g0 += max_genes) {
             const int n_pos = (t.n_genes - g0) < max_genes ? (t.n_genes - g0) : max_genes;
             for (int ps = 0; ps < passes; ++ps) {
+                const bool pair = pass_pairs && ps + 1 < passes;
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps, scr.SR.p, st));
                 if (tw) SCDE_CUDA(launch_sentinel_ranges(q2, g0, n_pos, ps, twin->scr->SR.p, st));
-                if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, tw ? 2 : 1);
+                if (pair) SCDE_CUDA(launch_sentinel_ranges(q, g0, n_pos, ps + 1, scr.SR2.p, st));
+                if (tm) tm->end(SCDE_B200_T_OTHER, e0, st, (tw || pair) ? 2 : 1);
                 e0 = tm ? tm->begin(st) : -1;
+                if (pair) {  // make_params adds the pass offset to both W pointers: the twin is the next pass
+                    q.W8_twin = q.W8 + (size_t)n_w_rows * Q_WB;
+                    q.t_twin = scr.T2.p;
+                }
                 SCDE_CUDA(launch_contract_i8_pass(q, g0, n_pos, ps, ctx->n_sm, scr.T.p, st));
+                if (pair) {
+                    q.W8_twin = nullptr;
+                    q.t_twin = nullptr;
+                }
                 if (tm) tm->end(SCDE_B200_T_CONTRACT, e0, st, 1);
                 e0 = tm ? tm->begin(st) : -1;
                 SCDE_CUDA(launch_softmax_i8(q, g0, n_pos, ps, scr.T.p, scr.SR.p, scr.spart.p, ctx->n_sm, st));
                 if (tw)
                     SCDE_CUDA(launch_softmax_i8(q2, g0, n_pos, ps, twin->scr->T.p, twin->scr->SR.p, twin->scr->spart.p,
                                                 ctx->n_sm, st));
-                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, tw ? 4 : 2);
+                if (pair) {
+                    SCDE_CUDA(launch_softmax_i8(q, g0, n_pos, ps + 1, scr.T2.p, scr.SR2.p, scr.spart.p, ctx->n_sm, st));
+                    ++ps;
+                }
+                if (tm) tm->end(SCDE_B200_T_SOFTMAX, e0, st, (tw || pair) ? 4 : 2);
             }
         }
         if (tw && twin_done) *twin_done = true;

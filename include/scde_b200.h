@@ -240,6 +240,10 @@ typedef struct {
     double *adjusted_difference_posterior; /* n x (4K-3) */
     double *joint_posteriors[2];           /* n x K each */
     double *batch_joint_posteriors[2];     /* n x K each */
+    /* cZ = sign(Z) qnorm(p.adjust(pnorm(|Z|, lower = F), "BH"), lower = F) (R/functions.R:5051) of the matching Z output, n
+     * each; computed on the host over the genes THIS call processes -- the reference's cZ when that is every gene (with a
+     * gene range the caller gathers Z and uses scde_b200_bh_cz).  Filled by scde_b200_expression_difference only. */
+    double *cz, *batch_cz, *adjusted_cz;
 } scde_b200_diff_out;
 
 /* Per-stage device timings of the last run on a job, in milliseconds (CUDA events on the context stream),

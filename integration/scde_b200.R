@@ -32,16 +32,15 @@ scde.expression.difference.b200 <- function(models, counts, prior, groups = NULL
              if(correct.batch) length(levels(batch)) else 0L, as.integer(n.randomizations), 1L, as.integer(zidx(rv)),
              as.integer(zidx(arv)), as.integer("corr.ltheta.b" %in% colnames(models)), as.integer("conc.a2" %in% colnames(models)),
              as.integer(devices), PACKAGE = "scde")
-  if(correct.batch) names(r) <- c("idx", "z", "batch.idx", "batch.z", "adjusted.idx", "adjusted.z")
-  frame <- function(idx, z, grid) {                          # quick.distribution.summary, R/functions.R:5045-5052
+  if(correct.batch) names(r) <- c("idx", "z", "cz", "batch.idx", "batch.z", "batch.cz", "adjusted.idx", "adjusted.z", "adjusted.cz")
+  frame <- function(idx, z, cz, grid) {                      # quick.distribution.summary, R/functions.R:5045-5052
     dq <- cbind(lb = grid[idx[, 1] + 1], mle = grid[idx[, 2] + 1], ub = grid[idx[, 3] + 1]) / log10(2)
     cq <- rep(0, nrow(dq)); cq[dq[, 1] > 0] <- dq[dq[, 1] > 0, 1]; cq[dq[, 3] < 0] <- dq[dq[, 3] < 0, 3]
-    z <- as.numeric(z)
-    data.frame(dq, ce = cq, Z = z, cZ = sign(z) * qnorm(p.adjust(pnorm(abs(z), lower.tail = FALSE), method = "BH"), lower.tail = FALSE),
-               row.names = rownames(counts))
+    # cZ comes from the library (BH over all genes of the call); in R: sign(z) * qnorm(p.adjust(pnorm(abs(z), lower.tail = F), "BH"), lower.tail = F)
+    data.frame(dq, ce = cq, Z = as.numeric(z), cZ = as.numeric(cz), row.names = rownames(counts))
   }
   if(correct.batch)
-    return(list(batch.adjusted = frame(r$adjusted.idx, r$adjusted.z, arv), results = frame(r$idx, r$z, rv),
-                batch.effect = frame(r$batch.idx, r$batch.z, rv)))
-  frame(r$idx, r$z, rv)
+    return(list(batch.adjusted = frame(r$adjusted.idx, r$adjusted.z, r$adjusted.cz, arv), results = frame(r$idx, r$z, r$cz, rv),
+                batch.effect = frame(r$batch.idx, r$batch.z, r$batch.cz, rv)))
+  frame(r$idx, r$z, r$cz, rv)
 }

@@ -183,7 +183,7 @@ RcppExport SEXP jpmatLogBatchBoot(SEXP Matll, SEXP Comp, SEXP Nboot, SEXP Seed) 
 //   Group    integer vector, 0 / 1 per cell, negative = NA;   Batch: integer codes 0..L-1 (negative = NA) or length 0
 //   ZeroIndex / ZeroIndexAdjusted: 1-based H0 grid positions (length 1 or genes)
 //   Devices  integer vector of CUDA device ids (length 0: SCDE_B200_DEVICES, else device 0) -- the n.cores of the GPU path
-// Returns list(idx, z[, batch.idx, batch.z, adjusted.idx, adjusted.z]).
+// Returns list(idx, z, cz[, batch.idx, batch.z, batch.cz, adjusted.idx, adjusted.z, adjusted.cz]).
 RcppExport SEXP scde_b200_diff(SEXP Counts, SEXP Models, SEXP BatchModels, SEXP PriorX, SEXP PriorY, SEXP Group, SEXP Batch,
                                SEXP NBatchLevels, SEXP Nboot, SEXP Seed, SEXP ZeroIndex, SEXP ZeroIndexAdjusted,
                                SEXP LocalThetaFit, SEXP SquareLogitConc, SEXP Devices) {
@@ -216,14 +216,18 @@ RcppExport SEXP scde_b200_diff(SEXP Counts, SEXP Models, SEXP BatchModels, SEXP 
     a.batch_square_logit_conc = a.square_logit_conc;
     std::vector<int> idx((size_t)3 * G), bidx(has_batch ? (size_t)3 * G : 0), aidx(has_batch ? (size_t)3 * G : 0);
     Rcpp::NumericMatrix z(G, 1), bz(has_batch ? G : 0, 1), az(has_batch ? G : 0, 1);
+    Rcpp::NumericMatrix cz(G, 1), bcz(has_batch ? G : 0, 1), acz(has_batch ? G : 0, 1);  // BH-corrected (R/functions.R:5051)
     scde_b200_diff_out o = scde_b200_diff_out();
     o.idx = idx.data();
     o.z = z.begin();
+    o.cz = cz.begin();
     if (has_batch) {
         o.batch_idx = bidx.data();
         o.batch_z = bz.begin();
+        o.batch_cz = bcz.begin();
         o.adjusted_idx = aidx.data();
         o.adjusted_z = az.begin();
+        o.adjusted_cz = acz.begin();
     }
     std::vector<int> dv(devs.begin(), devs.end());
     check(scde_b200_expression_difference(context(dv), &a, &o, NULL));
@@ -232,13 +236,18 @@ RcppExport SEXP scde_b200_diff(SEXP Counts, SEXP Models, SEXP BatchModels, SEXP 
         for (size_t i = 0; i < v.size(); ++i) m.begin()[i] = v[i];
         return m;
     };
-    if (!has_batch) return Rcpp::List::create(Rcpp::Named("idx") = Rcpp::wrap(as_matrix(idx)), Rcpp::Named("z") = Rcpp::wrap(z));
-    Rcpp::List out(6);  // idx, z, batch.idx, batch.z, adjusted.idx, adjusted.z (names set by the R wrapper)
+    if (!has_batch)
+        return Rcpp::List::create(Rcpp::Named("idx") = Rcpp::wrap(as_matrix(idx)), Rcpp::Named("z") = Rcpp::wrap(z),
+                                  Rcpp::Named("cz") = Rcpp::wrap(cz));
+    Rcpp::List out(9);  // idx, z, cz, batch.idx, batch.z, batch.cz, adjusted.idx, adjusted.z, adjusted.cz (named by the R wrapper)
     out[0] = as_matrix(idx);
     out[1] = z;
-    out[2] = as_matrix(bidx);
-    out[3] = bz;
-    out[4] = as_matrix(aidx);
-    out[5] = az;
+    out[2] = cz;
+    out[3] = as_matrix(bidx);
+    out[4] = bz;
+    out[5] = bcz;
+    out[6] = as_matrix(aidx);
+    out[7] = az;
+    out[8] = acz;
     return out;
 }

@@ -47,6 +47,7 @@ class DiffOut(C.Structure):
         ("difference_posterior", f64p), ("batch_difference_posterior", f64p),
         ("adjusted_difference_posterior", f64p),
         ("joint_posteriors", f64p * 2), ("batch_joint_posteriors", f64p * 2),
+        ("cz", f64p), ("batch_cz", f64p), ("adjusted_cz", f64p),
     ]
 
 

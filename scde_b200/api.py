@@ -379,17 +379,24 @@ def _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_co
     return a, keep_alive, G, K, has_batch
 
 
-def _diff_out(G, K, has_batch, want_posteriors, joint_posteriors):
+def _diff_out(G, K, has_batch, want_posteriors, joint_posteriors, want_cz=False):
     """scde_b200_diff_out pointing into freshly allocated host arrays; returns (out, dict of those arrays)."""
     o = _lib.DiffOut()
     res = {"idx": np.empty((G, 3), np.int32, order="F"), "z": np.empty(G)}
     o.idx, o.z = p_i32(res["idx"]), p_f64(res["z"])
+    if want_cz:  # BH-corrected cZ over the genes of the call (scde_b200_expression_difference only)
+        res["cz"] = np.empty(G)
+        o.cz = p_f64(res["cz"])
     if has_batch:
         for k in ("batch", "adjusted"):
             res[k + "_idx"] = np.empty((G, 3), np.int32, order="F")
             res[k + "_z"] = np.empty(G)
+            if want_cz:
+                res[k + "_cz"] = np.empty(G)
         o.batch_idx, o.batch_z = p_i32(res["batch_idx"]), p_f64(res["batch_z"])
         o.adjusted_idx, o.adjusted_z = p_i32(res["adjusted_idx"]), p_f64(res["adjusted_z"])
+        if want_cz:
+            o.batch_cz, o.adjusted_cz = p_f64(res["batch_cz"]), p_f64(res["adjusted_cz"])
     if want_posteriors:
         res["difference_posterior"] = np.empty((G, 2 * K - 1), order="F")
         o.difference_posterior = p_f64(res["difference_posterior"])
@@ -419,7 +426,7 @@ def expression_difference_call(ctx: _lib.Context, counts: np.ndarray, mm: np.nda
     a, keep_alive, G, K, has_batch = _diff_args(counts, mm, prior_x, prior_y, group_codes, n_boot, seed, batch_codes,
                                                 n_batch_levels, zero_index, zero_index_adjusted, local_theta, sqlogit,
                                                 boot_idx, gene_range, batch_mm, batch_local_theta, batch_sqlogit)
-    o, res = _diff_out(G, K, has_batch, want_posteriors, joint_posteriors)
+    o, res = _diff_out(G, K, has_batch, want_posteriors, joint_posteriors, want_cz=tuple(gene_range) == (0, 0))
     st = _lib.Stats()
     check(lib().scde_b200_expression_difference(ctx.handle, C.byref(a), C.byref(o), C.byref(st)))
     del keep_alive
@@ -536,7 +543,7 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
                                      batch_sqlogit=bsq)
     if verbose:
         sys.stdout.write("summarizing differences\n")
-    bdiffp_rep = _summary_frame(res["idx"], res["z"], diffv, genes)
+    bdiffp_rep = _summary_frame(res["idx"], res["z"], diffv, genes, cz=res.get("cz"))
     with np.errstate(over="ignore"):
         kcols = ["%.15g" % v for v in np.exp(marginals_from_prior(prior))]
 
@@ -548,9 +555,9 @@ def scde_expression_difference(models: pd.DataFrame, counts, prior, groups=None,
         return d
 
     if correct_batch:
-        out = {"batch.adjusted": _summary_frame(res["adjusted_idx"], res["adjusted_z"], adiffv, genes),
+        out = {"batch.adjusted": _summary_frame(res["adjusted_idx"], res["adjusted_z"], adiffv, genes, cz=res.get("adjusted_cz")),
                "results": bdiffp_rep,
-               "batch.effect": _summary_frame(res["batch_idx"], res["batch_z"], diffv, genes)}
+               "batch.effect": _summary_frame(res["batch_idx"], res["batch_z"], diffv, genes, cz=res.get("batch_cz"))}
         if return_posteriors:
             out.update(_posts())
             out["batch.adjusted.difference.posterior"] = pd.DataFrame(

@@ -2264,8 +2264,20 @@ int scde_b200_expression_difference(scde_b200_ctx *ctx, const scde_b200_diff_arg
                                     scde_b200_stats *stats) {
     CHECK_CTX(ctx);
     if (!args || !out) return SCDE_B200_EINVAL;
-    if (!ctx->children.empty()) return expression_difference_multi(ctx, args, out, stats);
-    return expression_difference_single(ctx, args, out, stats, nullptr);
+    if ((out->cz && !out->z) || (out->batch_cz && !out->batch_z) || (out->adjusted_cz && !out->adjusted_z)) {
+        set_error("expression_difference: a cZ output needs the matching Z output");
+        return SCDE_B200_EINVAL;
+    }
+    const int r = !ctx->children.empty() ? expression_difference_multi(ctx, args, out, stats)
+                                         : expression_difference_single(ctx, args, out, stats, nullptr);
+    if (r != SCDE_B200_OK) return r;
+    // Benjamini-Hochberg over the genes of this call, once, on the host (all shards of a multi-device call have landed)
+    const int n = (args->gene_begin == 0 && args->gene_end == 0) ? args->n_genes : args->gene_end - args->gene_begin;
+    const bool has_batch = args->batch != nullptr && args->n_batch_levels > 1;
+    if (out->cz) scde::bh_cz(out->z, n, out->cz);
+    if (has_batch && out->batch_cz) scde::bh_cz(out->batch_z, n, out->batch_cz);
+    if (has_batch && out->adjusted_cz) scde::bh_cz(out->adjusted_z, n, out->adjusted_cz);
+    return SCDE_B200_OK;
 }
 
 }  // extern "C"

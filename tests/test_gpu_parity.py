@@ -568,7 +568,7 @@ def test_one_shot_call_split_front_with_batch(ctx):
     one, two = _call_and_job(ctx, w, counts, **kw)
     n_cmp = 0
     for k, v in one.items():
-        if isinstance(v, np.ndarray):
+        if isinstance(v, np.ndarray) and not k.endswith("cz"):  # cZ (BH over the call's genes) is an output of the one-shot call only
             assert np.array_equal(v, two[k]), k
             n_cmp += 1
     assert n_cmp >= 4
@@ -923,3 +923,46 @@ def test_twin_batch_joints_equal_separate_launches(ctx):
     # one launch per joint and pass: 4 joints x 2 passes; shared: the group joints pair their two passes (1 launch each), the
     # batch joints pair up per pass (2 launches)
     assert res[1]["stats"]["launches"]["contract"] == 8 and res[0]["stats"]["launches"]["contract"] == 4
+
+
+@pytest.mark.parametrize("batch", [False, True])
+def test_r_shim_fused_entry(ctx, batch):
+    """`.Call("scde_b200_diff", ...)` of the R-package shim (integration/scde_b200_shim.cpp; what
+    scde.expression.difference.b200 in integration/scde_b200.R calls) with .Call-shaped arguments: grid indices, Z and
+    the BH-corrected cZ equal what the Python host layer gets from the same library call."""
+    import ctypes
+    import os
+
+    path = os.path.abspath(os.path.join(helpers.GOLD, "..", "..", "integration", "_build", "libscde_shim.so"))
+    if not os.path.exists(path):
+        pytest.skip("integration/_build/libscde_shim.so not built")
+    shim = ctypes.CDLL(path)
+    w = synth.make_workload(5 if batch else 3, n_genes=120, n_cells=40, seed=29, batch=batch)
+    mm, lt, sq = api.pack_models(w.models)
+    x, y = w.prior["x"].to_numpy(), w.prior["y"].to_numpy()
+    K, G, Cn = len(x), 120, 40
+    counts = np.asfortranarray(w.counts, dtype=np.int32)
+    group = np.asarray(w.groups.codes, dtype=np.int32)
+    bc = np.asarray(w.batch.codes, dtype=np.int32) if batch else None
+    n_sets = 3 if batch else 1
+    idx, z, cz = np.zeros(n_sets * 3 * G), np.zeros(n_sets * G), np.zeros(n_sets * G)
+    err = ctypes.create_string_buffer(256)
+    dev = np.zeros(1, dtype=np.int32)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    rc = shim.shim_diff(counts.ctypes.data_as(ip), G, Cn, np.asfortranarray(mm).ctypes.data_as(dp), x.ctypes.data_as(dp),
+                        y.ctypes.data_as(dp), K, group.ctypes.data_as(ip), bc.ctypes.data_as(ip) if batch else None,
+                        2 if batch else 0, 100, K, 2 * K - 1, dev.ctypes.data_as(ip), 1, idx.ctypes.data_as(dp),
+                        z.ctypes.data_as(dp), cz.ctypes.data_as(dp), err)
+    assert rc == 0, err.value
+    want = api.expression_difference_call(ctx, counts, mm, x, y, group, 100, 1, batch_codes=bc, n_batch_levels=2 if batch else 0,
+                                          zero_index=[K], zero_index_adjusted=[2 * K - 1], local_theta=lt, sqlogit=sq)
+    names = [("idx", "z", "cz")] + ([("batch_idx", "batch_z", "batch_cz"), ("adjusted_idx", "adjusted_z", "adjusted_cz")] if batch else [])
+    for s, (ki, kz, kc) in enumerate(names):
+        assert np.array_equal(idx[s * 3 * G:(s + 1) * 3 * G].reshape(3, G).T, want[ki])
+        assert np.array_equal(z[s * G:(s + 1) * G], want[kz])
+        assert np.array_equal(cz[s * G:(s + 1) * G], want[kc])
+    # and cZ is the reference's: BH over all genes (oracle)
+    pv = np.array([O.pnorm_upper(abs(v)) for v in want["z"]])
+    adj = O.p_adjust_bh(pv)
+    ref_cz = np.sign(want["z"]) * np.array([O.qnorm_upper(p) for p in adj])
+    np.testing.assert_allclose(want["cz"], ref_cz, rtol=1e-9, atol=1e-12)
